@@ -1,0 +1,161 @@
+/* resuneta.h — C-ABI of libresuneta.so: the B200 (sm_100a) kernels behind the ResUnet-a
+ * multitask hot path.  Plain pointers and sizes only; all tensors are caller-owned device
+ * memory, NHWC, dense.  Every launch is asynchronous on the given cudaStream_t (passed as
+ * void*), never synchronises the host and never allocates.  Return value: 0 on success,
+ * <0 = RSA_ERR_*; rsa_last_error() returns a thread-local message.
+ *
+ * Each entry point replaces work that the reference delegates to TensorFlow/Keras library
+ * kernels (the reference has no native code of its own); the call sites it
+ * stands in for are cited per function as  file:line  relative to the reference repo.
+ *
+ * dtype codes: RSA_F32 = 0 (validation mode), RSA_BF16 = 1 (performance mode).
+ */
+#ifndef RESUNETA_H
+#define RESUNETA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSA_F32 0
+#define RSA_BF16 1
+
+#define RSA_OK 0
+#define RSA_ERR_SHAPE (-1)
+#define RSA_ERR_DTYPE (-2)
+#define RSA_ERR_ALIGN (-3)
+#define RSA_ERR_ARCH (-4)
+#define RSA_ERR_CUDA (-5)
+
+#define RSA_MAX_SEG 16
+
+/* One K-segment of an implicit GEMM: `C` channels gathered from `src` (N,Hs,Ws,C) at
+ *   hs = ((h*mult) >> shift) + off_h ,  ws = ((w*mult) >> shift) + off_w
+ * for output pixel (n,h,w); out-of-range source pixels contribute 0 ('same' zero padding is
+ * applied AFTER any preceding BN+ReLU, model2.py:17-20).  aligned!=0 additionally requires
+ * (h*mult) and (w*mult) to be multiples of 1<<shift (transposed stride-2 gather).
+ * relu_in!=0 applies max(.,0) to the gathered value (combine, model2.py:82).
+ * w_off = element offset of this segment's weight block inside `w`. */
+typedef struct {
+  const void* src;
+  int32_t C, Hs, Ws;
+  int32_t mult, shift, off_h, off_w;
+  int32_t relu_in, aligned;
+  int64_t w_off;
+} rsa_seg_t;
+
+const char* rsa_version(void);
+const char* rsa_last_error(void);
+/* 0 if the current device is sm_100 (B200); RSA_ERR_ARCH otherwise. */
+int rsa_device_check(void);
+
+/* ---- generic implicit GEMM (fp32 accumulate, CUDA cores) --------------------------------
+ * out[m, co] = epi( sum_seg sum_c gather(seg, m)[c] * B_seg[c, co] + bias[co] )
+ *   transB==0: B_seg[c,co] = w[w_off + c*ldw + co]      (HWIO kernels / [K,Co] matrices)
+ *   transB!=0: B_seg[c,co] = w[w_off + co*ldw + c]      (data gradients)
+ * epi: += residual[m,co]; += old out (accumulate); relu; *= (mask[m,co] > 0); optional
+ * per-channel sum / sum-of-squares of the stored values atomically added into stats[2*Co]
+ * (double) — the statistics the next BatchNormalization needs.
+ * Replaces: Conv2D 3x3 dilated 'same' (model2.py:19-24), Conv2D 1x1 / stride 2
+ * (model2.py:37,84,92,101-111), UpSampling2D+Concatenate gathers (model2.py:55-76,83,91),
+ * head convs (model2.py:153-188) and all their data gradients. */
+int rsa_igemm_fwd(const rsa_seg_t* segs, int nseg, int in_dtype, const float* w, int ldw, int transB,
+                  const float* bias, void* out, int out_dtype, const void* residual, const void* mask,
+                  double* stats, int N, int Ho, int Wo, int Co, int accumulate, int relu, void* stream);
+
+/* dw[w_off + c*ldw + co] += sum_m gather(seg,m)[c] * dy[m,co];  dbias[co] += sum_m dy[m,co]
+ * (dbias may be NULL).  dw/dbias are fp32 and must be zeroed by the caller once per step. */
+int rsa_igemm_wgrad(const rsa_seg_t* segs, int nseg, int in_dtype, const void* dy, int dy_dtype,
+                    float* dw, int ldw, float* dbias, int N, int Ho, int Wo, int Co, void* stream);
+
+/* ---- BatchNormalization (keras defaults eps=1e-3, momentum=.99; model2.py:17,21,38,86,93) --
+ * Statistics travel as double[2*C] = {sum_c, sumsq_c} over `count` elements per channel.
+ * stats==NULL selects inference mode (moving statistics). */
+int rsa_bn_stats(const void* x, int dtype, int64_t M, int C, double* stats, void* stream);
+/* nout outputs y_k = act(gamma_k * xhat + beta_k), all sharing the statistics of x
+ * (the ResBlock-a branches normalise the same input, model2.py:17). */
+int rsa_bn_apply(const void* x, int dtype, int64_t M, int C, int nout, void* const* outs,
+                 const float* const* gammas, const float* const* betas, const double* stats, double count,
+                 const float* const* moving_means, const float* const* moving_vars, float eps, int relu,
+                 void* stream);
+/* red[2*C] (double, zeroed by caller) += { sum g, sum g*xhat },  g = dy * (act>0 if act) */
+int rsa_bn_bwd_reduce(const void* dy, const void* x, const void* act, int dtype, int64_t M, int C,
+                      const double* stats, double count, float eps, double* red, void* stream);
+/* dx (=|+=) gamma*invstd*(g - red0/count - xhat*red1/count); dgamma = red1, dbeta = red0 */
+int rsa_bn_bwd_apply(const void* dy, const void* x, const void* act, int dtype, int64_t M, int C,
+                     const double* stats, double count, float eps, const float* gamma, const double* red,
+                     void* dx, int accumulate, float* dgamma, float* dbeta, void* stream);
+/* statistics of y = gamma*xhat+beta derived analytically from the statistics of x */
+int rsa_bn_derive_stats(const double* src_stats, double count, const float* gamma, const float* beta,
+                        float eps, double* dst_stats, double dst_count, int C, void* stream);
+/* moving <- moving*momentum + batch*(1-momentum) for a table of BN layers in one launch.
+ * table[i] = {stats_off, C, mean_off, var_off} (int64 x4); counts[i] = {count, count_full}
+ * (count_full = element count of the tensor keras normalised; differs when the BN was evaluated
+ * at pooled resolution).  TF feeds the Bessel-corrected variance. */
+int rsa_bn_update_moving(const double* stats_base, float* param_base, const int64_t* table,
+                         const double* counts, int nlayers, float momentum, void* stream);
+
+/* ---- PSPPooling pyramid (model2.py:41-79) ---------------------------------------------------
+ * One pass over x (N,H,W,C) producing the stride-k max-pools k=2,4,8 (NULL to skip a level). */
+int rsa_maxpool_pyr_fwd(const void* x, int dtype, int N, int H, int W, int C, void* p2, void* p4, void* p8,
+                        void* stream);
+/* dx (=|+=) sum_k dp_k routed to the first maximum of each window (row-major scan order). */
+int rsa_maxpool_pyr_bwd(const void* x, int dtype, int N, int H, int W, int C, const void* dp2,
+                        const void* dp4, const void* dp8, void* dx, int accumulate, void* stream);
+/* stride-k window sums k=2,4,8 (adjoint of nearest up-sampling, UpSampling2D model2.py:55-60) */
+int rsa_sumpool_pyr(const void* x, int dtype, int N, int H, int W, int C, void* s2, void* s4, void* s8,
+                    void* stream);
+
+/* ---- head activations (model2.py:162,171,182,186) — fp32 [M,C], in place allowed ---------- */
+int rsa_softmax_fwd(const float* z, float* p, int64_t M, int C, void* stream);
+int rsa_softmax_bwd(const float* p, const float* dp, float* dz, int64_t M, int C, void* stream);
+int rsa_sigmoid_fwd(const float* z, float* p, int64_t n, void* stream);
+int rsa_sigmoid_bwd(const float* p, const float* dp, float* dz, int64_t n, void* stream);
+
+/* ---- Tanimoto dual loss (multitasking_utils.py:38-85) ---------------------------------------
+ * sums[B,C,5] (double, zeroed) += { Σp, Σp², Σl, Σl², Σp·l } over H*W */
+int rsa_tanimoto_sums(const float* pred, const float* label, int B, int64_t HW, int C, double* sums,
+                      void* stream);
+/* loss_b[B]; loss_mean[1] = mean_b loss_b; coef[B,C,3] with
+ * d(scale*loss_mean)/d pred[b,x,c] = coef0 + coef1*pred + coef2*label (gradient flows through the
+ * prediction-derived class weights of the first term, multitasking_utils.py:79). */
+int rsa_tanimoto_finalize(const double* sums, int B, int64_t HW, int C, float scale, float* loss_b,
+                          float* loss_mean, float* coef, void* stream);
+int rsa_tanimoto_bwd(const float* pred, const float* label, const float* coef, int B, int64_t HW, int C,
+                     float* dpred, void* stream);
+
+/* ---- element-wise losses, keras SUM_OVER_BATCH_SIZE mean over [B,H,W] -------------------------
+ * kind: 0 weighted/plain categorical CE (utils.py:466-491; weights NULL = 1), 1 binary CE,
+ * 2 mean squared error (train_ISPRS.py:426-428).  loss_sum[1] (double, zeroed) += Σ_pixels loss. */
+int rsa_pixel_loss_fwd(int kind, const float* pred, const float* label, const float* weights, int64_t M,
+                       int C, double* loss_sum, void* stream);
+int rsa_pixel_loss_bwd(int kind, const float* pred, const float* label, const float* weights, int64_t M,
+                       int C, float scale, float* dpred, void* stream);
+
+/* seg metrics (train_ISPRS.py:446-449): out[5] (int64, zeroed) += {argmax matches, TP, FP, TN, FN}@0.5 */
+int rsa_seg_metrics(const float* pred, const float* label, int64_t M, int C, int64_t* out, void* stream);
+
+/* ---- optimizers (train_ISPRS.py:404-407; keras forms) ---------------------------- */
+/* lr_dev != NULL: the step size is read from device memory (lets a captured CUDA graph be replayed
+ * while keras' bias-corrected lr_t / a changed optimizer.lr varies from step to step). */
+int rsa_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t,
+                  const float* lr_dev, float beta1, float beta2, float eps, float grad_scale, void* stream);
+int rsa_sgd_step(float* param, const float* grad, float* vel, int64_t n, float lr, const float* lr_dev,
+                 float momentum, float grad_scale, void* stream);
+
+/* ---- inference side (test_ISPRS.py:295-314) -----------------------------------------------------
+ * pred_label[m] = argmax_c prob[m,c] (first maximum, numpy semantics); optional confusion matrix
+ * cm[K,K] (int64, zeroed; rows = true label) += counts, with true_label int32 in [0,K). */
+int rsa_argmax_confusion(const float* prob, int64_t M, int C, int32_t* pred_label, const int32_t* true_label,
+                         int K, int64_t* cm, void* stream);
+
+/* dst (=|+=) src, identity branch of the ResBlock-a backward (Add, model2.py:31) */
+int rsa_axpy(void* dst, const void* src, int dtype, int64_t n, int accumulate, void* stream);
+
+/* dtype conversion helper (host tensors arrive as fp32, train_ISPRS.py:122-141) */
+int rsa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

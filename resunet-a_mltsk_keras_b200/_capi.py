@@ -1,0 +1,308 @@
+"""ctypes binding of libresuneta.so (C-ABI declared in include/resuneta.h).
+
+Every method of :class:`Lib` validates/convert its arguments ONCE and returns a callable
+``launch(stream)`` that issues the kernel on the given ``cudaStream_t`` — the execution plans
+(graph.py) pre-bind all launches at plan-build time so that a training step is a flat loop of
+C calls (and can be captured in a CUDA graph).  Tensors are torch CUDA tensors used purely as
+device-memory handles (``data_ptr()``); they can equally come from DLPack
+(``torch.from_dlpack``) — the boundary itself only sees raw pointers.
+
+There is NO CPU fallback: if the shared library is missing or the device is not sm_100 the
+constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libresuneta.so")
+
+RSA_F32, RSA_BF16 = 0, 1
+MAX_SEG = 16
+
+
+class SegC(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("C", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32),
+                ("mult", C.c_int32), ("shift", C.c_int32), ("off_h", C.c_int32), ("off_w", C.c_int32),
+                ("relu_in", C.c_int32), ("aligned", C.c_int32), ("w_off", C.c_int64)]
+
+
+@dataclass
+class Seg:
+    """One K-segment of an implicit GEMM (see rsa_seg_t in include/resuneta.h)."""
+    src: torch.Tensor
+    C: int
+    Hs: int
+    Ws: int
+    mult: int = 1
+    shift: int = 0
+    off_h: int = 0
+    off_w: int = 0
+    relu_in: bool = False
+    aligned: bool = False
+    w_off: int = 0
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return RSA_F32
+    if t.dtype == torch.bfloat16:
+        return RSA_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+_SIGS = {
+    "rsa_igemm_fwd": [C.POINTER(SegC), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                      C.c_int, C.c_void_p],
+    "rsa_igemm_wgrad": [C.POINTER(SegC), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "rsa_bn_stats": [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p],
+    "rsa_bn_apply": [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_double,
+                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_float, C.c_int, C.c_void_p],
+    "rsa_bn_bwd_reduce": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_double,
+                          C.c_float, C.c_void_p, C.c_void_p],
+    "rsa_bn_bwd_apply": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_double,
+                         C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                         C.c_void_p],
+    "rsa_bn_derive_stats": [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_double,
+                            C.c_int, C.c_void_p],
+    "rsa_bn_update_moving": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p],
+    "rsa_maxpool_pyr_fwd": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                            C.c_void_p, C.c_void_p],
+    "rsa_maxpool_pyr_bwd": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p],
+    "rsa_sumpool_pyr": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                        C.c_void_p, C.c_void_p],
+    "rsa_softmax_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p],
+    "rsa_softmax_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p],
+    "rsa_sigmoid_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+    "rsa_sigmoid_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+    "rsa_tanimoto_sums": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p],
+    "rsa_tanimoto_finalize": [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p],
+    "rsa_tanimoto_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p],
+    "rsa_pixel_loss_fwd": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                           C.c_void_p],
+    "rsa_pixel_loss_bwd": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+                           C.c_void_p, C.c_void_p],
+    "rsa_seg_metrics": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p],
+    "rsa_adam_step": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_float,
+                      C.c_float, C.c_float, C.c_float, C.c_void_p],
+    "rsa_sgd_step": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_float, C.c_float,
+                     C.c_void_p],
+    "rsa_argmax_confusion": [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                             C.c_void_p],
+    "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
+    "rsa_cast": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p],
+}
+
+EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check"])
+
+
+def load_cdll(path=LIB_PATH):
+    """dlopen the library and declare prototypes.  No device needed (used by the CPU symbol test)."""
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    dll = C.CDLL(path)
+    for name, sig in _SIGS.items():
+        fn = getattr(dll, name)
+        fn.argtypes = sig
+        fn.restype = C.c_int
+    dll.rsa_version.restype = C.c_char_p
+    dll.rsa_last_error.restype = C.c_char_p
+    dll.rsa_device_check.restype = C.c_int
+    for extra in ("rsa_conv_tc_fwd", "rsa_conv_tc_wgrad", "rsa_conv_tc_supported"):
+        if hasattr(dll, extra):
+            getattr(dll, extra).restype = C.c_int
+    return dll
+
+
+class Lib:
+    """Kernel launcher over the C-ABI.  Methods return ``launch(stream:int)`` callables."""
+
+    is_emulation = False
+
+    def __init__(self, path=LIB_PATH, check_device=True):
+        self.dll = load_cdll(path)
+        if check_device:
+            if not torch.cuda.is_available():
+                raise RuntimeError("libresuneta needs a CUDA device (B200); there is no CPU path")
+            rc = self.dll.rsa_device_check()
+            if rc:
+                raise RuntimeError("rsa_device_check: " + self.dll.rsa_last_error().decode())
+        self.launches = 0   # kernels launched through this object (bench.py's gpu_launches claim)
+
+    # ------------------------------------------------------------------------------------------
+    def _bind(self, name, *args, keep=()):
+        fn = getattr(self.dll, name)
+        dll = self.dll
+        lib = self
+
+        def launch(stream, _fn=fn, _args=args, _keep=keep):
+            rc = _fn(*_args, stream)
+            lib.launches += 1
+            if rc:
+                raise RuntimeError(f"{name} failed ({rc}): {dll.rsa_last_error().decode()}")
+        launch.kernel = name
+        return launch
+
+    @staticmethod
+    def _segs(segs):
+        assert 1 <= len(segs) <= MAX_SEG, len(segs)
+        arr = (SegC * len(segs))()
+        dt = None
+        for i, s in enumerate(segs):
+            d = dtype_code(s.src)
+            assert dt is None or dt == d, "all segments must share a dtype"
+            dt = d
+            arr[i] = SegC(s.src.data_ptr(), s.C, s.Hs, s.Ws, s.mult, s.shift, s.off_h, s.off_w,
+                          int(s.relu_in), int(s.aligned), s.w_off)
+        return arr, dt
+
+    # -- implicit GEMM -------------------------------------------------------------------------
+    def igemm_fwd(self, segs, w, ldw, transB, bias, out, N, Ho, Wo, Co, residual=None, mask=None, stats=None,
+                  accumulate=False, relu=False):
+        arr, dt = self._segs(segs)
+        assert w.dtype == torch.float32 and (bias is None or bias.dtype == torch.float32)
+        return self._bind("rsa_igemm_fwd", arr, len(segs), dt, _p(w), ldw, int(transB), _p(bias), _p(out),
+                          dtype_code(out), _p(residual), _p(mask), _p(stats), N, Ho, Wo, Co, int(accumulate),
+                          int(relu), keep=(segs, w, bias, out, residual, mask, stats))
+
+    def igemm_wgrad(self, segs, dy, dw, ldw, dbias, N, Ho, Wo, Co):
+        arr, dt = self._segs(segs)
+        assert dw.dtype == torch.float32
+        return self._bind("rsa_igemm_wgrad", arr, len(segs), dt, _p(dy), dtype_code(dy), _p(dw), ldw, _p(dbias),
+                          N, Ho, Wo, Co, keep=(segs, dy, dw, dbias))
+
+    # -- batch norm -----------------------------------------------------------------------------
+    def bn_stats(self, x, M, C_, stats):
+        return self._bind("rsa_bn_stats", _p(x), dtype_code(x), M, C_, _p(stats), keep=(x, stats))
+
+    @staticmethod
+    def _ptr_array(ts):
+        if ts is None:
+            return None
+        arr = (C.c_void_p * len(ts))()
+        for i, t in enumerate(ts):
+            arr[i] = t.data_ptr()
+        return arr
+
+    def bn_apply(self, x, M, C_, outs, gammas, betas, stats, count, mmeans, mvars, eps, relu):
+        return self._bind("rsa_bn_apply", _p(x), dtype_code(x), M, C_, len(outs), self._ptr_array(outs),
+                          self._ptr_array(gammas), self._ptr_array(betas), _p(stats), float(count),
+                          self._ptr_array(mmeans), self._ptr_array(mvars), float(eps), int(relu),
+                          keep=(x, outs, gammas, betas, stats, mmeans, mvars))
+
+    def bn_bwd_reduce(self, dy, x, act, M, C_, stats, count, eps, red):
+        return self._bind("rsa_bn_bwd_reduce", _p(dy), _p(x), _p(act), dtype_code(x), M, C_, _p(stats),
+                          float(count), float(eps), _p(red), keep=(dy, x, act, stats, red))
+
+    def bn_bwd_apply(self, dy, x, act, M, C_, stats, count, eps, gamma, red, dx, accumulate, dgamma, dbeta):
+        return self._bind("rsa_bn_bwd_apply", _p(dy), _p(x), _p(act), dtype_code(x), M, C_, _p(stats),
+                          float(count), float(eps), _p(gamma), _p(red), _p(dx), int(accumulate), _p(dgamma),
+                          _p(dbeta), keep=(dy, x, act, stats, gamma, red, dx, dgamma, dbeta))
+
+    def bn_derive_stats(self, src_stats, count, gamma, beta, eps, dst_stats, dst_count, C_):
+        return self._bind("rsa_bn_derive_stats", _p(src_stats), float(count), _p(gamma), _p(beta), float(eps),
+                          _p(dst_stats), float(dst_count), C_, keep=(src_stats, gamma, beta, dst_stats))
+
+    def bn_update_moving(self, stats_base, param_base, table, counts, nlayers, momentum):
+        return self._bind("rsa_bn_update_moving", _p(stats_base), _p(param_base), _p(table), _p(counts), nlayers,
+                          float(momentum), keep=(stats_base, param_base, table, counts))
+
+    # -- pooling pyramid ------------------------------------------------------------------------
+    def maxpool_pyr_fwd(self, x, N, H, W, C_, p2, p4, p8):
+        return self._bind("rsa_maxpool_pyr_fwd", _p(x), dtype_code(x), N, H, W, C_, _p(p2), _p(p4), _p(p8),
+                          keep=(x, p2, p4, p8))
+
+    def maxpool_pyr_bwd(self, x, N, H, W, C_, dp2, dp4, dp8, dx, accumulate):
+        return self._bind("rsa_maxpool_pyr_bwd", _p(x), dtype_code(x), N, H, W, C_, _p(dp2), _p(dp4), _p(dp8),
+                          _p(dx), int(accumulate), keep=(x, dp2, dp4, dp8, dx))
+
+    def sumpool_pyr(self, x, N, H, W, C_, s2, s4, s8):
+        return self._bind("rsa_sumpool_pyr", _p(x), dtype_code(x), N, H, W, C_, _p(s2), _p(s4), _p(s8),
+                          keep=(x, s2, s4, s8))
+
+    # -- heads / losses -------------------------------------------------------------------------
+    def softmax_fwd(self, z, p, M, C_):
+        return self._bind("rsa_softmax_fwd", _p(z), _p(p), M, C_, keep=(z, p))
+
+    def softmax_bwd(self, p, dp, dz, M, C_):
+        return self._bind("rsa_softmax_bwd", _p(p), _p(dp), _p(dz), M, C_, keep=(p, dp, dz))
+
+    def sigmoid_fwd(self, z, p, n):
+        return self._bind("rsa_sigmoid_fwd", _p(z), _p(p), n, keep=(z, p))
+
+    def sigmoid_bwd(self, p, dp, dz, n):
+        return self._bind("rsa_sigmoid_bwd", _p(p), _p(dp), _p(dz), n, keep=(p, dp, dz))
+
+    def tanimoto_sums(self, pred, label, B, HW, C_, sums):
+        return self._bind("rsa_tanimoto_sums", _p(pred), _p(label), B, HW, C_, _p(sums), keep=(pred, label, sums))
+
+    def tanimoto_finalize(self, sums, B, HW, C_, scale, loss_b, loss_mean, coef):
+        return self._bind("rsa_tanimoto_finalize", _p(sums), B, HW, C_, float(scale), _p(loss_b), _p(loss_mean),
+                          _p(coef), keep=(sums, loss_b, loss_mean, coef))
+
+    def tanimoto_bwd(self, pred, label, coef, B, HW, C_, dpred):
+        return self._bind("rsa_tanimoto_bwd", _p(pred), _p(label), _p(coef), B, HW, C_, _p(dpred),
+                          keep=(pred, label, coef, dpred))
+
+    def pixel_loss_fwd(self, kind, pred, label, weights, M, C_, loss_sum):
+        return self._bind("rsa_pixel_loss_fwd", kind, _p(pred), _p(label), _p(weights), M, C_, _p(loss_sum),
+                          keep=(pred, label, weights, loss_sum))
+
+    def pixel_loss_bwd(self, kind, pred, label, weights, M, C_, scale, dpred):
+        return self._bind("rsa_pixel_loss_bwd", kind, _p(pred), _p(label), _p(weights), M, C_, float(scale),
+                          _p(dpred), keep=(pred, label, weights, dpred))
+
+    def seg_metrics(self, pred, label, M, C_, out):
+        return self._bind("rsa_seg_metrics", _p(pred), _p(label), M, C_, _p(out), keep=(pred, label, out))
+
+    def argmax_confusion(self, prob, M, C_, pred_label, true_label, K, cm):
+        return self._bind("rsa_argmax_confusion", _p(prob), M, C_, _p(pred_label), _p(true_label), K, _p(cm),
+                          keep=(prob, pred_label, true_label, cm))
+
+    # -- optimizers / misc ----------------------------------------------------------------------
+    def adam_step(self, param, grad, m, v, n, lr_dev, b1, b2, eps, grad_scale):
+        """lr_dev: 1-element fp32 device tensor holding keras' bias-corrected lr_t for this step."""
+        return self._bind("rsa_adam_step", _p(param), _p(grad), _p(m), _p(v), n, 0.0, _p(lr_dev), float(b1),
+                          float(b2), float(eps), float(grad_scale), keep=(param, grad, m, v, lr_dev))
+
+    def sgd_step(self, param, grad, vel, n, lr_dev, momentum, grad_scale):
+        return self._bind("rsa_sgd_step", _p(param), _p(grad), _p(vel), n, 0.0, _p(lr_dev), float(momentum),
+                          float(grad_scale), keep=(param, grad, vel, lr_dev))
+
+    def axpy(self, dst, src, n, accumulate):
+        return self._bind("rsa_axpy", _p(dst), _p(src), dtype_code(dst), n, int(accumulate), keep=(dst, src))
+
+    def cast(self, src, dst, n):
+        return self._bind("rsa_cast", _p(src), dtype_code(src), _p(dst), dtype_code(dst), n, keep=(src, dst))
+
+
+_LIB = None
+
+
+def get_lib():
+    """Process-wide launcher; raises if the CUDA extension or device is missing."""
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib()
+    return _LIB
+
+
+def set_lib(lib):
+    """Test hook: install another launcher object (the CPU test-suite installs an emulation that
+    exercises the host-side graph logic; product code never does this)."""
+    global _LIB
+    _LIB = lib

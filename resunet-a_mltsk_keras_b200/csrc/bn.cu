@@ -1,0 +1,364 @@
+// bn.cu — BatchNormalization forward / backward on NHWC tensors viewed as [M, C].
+//
+// Keras semantics (model2.py:17,21,38,86,93): training mode normalises with the
+// batch mean and *biased* variance, eps = 1e-3; the moving averages take the Bessel-corrected
+// variance with momentum 0.99.  Statistics are exchanged as double {sum, sumsq} so that the
+// producers (conv epilogues) can accumulate them with atomics and fp32 validation mode keeps
+// 1e-4 at a million pixels per channel.  All kernels are HBM-bound: 16-byte vector access,
+// channel-contiguous, coefficient tables staged once per block in shared memory.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int MAX_OUT = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(NT) bn_stats_kernel(const T* __restrict__ x, int64_t M, int C,
+                                                      double* __restrict__ stats, int rows_per_block) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm[];           // [2][NT*V]
+  const int tpr = C / V;                  // threads per row
+  const int rpi = NT / tpr;               // rows per iteration
+  const int tid = threadIdx.x;
+  const int cg = tid % tpr, r0 = tid / tpr;
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
+  int64_t rend = min(M, rbeg + rows_per_block);
+  if (r0 < rpi) {
+    for (int64_t r = rbeg + r0; r < rend; r += rpi) {
+      float v[V];
+      ldv<T>(x + r * C + cg * V, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+    }
+  }
+  float* ss = sm;
+  float* sq = sm + NT * V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { ss[tid * V + i] = s[i]; sq[tid * V + i] = q[i]; }
+  __syncthreads();
+  for (int c = tid; c < C; c += NT) {
+    int g = c / V, i = c % V;
+    double a = 0, b = 0;
+    for (int r = 0; r < rpi; ++r) {
+      a += ss[(r * tpr + g) * V + i];
+      b += sq[(r * tpr + g) * V + i];
+    }
+    atomicAdd(stats + c, a);
+    atomicAdd(stats + C + c, b);
+  }
+}
+
+struct ApplyParams {
+  void* out[MAX_OUT];
+  const float* gamma[MAX_OUT];
+  const float* beta[MAX_OUT];
+  const float* mmean[MAX_OUT];
+  const float* mvar[MAX_OUT];
+  int nout;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT) bn_apply_kernel(const T* __restrict__ x, int64_t nvec, int C,
+                                                      const ApplyParams ap, const double* __restrict__ stats,
+                                                      double count, float eps, int relu) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm[];   // [nout][2][C]: scale, shift
+  for (int i = threadIdx.x; i < ap.nout * C; i += NT) {
+    int k = i / C, c = i % C;
+    float mean, invstd;
+    bn_mean_invstd(stats, count, C, c, eps, ap.mmean[k], ap.mvar[k], mean, invstd);
+    float sc = ap.gamma[k][c] * invstd;
+    sm[(k * 2) * C + c] = sc;
+    sm[(k * 2 + 1) * C + c] = ap.beta[k][c] - mean * sc;
+  }
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * NT) {
+    float v[V];
+    ldv<T>(x + i * V, v);
+    int c0 = (int)((i * V) % C);
+    for (int k = 0; k < ap.nout; ++k) {
+      const float* sc = sm + (k * 2) * C + c0;
+      const float* sh = sm + (k * 2 + 1) * C + c0;
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float t = fmaf(v[j], sc[j], sh[j]);
+        o[j] = relu ? fmaxf(t, 0.f) : t;
+      }
+      stv<T>(reinterpret_cast<T*>(ap.out[k]) + i * V, o);
+    }
+  }
+}
+
+// red[c] += sum g ; red[C+c] += sum g*xhat
+template <typename T>
+__global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                           const T* __restrict__ act, int64_t M, int C,
+                                                           const double* __restrict__ stats, double count,
+                                                           float eps, double* __restrict__ red,
+                                                           int rows_per_block) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm[];   // [2][NT*V]
+  const int tpr = C / V, rpi = NT / tpr, tid = threadIdx.x;
+  const int cg = tid % tpr, r0 = tid / tpr;
+  float mean[V], inv[V], s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    bn_mean_invstd(stats, count, C, cg * V + i, eps, nullptr, nullptr, mean[i], inv[i]);
+    s[i] = 0.f; q[i] = 0.f;
+  }
+  int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
+  int64_t rend = min(M, rbeg + rows_per_block);
+  if (r0 < rpi) {
+    for (int64_t r = rbeg + r0; r < rend; r += rpi) {
+      float g[V], xv[V], a[V];
+      int64_t o = r * C + cg * V;
+      ldv<T>(dy + o, g);
+      ldv<T>(x + o, xv);
+      if (act) {
+        ldv<T>(act + o, a);
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] = a[i] > 0.f ? g[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += g[i]; q[i] += g[i] * (xv[i] - mean[i]) * inv[i]; }
+    }
+  }
+  float* ss = sm;
+  float* sq = sm + NT * V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { ss[tid * V + i] = s[i]; sq[tid * V + i] = q[i]; }
+  __syncthreads();
+  for (int c = tid; c < C; c += NT) {
+    int g = c / V, i = c % V;
+    double a = 0, b = 0;
+    for (int r = 0; r < rpi; ++r) {
+      a += ss[(r * tpr + g) * V + i];
+      b += sq[(r * tpr + g) * V + i];
+    }
+    atomicAdd(red + c, a);
+    atomicAdd(red + C + c, b);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                          const T* __restrict__ act, int64_t nvec, int C,
+                                                          const double* __restrict__ stats, double count,
+                                                          float eps, const float* __restrict__ gamma,
+                                                          const double* __restrict__ red, T* __restrict__ dx,
+                                                          int accumulate, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm[];   // [4][C]: mean, invstd, k0 = gamma*invstd, (c1 = sum g / n, c2 = sum g xhat / n) packed
+  float* s_mean = sm;
+  float* s_inv = sm + C;
+  float* s_c1 = sm + 2 * C;
+  float* s_c2 = sm + 3 * C;
+  float* s_g = sm + 4 * C;
+  for (int c = threadIdx.x; c < C; c += NT) {
+    float mean, inv;
+    bn_mean_invstd(stats, count, C, c, eps, nullptr, nullptr, mean, inv);
+    s_mean[c] = mean;
+    s_inv[c] = inv;
+    s_c1[c] = (float)(red[c] / count);
+    s_c2[c] = (float)(red[C + c] / count);
+    s_g[c] = gamma[c] * inv;
+    if (blockIdx.x == 0) {
+      if (dgamma) dgamma[c] = (float)red[C + c];
+      if (dbeta) dbeta[c] = (float)red[c];
+    }
+  }
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * NT) {
+    float g[V], xv[V], o[V];
+    ldv<T>(dy + i * V, g);
+    ldv<T>(x + i * V, xv);
+    if (act) {
+      float a[V];
+      ldv<T>(act + i * V, a);
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+    }
+    if (accumulate) ldv<T>(dx + i * V, o);
+    int c0 = (int)((i * V) % C);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      int c = c0 + j;
+      float xh = (xv[j] - s_mean[c]) * s_inv[c];
+      float d = s_g[c] * (g[j] - s_c1[c] - xh * s_c2[c]);
+      o[j] = accumulate ? o[j] + d : d;
+    }
+    stv<T>(dx + i * V, o);
+  }
+}
+
+__global__ void bn_derive_stats_kernel(const double* __restrict__ src, double count, const float* gamma,
+                                       const float* beta, float eps, double* __restrict__ dst, double dcount,
+                                       int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mu = src[c] / count;
+  double var = src[C + c] / count - mu * mu;
+  if (var < 0) var = 0;
+  double g = gamma[c], b = beta[c];
+  double vy = g * g * var / (var + (double)eps);   // biased variance of gamma*xhat+beta
+  dst[c] = dcount * b;
+  dst[C + c] = dcount * (vy + b * b);
+}
+
+__global__ void bn_update_moving_kernel(const double* __restrict__ stats_base, float* __restrict__ param_base,
+                                        const int64_t* __restrict__ table, const double* __restrict__ counts,
+                                        int nlayers, float momentum) {
+  int layer = blockIdx.x;
+  if (layer >= nlayers) return;
+  const int64_t soff = table[layer * 4 + 0];
+  const int C = (int)table[layer * 4 + 1];
+  float* mm = param_base + table[layer * 4 + 2];
+  float* mv = param_base + table[layer * 4 + 3];
+  const double n = counts[layer * 2 + 0], nfull = counts[layer * 2 + 1];
+  const double* st = stats_base + soff;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double mu = st[c] / n;
+    double var = st[C + c] / n - mu * mu;
+    if (var < 0) var = 0;
+    double var_u = nfull > 1.0 ? var * (nfull / (nfull - 1.0)) : var;
+    mm[c] = (float)((double)mm[c] * momentum + mu * (1.0 - (double)momentum));
+    mv[c] = (float)((double)mv[c] * momentum + var_u * (1.0 - (double)momentum));
+  }
+}
+
+template <typename T> bool bn_shape_ok(int C) {
+  constexpr int V = Vec16<T>::N;
+  if (C < V || C % V) return false;
+  int tpr = C / V;
+  return tpr <= NT && (NT % tpr) == 0;
+}
+
+inline int grid_for(int64_t nvec) {
+  int64_t b = ceil_div64(nvec, NT);
+  int64_t cap = (int64_t)rsa_num_sms() * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int rsa_bn_stats(const void* x, int dtype, int64_t M, int C, double* stats, void* stream) {
+  RSA_REQUIRE(x && stats && M > 0, RSA_ERR_SHAPE, "bn_stats: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 4);
+  if (rows < 64) rows = 64;
+  int grid = (int)ceil_div64(M, rows);
+  if (dtype == RSA_F32) {
+    RSA_REQUIRE(bn_shape_ok<float>(C), RSA_ERR_SHAPE, "bn_stats: C=%d unsupported", C);
+    bn_stats_kernel<float><<<grid, NT, 2 * NT * 4 * sizeof(float), st>>>((const float*)x, M, C, stats, rows);
+  } else if (dtype == RSA_BF16) {
+    RSA_REQUIRE(bn_shape_ok<bf16>(C), RSA_ERR_SHAPE, "bn_stats: C=%d unsupported", C);
+    bn_stats_kernel<bf16><<<grid, NT, 2 * NT * 8 * sizeof(float), st>>>((const bf16*)x, M, C, stats, rows);
+  } else {
+    RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_stats: bad dtype");
+  }
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+extern "C" int rsa_bn_apply(const void* x, int dtype, int64_t M, int C, int nout, void* const* outs,
+                            const float* const* gammas, const float* const* betas, const double* stats,
+                            double count, const float* const* moving_means, const float* const* moving_vars,
+                            float eps, int relu, void* stream) {
+  RSA_REQUIRE(x && outs && gammas && betas && M > 0 && nout >= 1 && nout <= MAX_OUT, RSA_ERR_SHAPE,
+              "bn_apply: bad args");
+  RSA_REQUIRE(stats || (moving_means && moving_vars), RSA_ERR_SHAPE, "bn_apply: no statistics given");
+  ApplyParams ap;
+  ap.nout = nout;
+  for (int k = 0; k < MAX_OUT; ++k) {
+    int kk = k < nout ? k : 0;
+    ap.out[k] = outs[kk]; ap.gamma[k] = gammas[kk]; ap.beta[k] = betas[kk];
+    ap.mmean[k] = moving_means ? moving_means[kk] : nullptr;
+    ap.mvar[k] = moving_vars ? moving_vars[kk] : nullptr;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = (size_t)nout * 2 * C * sizeof(float);
+  if (dtype == RSA_F32) {
+    RSA_REQUIRE(C % 4 == 0, RSA_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 4", C);
+    int64_t nvec = M * C / 4;
+    bn_apply_kernel<float><<<grid_for(nvec), NT, smem, st>>>((const float*)x, nvec, C, ap, stats, count, eps, relu);
+  } else if (dtype == RSA_BF16) {
+    RSA_REQUIRE(C % 8 == 0, RSA_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 8", C);
+    int64_t nvec = M * C / 8;
+    bn_apply_kernel<bf16><<<grid_for(nvec), NT, smem, st>>>((const bf16*)x, nvec, C, ap, stats, count, eps, relu);
+  } else {
+    RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_apply: bad dtype");
+  }
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+extern "C" int rsa_bn_bwd_reduce(const void* dy, const void* x, const void* act, int dtype, int64_t M, int C,
+                                 const double* stats, double count, float eps, double* red, void* stream) {
+  RSA_REQUIRE(dy && x && stats && red && M > 0, RSA_ERR_SHAPE, "bn_bwd_reduce: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 4);
+  if (rows < 64) rows = 64;
+  int grid = (int)ceil_div64(M, rows);
+  if (dtype == RSA_F32) {
+    RSA_REQUIRE(bn_shape_ok<float>(C), RSA_ERR_SHAPE, "bn_bwd_reduce: C=%d unsupported", C);
+    bn_bwd_reduce_kernel<float><<<grid, NT, 2 * NT * 4 * sizeof(float), st>>>(
+        (const float*)dy, (const float*)x, (const float*)act, M, C, stats, count, eps, red, rows);
+  } else if (dtype == RSA_BF16) {
+    RSA_REQUIRE(bn_shape_ok<bf16>(C), RSA_ERR_SHAPE, "bn_bwd_reduce: C=%d unsupported", C);
+    bn_bwd_reduce_kernel<bf16><<<grid, NT, 2 * NT * 8 * sizeof(float), st>>>(
+        (const bf16*)dy, (const bf16*)x, (const bf16*)act, M, C, stats, count, eps, red, rows);
+  } else {
+    RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_bwd_reduce: bad dtype");
+  }
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+extern "C" int rsa_bn_bwd_apply(const void* dy, const void* x, const void* act, int dtype, int64_t M, int C,
+                                const double* stats, double count, float eps, const float* gamma,
+                                const double* red, void* dx, int accumulate, float* dgamma, float* dbeta,
+                                void* stream) {
+  RSA_REQUIRE(dy && x && stats && red && gamma && dx && M > 0, RSA_ERR_SHAPE, "bn_bwd_apply: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = (size_t)5 * C * sizeof(float);
+  if (dtype == RSA_F32) {
+    RSA_REQUIRE(C % 4 == 0, RSA_ERR_SHAPE, "bn_bwd_apply: C=%d must be a multiple of 4", C);
+    int64_t nvec = M * C / 4;
+    bn_bwd_apply_kernel<float><<<grid_for(nvec), NT, smem, st>>>((const float*)dy, (const float*)x,
+        (const float*)act, nvec, C, stats, count, eps, gamma, red, (float*)dx, accumulate, dgamma, dbeta);
+  } else if (dtype == RSA_BF16) {
+    RSA_REQUIRE(C % 8 == 0, RSA_ERR_SHAPE, "bn_bwd_apply: C=%d must be a multiple of 8", C);
+    int64_t nvec = M * C / 8;
+    bn_bwd_apply_kernel<bf16><<<grid_for(nvec), NT, smem, st>>>((const bf16*)dy, (const bf16*)x,
+        (const bf16*)act, nvec, C, stats, count, eps, gamma, red, (bf16*)dx, accumulate, dgamma, dbeta);
+  } else {
+    RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_bwd_apply: bad dtype");
+  }
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+extern "C" int rsa_bn_derive_stats(const double* src_stats, double count, const float* gamma, const float* beta,
+                                   float eps, double* dst_stats, double dst_count, int C, void* stream) {
+  RSA_REQUIRE(src_stats && gamma && beta && dst_stats && C > 0, RSA_ERR_SHAPE, "bn_derive_stats: bad args");
+  bn_derive_stats_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src_stats, count, gamma, beta, eps,
+                                                                            dst_stats, dst_count, C);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+extern "C" int rsa_bn_update_moving(const double* stats_base, float* param_base, const int64_t* table,
+                                    const double* counts, int nlayers, float momentum, void* stream) {
+  RSA_REQUIRE(stats_base && param_base && table && counts && nlayers > 0, RSA_ERR_SHAPE,
+              "bn_update_moving: bad args");
+  bn_update_moving_kernel<<<nlayers, 128, 0, (cudaStream_t)stream>>>(stats_base, param_base, table, counts,
+                                                                     nlayers, momentum);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}

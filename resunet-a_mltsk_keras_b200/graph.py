@@ -1,0 +1,741 @@
+"""Execution plans for the ResUnet-a hot path: forward ops, backward tape, buffers.
+
+A :class:`Net` owns the parameters (one flat fp32 buffer, Keras names and HWIO kernels, see
+SURVEY.md §C) and builds :class:`Plan` objects — flat lists of pre-bound kernel launches for a
+given (batch, mode).  The graph that the reference expresses as ~294 Keras layers
+(ResUnet_a/model2.py:14-193, ResUnet_a/model.py:14-171) is emitted here as ~10 kernel kinds:
+
+  * every convolution is an implicit GEMM over K-segments (``_capi.Seg``): dilated 3x3 taps,
+    channel concat, nearest up-sampling and stride-2 sampling are gather maps, so no padded,
+    concatenated or up-sampled tensor is ever materialised;
+  * training-mode BatchNormalization is split into {statistics in the producer's epilogue,
+    normalise(+ReLU) in one light pass that writes all branch variants at once};
+  * 1x1 convolutions that keras applies to an up-sampled tensor (PSPPooling model2.py:55-68,
+    UpSampling model2.py:89-94) run at the pooled resolution — Conv1x1(Up(x)) == Up(Conv1x1(x))
+    and the biased batch statistics of Up(t) equal those of t.
+
+Backward is a tape of closures emitted in reverse; gradient buffers are written by their first
+consumer and accumulated by the others (``Plan.gacc``).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from ._capi import Seg
+
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.99
+FILTERS = [32, 64, 128, 256, 512, 1024]
+DILATIONS = [[1, 3, 15, 31], [1, 3, 15, 31], [1, 3, 15], [1, 3, 15], [1], [1]]
+ALIGN = 64   # every parameter starts on a 256-byte boundary inside the flat buffer
+
+
+def psp_levels(img_width):
+    """PSPPooling levels are gated on the *input patch* width (model2.py:49-52)."""
+    lv = [1, 2]
+    if img_width >= 128:
+        lv.append(4)
+    if img_width >= 256:
+        lv.append(8)
+    return lv
+
+
+class T:
+    """Activation tensor handle (NHWC, dense)."""
+    __slots__ = ("name", "N", "H", "W", "C", "dtype", "data", "grad", "grad_written", "needs_grad",
+                 "relu_masked", "stats", "count")
+
+    def __init__(self, name, N, H, W, C, dtype):
+        self.name, self.N, self.H, self.W, self.C, self.dtype = name, N, H, W, C, dtype
+        self.data = None
+        self.grad = None
+        self.grad_written = False
+        self.needs_grad = True
+        self.relu_masked = False   # value went through a fused ReLU: writers of .grad mask with data>0
+        self.stats = None          # double[2C] {sum, sumsq} view, valid after the producer ran
+        self.count = 0.0           # elements per channel behind .stats
+
+    @property
+    def M(self):
+        return self.N * self.H * self.W
+
+    @property
+    def shape(self):
+        return (self.N, self.H, self.W, self.C)
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient buffers; trainable tensors first."""
+
+    def __init__(self):
+        self.spec = OrderedDict()   # name -> (shape, trainable, init)
+        self.off = {}
+        self.n_train = 0
+        self.n_total = 0
+        self.data = None
+        self.grad = None
+
+    def add(self, name, shape, trainable, init):
+        if name in self.spec:
+            raise ValueError(f"duplicate parameter {name}")
+        self.spec[name] = (tuple(shape), trainable, init)
+
+    def finalize(self, device, seed):
+        off = 0
+        for trainable in (True, False):
+            for name, (shape, tr, _) in self.spec.items():
+                if tr != trainable:
+                    continue
+                self.off[name] = off
+                n = math.prod(shape)
+                off += (n + ALIGN - 1) // ALIGN * ALIGN
+            if trainable:
+                self.n_train = off
+        self.n_total = off
+        host = torch.zeros(self.n_total, dtype=torch.float32)
+        gen = torch.Generator().manual_seed(seed)
+        for name, (shape, _, init) in self.spec.items():
+            n = math.prod(shape)
+            v = host[self.off[name]:self.off[name] + n].view(shape)
+            if init == "glorot":
+                kh, kw, cin, cout = shape
+                limit = math.sqrt(6.0 / (kh * kw * cin + kh * kw * cout))
+                v.copy_(((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * limit).float())
+            elif init == "ones":
+                v.fill_(1.0)
+        self.data = host.to(device)
+        self.grad = torch.zeros(self.n_train, dtype=torch.float32, device=device)
+
+    def view(self, name):
+        shape = self.spec[name][0]
+        o = self.off[name]
+        return self.data[o:o + math.prod(shape)].view(shape)
+
+    def flat(self, name):
+        shape = self.spec[name][0]
+        o = self.off[name]
+        return self.data[o:o + math.prod(shape)]
+
+    def gflat(self, name):
+        shape, tr, _ = self.spec[name]
+        assert tr
+        o = self.off[name]
+        return self.grad[o:o + math.prod(shape)]
+
+    def gview(self, name):
+        return self.gflat(name).view(self.spec[name][0])
+
+
+class Plan:
+    """One walk of the network for a fixed batch size and mode.
+
+    spec_only=True registers parameters only (no allocation, no launches)."""
+
+    def __init__(self, net, N, training, spec_only=False, with_loss=False):
+        self.net = net
+        self.lib = net.lib
+        self.N = N
+        self.training = training
+        self.spec_only = spec_only
+        self.with_loss = with_loss
+        self.device = net.device
+        self.adt = net.act_dtype
+        self._nconv = 0
+        self._nbn = 0
+        self.fwd = []        # launch(stream) callables
+        self.bwd = []
+        self.tape = []       # closures that emit backward launches (run reversed)
+        self.bn_table = []   # (stats view, C, moving_mean name, moving_var name, count, count_full)
+        self._scratch_chunks = []
+        self.scratch = None
+        self.tensors = []
+        self.outputs = OrderedDict()
+        self.labels = OrderedDict()
+        self.loss_out = OrderedDict()
+        self.bytes = 0
+        self.metrics = None
+        self.bn_update = None
+        self.res_f32 = None   # [8] fp32: tanimoto loss means per head
+        self.res_z = None     # 16 zeroed 8-byte words: [0..7] pixel-loss sums (double), [8..12] seg metrics (int64)
+
+    # -- names (keras creation order) -----------------------------------------------------------
+    def name_conv(self):
+        i = self._nconv
+        self._nconv += 1
+        return "conv2d" if i == 0 else f"conv2d_{i}"
+
+    def name_bn(self):
+        i = self._nbn
+        self._nbn += 1
+        return "batch_normalization" if i == 0 else f"batch_normalization_{i}"
+
+    # -- memory -----------------------------------------------------------------------------------
+    def alloc(self, shape, dtype):
+        if self.spec_only:
+            return None
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self.bytes += t.numel() * t.element_size()
+        return t
+
+    def tensor(self, name, H, W, C, dtype=None, N=None):
+        t = T(name, self.N if N is None else N, H, W, C, dtype or self.adt)
+        t.data = self.alloc(t.shape, t.dtype)
+        self.tensors.append(t)
+        return t
+
+    def zeroed(self, n):
+        """n 8-byte words of scratch, zeroed at the start of every step (double / int64 views)."""
+        if self.spec_only:
+            return None
+        holder = [None]
+        self._scratch_chunks.append((n, holder))
+        return holder
+
+    def _finalize_scratch(self):
+        total = sum((n + 7) // 8 * 8 for n, _ in self._scratch_chunks)
+        self.scratch = torch.zeros(max(total, 8), dtype=torch.float64, device=self.device)
+        off = 0
+        for n, holder in self._scratch_chunks:
+            holder[0] = self.scratch[off:off + n]
+            off += (n + 7) // 8 * 8
+
+    def gacc(self, t):
+        """Gradient buffer of t and whether the caller must accumulate into it."""
+        if t.grad is None:
+            t.grad = self.alloc(t.shape, t.dtype)
+        acc = t.grad_written
+        t.grad_written = True
+        return t.grad, acc
+
+    def P(self, name):
+        return self.net.params.flat(name)
+
+    def G(self, name):
+        return self.net.params.gflat(name)
+
+    # -- parameter registration (spec pass) ---------------------------------------------------------
+    def _reg_conv(self, name, k, cin, cout):
+        if self.spec_only and name + "/kernel" not in self.net.params.spec:
+            self.net.params.add(name + "/kernel", (k, k, cin, cout), True, "glorot")
+            self.net.params.add(name + "/bias", (cout,), True, "zeros")
+
+    def _reg_bn(self, name, c):
+        if self.spec_only and name + "/gamma" not in self.net.params.spec:
+            self.net.params.add(name + "/gamma", (c,), True, "ones")
+            self.net.params.add(name + "/beta", (c,), True, "zeros")
+            self.net.params.add(name + "/moving_mean", (c,), False, "zeros")
+            self.net.params.add(name + "/moving_variance", (c,), False, "ones")
+
+    def _new_stats(self, t, count):
+        if self.training and not self.spec_only:
+            t.stats = self.zeroed(2 * t.C)
+            t.count = float(count)
+
+    # ---------------------------------------------------------------------------------------------
+    # generic 1x1 convolution over gathered / concatenated inputs
+    # ---------------------------------------------------------------------------------------------
+    def conv1x1(self, inputs, cout, name, stats=False, out_dtype=None, bias_grad=True):
+        """inputs: list of (T, mode, relu_in); mode = 'plain' | 's2' | ('up', s).
+        keras: Conv2D(cout,(1,1)) on Concatenate/UpSampling2D/strides=2 inputs
+        (model2.py:37,84,92,101-111,159-187)."""
+        k_total = sum(t.C for t, _, _ in inputs)
+        self._reg_conv(name, 1, k_total, cout)
+        t0, m0, _ = inputs[0]
+        if m0 == "plain":
+            Ho, Wo = t0.H, t0.W
+        elif m0 == "s2":
+            Ho, Wo = (t0.H + 1) // 2, (t0.W + 1) // 2
+        else:
+            Ho, Wo = t0.H << m0[1], t0.W << m0[1]
+        out = self.tensor(name, Ho, Wo, cout, out_dtype)
+        if self.spec_only:
+            return out
+        if stats:
+            self._new_stats(out, out.M)
+        lib, N = self.lib, self.N
+        W_ = self.P(name + "/kernel")
+        b_ = self.P(name + "/bias")
+        segs, koff = [], 0
+        for t, mode, relu_in in inputs:
+            if mode == "plain":
+                assert (t.H, t.W) == (Ho, Wo), (name, t.shape, Ho, Wo)
+                s = Seg(t.data, t.C, t.H, t.W, relu_in=relu_in, w_off=koff * cout)
+            elif mode == "s2":
+                s = Seg(t.data, t.C, t.H, t.W, mult=2, relu_in=relu_in, w_off=koff * cout)
+            else:
+                assert (t.H << mode[1], t.W << mode[1]) == (Ho, Wo), (name, t.shape, Ho, Wo)
+                s = Seg(t.data, t.C, t.H, t.W, shift=mode[1], relu_in=relu_in, w_off=koff * cout)
+            segs.append(s)
+            koff += t.C
+        st = out.stats
+        self.fwd.append(self._late(lambda: lib.igemm_fwd(segs, W_, cout, False, b_, out.data, N, Ho, Wo, cout,
+                                                          stats=st[0] if st else None)))
+        if self.training:
+            self.tape.append(lambda: self._conv1x1_bwd(inputs, segs, out, name, cout, bias_grad))
+        return out
+
+    def _late(self, make):
+        """Bind a launch lazily: scratch views (statistics) only exist after _finalize_scratch()."""
+        cell = []
+
+        def launch(stream):
+            if not cell:
+                cell.append(make())
+            cell[0](stream)
+        launch.make = make
+        launch.cell = cell
+        return launch
+
+    def _conv1x1_bwd(self, inputs, segs, out, name, cout, bias_grad):
+        lib, N = self.lib, self.N
+        if out.grad is None:
+            return   # nothing consumed this output
+        dy = out.grad
+        W_ = self.P(name + "/kernel")
+        dW = self.G(name + "/kernel")
+        db = self.G(name + "/bias") if bias_grad else None
+        self.bwd.append(lib.igemm_wgrad(segs, dy, dW, cout, db, N, out.H, out.W, cout))
+        pyr = {}
+        koff = 0
+        for t, mode, relu_in in inputs:
+            if t.needs_grad:
+                g, acc = self.gacc(t)
+                mask = t.data if (relu_in or t.relu_masked) else None
+                woff = koff * cout
+                if mode == "plain":
+                    sg = [Seg(dy, cout, out.H, out.W, w_off=woff)]
+                elif mode == "s2":
+                    sg = [Seg(dy, cout, out.H, out.W, shift=1, aligned=True, w_off=woff)]
+                elif mode[1] == 1:
+                    sg = [Seg(dy, cout, out.H, out.W, mult=2, off_h=i, off_w=j, w_off=woff)
+                          for i in (0, 1) for j in (0, 1)]
+                else:
+                    if not pyr:   # adjoint of nearest up-sampling = window sums of dy, one pass for all levels
+                        need = sorted({m[1] for _, m, _ in inputs if isinstance(m, tuple) and m[1] > 1})
+                        lv = {s: self.alloc((N, out.H >> s, out.W >> s, cout), dy.dtype) for s in need}
+                        self.bwd.append(lib.sumpool_pyr(dy, N, out.H, out.W, cout, lv.get(1), lv.get(2), lv.get(3)))
+                        pyr.update(lv)
+                    sg = [Seg(pyr[mode[1]], cout, t.H, t.W, w_off=woff)]
+                self.bwd.append(lib.igemm_fwd(sg, W_, cout, True, None, g, N, t.H, t.W, t.C, mask=mask,
+                                              accumulate=acc))
+            koff += t.C
+
+    # ---------------------------------------------------------------------------------------------
+    # 3x3 dilated 'same' convolution (ResBlock-a branches model2.py:19-24, heads :153-178)
+    # ---------------------------------------------------------------------------------------------
+    def conv3x3(self, x, cout, dil, name, relu=False, residual=None, out=None, stats=False, bias_grad=True):
+        self._reg_conv(name, 3, x.C, cout)
+        accumulate = out is not None
+        if out is None:
+            out = self.tensor(name, x.H, x.W, cout)
+        if self.spec_only:
+            return out
+        if stats:
+            self._new_stats(out, out.M)
+        out.relu_masked = relu
+        lib, N, H, W, C = self.lib, self.N, x.H, x.W, x.C
+        W_ = self.P(name + "/kernel")
+        b_ = self.P(name + "/bias")
+        segs = [Seg(x.data, C, H, W, off_h=(ky - 1) * dil, off_w=(kx - 1) * dil, w_off=(ky * 3 + kx) * C * cout)
+                for ky in range(3) for kx in range(3)]
+        st = out.stats
+        res = residual.data if residual is not None else None
+        self.fwd.append(self._late(lambda: lib.igemm_fwd(segs, W_, cout, False, b_, out.data, N, H, W, cout,
+                                                          residual=res, stats=st[0] if st else None,
+                                                          accumulate=accumulate, relu=relu)))
+        if self.training:
+            def bwd():
+                if out.grad is None:
+                    return
+                dy = out.grad
+                dW = self.G(name + "/kernel")
+                db = self.G(name + "/bias") if bias_grad else None
+                self.bwd.append(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout))
+                if x.needs_grad:
+                    g, acc = self.gacc(x)
+                    sg = [Seg(dy, cout, H, W, off_h=-(ky - 1) * dil, off_w=-(kx - 1) * dil,
+                              w_off=(ky * 3 + kx) * C * cout) for ky in range(3) for kx in range(3)]
+                    mask = x.data if x.relu_masked else None
+                    self.bwd.append(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask, accumulate=acc))
+            self.tape.append(bwd)
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    # BatchNormalization (+ReLU), one input -> len(names) outputs (model2.py:17,21,38,86,93)
+    # ---------------------------------------------------------------------------------------------
+    def bn(self, x, names, relu, full_mult=1, derive=False):
+        for n in names:
+            self._reg_bn(n, x.C)
+        outs = [self.tensor(n, x.H, x.W, x.C) for n in names]
+        if self.spec_only:
+            return outs
+        lib, M, C = self.lib, x.M, x.C
+        gam = [self.P(n + "/gamma") for n in names]
+        bet = [self.P(n + "/beta") for n in names]
+        mm = [self.P(n + "/moving_mean") for n in names]
+        mv = [self.P(n + "/moving_variance") for n in names]
+        if self.training:
+            if x.stats is None:   # producer could not fuse the statistics: one extra pass
+                self._new_stats(x, x.M)
+                xs = x.stats
+                self.fwd.append(self._late(lambda: lib.bn_stats(x.data, M, C, xs[0])))
+            xs, cnt = x.stats, x.count
+            for n in names:
+                self.bn_table.append((xs, C, n + "/moving_mean", n + "/moving_variance", cnt, cnt * full_mult))
+            self.fwd.append(self._late(lambda: lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, xs[0],
+                                                             cnt, None, None, BN_EPS, relu)))
+            if derive:   # statistics of y = gamma*xhat+beta are known in closed form (oracle G4)
+                o = outs[0]
+                self._new_stats(o, o.M)
+                os_ = o.stats
+                self.fwd.append(self._late(lambda: lib.bn_derive_stats(xs[0], cnt, gam[0], bet[0], BN_EPS, os_[0],
+                                                                        float(o.M), C)))
+            reds = [self.zeroed(2 * C) for _ in names]
+
+            def bwd():
+                for k, o in enumerate(outs):
+                    if o.grad is None:
+                        continue
+                    act = o.data if relu else None
+                    self.bwd.append(self._late(lambda k=k, o=o, act=act: lib.bn_bwd_reduce(
+                        o.grad, x.data, act, M, C, xs[0], cnt, BN_EPS, reds[k][0])))
+                    if x.needs_grad:
+                        g, acc = self.gacc(x)
+                        self.bwd.append(self._late(lambda k=k, o=o, act=act, g=g, acc=acc: lib.bn_bwd_apply(
+                            o.grad, x.data, act, M, C, xs[0], cnt, BN_EPS, gam[k], reds[k][0], g, acc,
+                            self.G(names[k] + "/gamma"), self.G(names[k] + "/beta"))))
+            self.tape.append(bwd)
+        else:
+            self.fwd.append(lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, None, 1.0, mm, mv, BN_EPS,
+                                         relu))
+        return outs
+
+    # ---------------------------------------------------------------------------------------------
+    def identity_add(self, x, out):
+        """Backward of the identity term of Add([x, b_1..b_k]) (model2.py:27-31): x.grad += out.grad."""
+        if self.spec_only or not self.training:
+            return
+
+        def bwd():
+            if out.grad is None or not x.needs_grad:
+                return
+            if x.grad is None:
+                x.grad = out.grad          # alias: branch gradients accumulate on top of d(out)
+                x.grad_written = True
+            else:
+                g, acc = self.gacc(x)
+                self.bwd.append(self.lib.axpy(g, out.grad, x.M * x.C, acc))
+        self.tape.append(bwd)
+
+    def maxpool(self, x, levels):
+        """MaxPooling2D(k, strides=k) for k in levels (subset of 2,4,8) in one pass (model2.py:47-52)."""
+        outs = {k: self.tensor(f"pool{k}", x.H // k, x.W // k, x.C) for k in levels}
+        if self.spec_only:
+            return outs
+        lib, N = self.lib, self.N
+        d = lambda k: outs[k].data if k in outs else None
+        self.fwd.append(lib.maxpool_pyr_fwd(x.data, N, x.H, x.W, x.C, d(2), d(4), d(8)))
+        if self.training:
+            def bwd():
+                gr = lambda k: outs[k].grad if k in outs else None
+                if all(gr(k) is None for k in (2, 4, 8)) or not x.needs_grad:
+                    return
+                g, acc = self.gacc(x)
+                self.bwd.append(lib.maxpool_pyr_bwd(x.data, N, x.H, x.W, x.C, gr(2), gr(4), gr(8), g, acc))
+            self.tape.append(bwd)
+        return outs
+
+    def activation(self, z, kind):
+        """softmax / sigmoid head activation in place on fp32 logits (model2.py:162,171,182,186)."""
+        p = T(z.name + "/" + kind, z.N, z.H, z.W, z.C, z.dtype)
+        p.data = z.data
+        if self.spec_only:
+            return p
+        lib = self.lib
+        if kind == "softmax":
+            self.fwd.append(lib.softmax_fwd(z.data, p.data, z.M, z.C))
+        else:
+            self.fwd.append(lib.sigmoid_fwd(z.data, p.data, z.M * z.C))
+        if self.training:
+            def bwd():
+                if p.grad is None:
+                    return
+                z.grad = p.grad
+                z.grad_written = True
+                if kind == "softmax":
+                    self.bwd.append(lib.softmax_bwd(p.data, p.grad, z.grad, z.M, z.C))
+                else:
+                    self.bwd.append(lib.sigmoid_bwd(p.data, p.grad, z.grad, z.M * z.C))
+            self.tape.append(bwd)
+        return p
+
+    # ---------------------------------------------------------------------------------------------
+    # losses and metrics (train_ISPRS.py:411-452)
+    # ---------------------------------------------------------------------------------------------
+    def attach_loss(self, head, p, kind, weight, class_weights=None):
+        """kind: 'tanimoto' | 'cce' | 'bce' | 'mse'.  Forward value lands in loss_out[head]."""
+        lib = self.lib
+        y = self.tensor("label/" + head, p.H, p.W, p.C, torch.float32)
+        y.needs_grad = False
+        self.labels[head] = y
+        B, HW, C = p.N, p.H * p.W, p.C
+        if self.res_f32 is None:
+            self.res_f32 = torch.zeros(8, dtype=torch.float32, device=self.device)
+            self.res_z = self.zeroed(16)
+        slot = len(self.loss_out)
+        rz = self.res_z
+        if kind == "tanimoto":
+            sums = self.zeroed(B * C * 5)
+            res = self.res_f32[slot:slot + 1]
+            coef = self.alloc((B * C * 3,), torch.float32)
+            self.fwd.append(self._late(lambda: lib.tanimoto_sums(p.data, y.data, B, HW, C, sums[0])))
+            self.fwd.append(self._late(lambda: lib.tanimoto_finalize(sums[0], B, HW, C, weight, None, res, coef)))
+            self.loss_out[head] = ("mean", slot)
+            if self.training:
+                def bwd():
+                    g, acc = self.gacc(p)
+                    assert not acc
+                    self.bwd.append(lib.tanimoto_bwd(p.data, y.data, coef, B, HW, C, g))
+                self.tape.append(bwd)
+        else:
+            code = {"cce": 0, "bce": 1, "mse": 2}[kind]
+            cw = None
+            if class_weights is not None:
+                cw = torch.tensor(list(class_weights), dtype=torch.float32).to(self.device)
+                assert cw.numel() == C
+            self.fwd.append(self._late(lambda: lib.pixel_loss_fwd(code, p.data, y.data, cw, B * HW, C,
+                                                                  rz[0][slot:slot + 1])))
+            self.loss_out[head] = ("sum", slot, float(B * HW))
+            if self.training:
+                def bwd():
+                    g, acc = self.gacc(p)
+                    assert not acc
+                    self.bwd.append(lib.pixel_loss_bwd(code, p.data, y.data, cw, B * HW, C, weight / (B * HW), g))
+                self.tape.append(bwd)
+
+    def attach_seg_metrics(self, p):
+        y = self.labels["seg"]
+        rz = self.res_z
+        self.metrics = True
+        self.fwd.append(self._late(lambda: self.lib.seg_metrics(p.data, y.data, p.M, p.C,
+                                                                 rz[0][8:13].view(torch.int64))))
+
+    # ---------------------------------------------------------------------------------------------
+    def finish(self):
+        """Bind late launches, emit the backward list and the moving-statistics update."""
+        if self.spec_only:
+            return
+        lib = self.lib
+        if self.training:
+            for rec in reversed(self.tape):
+                rec()
+        self._finalize_scratch()
+        if self.training and self.bn_table:
+            base = self.scratch
+            pbase = self.net.params.data
+            esz = base.element_size()
+            tab, cnt = [], []
+            for (st, C, mmn, mvn, n, nfull) in self.bn_table:
+                soff = (st[0].data_ptr() - base.data_ptr()) // esz
+                tab += [soff, C, self.net.params.off[mmn], self.net.params.off[mvn]]
+                cnt += [n, nfull]
+            self._bn_tab = torch.tensor(tab, dtype=torch.int64).to(self.device)
+            self._bn_cnt = torch.tensor(cnt, dtype=torch.float64).to(self.device)
+            self.bn_update = lib.bn_update_moving(base, pbase, self._bn_tab, self._bn_cnt, len(self.bn_table),
+                                                  BN_MOMENTUM)
+        # resolve late bindings now so that the first step is not special (and graph capture is clean)
+        for op in self.fwd + self.bwd:
+            if hasattr(op, "make") and not op.cell:
+                op.cell.append(op.make())
+
+    def zero_scratch(self, stream):
+        self.scratch.zero_()
+
+
+# ------------------------------------------------------------------------------------------------------
+# network definition (shared by the spec pass and every plan)
+# ------------------------------------------------------------------------------------------------------
+def _resblock(pl, x, f, dils, identity):
+    """ResBlock-a: x + Σ_d Conv3x3_d(ReLU(BN(Conv3x3_d(ReLU(BN_d(x)))))) (model2.py:15-34);
+    model.py:15-33 has no identity term."""
+    names = [(pl.name_bn(), pl.name_conv(), pl.name_bn(), pl.name_conv()) for _ in dils]
+    for nb1, nc1, nb2, nc2 in names:     # register in keras creation order (branch by branch)
+        pl._reg_bn(nb1, x.C)
+        pl._reg_conv(nc1, 3, x.C, f)
+        pl._reg_bn(nb2, f)
+        pl._reg_conv(nc2, 3, f, f)
+    a1 = pl.bn(x, [n[0] for n in names], relu=True)     # every branch normalises the same input
+    out = pl.tensor("resblock_out", x.H, x.W, f)
+    if identity:
+        pl.identity_add(x, out)
+    for i, d in enumerate(dils):
+        y1 = pl.conv3x3(a1[i], f, d, names[i][1], stats=True, bias_grad=False)   # bias before BN: zero gradient
+        a2 = pl.bn(y1, [names[i][2]], relu=True)[0]
+        _conv_into(pl, a2, f, d, names[i][3], out, first=(i == 0), residual=x if identity else None)
+    return out
+
+
+def _conv_into(pl, a, f, d, name, out, first, residual):
+    """Second conv of a branch: writes (first) or accumulates into the block output; the first one
+    also adds the identity input so that the branch sum + identity never exist as separate tensors."""
+    pl._reg_conv(name, 3, a.C, f)
+    if pl.spec_only:
+        return
+    lib, N, H, W, C = pl.lib, pl.N, a.H, a.W, a.C
+    W_ = pl.P(name + "/kernel")
+    b_ = pl.P(name + "/bias")
+    segs = [Seg(a.data, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
+            for ky in range(3) for kx in range(3)]
+    res = residual.data if (first and residual is not None) else None
+    pl.fwd.append(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res, accumulate=not first))
+    if pl.training:
+        def bwd():
+            if out.grad is None:
+                return
+            dy = out.grad
+            pl.bwd.append(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N, H, W, f))
+            g, acc = pl.gacc(a)
+            sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
+                  for ky in range(3) for kx in range(3)]
+            pl.bwd.append(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc))
+        pl.tape.append(bwd)
+
+
+def _psp(pl, x, f, v2):
+    """PSPPooling (model2.py:41-79 / model.py:35-64) at pooled resolution, no concat buffer."""
+    levels = psp_levels(pl.net.img_width)
+    pooled = {1: x}
+    if len(levels) > 1:
+        pooled.update(pl.maxpool(x, [k for k in levels if k > 1]))
+    br = []
+    for k in levels:
+        cn = pl.name_conv()
+        c = pl.conv1x1([(pooled[k], "plain", False)], f // 4, cn, stats=v2, bias_grad=not v2)
+        if v2:
+            c = pl.bn(c, [pl.name_bn()], relu=False, full_mult=k * k)[0]
+        s = int(math.log2(k))
+        br.append((c, "plain" if s == 0 else ("up", s), False))
+    cn = pl.name_conv()
+    y = pl.conv1x1(br + [(x, "plain", False)], f, cn, stats=v2, bias_grad=not v2)
+    if v2:
+        y = pl.bn(y, [pl.name_bn()], relu=True)[0]   # Conv2DN then the call-site ReLU (model2.py:116,142)
+    return y
+
+
+def define_network(pl):
+    net = pl.net
+    v2 = net.variant == "v2"
+    n = net.num_classes
+    x = pl.tensor("input", net.img_height, net.img_width, net.img_channel)
+    x.needs_grad = False
+    pl.input = x
+    t = pl.conv1x1([(x, "plain", False)], 32, pl.name_conv(), stats=True)           # stem, model2.py:101
+    skips = [t]
+    for lvl, (f, dils) in enumerate(zip(FILTERS, DILATIONS)):
+        if lvl > 0:
+            t = pl.conv1x1([(t, "s2", False)], f, pl.name_conv(), stats=True)       # model2.py:103-111
+        t = _resblock(pl, t, f, dils, identity=v2)
+        if lvl < 5:
+            skips.append(t)
+    t = _psp(pl, t, 1024, v2)
+    for lvl in range(4, -1, -1):
+        f, dils = FILTERS[lvl], DILATIONS[lvl]
+        skip = skips[lvl + 1]
+        if v2:
+            # UpSampling: up2 -> conv(f/2) -> BN evaluated before the up-sampling (model2.py:89-94),
+            # then combine: ReLU, concat skip, conv(f), BN (model2.py:81-87)
+            u = pl.conv1x1([(t, "plain", False)], f // 2, pl.name_conv(), stats=True, bias_grad=False)
+            v = pl.bn(u, [pl.name_bn()], relu=True, full_mult=4)[0]
+            z = pl.conv1x1([(v, ("up", 1), False), (skip, "plain", False)], f, pl.name_conv(), stats=True,
+                           bias_grad=False)
+            t = pl.bn(z, [pl.name_bn()], relu=False, derive=True)[0]
+        else:
+            u = pl.conv1x1([(t, "plain", False)], f, pl.name_conv())                # model.py:93-94
+            t = pl.conv1x1([(u, ("up", 1), True), (skip, "plain", False)], f, pl.name_conv(), stats=True)
+        t = _resblock(pl, t, f, dils, identity=v2)
+    xc = pl.conv1x1([(t, "plain", True), (skips[0], "plain", False)], 32, pl.name_conv(), stats=v2,
+                    bias_grad=not v2)                                               # model2.py:140
+    if v2:
+        x_comb = pl.bn(xc, [pl.name_bn()], relu=False)[0]
+    else:
+        x_comb = xc
+    x_psp = _psp(pl, x_comb, 32, v2)
+    f32 = torch.float32
+    if not net.multitask:
+        z = pl.conv1x1([(x_psp, "plain", False)], n, pl.name_conv(), out_dtype=f32)
+        pl.outputs["seg"] = pl.activation(z, "softmax")
+        return
+    h = pl.conv3x3(x_psp, 32, 1, "seg1", relu=True)
+    h = pl.conv3x3(h, 32, 1, "seg2", relu=True)
+    z = pl.conv1x1([(h, "plain", False)], n, "seg3", out_dtype=f32)
+    pl.outputs["seg"] = pl.activation(z, "softmax")
+    h = pl.conv3x3(x_psp, 32, 1, pl.name_conv(), relu=True)
+    z = pl.conv1x1([(h, "plain", False)], n, pl.name_conv(), out_dtype=f32)
+    pl.outputs["bound"] = pl.activation(z, "sigmoid")
+    h = pl.conv3x3(x_comb, 32, 1, pl.name_conv(), relu=True)
+    h = pl.conv3x3(h, 32, 1, pl.name_conv(), relu=True)
+    z = pl.conv1x1([(h, "plain", False)], n, pl.name_conv(), out_dtype=f32)
+    pl.outputs["dist"] = pl.activation(z, "softmax")                                 # softmax, model2.py:182
+    z = pl.conv1x1([(x_comb, "plain", False)], 3, "color", out_dtype=f32)
+    pl.outputs["color"] = pl.activation(z, "sigmoid")
+
+
+class Net:
+    """Parameters + plan cache for one ResUnet-a instance."""
+
+    def __init__(self, input_shape, num_classes, multitask, variant="v2", dtype="bf16", seed=1234, lib=None,
+                 device=None):
+        from . import _capi
+        self.lib = lib or _capi.get_lib()
+        self.img_height, self.img_width, self.img_channel = input_shape
+        self.num_classes = num_classes
+        self.multitask = bool(multitask)
+        self.variant = variant
+        self.act_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[dtype]
+        self.dtype_name = dtype
+        if device is None:
+            device = torch.device("cpu") if getattr(self.lib, "is_emulation", False) else torch.device(
+                "cuda", torch.cuda.current_device())
+        self.device = device
+        if self.img_height % 32 or self.img_width % 32 or self.img_height != self.img_width:
+            raise ValueError("ResUnet-a d6 needs square inputs with a side that is a multiple of 32")
+        if (self.img_width // 32) % max(psp_levels(self.img_width)):
+            raise ValueError(f"input width {self.img_width}: the 1/32-resolution map is not divisible by the "
+                             f"PSPPooling levels {psp_levels(self.img_width)} (keras fails the same way)")
+        self.params = ParamStore()
+        spec = Plan(self, 1, True, spec_only=True)
+        define_network(spec)
+        self.output_names = list(spec.outputs)
+        self.params.finalize(self.device, seed)
+        self.plans = {}
+
+    def plan(self, N, training, loss_spec=None):
+        """loss_spec: None or tuple of (head, kind, weight, class_weights) — part of the cache key."""
+        key = (N, training, loss_spec)
+        if key not in self.plans:
+            pl = Plan(self, N, training, with_loss=loss_spec is not None)
+            define_network(pl)
+            if loss_spec is not None:
+                for head, kind, weight, cw in loss_spec:
+                    pl.attach_loss(head, pl.outputs[head], kind, weight, cw)
+                pl.attach_seg_metrics(pl.outputs["seg"])
+            pl.finish()
+            self.plans[key] = pl
+        return self.plans[key]
+
+    # -- weights interchange (keras names, HWIO) ----------------------------------------------------------
+    def get_weights(self):
+        return OrderedDict((k, self.params.view(k).detach().cpu().clone()) for k in self.params.spec)
+
+    def set_weights(self, weights):
+        for k, v in weights.items():
+            if k not in self.params.spec:
+                raise KeyError(f"unknown parameter {k}")
+            dst = self.params.view(k)
+            v = torch.as_tensor(v, dtype=torch.float32)
+            if tuple(v.shape) != tuple(dst.shape):
+                raise ValueError(f"shape mismatch for {k}: {tuple(v.shape)} vs {tuple(dst.shape)}")
+            dst.copy_(v.to(self.device))

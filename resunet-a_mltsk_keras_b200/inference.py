@@ -1,0 +1,120 @@
+"""Sliding-window inference side of the hot path (test_ISPRS.py:26-36,48-87,102-152,295-314).
+
+chop -> predict -> argmax -> confusion matrix / metrics -> reconstruction.  The patch extraction and
+the paste-back are pure index arithmetic on host arrays (as in the reference); argmax and the K x K
+confusion histogram run on the device right behind the forward pass (rsa_argmax_confusion, int64
+counts, bit-exact), so the 35 M-pixel label arrays of a 6000^2 scene never round-trip as fp32
+probabilities.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def extract_patches(img, patch_size):
+    """Non-overlapping stride=patch_size tiles, row-major (h outer, w inner), remainder dropped
+    (extract_patches_train / extract_patches_test, test_ISPRS.py:102-152).  Works for (H,W) and (H,W,C)."""
+    img = np.asarray(img)
+    h, w = img.shape[:2]
+    nh, nw = h // patch_size, w // patch_size
+    v = img[:nh * patch_size, :nw * patch_size]
+    v = v.reshape((nh, patch_size, nw, patch_size) + img.shape[2:])
+    v = np.swapaxes(v, 1, 2)
+    return np.ascontiguousarray(v.reshape((nh * nw, patch_size, patch_size) + img.shape[2:]))
+
+
+def pred_recostruction(patch_size, pred_labels, binary_img_test_ref, img_type=1):
+    """Paste patch predictions back row-major into a zero-initialised float64 image of the reference
+    shape; the right/bottom remainder stays 0 (test_ISPRS.py:48-87; spelling kept from the reference)."""
+    h, w = np.asarray(binary_img_test_ref).shape[:2]
+    nh, nw = h // patch_size, w // patch_size
+    pred_labels = np.asarray(pred_labels)
+    tail = pred_labels.shape[3:] if img_type == 2 else ()
+    out = np.zeros((h, w) + tail)
+    p = pred_labels[:nh * nw].reshape((nh, nw, patch_size, patch_size) + tail)
+    p = np.swapaxes(p, 1, 2).reshape((nh * patch_size, nw * patch_size) + tail)
+    out[:nh * patch_size, :nw * patch_size] = p
+    return out
+
+
+def confusion_matrix(y_true, y_pred, labels=None):
+    """sklearn.metrics.confusion_matrix semantics on host arrays (test_ISPRS.py:314): int64, rows = true,
+    labels = sorted union of the values present."""
+    y_true = np.asarray(y_true).ravel()
+    y_pred = np.asarray(y_pred).ravel()
+    if labels is None:
+        labels = np.union1d(np.unique(y_true), np.unique(y_pred))
+    labels = np.asarray(labels)
+    k = len(labels)
+    ti = np.searchsorted(labels, y_true)
+    pi = np.searchsorted(labels, y_pred)
+    ok = (ti < k) & (pi < k)
+    ok &= (labels[np.minimum(ti, k - 1)] == y_true) & (labels[np.minimum(pi, k - 1)] == y_pred)
+    cm = np.bincount(ti[ok] * k + pi[ok], minlength=k * k).astype(np.int64)
+    return cm.reshape(k, k)
+
+
+def compact_confusion(cm_full):
+    """Drop classes that appear neither as truth nor as prediction — sklearn builds the matrix over the
+    union of labels present, so it can be smaller than num_classes^2."""
+    cm_full = np.asarray(cm_full)
+    present = (cm_full.sum(0) + cm_full.sum(1)) > 0
+    return cm_full[np.ix_(present, present)], np.nonzero(present)[0]
+
+
+def metrics_from_confusion(cm):
+    """accuracy, f1, recall, precision (x100, per class) — utils.py:52-57 / test_ISPRS.py:39-45."""
+    cm = np.asarray(cm, dtype=np.float64)
+    diag = np.diag(cm)
+    acc = 100.0 * diag.sum() / cm.sum()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rec = np.where(cm.sum(1) > 0, diag / cm.sum(1), 0.0)
+        prec = np.where(cm.sum(0) > 0, diag / cm.sum(0), 0.0)
+        f1 = np.where(rec + prec > 0, 2 * rec * prec / (rec + prec), 0.0)
+    return acc, 100 * f1, 100 * rec, 100 * prec
+
+
+def compute_metrics(true_labels, predicted_labels):
+    """Same return tuple as utils.compute_metrics (utils.py:52-57)."""
+    return metrics_from_confusion(confusion_matrix(true_labels, predicted_labels))
+
+
+def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, num_classes=None):
+    """Whole-scene inference (test_ISPRS.py:268-333): returns dict with
+    ``seg_pred`` [P,ps,ps] int32, ``reconstructed`` (H,W) float64, and — when ``reference`` (H,W)
+    integer labels is given — ``confusion`` (sklearn-shaped int64), ``labels`` and ``metrics``."""
+    net = model.net
+    lib = net.lib
+    K = int(num_classes or net.num_classes)
+    patches = extract_patches(image, patch_size)
+    P = patches.shape[0]
+    ref_p = None
+    if reference is not None:
+        ref_p = extract_patches(np.asarray(reference), patch_size).astype(np.int32)
+    dev = net.device
+    seg_pred = np.empty((P, patch_size, patch_size), dtype=np.int32)
+    cm = torch.zeros(K * K, dtype=torch.int64, device=dev)
+    stream = model._stream()
+    for i in range(0, P, batch_size):
+        xb = patches[i:i + batch_size]
+        n = xb.shape[0]
+        pl = net.plan(n, False, None)
+        model._load_inputs(pl, xb, None)
+        model._execute(pl, False)
+        prob = pl.outputs["seg"]
+        lab = torch.empty(prob.M, dtype=torch.int32, device=dev)
+        tl = None
+        if ref_p is not None:
+            tl = torch.from_numpy(ref_p[i:i + n].reshape(-1)).to(dev)
+        lib.argmax_confusion(prob.data, prob.M, prob.C, lab, tl, K, cm if tl is not None else None)(model._stream())
+        seg_pred[i:i + n] = lab.cpu().numpy().reshape(n, patch_size, patch_size)
+    out = dict(seg_pred=seg_pred)
+    h, w = np.asarray(image).shape[:2]
+    out["reconstructed"] = pred_recostruction(patch_size, seg_pred, np.zeros((h, w), dtype=np.uint8))
+    if ref_p is not None:
+        full = cm.cpu().numpy().reshape(K, K)
+        out["confusion_full"] = full
+        out["confusion"], out["labels"] = compact_confusion(full)
+        out["metrics"] = metrics_from_confusion(out["confusion"])
+    return out
