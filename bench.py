@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — train patches/s of the ResUnet-a d6 multitask hot path (BASELINE.json config 2).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
+
+A "step" = one fwd + bwd + Adam update of model2 (multitask, Tanimoto dual x4) on a synthetic batch of
+16 patches 256x256x3 per GPU.  Prints ONE JSON line (rank 0).  `value` times the step with inputs
+resident in HBM (CUDA events, max over ranks); `e2e` times Model.train_on_batch with HOST numpy
+buffers (pinned H2D of the batch + D2H of the 10 step results inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FLOP_PER_PATCH_CONV = 224.7e9      # ResBlock-a 3x3 convs fwd+bwd, dense 9-tap count
+FLOP_PER_PATCH_ALL = 252.4e9
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def synth(batch, hw, n, seed):
+    from oracle import resuneta_oracle as O   # data generator shared with the tests (not the product path)
+    return O.synth_batch(batch, hw, 3, n, seed=seed, block=16)
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(steps, warmup, hw, n, batch, threads=None):
+    """patches/s of the CPU restatement of the reference (torch fp32, all host threads): one
+    fwd+bwd+Adam step of model2 multitask + Tanimoto dual on a bounded sample of `batch` patches."""
+    from oracle import resuneta_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    p = O.init_params((hw, hw, 3), n, True, "v2", seed=1234)
+    x, y = O.synth_batch(batch, hw, 3, n, seed=1234, block=16)
+    xt = torch.from_numpy(x)
+    yt = {k: torch.from_numpy(v) for k, v in y.items()}
+    opt = O.Adam(lr=1e-3)
+    losses = {k: O.tanimoto_dual_loss for k in yt}
+    for _ in range(warmup):
+        O.train_on_batch(p, opt, xt, yt, losses, {}, n)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_on_batch(p, opt, xt, yt, losses, {}, n)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    rate, sps, threads = cpu_reference_rate(steps, warm, args.hw, args.classes, args.ref_batch)
+    sample = f"{steps} fwd+bwd+Adam steps of batch {args.ref_batch} ({args.hw}x{args.hw}x3), torch-CPU fp32 oracle port"
+    line = dict(impl="reference", metric="train patches/s (256^2, multitask fwd+bwd)", value=rate, unit="patches/s",
+                n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=sps * 1e3, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="config2: ResUnet-a d6 model2 multitask fwd+bwd+Adam, Tanimoto dual x4, "
+                                     f"{args.hw}x{args.hw}x3, {args.classes} classes",
+                            per_step_batch=args.ref_batch, note="TensorFlow is not installable here; this is the "
+                            "CPU restatement (oracle port) of the reference on the host cores"),
+                cpu_baseline=dict(value=rate, unit="patches/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=rate, unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    from resuneta_b200 import Adam, Tanimoto_dual_loss
+    from resuneta_b200.builder import build_model
+    from resuneta_b200.distribute import MirroredStrategy
+    strat = MirroredStrategy()
+    if world > 1:
+        dist.barrier()
+    heads = ("seg", "bound", "dist", "color")
+    with strat.scope():
+        model = build_model((args.hw, args.hw, 3), args.classes, True, "v2", dtype=args.dtype, seed=1234)
+        model.compile(optimizer=Adam(lr=1e-3), loss={h: Tanimoto_dual_loss() for h in heads},
+                      loss_weights={h: 1.0 for h in heads})
+    lib = model.net.lib
+    x, y = synth(args.batch, args.hw, args.classes, 1234 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up through the public API (stages inputs, captures the CUDA graph at N=1) ----------------
+    for _ in range(max(args.warmup, 3)):
+        last = model.train_on_batch(x, y)
+    pl = model.net.plan(args.batch, True, model.loss_spec)
+    ops_per_step = len(pl.fwd) + len(pl.bwd) + 2      # + bn_update_moving + optimizer (memsets not counted)
+
+    # ---- device-resident timed region --------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        model._push_lr()
+        model._execute(pl, True)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.batch * world * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end through Model.train_on_batch with host buffers ---------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = model.train_on_batch(x, y)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = args.batch * world * args.steps / t.item()
+    h2d, d2h = model.last_h2d_bytes, model.last_d2h_bytes
+
+    # ---- roofline of the dominant kernel family: the ResBlock-a / head 3x3 convolutions ------------------
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        stream = torch.cuda.current_stream().cuda_stream
+        evs, flops, nconv = [], 0.0, 0
+        torch.cuda.synchronize()
+        model._push_lr()
+        pl.scratch.zero_()
+        model.net.params.grad.zero_()
+        seq = list(pl.fwd) + [pl.bn_update] + list(pl.bwd)
+        for op in seq:
+            tag = getattr(op, "tag", None)
+            if tag:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                op(stream)
+                b.record()
+                evs.append((a, b))
+                flops += op.flops
+                nconv += 1
+            else:
+                op(stream)
+        model._opt_launch(stream)
+        torch.cuda.synchronize()
+        conv_ms = sum(a.elapsed_time(b) for a, b in evs)
+        achieved = flops / (conv_ms / 1e3) / 1e12
+        roof = dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s", frac=achieved / pk["tf_sust"],
+                    traffic=None, kernel="3x3 conv fwd+dgrad+wgrad (ResBlock-a + heads)", launches=nconv,
+                    avg_launch_ms=conv_ms / max(nconv, 1), conv_ms_per_step=conv_ms,
+                    conv_share_of_step=conv_ms / (ms_total / args.steps), frac_of_burst=achieved / pk["tf_burst"],
+                    peak_source=pk["src"] + " (sustained: timed inside a long step)",
+                    algorithmic_flop_per_launch=flops / max(nconv, 1))
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sps, threads = cpu_reference_rate(2, 1, args.hw, args.classes, args.ref_batch)
+        cpu = dict(value=rate, unit="patches/s", cores=threads, kind="port",
+                   sample=f"2 fwd+bwd+Adam steps of batch {args.ref_batch} after 1 warm-up, torch-CPU fp32 oracle "
+                          f"(stand-in for the reference's TF-CPU path)")
+    if rank == 0:
+        line = dict(metric="train patches/s (256^2, multitask fwd+bwd)", value=value, unit="patches/s", n_gpus=world,
+                    steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
+                    config=dict(workload="config2: ResUnet-a d6 model2 multitask fwd+bwd+Adam, Tanimoto dual x4, "
+                                         f"{args.hw}x{args.hw}x3, {args.classes} classes, batch {args.batch}/GPU",
+                                global_batch=args.batch * world, parallelism=f"dp{world}",
+                                l2="working set per step (>8 GB of activations) is far larger than the 126 MB L2",
+                                cuda_graph=bool(model.use_cuda_graph and world == 1),
+                                conv_engine=getattr(model.net, "conv_engine", "igemm_simt")),
+                    e2e=dict(value=e2e, unit="patches/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    gpu_launches=ops_per_step * args.steps, launches_per_step=ops_per_step,
+                    clocks=clocks, roofline=roof, cpu_baseline=cpu, last_loss=last[0],
+                    tflops_all_convs=FLOP_PER_PATCH_ALL * value / 1e12)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--classes", type=int, default=6)
+    ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path for the product arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+"""Batch-sharded data-parallel training: one process per GPU, NCCL over NVLink/NVSwitch.
+
+Replaces ``tf.distribute.MirroredStrategy`` (train_ISPRS.py:347,432; test_ISPRS.py:276-277) — the
+reference's single-process in-graph replication — with the B200 idiom: ``torchrun`` starts one rank
+per GPU, every rank owns a full replica, BatchNormalization statistics stay per-replica (plain
+``BatchNormalization`` under MirroredStrategy is not synchronised) and the only
+exchange is one sum-all-reduce of the flat fp32 gradient buffer per step.  The buffer is cut into
+buckets in *backward completion order* and each bucket's all-reduce is issued on NCCL's stream the
+moment its last producer kernel has been enqueued, so the transfer overlaps the rest of backward.
+The mean (1/world) is folded into the optimizer kernel's grad_scale.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+
+import torch
+import torch.distributed as dist
+
+_CURRENT = None
+
+
+def current_strategy():
+    return _CURRENT
+
+
+class DataParallel:
+    def __init__(self, group=None, n_buckets=8):
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_buckets = n_buckets
+        self._sched = {}
+
+    # ---------------------------------------------------------------------------------------------------
+    def broadcast_parameters(self, params):
+        """Identical initial replicas (MirroredStrategy mirrors variables at creation)."""
+        if self.world_size > 1:
+            dist.broadcast(params.data, src=0, group=self.group)
+
+    def _schedule(self, pl, params):
+        """bucket list [(ready_op_index, lo, hi)] sorted by readiness."""
+        key = id(pl)
+        if key in self._sched:
+            return self._sched[key]
+        n = params.n_train
+        ready = torch.full((n,), -1, dtype=torch.int32)
+        for name, idx in pl.grad_ready.items():
+            o = params.off[name]
+            sz = 1
+            for d in params.spec[name][0]:
+                sz *= d
+            ready[o:o + sz] = idx
+        # padding / never-written (exactly-zero) gradients are ready from the start
+        nb = max(1, min(self.n_buckets, n // 1024))
+        edges = [n * i // nb for i in range(nb + 1)]
+        buckets = []
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            buckets.append((int(ready[lo:hi].max().item()), lo, hi))
+        buckets.sort()
+        self._sched[key] = buckets
+        return buckets
+
+    def run_backward(self, pl, stream, params=None):
+        """Run the backward launches, issuing bucket all-reduces as their gradients complete."""
+        params = params or pl.net.params
+        buckets = list(self._schedule(pl, params))
+        handles = []
+        bi = 0
+        for i, op in enumerate(pl.bwd):
+            op(stream)
+            while bi < len(buckets) and buckets[bi][0] <= i:
+                _, lo, hi = buckets[bi]
+                handles.append(dist.all_reduce(params.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                               async_op=True))
+                bi += 1
+        while bi < len(buckets):
+            _, lo, hi = buckets[bi]
+            handles.append(dist.all_reduce(params.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                           async_op=True))
+            bi += 1
+        for h in handles:
+            h.wait()          # the compute stream waits for NCCL before the optimizer kernel
+
+    def sync_moving_statistics(self, params):
+        """BN moving mean/variance are per-replica during training and mean-aggregated when read
+        (MirroredStrategy's ON_READ / MEAN aggregation)."""
+        if self.world_size > 1:
+            tail = params.data[params.n_train:]
+            dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group)
+            tail.div_(self.world_size)
+
+    def all_reduce_sum_(self, t):
+        if self.world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class MirroredStrategy:
+    """Drop-in for ``tf.distribute.MirroredStrategy()``: under ``torchrun`` (WORLD_SIZE > 1) models
+    compiled inside ``scope()`` train data-parallel; in a single process it is a no-op."""
+
+    def __init__(self, backend=None, n_buckets=8):
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1 and not dist.is_initialized():
+            use_cuda = torch.cuda.is_available()
+            if use_cuda:
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group(backend=backend or ("nccl" if use_cuda else "gloo"))
+        self.dp = DataParallel(n_buckets=n_buckets)
+        self.num_replicas_in_sync = self.dp.world_size
+
+    @contextlib.contextmanager
+    def scope(self):
+        global _CURRENT
+        prev, _CURRENT = _CURRENT, self
+        try:
+            yield self
+        finally:
+            _CURRENT = prev

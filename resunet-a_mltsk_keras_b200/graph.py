@@ -158,6 +158,7 @@ class Plan:
         self.bytes = 0
         self.metrics = None
         self.bn_update = None
+        self.grad_ready = {}  # param name -> index of the backward op that completes its gradient
         self.res_f32 = None   # [8] fp32: tanimoto loss means per head
         self.res_z = None     # 16 zeroed 8-byte words: [0..7] pixel-loss sums (double), [8..12] seg metrics (int64)
 
@@ -209,6 +210,16 @@ class Plan:
         acc = t.grad_written
         t.grad_written = True
         return t.grad, acc
+
+    @staticmethod
+    def _tag(op, tag, flops):
+        op.tag = tag
+        op.flops = flops
+        return op
+
+    def _ready(self, *names):
+        for n in names:
+            self.grad_ready[n] = len(self.bwd) - 1
 
     def P(self, name):
         return self.net.params.flat(name)
@@ -298,6 +309,7 @@ class Plan:
         dW = self.G(name + "/kernel")
         db = self.G(name + "/bias") if bias_grad else None
         self.bwd.append(lib.igemm_wgrad(segs, dy, dW, cout, db, N, out.H, out.W, cout))
+        self._ready(name + "/kernel", name + "/bias")
         pyr = {}
         koff = 0
         for t, mode, relu_in in inputs:
@@ -343,9 +355,10 @@ class Plan:
                 for ky in range(3) for kx in range(3)]
         st = out.stats
         res = residual.data if residual is not None else None
-        self.fwd.append(self._late(lambda: lib.igemm_fwd(segs, W_, cout, False, b_, out.data, N, H, W, cout,
-                                                          residual=res, stats=st[0] if st else None,
-                                                          accumulate=accumulate, relu=relu)))
+        flops = 2.0 * N * H * W * 9 * C * cout
+        self.fwd.append(self._tag(self._late(lambda: lib.igemm_fwd(
+            segs, W_, cout, False, b_, out.data, N, H, W, cout, residual=res, stats=st[0] if st else None,
+            accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
         if self.training:
             def bwd():
                 if out.grad is None:
@@ -353,13 +366,16 @@ class Plan:
                 dy = out.grad
                 dW = self.G(name + "/kernel")
                 db = self.G(name + "/bias") if bias_grad else None
-                self.bwd.append(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout))
+                self.bwd.append(self._tag(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout), "conv3x3_wgrad",
+                                          flops))
+                self._ready(name + "/kernel", name + "/bias")
                 if x.needs_grad:
                     g, acc = self.gacc(x)
                     sg = [Seg(dy, cout, H, W, off_h=-(ky - 1) * dil, off_w=-(kx - 1) * dil,
                               w_off=(ky * 3 + kx) * C * cout) for ky in range(3) for kx in range(3)]
                     mask = x.data if x.relu_masked else None
-                    self.bwd.append(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask, accumulate=acc))
+                    self.bwd.append(self._tag(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask,
+                                                            accumulate=acc), "conv3x3_dgrad", flops))
             self.tape.append(bwd)
         return out
 
@@ -387,7 +403,7 @@ class Plan:
                 self.bn_table.append((xs, C, n + "/moving_mean", n + "/moving_variance", cnt, cnt * full_mult))
             self.fwd.append(self._late(lambda: lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, xs[0],
                                                              cnt, None, None, BN_EPS, relu)))
-            if derive:   # statistics of y = gamma*xhat+beta are known in closed form (oracle G4)
+            if derive:   # statistics of y = gamma*xhat+beta are known in closed form
                 o = outs[0]
                 self._new_stats(o, o.M)
                 os_ = o.stats
@@ -407,6 +423,7 @@ class Plan:
                         self.bwd.append(self._late(lambda k=k, o=o, act=act, g=g, acc=acc: lib.bn_bwd_apply(
                             o.grad, x.data, act, M, C, xs[0], cnt, BN_EPS, gam[k], reds[k][0], g, acc,
                             self.G(names[k] + "/gamma"), self.G(names[k] + "/beta"))))
+                        self._ready(names[k] + "/gamma", names[k] + "/beta")
             self.tape.append(bwd)
         else:
             self.fwd.append(lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, None, 1.0, mm, mv, BN_EPS,
@@ -590,17 +607,22 @@ def _conv_into(pl, a, f, d, name, out, first, residual):
     segs = [Seg(a.data, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
             for ky in range(3) for kx in range(3)]
     res = residual.data if (first and residual is not None) else None
-    pl.fwd.append(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res, accumulate=not first))
+    flops = 2.0 * N * H * W * 9 * C * f
+    pl.fwd.append(pl._tag(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res,
+                                        accumulate=not first), "conv3x3_fwd", flops))
     if pl.training:
         def bwd():
             if out.grad is None:
                 return
             dy = out.grad
-            pl.bwd.append(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N, H, W, f))
+            pl.bwd.append(pl._tag(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N, H, W,
+                                                  f), "conv3x3_wgrad", flops))
+            pl._ready(name + "/kernel", name + "/bias")
             g, acc = pl.gacc(a)
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
                   for ky in range(3) for kx in range(3)]
-            pl.bwd.append(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc))
+            pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
+                                  "conv3x3_dgrad", flops))
         pl.tape.append(bwd)
 
 

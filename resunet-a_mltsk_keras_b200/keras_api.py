@@ -241,6 +241,12 @@ class Model:
             self.metrics_names = ["loss", "accuracy", "true_positives", "false_positives", "true_negatives",
                                   "false_negatives"]
         self._graphs.clear()
+        from . import distribute
+        strat = distribute.current_strategy()
+        if strat is not None and strat.dp.world_size > 1:
+            self.dp = strat.dp
+            self.dp.broadcast_parameters(self.net.params)
+            self._opt_state = None
 
     # -- data movement -------------------------------------------------------------------------------------
     def _stream(self):
@@ -297,7 +303,7 @@ class Model:
                     if k in self._opt_state:
                         self._opt_state[k].copy_(torch.from_numpy(np.asarray(v)).to(dev))
             self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-            self._lr_host = torch.zeros(1, dtype=torch.float32, pin_memory=dev.type != "cpu")
+            self._lr_host = torch.zeros(64, dtype=torch.float32, pin_memory=dev.type != "cpu")
             lib, opt, n = self.net.lib, self.optimizer, ps.n_train
             gs = 1.0 / (self.dp.world_size if self.dp else 1)
             if isinstance(opt, Adam):
@@ -315,8 +321,9 @@ class Model:
             lr_t = opt.lr * math.sqrt(1.0 - opt.beta_2 ** t) / (1.0 - opt.beta_1 ** t)
         else:
             lr_t = opt.lr
-        self._lr_host[0] = lr_t
-        self._lr_dev.copy_(self._lr_host, non_blocking=True)
+        slot = opt.iterations % 64      # ring of pinned slots: up to 64 steps may be in flight
+        self._lr_host[slot] = lr_t
+        self._lr_dev.copy_(self._lr_host[slot:slot + 1], non_blocking=True)
 
     # -- the step itself ----------------------------------------------------------------------------------------
     def _run_train_ops(self, pl, stream):
@@ -481,6 +488,8 @@ class Model:
         self.net.set_weights(w)
 
     def save(self, path):
+        if self.dp is not None:
+            self.dp.sync_moving_statistics(self.net.params)
         w = {k: v.numpy() for k, v in self.net.get_weights().items()}
         cfg = dict(self.config)
         if self.optimizer is not None:

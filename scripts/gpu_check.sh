@@ -1,0 +1,16 @@
+#!/bin/bash
+# One gpurun call: build check, kernel + model parity tests, smoke, short bench.  Logs -> gpurun_out/
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+timeout 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 600 > gpurun_out/test_kernels.log 2>&1
+echo "kernels rc=$?" >> gpurun_out/summary.txt
+timeout 1500 python -m pytest tests/test_model_gpu.py -q -m gpu --timeout 900 > gpurun_out/test_model.log 2>&1
+echo "model rc=$?" >> gpurun_out/summary.txt
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/summary.txt
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2>&1
+echo "bench rc=$?" >> gpurun_out/summary.txt
+tail -5 gpurun_out/test_kernels.log gpurun_out/test_model.log gpurun_out/smoke.log gpurun_out/bench.log
+cat gpurun_out/summary.txt

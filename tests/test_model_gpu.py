@@ -1,0 +1,180 @@
+"""Model-level parity on the B200 through the public (Keras-style) API, against the CPU oracle.
+
+Tolerances are north_star's: rel-L2 <= 1e-4 in fp32 validation mode, <= 1e-2 in bf16 mode (fp32
+accumulate), seg argmax agreement >= 99.9 %, confusion matrix bit-exact given identical logits."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import resuneta_oracle as O  # noqa: E402
+from resuneta_b200 import (Adam, SGD, BinaryCrossentropy, MeanSquaredError, Tanimoto_dual_loss,  # noqa: E402
+                           weighted_categorical_crossentropy)
+from resuneta_b200.builder import build_model  # noqa: E402
+from resuneta_b200 import inference  # noqa: E402
+
+LW = dict(seg=1.0, bound=0.7, dist=1.3, color=0.5)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def rand_params(variant, hw, cin, n, multitask=True, seed=7):
+    p = O.init_params((hw, hw, cin), n, multitask, variant, seed=seed)
+    g = torch.Generator().manual_seed(0)
+    for k in p:
+        if k.endswith("/gamma"):
+            p[k] = 0.5 + torch.rand(p[k].shape, generator=g)
+        if k.endswith("/beta") or k.endswith("/bias"):
+            p[k] = 0.2 * torch.randn(p[k].shape, generator=g)
+        if k.endswith("/moving_mean"):
+            p[k] = 0.1 * torch.randn(p[k].shape, generator=g)
+        if k.endswith("/moving_variance"):
+            p[k] = 0.5 + torch.rand(p[k].shape, generator=g)
+    return p
+
+
+@pytest.mark.parametrize("variant,hw,cin,n", [("v2", 64, 3, 5), ("v1", 64, 3, 5), ("v2", 128, 14, 3)])
+def test_fp32_predict_matches_oracle(variant, hw, cin, n):
+    p = rand_params(variant, hw, cin, n)
+    m = build_model((hw, hw, cin), n, True, variant, dtype="fp32")
+    m.net.set_weights(p)
+    x = np.random.RandomState(1).rand(3, hw, hw, cin).astype(np.float32)
+    out = m.predict(x, batch_size=2)
+    ref = O.forward(p, torch.from_numpy(x), False, n, True, variant)
+    for k in out:
+        assert rel_l2(out[k], ref[k].numpy()) <= 1e-4, k
+    agree = (out["seg"].argmax(-1) == ref["seg"].numpy().argmax(-1)).mean()
+    assert agree >= 0.999
+
+
+@pytest.mark.parametrize("variant,kind", [("v2", "tanimoto"), ("v2", "other"), ("v1", "tanimoto")])
+def test_fp32_train_step_matches_fp64_oracle(variant, kind):
+    n, hw = 5, 64
+    p = rand_params(variant, hw, 3, n)
+    m = build_model((hw, hw, 3), n, True, variant, dtype="fp32")
+    m.net.set_weights(p)
+    if kind == "tanimoto":
+        mine = {k: Tanimoto_dual_loss() for k in LW}
+        theirs = {k: O.tanimoto_dual_loss for k in LW}
+    else:
+        w = [1.1, 2.0, 0.5, 3.0, 0.0]
+        mine = dict(seg=weighted_categorical_crossentropy(w), bound=BinaryCrossentropy(), dist=MeanSquaredError(),
+                    color=MeanSquaredError())
+        theirs = dict(seg=O.weighted_categorical_crossentropy(w), bound=O.binary_crossentropy,
+                      dist=O.mean_squared_error, color=O.mean_squared_error)
+    m.compile(optimizer=SGD(lr=1e-2, momentum=0.8), loss=mine, loss_weights=LW)
+    x, y = O.synth_batch(2, hw, 3, n, seed=11, block=8)
+    res = m.train_on_batch(x, y)
+    p64 = {k: v.double() for k, v in p.items()}
+    y64 = {k: torch.from_numpy(v).double() for k, v in y.items()}
+    tot, per, out, grads, new_state = O.loss_and_grads(p64, torch.from_numpy(x).double(), y64, theirs, LW, n, True,
+                                                       variant, True)
+    assert abs(res[0] - tot.item()) <= 1e-4 * abs(tot.item())
+    for a, b in zip(res[1:5], per):
+        assert abs(a - b.item()) <= 1e-4 * max(abs(b.item()), 1e-3)
+    np.testing.assert_allclose(res[5:], O.seg_metrics(y64["seg"], out["seg"]), rtol=0, atol=2.0)
+    tol = 2e-2 if variant == "v1" else 2e-3     # ReLU-mask flips, see tests/test_host_logic_cpu.py
+    gmax = max(g.norm().item() for g in grads.values())
+    w_after = m.net.get_weights()
+    for k, g in grads.items():
+        mine_g = (p64[k] - w_after[k].double()) / 1e-2      # SGD first step: p - lr*g
+        err = (mine_g - g).norm().item()
+        assert err <= tol * g.norm().item() + 2e-5 * gmax, (k, err, g.norm().item())
+    for k, v in new_state.items():
+        np.testing.assert_allclose(w_after[k].numpy(), v.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fp32_adam_training_tracks_oracle_and_cuda_graph_equals_eager():
+    n, hw = 4, 64
+    p = rand_params("v2", hw, 3, n, seed=3)
+    x, y = O.synth_batch(4, hw, 3, n, seed=5, block=16)
+    runs = []
+    for use_graph in (True, False):
+        m = build_model((hw, hw, 3), n, True, "v2", dtype="fp32")
+        m.use_cuda_graph = use_graph
+        m.net.set_weights(p)
+        m.compile(optimizer=Adam(lr=1e-3), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+        runs.append([m.train_on_batch(x, y) for _ in range(4)] + [m.test_on_batch(x, y)])
+    for a, b in zip(*runs):
+        np.testing.assert_allclose(a[:5], b[:5], rtol=2e-3)      # wgrad atomics: order-dependent fp32 sums
+    po = {k: v.clone() for k, v in p.items()}
+    opt = O.Adam(lr=1e-3)
+    xt = torch.from_numpy(x)
+    yt = {k: torch.from_numpy(v) for k, v in y.items()}
+    theirs = {k: O.tanimoto_dual_loss for k in LW}
+    ref = [O.train_on_batch(po, opt, xt, yt, theirs, LW, n) for _ in range(4)] + [O.test_on_batch(po, xt, yt, theirs, LW, n)]
+    for step, (a, b) in enumerate(zip(runs[0], ref)):
+        np.testing.assert_allclose(a[:5], b[:5], rtol=1e-4 if step == 0 else 2e-2)
+    assert runs[0][3][0] < runs[0][0][0]      # the loss goes down
+
+
+def _train_toy(m, n, hw, steps, seed=0):
+    """A learnable toy task so that predictions become confident: class = quantised mean colour of
+    16x16 blocks."""
+    rng = np.random.RandomState(seed)
+    last = None
+    for _ in range(steps):
+        base = rng.rand(4, hw // 16, hw // 16, 1)
+        cls = np.minimum((base[..., 0] * n).astype(int), n - 1)
+        x = np.repeat(np.repeat(base, 16, 1), 16, 2) + 0.05 * rng.randn(4, hw, hw, 3)
+        cls = np.repeat(np.repeat(cls, 16, 1), 16, 2)
+        seg = np.eye(n, dtype=np.float32)[cls]
+        y = dict(seg=seg, bound=(rng.rand(4, hw, hw, n) < 0.1).astype(np.float32),
+                 dist=seg.copy(), color=np.clip(x, 0, 1).astype(np.float32))
+        last = m.train_on_batch(x.astype(np.float32), y)
+    return x.astype(np.float32), cls, last
+
+
+def test_bf16_mode_parity_argmax_and_confusion():
+    n, hw = 4, 64
+    m32 = build_model((hw, hw, 3), n, True, "v2", dtype="fp32", seed=5)
+    m32.compile(optimizer=Adam(lr=2e-3), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+    x, cls, last = _train_toy(m32, n, hw, 60)
+    w = m32.net.get_weights()
+    mb = build_model((hw, hw, 3), n, True, "v2", dtype="bf16")
+    mb.net.set_weights(w)
+    ref = O.forward(w, torch.from_numpy(x), False, n, True, "v2")
+    out = mb.predict(x, batch_size=4)
+    for k in out:
+        assert rel_l2(out[k], ref[k].numpy()) <= 1e-2, (k, rel_l2(out[k], ref[k].numpy()))
+    pred_ref = ref["seg"].numpy().argmax(-1)
+    agree = (out["seg"].argmax(-1) == pred_ref).mean()
+    assert agree >= 0.999, agree
+    # bf16 training step: loss within 1e-2 of the oracle's
+    mb.compile(optimizer=SGD(lr=1e-3, momentum=0.8), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+    y = dict(seg=np.eye(n, dtype=np.float32)[cls], bound=np.zeros((4, hw, hw, n), np.float32),
+             dist=np.eye(n, dtype=np.float32)[cls], color=np.clip(x, 0, 1))
+    res = mb.train_on_batch(x, y)
+    yt = {k: torch.from_numpy(v) for k, v in y.items()}
+    tot, per, _, _, _ = O.loss_and_grads(w, torch.from_numpy(x), yt, {k: O.tanimoto_dual_loss for k in LW}, LW, n)
+    assert abs(res[0] - tot.item()) <= 1e-2 * abs(tot.item())
+    # confusion matrix from the device kernel == sklearn on the same predictions (bit-exact)
+    from sklearn.metrics import confusion_matrix
+    scene = np.concatenate([np.concatenate(list(x[:2]), 1), np.concatenate(list(x[2:]), 1)], 0)   # 128x128 scene
+    ref_lab = np.concatenate([np.concatenate(list(cls[:2]), 1), np.concatenate(list(cls[2:]), 1)], 0)
+    r = inference.predict_scene(m32, np.pad(scene, ((0, 10), (0, 7), (0, 0))), np.pad(ref_lab, ((0, 10), (0, 7))),
+                                patch_size=hw, batch_size=3, num_classes=n)
+    pr = m32.predict(inference.extract_patches(scene, hw), batch_size=4)["seg"].argmax(-1)
+    tl = inference.extract_patches(ref_lab, hw)
+    np.testing.assert_array_equal(r["seg_pred"], pr)
+    np.testing.assert_array_equal(r["confusion"], confusion_matrix(tl.ravel(), pr.ravel()))
+    assert r["reconstructed"].shape == (138, 135) and (r["reconstructed"][128:] == 0).all()
+    np.testing.assert_array_equal(r["reconstructed"][:128, :128], O.pred_reconstruction(hw, pr, (128, 128)))
+    acc, f1, rec, prec = r["metrics"]
+    assert acc > 80.0      # the toy task is learnable: the trained fp32 model segments it
+
+
+def test_single_task_256_forward_config1_shape():
+    # BASELINE config 1: single-task forward, 256x256x3, batch 1, 6 classes, inference-mode BN
+    p = rand_params("v2", 256, 3, 6, multitask=False)
+    m = build_model((256, 256, 3), 6, False, "v2", dtype="fp32")
+    m.net.set_weights(p)
+    x = np.random.RandomState(0).rand(1, 256, 256, 3).astype(np.float32)
+    out = m.predict(x, batch_size=1)
+    ref = O.forward(p, torch.from_numpy(x), False, 6, False, "v2").numpy()
+    assert out.shape == (1, 256, 256, 6)
+    assert rel_l2(out, ref) <= 1e-4
