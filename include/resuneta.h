@@ -149,6 +149,21 @@ int rsa_sgd_step(float* param, const float* grad, float* vel, int64_t n, float l
 int rsa_argmax_confusion(const float* prob, int64_t M, int C, int32_t* pred_label, const int32_t* true_label,
                          int K, int64_t* cm, void* stream);
 
+/* ---- tensor-core (tcgen05 + TMA) convolution, bf16 mode ------------------------------------------------
+ * out[n,h,w,:] = epi( sum_tap sum_ci x[n, h+dy*dil, w+dx*dil, ci] * wt[tap][co][ci] + bias ), taps = 9 (3x3)
+ * or 1; x/out/residual/mask bf16 NHWC, wt bf16 [taps][Cout][Cin]; dil < 0 gives the data gradient when wt
+ * is the [tap][Cin_fwd][Cout_fwd] copy.  Epilogue flags as rsa_igemm_fwd.  Replaces cuDNN's dilated
+ * Conv2D forward / backward-data that keras calls at model2.py:19-24,153-178. */
+int rsa_conv_tc_supported(int N, int H, int W, int Cin, int Cout);
+int rsa_conv_tc_fwd(const void* x, const void* wt, const float* bias, void* out, const void* residual,
+                    const void* mask, double* stats, int N, int H, int W, int Cin, int Cout, int taps, int dil,
+                    int accumulate, int relu, void* stream);
+/* bf16 copies of the fp32 HWIO master kernels for the tensor-core path, all layers in one launch.
+ * table (device): nlayers entries {int64 src_off, int64 fwd_off, int64 bwd_off, int32 taps, Cin, Cout, pad};
+ * fwd copy is [tap][Cout][Cin], bwd copy is [tap][Cin][Cout]. */
+int rsa_pack_weights_tc(const float* params, void* shadow, const void* table, int nlayers, long long max_elems,
+                        void* stream);
+
 /* dst (=|+=) src, identity branch of the ResBlock-a backward (Add, model2.py:31) */
 int rsa_axpy(void* dst, const void* src, int dtype, int64_t n, int accumulate, void* stream);
 

@@ -103,10 +103,13 @@ _SIGS = {
     "rsa_argmax_confusion": [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                              C.c_void_p],
     "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
+    "rsa_conv_tc_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "rsa_pack_weights_tc": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p],
     "rsa_cast": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check"])
+EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported"])
 
 
 def load_cdll(path=LIB_PATH):
@@ -122,9 +125,8 @@ def load_cdll(path=LIB_PATH):
     dll.rsa_version.restype = C.c_char_p
     dll.rsa_last_error.restype = C.c_char_p
     dll.rsa_device_check.restype = C.c_int
-    for extra in ("rsa_conv_tc_fwd", "rsa_conv_tc_wgrad", "rsa_conv_tc_supported"):
-        if hasattr(dll, extra):
-            getattr(dll, extra).restype = C.c_int
+    dll.rsa_conv_tc_supported.argtypes = [C.c_int] * 5
+    dll.rsa_conv_tc_supported.restype = C.c_int
     return dll
 
 
@@ -272,6 +274,21 @@ class Lib:
     def argmax_confusion(self, prob, M, C_, pred_label, true_label, K, cm):
         return self._bind("rsa_argmax_confusion", _p(prob), M, C_, _p(pred_label), _p(true_label), K, _p(cm),
                           keep=(prob, pred_label, true_label, cm))
+
+    # -- tensor-core convolution (bf16) ------------------------------------------------------------
+    def conv_tc_supported(self, N, H, W, Cin, Cout):
+        return bool(self.dll.rsa_conv_tc_supported(N, H, W, Cin, Cout))
+
+    def conv_tc_fwd(self, x, wt, bias, out, N, H, W, Cin, Cout, taps, dil, residual=None, mask=None, stats=None,
+                    accumulate=False, relu=False):
+        assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+        return self._bind("rsa_conv_tc_fwd", _p(x), _p(wt), _p(bias), _p(out), _p(residual), _p(mask), _p(stats),
+                          N, H, W, Cin, Cout, taps, dil, int(accumulate), int(relu),
+                          keep=(x, wt, bias, out, residual, mask, stats))
+
+    def pack_weights_tc(self, params, shadow, table, nlayers, max_elems):
+        return self._bind("rsa_pack_weights_tc", _p(params), _p(shadow), _p(table), nlayers, max_elems,
+                          keep=(params, shadow, table))
 
     # -- optimizers / misc ----------------------------------------------------------------------
     def adam_step(self, param, grad, m, v, n, lr_dev, b1, b2, eps, grad_scale):

@@ -356,9 +356,15 @@ class Plan:
         st = out.stats
         res = residual.data if residual is not None else None
         flops = 2.0 * N * H * W * 9 * C * cout
-        self.fwd.append(self._tag(self._late(lambda: lib.igemm_fwd(
-            segs, W_, cout, False, b_, out.data, N, H, W, cout, residual=res, stats=st[0] if st else None,
-            accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
+        tcw = self.net.tc_weights(name, N, H, W)
+        if tcw is not None:
+            self.fwd.append(self._tag(self._late(lambda: lib.conv_tc_fwd(
+                x.data, tcw[0], b_, out.data, N, H, W, C, cout, 9, dil, residual=res,
+                stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
+        else:
+            self.fwd.append(self._tag(self._late(lambda: lib.igemm_fwd(
+                segs, W_, cout, False, b_, out.data, N, H, W, cout, residual=res, stats=st[0] if st else None,
+                accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
         if self.training:
             def bwd():
                 if out.grad is None:
@@ -374,8 +380,12 @@ class Plan:
                     sg = [Seg(dy, cout, H, W, off_h=-(ky - 1) * dil, off_w=-(kx - 1) * dil,
                               w_off=(ky * 3 + kx) * C * cout) for ky in range(3) for kx in range(3)]
                     mask = x.data if x.relu_masked else None
-                    self.bwd.append(self._tag(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask,
-                                                            accumulate=acc), "conv3x3_dgrad", flops))
+                    if tcw is not None:
+                        self.bwd.append(self._tag(lib.conv_tc_fwd(dy, tcw[1], None, g, N, H, W, cout, C, 9, -dil,
+                                                                  mask=mask, accumulate=acc), "conv3x3_dgrad", flops))
+                    else:
+                        self.bwd.append(self._tag(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask,
+                                                                accumulate=acc), "conv3x3_dgrad", flops))
             self.tape.append(bwd)
         return out
 
@@ -608,8 +618,13 @@ def _conv_into(pl, a, f, d, name, out, first, residual):
             for ky in range(3) for kx in range(3)]
     res = residual.data if (first and residual is not None) else None
     flops = 2.0 * N * H * W * 9 * C * f
-    pl.fwd.append(pl._tag(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res,
-                                        accumulate=not first), "conv3x3_fwd", flops))
+    tcw = pl.net.tc_weights(name, N, H, W)
+    if tcw is not None:
+        pl.fwd.append(pl._tag(lib.conv_tc_fwd(a.data, tcw[0], b_, out.data, N, H, W, C, f, 9, d, residual=res,
+                                              accumulate=not first), "conv3x3_fwd", flops))
+    else:
+        pl.fwd.append(pl._tag(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res,
+                                            accumulate=not first), "conv3x3_fwd", flops))
     if pl.training:
         def bwd():
             if out.grad is None:
@@ -621,8 +636,12 @@ def _conv_into(pl, a, f, d, name, out, first, residual):
             g, acc = pl.gacc(a)
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
                   for ky in range(3) for kx in range(3)]
-            pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
-                                  "conv3x3_dgrad", flops))
+            if tcw is not None:
+                pl.bwd.append(pl._tag(lib.conv_tc_fwd(dy, tcw[1], None, g, N, H, W, f, C, 9, -d, accumulate=acc),
+                                      "conv3x3_dgrad", flops))
+            else:
+                pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
+                                      "conv3x3_dgrad", flops))
         pl.tape.append(bwd)
 
 
@@ -733,6 +752,55 @@ class Net:
         self.output_names = list(spec.outputs)
         self.params.finalize(self.device, seed)
         self.plans = {}
+        self._init_tensor_core_path()
+
+    # -- bf16 tensor-core path: bf16 weight copies [tap][Cout][Cin] (fwd) / [tap][Cin][Cout] (dgrad) -------
+    def _init_tensor_core_path(self):
+        import os
+        import struct
+        self.tc = {}
+        self.shadow = None
+        self.pack_launch = None
+        self.shadow_dirty = True
+        engine = os.environ.get("RSA_CONV_ENGINE", "tc")
+        if (self.act_dtype != torch.bfloat16 or getattr(self.lib, "is_emulation", False) or engine != "tc"
+                or not hasattr(self.lib, "conv_tc_fwd")):
+            self.conv_engine = "igemm_simt"
+            return
+        okc = lambda c: c == 32 or (c >= 64 and c % 64 == 0)
+        off, table, max_elems = 0, b"", 0
+        for name, (shape, _, _) in self.params.spec.items():
+            if not name.endswith("/kernel") or shape[0] != 3:
+                continue
+            _, _, cin, cout = shape
+            if not (okc(cin) and okc(cout)):
+                continue
+            n = 9 * cin * cout
+            self.tc[name[:-len("/kernel")]] = (off, off + n, cin, cout)
+            table += struct.pack("<qqqiiii", self.params.off[name], off, off + n, 9, cin, cout, 0)
+            off += 2 * n
+            max_elems = max(max_elems, n)
+        if not self.tc:
+            self.conv_engine = "igemm_simt"
+            return
+        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=self.device)
+        self._pack_table = torch.frombuffer(bytearray(table), dtype=torch.uint8).to(self.device)
+        self.pack_launch = self.lib.pack_weights_tc(self.params.data, self.shadow, self._pack_table, len(self.tc),
+                                                    max_elems)
+        self.conv_engine = "tcgen05 fwd+dgrad / simt wgrad"
+
+    def tc_weights(self, name, N, H, W):
+        """(fwd copy, dgrad copy) bf16 views if the tensor-core kernel handles this layer at this size."""
+        ent = self.tc.get(name)
+        if ent is None or not self.lib.conv_tc_supported(N, H, W, ent[2], ent[3]):
+            return None
+        n = 9 * ent[2] * ent[3]
+        return self.shadow[ent[0]:ent[0] + n], self.shadow[ent[1]:ent[1] + n]
+
+    def ensure_shadow(self, stream):
+        if self.pack_launch is not None and self.shadow_dirty:
+            self.pack_launch(stream)
+            self.shadow_dirty = False
 
     def plan(self, N, training, loss_spec=None):
         """loss_spec: None or tuple of (head, kind, weight, class_weights) — part of the cache key."""
@@ -761,3 +829,4 @@ class Net:
             if tuple(v.shape) != tuple(dst.shape):
                 raise ValueError(f"shape mismatch for {k}: {tuple(v.shape)} vs {tuple(dst.shape)}")
             dst.copy_(v.to(self.device))
+        self.shadow_dirty = True

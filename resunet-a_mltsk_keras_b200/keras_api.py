@@ -329,6 +329,8 @@ class Model:
     def _run_train_ops(self, pl, stream):
         pl.scratch.zero_()
         self.net.params.grad.zero_()
+        if self.net.pack_launch is not None:      # refresh the bf16 weight copies of the tensor-core path
+            self.net.pack_launch(stream)
         for op in pl.fwd:
             op(stream)
         if pl.bn_update is not None:
@@ -346,13 +348,19 @@ class Model:
             op(stream)
 
     def _execute(self, pl, train):
+        if train:
+            self.net.shadow_dirty = True      # parameters change: bf16 copies are refreshed lazily for eval
         stream = self._stream()
         run = self._run_train_ops if train else self._run_eval_ops
         can_graph = (self.use_cuda_graph and self.net.device.type == "cuda"
                      and not (train and self.dp is not None and self.dp.world_size > 1))
         if not can_graph:
+            if not train:
+                self.net.ensure_shadow(stream)
             run(pl, stream)
             return
+        if not train:
+            self.net.ensure_shadow(stream)
         key = (id(pl), train)
         g = self._graphs.get(key)
         if g is None:

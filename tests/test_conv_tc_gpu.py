@@ -1,0 +1,102 @@
+"""tcgen05/TMA convolution kernel (conv_tc.cu) through the C-ABI against the fp64 emulation of the same
+implicit GEMM on bf16-rounded operands.  Kept in its own file so that it runs in its own process on the
+GPU box.  Tolerance: 1e-2 of the output range (bf16 output rounding + fp32 accumulation order)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from emul_lib import EmulLib  # noqa: E402
+from resuneta_b200._capi import Seg  # noqa: E402
+
+EMU = EmulLib()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from resuneta_b200 import _capi
+    return _capi.Lib()
+
+
+def rnd(shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+# ---- tensor-core (tcgen05 + TMA) convolution vs the fp64 emulation of the same implicit GEMM --------------
+def _pack(w_hwio_flat, taps, cin, cout):
+    w = w_hwio_flat.view(taps, cin, cout)
+    return w.permute(0, 2, 1).contiguous().to(torch.bfloat16), w.contiguous().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("N,H,C,Co,d", [(2, 32, 32, 32, 1), (2, 32, 32, 32, 15), (2, 64, 32, 32, 31), (2, 32, 64, 64, 3),
+                                        (3, 16, 128, 128, 1), (2, 16, 256, 256, 15), (4, 8, 512, 512, 1),
+                                        (1, 8, 1024, 1024, 1), (16, 4, 1024, 1024, 1), (2, 16, 64, 128, 3)])
+def test_conv_tc_fwd_and_dgrad(lib, N, H, C, Co, d):
+    W = H
+    assert lib.conv_tc_supported(N, H, W, C, Co)
+    dt = torch.bfloat16
+    x = rnd((N, H, W, C), dt, 1)
+    w = rnd((9 * C * Co,), torch.float32, 2, 1.0 / (3 * C ** 0.5))
+    w = w.to(dt).float()                                    # the emulation sees the same bf16-rounded weights
+    b = rnd((Co,), torch.float32, 3)
+    wf, wb = _pack(w, 9, C, Co)
+    segs = [Seg(x, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * Co)
+            for ky in range(3) for kx in range(3)]
+    out = rnd((N, H, W, Co), dt, 4)
+    res = rnd((N, H, W, Co), dt, 5)
+    stats = torch.zeros(2 * Co, dtype=torch.float64)
+    EMU.igemm_fwd(segs, w, Co, False, b, out, N, H, W, Co, residual=res, stats=stats, accumulate=True)(0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_out, d_stats = rnd((N, H, W, Co), dt, 4).cuda(), torch.zeros(2 * Co, dtype=torch.float64).cuda()
+    lib.conv_tc_fwd(x.cuda(), wf.cuda(), b.cuda(), d_out, N, H, W, C, Co, 9, d, residual=res.cuda(), stats=d_stats,
+                    accumulate=True)(st)
+    torch.cuda.synchronize()
+    scale = out.float().abs().max().item()
+    assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100, "forward"
+    np.testing.assert_allclose(d_stats.cpu().numpy(), stats.numpy(), rtol=2e-2, atol=2e-2 * N * H * W ** 0.5)
+    # relu + mask epilogue, no accumulate
+    mask = rnd((N, H, W, Co), dt, 6)
+    EMU.igemm_fwd(segs, w, Co, False, b, out, N, H, W, Co, relu=True, mask=mask)(0)
+    lib.conv_tc_fwd(x.cuda(), wf.cuda(), b.cuda(), d_out, N, H, W, C, Co, 9, d, relu=True, mask=mask.cuda())(st)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100, "relu/mask"
+    # data gradient: negated dilation, [tap][Cin][Cout] copy
+    dy = rnd((N, H, W, Co), dt, 7)
+    sg = [Seg(dy, Co, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * Co)
+          for ky in range(3) for kx in range(3)]
+    dx = torch.zeros((N, H, W, C), dtype=dt)
+    EMU.igemm_fwd(sg, w, Co, True, None, dx, N, H, W, C)(0)
+    d_dx = torch.zeros((N, H, W, C), dtype=dt).cuda()
+    lib.conv_tc_fwd(dy.cuda(), wb.cuda(), None, d_dx, N, H, W, Co, C, 9, -d)(st)
+    torch.cuda.synchronize()
+    assert (d_dx.cpu().float() - dx.float()).abs().max().item() <= dx.float().abs().max().item() / 100, "dgrad"
+
+
+def test_pack_weights_tc(lib):
+    import struct
+    layers = [(9, 32, 32), (9, 64, 128)]
+    total = sum(t * a * b for t, a, b in layers)
+    params = rnd((total + 64,), torch.float32, 1)
+    table, soff, doff = b"", 0, 0
+    for t, a, b in layers:
+        n = t * a * b
+        table += struct.pack("<qqqiiii", soff, doff, doff + n, t, a, b, 0)
+        soff += n
+        doff += 2 * n
+    shadow = torch.zeros(doff, dtype=torch.bfloat16).cuda()
+    tab = torch.frombuffer(bytearray(table), dtype=torch.uint8).cuda()
+    lib.pack_weights_tc(params.cuda(), shadow, tab, len(layers), max(t * a * b for t, a, b in layers))(
+        torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    soff = doff = 0
+    for t, a, b in layers:
+        n = t * a * b
+        wf, wb = _pack(params[soff:soff + n], t, a, b)
+        assert torch.equal(shadow[doff:doff + n].cpu(), wf.reshape(-1))
+        assert torch.equal(shadow[doff + n:doff + 2 * n].cpu(), wb.reshape(-1))
+        soff += n
+        doff += 2 * n
