@@ -158,6 +158,14 @@ int rsa_conv_tc_supported(int N, int H, int W, int Cin, int Cout);
 int rsa_conv_tc_fwd(const void* x, const void* wt, const float* bias, void* out, const void* residual,
                     const void* mask, double* stats, int N, int H, int W, int Cin, int Cout, int taps, int dil,
                     int accumulate, int relu, void* stream);
+/* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co];
+ * x, dy bf16 NHWC, Cin == Cout.  Replaces cuDNN's Conv2D backward-filter behind model2.py:19-24,153-178. */
+int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int dil,
+                      void* stream);
+/* db_k[c] += sum_m dy[m,c] for up to four bias gradients (NULL to skip): all branches of a ResBlock-a share
+ * d(out) (Add, model2.py:27-31). */
+int rsa_bias_grad(const void* dy, int dtype, long long M, int C, float* db0, float* db1, float* db2, float* db3,
+                  void* stream);
 /* bf16 copies of the fp32 HWIO master kernels for the tensor-core path, all layers in one launch.
  * table (device): nlayers entries {int64 src_off, int64 fwd_off, int64 bwd_off, int32 taps, Cin, Cout, pad};
  * fwd copy is [tap][Cout][Cin], bwd copy is [tap][Cin][Cout]. */

@@ -105,6 +105,10 @@ _SIGS = {
     "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
     "rsa_conv_tc_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "rsa_conv_tc_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                          C.c_void_p],
+    "rsa_bias_grad": [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.c_void_p],
     "rsa_pack_weights_tc": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p],
     "rsa_cast": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p],
 }
@@ -285,6 +289,15 @@ class Lib:
         return self._bind("rsa_conv_tc_fwd", _p(x), _p(wt), _p(bias), _p(out), _p(residual), _p(mask), _p(stats),
                           N, H, W, Cin, Cout, taps, dil, int(accumulate), int(relu),
                           keep=(x, wt, bias, out, residual, mask, stats))
+
+    def conv_tc_wgrad(self, x, dy, dw, N, H, W, Cin, Cout, dil):
+        assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32
+        return self._bind("rsa_conv_tc_wgrad", _p(x), _p(dy), _p(dw), N, H, W, Cin, Cout, dil, keep=(x, dy, dw))
+
+    def bias_grad(self, dy, M, C_, dbs):
+        d = list(dbs) + [None] * (4 - len(dbs))
+        return self._bind("rsa_bias_grad", _p(dy), dtype_code(dy), M, C_, _p(d[0]), _p(d[1]), _p(d[2]), _p(d[3]),
+                          keep=(dy, dbs))
 
     def pack_weights_tc(self, params, shadow, table, nlayers, max_elems):
         return self._bind("rsa_pack_weights_tc", _p(params), _p(shadow), _p(table), nlayers, max_elems,

@@ -68,17 +68,24 @@ __global__ void __launch_bounds__(NT) maxpool_pyr_fwd_kernel(const T* __restrict
   }
 }
 
-// first maximum (row-major scan, strict >) of the KxK sub-window at (i0,j0)
+// Route d to the first maximum (row-major scan) of the KxK sub-window at (i0,j0): max value first, then
+// the first position that equals it.  (An index-tracking arg-max followed by index compares was
+// mis-folded by nvcc 12.9 for K=2 — the "first position equal to the max" form has no such hazard.)
 template <int BS, int K>
-__device__ __forceinline__ void first_argmax(const float (&v)[BS][BS], int i0, int j0, int& ai, int& aj) {
-  float best = v[i0][j0];
-  ai = i0; aj = j0;
+__device__ __forceinline__ void route_first_max(const float (&v)[BS][BS], float (&g)[BS][BS], int i0, int j0, float d) {
+  float m = v[i0][j0];
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+#pragma unroll
+    for (int j = 0; j < K; ++j) m = fmaxf(m, v[i0 + i][j0 + j]);
+  bool taken = false;
 #pragma unroll
   for (int i = 0; i < K; ++i)
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      float t = v[i0 + i][j0 + j];
-      if (t > best) { best = t; ai = i0 + i; aj = j0 + j; }
+      const bool hit = !taken && (v[i0 + i][j0 + j] == m);
+      g[i0 + i][j0 + j] += hit ? d : 0.f;
+      taken = taken || hit;
     }
 }
 
@@ -111,13 +118,7 @@ __global__ void __launch_bounds__(NT) maxpool_pyr_bwd_kernel(const T* __restrict
 #pragma unroll
         for (int j = 0; j < BS / 2; ++j) {
           float d = ldf<T>(dp2 + (((int64_t)n * H2 + hb * (BS / 2) + i) * W2 + wb * (BS / 2) + j) * C + c);
-          int ai, aj;
-          first_argmax<BS, 2>(v, 2 * i, 2 * j, ai, aj);
-#pragma unroll
-          for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-              if (ai == 2 * i + a && aj == 2 * j + b) g[2 * i + a][2 * j + b] += d;
+          route_first_max<BS, 2>(v, g, 2 * i, 2 * j, d);
         }
     }
     if constexpr (BS >= 4) {
@@ -128,26 +129,14 @@ __global__ void __launch_bounds__(NT) maxpool_pyr_bwd_kernel(const T* __restrict
 #pragma unroll
           for (int j = 0; j < BS / 4; ++j) {
             float d = ldf<T>(dp4 + (((int64_t)n * H4 + hb * (BS / 4) + i) * W4 + wb * (BS / 4) + j) * C + c);
-            int ai, aj;
-            first_argmax<BS, 4>(v, 4 * i, 4 * j, ai, aj);
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int b = 0; b < 4; ++b)
-                if (ai == 4 * i + a && aj == 4 * j + b) g[4 * i + a][4 * j + b] += d;
+            route_first_max<BS, 4>(v, g, 4 * i, 4 * j, d);
           }
       }
     }
     if constexpr (BS >= 8) {
       if (dp8) {
         float d = ldf<T>(dp8 + (((int64_t)n * (H / 8) + hb) * (W / 8) + wb) * C + c);
-        int ai, aj;
-        first_argmax<BS, 8>(v, 0, 0, ai, aj);
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-          for (int b = 0; b < 8; ++b)
-            if (ai == a && aj == b) g[a][b] += d;
+        route_first_max<BS, 8>(v, g, 0, 0, d);
       }
     }
 #pragma unroll

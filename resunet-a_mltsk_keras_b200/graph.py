@@ -372,8 +372,14 @@ class Plan:
                 dy = out.grad
                 dW = self.G(name + "/kernel")
                 db = self.G(name + "/bias") if bias_grad else None
-                self.bwd.append(self._tag(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout), "conv3x3_wgrad",
-                                          flops))
+                if tcw is not None and C == cout:
+                    self.bwd.append(self._tag(lib.conv_tc_wgrad(x.data, dy, dW, N, H, W, C, cout, dil),
+                                              "conv3x3_wgrad", flops))
+                    if db is not None:
+                        self.bwd.append(lib.bias_grad(dy, N * H * W, cout, [db]))
+                else:
+                    self.bwd.append(self._tag(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout),
+                                              "conv3x3_wgrad", flops))
                 self._ready(name + "/kernel", name + "/bias")
                 if x.needs_grad:
                     g, acc = self.gacc(x)
@@ -455,6 +461,22 @@ class Plan:
             else:
                 g, acc = self.gacc(x)
                 self.bwd.append(self.lib.axpy(g, out.grad, x.M * x.C, acc))
+        self.tape.append(bwd)
+
+    def block_bias_grad(self, out, conv_names, f):
+        """Tensor-core path: the second-conv biases of all branches of a ResBlock-a share d(out); one
+        column-sum pass feeds them all (the SIMT wgrad kernel folds its own bias gradient instead)."""
+        if self.spec_only or not self.training:
+            return
+        if self.net.tc_weights(conv_names[0], self.N, out.H, out.W) is None or f != out.C:
+            return
+
+        def bwd():
+            if out.grad is None:
+                return
+            dbs = [self.G(n + "/bias") for n in conv_names]
+            self.bwd.append(self.lib.bias_grad(out.grad, out.M, out.C, dbs))
+            self._ready(*[n + "/bias" for n in conv_names])
         self.tape.append(bwd)
 
     def maxpool(self, x, levels):
@@ -596,6 +618,7 @@ def _resblock(pl, x, f, dils, identity):
         pl._reg_conv(nc2, 3, f, f)
     a1 = pl.bn(x, [n[0] for n in names], relu=True)     # every branch normalises the same input
     out = pl.tensor("resblock_out", x.H, x.W, f)
+    pl.block_bias_grad(out, [n[3] for n in names], f)
     if identity:
         pl.identity_add(x, out)
     for i, d in enumerate(dils):
@@ -630,8 +653,13 @@ def _conv_into(pl, a, f, d, name, out, first, residual):
             if out.grad is None:
                 return
             dy = out.grad
-            pl.bwd.append(pl._tag(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N, H, W,
-                                                  f), "conv3x3_wgrad", flops))
+            if tcw is not None and C == f:
+                # bias gradient: one column-sum of d(out) per block (block_bias_grad)
+                pl.bwd.append(pl._tag(lib.conv_tc_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, f, d),
+                                      "conv3x3_wgrad", flops))
+            else:
+                pl.bwd.append(pl._tag(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N,
+                                                      H, W, f), "conv3x3_wgrad", flops))
             pl._ready(name + "/kernel", name + "/bias")
             g, acc = pl.gacc(a)
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)

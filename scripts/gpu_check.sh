@@ -6,7 +6,6 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 timeout 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu --timeout 300 > gpurun_out/test_kernels.log 2>&1
 echo "kernels rc=$?" >> gpurun_out/summary.txt
-timeout 300 python scripts/debug_pool.py > gpurun_out/debug_pool.log 2>&1
 timeout 600 python -m pytest tests/test_conv_tc_gpu.py -q -m gpu --timeout 120 > gpurun_out/test_conv_tc.log 2>&1
 echo "conv_tc rc=$?" >> gpurun_out/summary.txt
 RSA_CONV_ENGINE=simt timeout 1500 python -m pytest tests/test_model_gpu.py -q -m gpu --timeout 900 > gpurun_out/test_model_simt.log 2>&1
@@ -17,5 +16,5 @@ timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/summary.txt
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2>&1
 echo "bench rc=$?" >> gpurun_out/summary.txt
-for f in test_kernels debug_pool test_conv_tc test_model_simt test_model smoke bench; do echo "== $f"; tail -n 5 gpurun_out/$f.log; done
+for f in test_kernels test_conv_tc test_model_simt test_model smoke bench; do echo "== $f"; tail -n 5 gpurun_out/$f.log; done
 cat gpurun_out/summary.txt

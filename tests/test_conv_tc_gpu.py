@@ -100,3 +100,27 @@ def test_pack_weights_tc(lib):
         assert torch.equal(shadow[doff + n:doff + 2 * n].cpu(), wb.reshape(-1))
         soff += n
         doff += 2 * n
+
+
+@pytest.mark.parametrize("N,H,C,d", [(2, 32, 32, 1), (2, 64, 32, 31), (2, 32, 64, 3), (3, 16, 128, 1), (2, 16, 256, 15),
+                                     (4, 8, 512, 1), (16, 4, 1024, 1), (16, 64, 32, 15)])
+def test_conv_tc_wgrad_and_bias_grad(lib, N, H, C, d):
+    W, dt = H, torch.bfloat16
+    x = rnd((N, H, W, C), dt, 1)
+    dy = rnd((N, H, W, C), dt, 2)
+    segs = [Seg(x, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * C)
+            for ky in range(3) for kx in range(3)]
+    dw = torch.zeros(9 * C * C, dtype=torch.float32)
+    db = torch.zeros(C, dtype=torch.float32)
+    EMU.igemm_wgrad(segs, dy, dw, C, db, N, H, W, C)(0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_dw = torch.zeros(9 * C * C, dtype=torch.float32).cuda()
+    lib.conv_tc_wgrad(x.cuda(), dy.cuda(), d_dw, N, H, W, C, C, d)(st)
+    d_db = [torch.zeros(C, dtype=torch.float32).cuda() for _ in range(3)]
+    lib.bias_grad(dy.cuda(), N * H * W, C, d_db)(st)
+    torch.cuda.synchronize()
+    scale = dw.abs().max().item()
+    err = (d_dw.cpu() - dw).abs().max().item()
+    assert err <= 2e-3 * scale, (err, scale)
+    for t_ in d_db:
+        np.testing.assert_allclose(t_.cpu().numpy(), db.numpy(), rtol=1e-3, atol=1e-3 * db.abs().max().item())

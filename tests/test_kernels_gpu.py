@@ -243,7 +243,7 @@ def test_pixel_losses(lib, kind):
     lab = torch.nn.functional.one_hot(torch.randint(0, C, (M,), generator=g), C).float()
     w = torch.tensor([1.1, 2.0, 0.5, 3.0, 0.0]) if kind == 0 else None
     ls = torch.zeros(1, dtype=torch.float64)
-    run_pair(lib, "pixel_loss_fwd", [kind, pred, lab, w, M, C, ls], {}, [6], 1e-5)
+    run_pair(lib, "pixel_loss_fwd", [kind, pred, lab, w, M, C, ls], {}, [6], 1e-4)   # fp32 logf per pixel
     dp = torch.zeros_like(pred)
     run_pair(lib, "pixel_loss_bwd", [kind, pred, lab, w, M, C, 0.37, dp], {}, [7], 1e-5, 1e-7)
 
