@@ -14,7 +14,8 @@ timeout 1500 python -m pytest tests/test_model_gpu.py -q -m gpu --timeout 900 -k
 echo "model(tc,bf16) rc=$?" >> gpurun_out/summary.txt
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/summary.txt
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2>&1
+timeout 600 python scripts/profile_step.py --detail > gpurun_out/profile_step.log 2>&1
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1
 echo "bench rc=$?" >> gpurun_out/summary.txt
-for f in test_kernels test_conv_tc test_model_simt test_model smoke bench; do echo "== $f"; tail -n 5 gpurun_out/$f.log; done
+for f in test_kernels test_conv_tc test_model_simt test_model smoke profile_step bench; do echo "== $f"; tail -n 12 gpurun_out/$f.log; done
 cat gpurun_out/summary.txt

@@ -81,14 +81,16 @@ def test_fp32_train_step_matches_fp64_oracle(variant, kind):
     gmax = max(g.norm().item() for g in grads.values())
     w_after = m.net.get_weights()
     for k, g in grads.items():
-        mine_g = (p64[k] - w_after[k].double()) / 1e-2      # SGD first step: p - lr*g
+        mine_g = m.net.params.gview(k).double().cpu()       # the gradient buffer of the step just taken
         err = (mine_g - g).norm().item()
         assert err <= tol * g.norm().item() + 2e-5 * gmax, (k, err, g.norm().item())
+        upd = (p64[k] - w_after[k].double()) / 1e-2          # SGD first step: p - lr*g (fp32 resolution ~1e-5)
+        assert (upd - g).norm().item() <= tol * g.norm().item() + 1e-4 * max(1.0, p64[k].norm().item()), k
     for k, v in new_state.items():
         np.testing.assert_allclose(w_after[k].numpy(), v.numpy(), rtol=1e-4, atol=1e-5)
 
 
-def test_fp32_adam_training_tracks_oracle_and_cuda_graph_equals_eager():
+def _multi_step(opt_mine, opt_theirs, steps=4):
     n, hw = 4, 64
     p = rand_params("v2", hw, 3, n, seed=3)
     x, y = O.synth_batch(4, hw, 3, n, seed=5, block=16)
@@ -97,19 +99,37 @@ def test_fp32_adam_training_tracks_oracle_and_cuda_graph_equals_eager():
         m = build_model((hw, hw, 3), n, True, "v2", dtype="fp32")
         m.use_cuda_graph = use_graph
         m.net.set_weights(p)
-        m.compile(optimizer=Adam(lr=1e-3), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
-        runs.append([m.train_on_batch(x, y) for _ in range(4)] + [m.test_on_batch(x, y)])
-    for a, b in zip(*runs):
-        np.testing.assert_allclose(a[:5], b[:5], rtol=2e-3)      # wgrad atomics: order-dependent fp32 sums
+        m.compile(optimizer=opt_mine(), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+        runs.append([m.train_on_batch(x, y) for _ in range(steps)] + [m.test_on_batch(x, y)])
     po = {k: v.clone() for k, v in p.items()}
-    opt = O.Adam(lr=1e-3)
+    opt = opt_theirs()
     xt = torch.from_numpy(x)
     yt = {k: torch.from_numpy(v) for k, v in y.items()}
     theirs = {k: O.tanimoto_dual_loss for k in LW}
-    ref = [O.train_on_batch(po, opt, xt, yt, theirs, LW, n) for _ in range(4)] + [O.test_on_batch(po, xt, yt, theirs, LW, n)]
+    ref = [O.train_on_batch(po, opt, xt, yt, theirs, LW, n) for _ in range(steps)] + [
+        O.test_on_batch(po, xt, yt, theirs, LW, n)]
+    return runs, ref
+
+
+def test_fp32_sgd_training_tracks_oracle_and_cuda_graph_equals_eager():
+    runs, ref = _multi_step(lambda: SGD(lr=1e-2, momentum=0.8), lambda: O.SGD(lr=1e-2, momentum=0.8))
+    for a, b in zip(*runs):                                   # replayed CUDA graph == eager launches
+        np.testing.assert_allclose(a[:5], b[:5], rtol=1e-3)
     for step, (a, b) in enumerate(zip(runs[0], ref)):
-        np.testing.assert_allclose(a[:5], b[:5], rtol=1e-4 if step == 0 else 2e-2)
-    assert runs[0][3][0] < runs[0][0][0]      # the loss goes down
+        np.testing.assert_allclose(a[:5], b[:5], rtol=1e-4 if step == 0 else 2e-3)
+    assert runs[0][3][0] < runs[0][0][0]                      # the loss goes down
+
+
+def test_fp32_adam_training_tracks_oracle():
+    # Adam's first steps move EVERY parameter by ~lr*sign(g), including the ones whose true gradient is zero
+    # (biases that the following BatchNormalization cancels): their sign is rounding noise in any
+    # implementation, so only the first step is bit-comparable; later steps are compared loosely and the
+    # inference-mode evaluation (moving statistics lag those biases) even more so.
+    runs, ref = _multi_step(lambda: Adam(lr=1e-3), lambda: O.Adam(lr=1e-3))
+    for step, (a, b) in enumerate(zip(runs[0], ref)):
+        tol = 1e-4 if step == 0 else (3e-2 if step < 4 else 1e-1)
+        np.testing.assert_allclose(a[:5], b[:5], rtol=tol)
+    assert runs[0][3][0] < runs[0][0][0]
 
 
 def _train_toy(m, n, hw, steps, seed=0):
@@ -134,6 +154,8 @@ def test_bf16_mode_parity_argmax_and_confusion():
     m32 = build_model((hw, hw, 3), n, True, "v2", dtype="fp32", seed=5)
     m32.compile(optimizer=Adam(lr=2e-3), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
     x, cls, last = _train_toy(m32, n, hw, 60)
+    m32.optimizer.lr = 0.0          # let the BN moving statistics (momentum .99) converge: 0.99^400 ~ 2 %
+    x, cls, last = _train_toy(m32, n, hw, 400, seed=1)
     w = m32.net.get_weights()
     mb = build_model((hw, hw, 3), n, True, "v2", dtype="bf16")
     mb.net.set_weights(w)
