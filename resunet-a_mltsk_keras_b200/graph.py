@@ -599,6 +599,7 @@ class Plan:
         for op in self.fwd + self.bwd:
             if hasattr(op, "make") and not op.cell:
                 op.cell.append(op.make())
+                op.kernel = getattr(op.cell[0], "kernel", "?")
 
     def zero_scratch(self, stream):
         self.scratch.zero_()
