@@ -77,7 +77,7 @@ def test_fp32_train_step_matches_fp64_oracle(variant, kind):
     for a, b in zip(res[1:5], per):
         assert abs(a - b.item()) <= 1e-4 * max(abs(b.item()), 1e-3)
     np.testing.assert_allclose(res[5:], O.seg_metrics(y64["seg"], out["seg"]), rtol=0, atol=2.0)
-    tol = 2e-2 if variant == "v1" else 5e-3     # ReLU-mask flips, see tests/test_host_logic_cpu.py
+    tol = 2e-2 if variant == "v1" else 1e-2     # ReLU-mask flips, see tests/test_host_logic_cpu.py
     gmax = max(g.norm().item() for g in grads.values())
     w_after = m.net.get_weights()
     for k, g in grads.items():
