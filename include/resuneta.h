@@ -158,6 +158,18 @@ int rsa_conv_tc_supported(int N, int H, int W, int Cin, int Cout);
 int rsa_conv_tc_fwd(const void* x, const void* wt, const float* bias, void* out, const void* residual,
                     const void* mask, double* stats, int N, int H, int W, int Cin, int Cout, int taps, int dil,
                     int accumulate, int relu, void* stream);
+/* Persistent generalisation of rsa_conv_tc_fwd (conv_tc2.cu):
+ * out[n,h,w,:Cout] = epi( sum_tap sum_src sum_c x_src[n, h*s+dy*dil, w*s+dx*dil, c] * wt[tap][co][koff_src+c]
+ *                        + bias + sum_u up_{shift_u}(q_u) )
+ * x0 / optional x1: bf16 NHWC sources, K-concatenated (taps = 1; Concatenate model2.py:83) or the single 3x3 source
+ * (taps = 9); wt bf16 [taps][CoutP][C0+C1], CoutP = Cout rounded up to the N tile with zero rows; in_stride 2 =
+ * Conv2D strides=2 (model2.py:103-111); q_u bf16 [N, H>>shift, W>>shift, Cout] are low-resolution addends that are
+ * nearest-up-sampled in the epilogue (UpSampling2D, model2.py:55-60,91); out bf16 or fp32. */
+int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int Cout);
+int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void* wt, int CoutP, const float* bias,
+                     void* out, int out_f32, const void* residual, const void* mask, double* stats, int N, int H,
+                     int W, int Cout, int taps, int dil, int in_stride, int nup, const void* const* up_ptrs,
+                     const int* up_shifts, int accumulate, int relu, void* stream);
 /* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co];
  * x, dy bf16 NHWC, Cin == Cout.  Replaces cuDNN's Conv2D backward-filter behind model2.py:19-24,153-178. */
 int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int dil,

@@ -105,6 +105,9 @@ _SIGS = {
     "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
     "rsa_conv_tc_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "rsa_conv_tc2_fwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                         C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_void_p],
     "rsa_bias_grad": [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -113,7 +116,8 @@ _SIGS = {
     "rsa_cast": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p],
 }
 
-EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported"])
+EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported",
+                                "rsa_conv_tc2_supported"])
 
 
 def load_cdll(path=LIB_PATH):
@@ -131,6 +135,8 @@ def load_cdll(path=LIB_PATH):
     dll.rsa_device_check.restype = C.c_int
     dll.rsa_conv_tc_supported.argtypes = [C.c_int] * 5
     dll.rsa_conv_tc_supported.restype = C.c_int
+    dll.rsa_conv_tc2_supported.argtypes = [C.c_int] * 6
+    dll.rsa_conv_tc2_supported.restype = C.c_int
     return dll
 
 
@@ -289,6 +295,27 @@ class Lib:
         return self._bind("rsa_conv_tc_fwd", _p(x), _p(wt), _p(bias), _p(out), _p(residual), _p(mask), _p(stats),
                           N, H, W, Cin, Cout, taps, dil, int(accumulate), int(relu),
                           keep=(x, wt, bias, out, residual, mask, stats))
+
+    def conv_tc2_supported(self, N, H, W, C0, C1, Cout):
+        return bool(self.dll.rsa_conv_tc2_supported(N, H, W, C0, C1, Cout))
+
+    def conv_tc2_fwd(self, x0, x1, wt, CoutP, bias, out, N, H, W, Cout, taps=1, dil=1, in_stride=1, ups=(),
+                     residual=None, mask=None, stats=None, accumulate=False, relu=False):
+        """ups: sequence of (q tensor, shift).  x1 may be None.  out bf16 or fp32."""
+        assert x0.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16
+        C0 = x0.shape[-1]
+        C1 = x1.shape[-1] if x1 is not None else 0
+        nup = len(ups)
+        up_ptrs = (C.c_void_p * max(nup, 1))()
+        up_sh = (C.c_int * max(nup, 1))()
+        for i, (q, sft) in enumerate(ups):
+            assert q.dtype == torch.bfloat16
+            up_ptrs[i] = q.data_ptr()
+            up_sh[i] = sft
+        return self._bind("rsa_conv_tc2_fwd", _p(x0), C0, _p(x1), C1, _p(wt), CoutP, _p(bias), _p(out),
+                          int(out.dtype == torch.float32), _p(residual), _p(mask), _p(stats), N, H, W, Cout, taps, dil,
+                          in_stride, nup, up_ptrs, up_sh, int(accumulate), int(relu),
+                          keep=(x0, x1, wt, bias, out, residual, mask, stats, ups, up_ptrs, up_sh))
 
     def conv_tc_wgrad(self, x, dy, dw, N, H, W, Cin, Cout, dil):
         assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32

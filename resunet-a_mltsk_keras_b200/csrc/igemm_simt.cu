@@ -262,14 +262,19 @@ __global__ void __launch_bounds__(NT) igemm_wgrad_kernel(const WgradParams p) {
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
   const bool do_bias = p.dbias != nullptr && blockIdx.x == 0 && ty == 0;
 
+  // pixel coordinates of this thread's load row, advanced incrementally (no per-iteration 64-bit division)
+  int pw, ph, pn;
+  {
+    int64_t m = mbeg + lp;
+    pw = (int)(m % p.Wo);
+    int64_t t = m / p.Wo;
+    ph = (int)(t % p.Ho);
+    pn = (int)(t / p.Ho);
+  }
   for (int64_t mb = mbeg; mb < mend; mb += WP) {
     int64_t m = mb + lp;
     float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
     if (m < mend) {
-      int pw = (int)(m % p.Wo);
-      int64_t t = m / p.Wo;
-      int ph = (int)(t % p.Ho);
-      int pn = (int)(t / p.Ho);
       int64_t soff = seg_src_offset(s, pn, ph, pw);
       int c = kc + lc;
       if (soff >= 0 && c < C) {
@@ -296,6 +301,8 @@ __global__ void __launch_bounds__(NT) igemm_wgrad_kernel(const WgradParams p) {
         }
       }
     }
+    pw += WP;                       // advance WP pixels along the row-major (n, h, w) order
+    while (pw >= p.Wo) { pw -= p.Wo; if (++ph == p.Ho) { ph = 0; ++pn; } }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { As[lp][lc + j] = a4[j]; Bs[lp][lc + j] = b4[j]; }
     __syncthreads();

@@ -124,3 +124,81 @@ def test_conv_tc_wgrad_and_bias_grad(lib, N, H, C, d):
     assert err <= 2e-3 * scale, (err, scale)
     for t_ in d_db:
         np.testing.assert_allclose(t_.cpu().numpy(), db.numpy(), rtol=1e-3, atol=1e-3 * db.abs().max().item())
+
+
+# ---- persistent generalised kernel (conv_tc2.cu) ------------------------------------------------------------
+def _up(t, s):
+    k = 1 << s
+    return t.repeat_interleave(k, 1).repeat_interleave(k, 2)
+
+
+@pytest.mark.parametrize("N,H,C,Co,d", [(2, 32, 32, 32, 1), (2, 64, 32, 32, 31), (2, 32, 64, 64, 3), (3, 16, 128, 128, 1),
+                                        (2, 16, 256, 256, 15), (4, 8, 512, 512, 1), (16, 4, 1024, 1024, 1),
+                                        (16, 64, 32, 32, 15), (5, 32, 64, 128, 3)])
+def test_conv_tc2_3x3_matches_emulation(lib, N, H, C, Co, d):
+    W, dt = H, torch.bfloat16
+    x = rnd((N, H, W, C), dt, 1)
+    w = rnd((9 * C * Co,), torch.float32, 2, 1.0 / (3 * C ** 0.5)).to(dt).float()
+    b = rnd((Co,), torch.float32, 3)
+    wf, _ = _pack(w, 9, C, Co)
+    segs = [Seg(x, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * Co)
+            for ky in range(3) for kx in range(3)]
+    out, res = rnd((N, H, W, Co), dt, 4), rnd((N, H, W, Co), dt, 5)
+    stats = torch.zeros(2 * Co, dtype=torch.float64)
+    EMU.igemm_fwd(segs, w, Co, False, b, out, N, H, W, Co, residual=res, stats=stats, accumulate=True)(0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_out, d_stats = rnd((N, H, W, Co), dt, 4).cuda(), torch.zeros(2 * Co, dtype=torch.float64).cuda()
+    lib.conv_tc2_fwd(x.cuda(), None, wf.cuda(), Co, b.cuda(), d_out, N, H, W, Co, taps=9, dil=d, residual=res.cuda(),
+                     stats=d_stats, accumulate=True)(st)
+    torch.cuda.synchronize()
+    scale = out.float().abs().max().item()
+    assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100
+    np.testing.assert_allclose(d_stats.cpu().numpy(), stats.numpy(), rtol=2e-2, atol=2e-2 * N * H * W ** 0.5)
+    mask = rnd((N, H, W, Co), dt, 6)
+    EMU.igemm_fwd(segs, w, Co, False, b, out, N, H, W, Co, relu=True, mask=mask)(0)
+    lib.conv_tc2_fwd(x.cuda(), None, wf.cuda(), Co, b.cuda(), d_out, N, H, W, Co, taps=9, dil=d, relu=True,
+                     mask=mask.cuda())(st)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100
+
+
+@pytest.mark.parametrize("N,H,C0,C1,Co,stride,ups,f32", [
+    (2, 64, 32, 32, 32, 1, (), False),            # final combine: two plain sources
+    (2, 64, 32, 0, 64, 2, (), False),             # down conv: stride 2
+    (2, 32, 64, 0, 64, 1, (1,), False),           # decoder combine: skip + up2(q)
+    (2, 64, 32, 0, 32, 1, (1, 2, 3), False),      # PSP final conv: x + up2/4/8 addends
+    (2, 32, 32, 0, 6, 1, (), True),               # head: 6 classes, fp32 logits, padded N
+    (2, 32, 64, 0, 16, 1, (), False),             # dec1 up conv: 64 -> 16
+    (2, 32, 16, 0, 32, 1, (), False),             # K = 16 source (SWIZZLE_32B)
+    (3, 8, 1024, 0, 256, 1, (), False),           # PSP mid branch
+    (2, 16, 256, 512, 512, 1, (), False),         # wide two-source concat
+    (2, 32, 32, 0, 8, 1, (), False)])             # PSP out branch: 8 channels, partial-chunk stores
+def test_conv_tc2_pointwise_modes(lib, N, H, C0, C1, Co, stride, ups, f32):
+    dt = torch.bfloat16
+    Hs = H * stride
+    x0 = rnd((N, Hs, Hs, C0), dt, 1)
+    x1 = rnd((N, Hs, Hs, C1), dt, 2) if C1 else None
+    K = C0 + C1
+    w = rnd((K * Co,), torch.float32, 3, 1.0 / K ** 0.5).to(dt).float()       # [K][Co]
+    b = rnd((Co,), torch.float32, 4)
+    BNt = 128 if Co >= 128 else (64 if Co >= 64 else (32 if Co >= 32 else 16))
+    CoP = (Co + BNt - 1) // BNt * BNt
+    wt = torch.zeros((1, CoP, K), dtype=dt)
+    wt[0, :Co] = w.view(K, Co).t().to(dt)
+    segs = [Seg(x0, C0, Hs, Hs, mult=stride, w_off=0)]
+    if C1:
+        segs.append(Seg(x1, C1, Hs, Hs, mult=stride, w_off=C0 * Co))
+    qs = [rnd((N, H >> s, H >> s, Co), dt, 10 + s) for s in ups]
+    res = sum((_up(q.float(), s) for q, s in zip(qs, ups)), torch.zeros((N, H, H, Co))) if ups else None
+    out = torch.zeros((N, H, H, Co), dtype=torch.float32 if f32 else dt)
+    stats = torch.zeros(2 * Co, dtype=torch.float64)
+    EMU.igemm_fwd(segs, w, Co, False, b, out, N, H, H, Co, residual=res, stats=stats)(0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_out = torch.zeros_like(out).cuda()
+    d_stats = torch.zeros(2 * Co, dtype=torch.float64).cuda()
+    lib.conv_tc2_fwd(x0.cuda(), x1.cuda() if C1 else None, wt.cuda(), CoP, b.cuda(), d_out, N, H, H, Co, taps=1,
+                     in_stride=stride, ups=[(q.cuda(), s) for q, s in zip(qs, ups)], stats=d_stats)(st)
+    torch.cuda.synchronize()
+    scale = out.float().abs().max().item()
+    assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100
+    np.testing.assert_allclose(d_stats.cpu().numpy(), stats.numpy(), rtol=2e-2, atol=2e-2 * N * H * H ** 0.5)
