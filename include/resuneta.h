@@ -164,16 +164,24 @@ int rsa_conv_tc_fwd(const void* x, const void* wt, const float* bias, void* out,
  * x0 / optional x1: bf16 NHWC sources, K-concatenated (taps = 1; Concatenate model2.py:83) or the single 3x3 source
  * (taps = 9); wt bf16 [taps][CoutP][C0+C1], CoutP = Cout rounded up to the N tile with zero rows; in_stride 2 =
  * Conv2D strides=2 (model2.py:103-111); q_u bf16 [N, H>>shift, W>>shift, Cout] are low-resolution addends that are
- * nearest-up-sampled in the epilogue (UpSampling2D, model2.py:55-60,91); out bf16 or fp32. */
+ * nearest-up-sampled in the epilogue (UpSampling2D, model2.py:55-60,91); out bf16 or fp32.  The sources use columns
+ * [k_base, k_base+C0+C1) of wt's K dimension of length k_total (0 = C0+C1); out_stride 2 scatters the result to the even
+ * pixels of a (2H,2W) tensor (data gradient of the stride-2 convolutions). */
 int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int Cout);
 int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void* wt, int CoutP, const float* bias,
                      void* out, int out_f32, const void* residual, const void* mask, double* stats, int N, int H,
                      int W, int Cout, int taps, int dil, int in_stride, int nup, const void* const* up_ptrs,
-                     const int* up_shifts, int accumulate, int relu, void* stream);
+                     const int* up_shifts, int k_base, int k_total, int out_stride, int accumulate, int relu,
+                     void* stream);
 /* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co];
  * x, dy bf16 NHWC, Cin == Cout.  Replaces cuDNN's Conv2D backward-filter behind model2.py:19-24,153-178. */
 int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int dil,
                       void* stream);
+/* dw[k*ldw + co] (fp32, zeroed by the caller once per step) += sum_pix x[n, h*s, w*s, k] * dz[n,h,w,co]: weight gradient
+ * of one source of a 1x1 convolution on the tensor cores; Cin, Cout powers of two >= 16, s = in_stride (1|2).
+ * Replaces the Conv2D 1x1 backward-filter behind model2.py:37,84,92,101-111. */
+int rsa_pw_wgrad_tc(const void* x, const void* dz, float* dw, int ldw, int N, int H, int W, int Cin, int Cout,
+                    int in_stride, void* stream);
 /* db_k[c] += sum_m dy[m,c] for up to four bias gradients (NULL to skip): all branches of a ResBlock-a share
  * d(out) (Add, model2.py:27-31). */
 int rsa_bias_grad(const void* dy, int dtype, long long M, int C, float* db0, float* db1, float* db2, float* db3,

@@ -107,9 +107,12 @@ _SIGS = {
                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc2_fwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                         C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p],
+                         C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                         C.c_int, C.c_void_p],
     "rsa_conv_tc_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_void_p],
+    "rsa_pw_wgrad_tc": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                        C.c_int, C.c_void_p],
     "rsa_bias_grad": [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                       C.c_void_p],
     "rsa_pack_weights_tc": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p],
@@ -300,7 +303,8 @@ class Lib:
         return bool(self.dll.rsa_conv_tc2_supported(N, H, W, C0, C1, Cout))
 
     def conv_tc2_fwd(self, x0, x1, wt, CoutP, bias, out, N, H, W, Cout, taps=1, dil=1, in_stride=1, ups=(),
-                     residual=None, mask=None, stats=None, accumulate=False, relu=False):
+                     residual=None, mask=None, stats=None, accumulate=False, relu=False, k_base=0, k_total=0,
+                     out_stride=1):
         """ups: sequence of (q tensor, shift).  x1 may be None.  out bf16 or fp32."""
         assert x0.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16
         C0 = x0.shape[-1]
@@ -314,12 +318,17 @@ class Lib:
             up_sh[i] = sft
         return self._bind("rsa_conv_tc2_fwd", _p(x0), C0, _p(x1), C1, _p(wt), CoutP, _p(bias), _p(out),
                           int(out.dtype == torch.float32), _p(residual), _p(mask), _p(stats), N, H, W, Cout, taps, dil,
-                          in_stride, nup, up_ptrs, up_sh, int(accumulate), int(relu),
+                          in_stride, nup, up_ptrs, up_sh, k_base, k_total, out_stride, int(accumulate), int(relu),
                           keep=(x0, x1, wt, bias, out, residual, mask, stats, ups, up_ptrs, up_sh))
 
     def conv_tc_wgrad(self, x, dy, dw, N, H, W, Cin, Cout, dil):
         assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32
         return self._bind("rsa_conv_tc_wgrad", _p(x), _p(dy), _p(dw), N, H, W, Cin, Cout, dil, keep=(x, dy, dw))
+
+    def pw_wgrad_tc(self, x, dz, dw, ldw, N, H, W, Cin, Cout, in_stride=1):
+        assert x.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16 and dw.dtype == torch.float32
+        return self._bind("rsa_pw_wgrad_tc", _p(x), _p(dz), _p(dw), ldw, N, H, W, Cin, Cout, in_stride,
+                          keep=(x, dz, dw))
 
     def bias_grad(self, dy, M, C_, dbs):
         d = list(dbs) + [None] * (4 - len(dbs))

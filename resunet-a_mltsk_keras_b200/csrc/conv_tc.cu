@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     int tap = (int)(t / e.Cin);
     bf16 b = __float2bfloat16_rn(v);
     shadow[e.bwd_off + i] = b;
-    shadow[e.fwd_off + ((long long)tap * e.Cout + co) * e.Cin + ci] = b;
+    shadow[e.fwd_off + ((long long)tap * (e.pad > 0 ? e.pad : e.Cout) + co) * e.Cin + ci] = b;
   }
 }
 
@@ -349,7 +349,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, int swizzl
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)(((8 * swizzle_bytes) >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(swizzle_bytes == 128 ? 2 : 4) << 61;
+  d |= (uint64_t)(swizzle_bytes == 128 ? 2 : (swizzle_bytes == 64 ? 4 : 6)) << 61;
   return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
@@ -566,6 +566,213 @@ extern "C" int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N
   if (CC == 32) return launch_wgrad<32, 32>(tmX, tmDY, p, grid, st);
   if (CC == 64) return launch_wgrad<64, 64>(tmX, tmDY, p, grid, st);
   return launch_wgrad<128, 128>(tmX, tmDY, p, grid, st);
+}
+
+namespace {
+// =====================================================================================================
+// Weight gradient of the 1x1 convolutions (Conv2D 1x1 bwd-filter; model2.py:37,84,92,101-111):
+//   dW[k][co] += sum_pix x[pix*stride, k] * dz[pix, co]
+// Same MN-major formulation as the 3x3 kernel above with one tap.  M = 128 rows of the accumulator hold
+// min(Cin,128) input channels; thinner sources (16/32/64 channels) fill the remaining M atoms with replicas of
+// the same TMA box (ignored by the epilogue) so that every MMA is the M=128 shape.
+// =====================================================================================================
+struct PwWgradParams {
+  int N, H, W, Cin, Cout, in_stride, ldw;
+  int TW, TH, TN, tiles_w, tiles_h, ntiles, tiles_per_cta;
+  int ncob, ncib;
+  float* dw;
+};
+
+template <int KA, int KB, int NB>
+struct PwCfg {
+  static constexpr int TP = 64;
+  static constexpr int NA = 128 / KA;                 // A atoms per MMA
+  static constexpr int NBA = NB / KB;                 // B atoms
+  static constexpr int A_SUB = TP * KA * 2;
+  static constexpr int B_SUB = TP * KB * 2;
+  static constexpr int STAGE_BYTES = NA * A_SUB + NBA * B_SUB;
+  static constexpr int STAGES = 5;
+  static constexpr int RING = STAGES * STAGE_BYTES;
+  static constexpr int TMEM_COLS = NB < 32 ? 32 : NB;
+  static constexpr int TOTAL = RING + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int KA, int KB, int NB>
+__global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                            const __grid_constant__ CUtensorMap tmDY,
+                                                            const PwWgradParams p) {
+  using Cfg = PwCfg<KA, KB, NB>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::RING);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cob = blockIdx.y % p.ncob, cib = blockIdx.y / p.ncob;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(p.ntiles, t_begin + p.tiles_per_cta);
+  const int real_atoms = (p.Cin >= 128 ? 128 : p.Cin) / KA;      // 1 or 2 (Cin >= 128 -> KA = 64)
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmDY);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        int tt = t;
+        const int tw = tt % p.tiles_w; tt /= p.tiles_w;
+        const int th = tt % p.tiles_h; tt /= p.tiles_h;
+        const int n0 = tt * p.TN, h0 = th * p.TH, w0 = tw * p.TW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int a = 0; a < Cfg::NA; ++a) {
+          const int c0 = cib * 128 + (a % real_atoms) * KA;       // replicas re-load atom (a % real_atoms)
+          tma_load_4d(sa + a * Cfg::A_SUB, &tmX, &full_bar[stage], c0, w0 * p.in_stride, h0 * p.in_stride, n0);
+        }
+#pragma unroll
+        for (int b = 0; b < Cfg::NBA; ++b)
+          tma_load_4d(sa + Cfg::NA * Cfg::A_SUB + b * Cfg::B_SUB, &tmDY, &full_bar[stage], cob * NB + b * KB, w0, h0, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_mn(128, NB);
+      int stage = 0, phase = 0;
+      uint32_t accum = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::NA * Cfg::A_SUB;
+#pragma unroll
+        for (int k = 0; k < Cfg::TP / 16; ++k) {
+          const uint64_t adesc = make_mnmajor_desc(sa + k * 16 * KA * 2, KA * 2, Cfg::A_SUB);
+          const uint64_t bdesc = make_mnmajor_desc(sb + k * 16 * KB * 2, KB * 2, Cfg::B_SUB);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, accum);
+          accum = 1;
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (t_begin < t_end) {
+      const int m = q * 32 + lane;
+      const int cinb = p.Cin >= 128 ? 128 : p.Cin;
+      const bool valid = m < cinb;
+      float* dst = p.dw + (size_t)(cib * 128 + m) * p.ldw + cob * NB;
+      const int ncol = p.Cout - cob * NB < NB ? p.Cout - cob * NB : NB;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NB; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < ncol) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS));
+  }
+}
+
+// SW32 variant of the MN-major descriptor is selected by swizzle_bytes == 32 inside make_mnmajor_desc2
+template <int KA, int KB, int NB>
+int launch_pw(const CUtensorMap& tmX, const CUtensorMap& tmDY, const PwWgradParams& p, dim3 grid, cudaStream_t st) {
+  using Cfg = PwCfg<KA, KB, NB>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pw_wgrad_kernel<KA, KB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::TOTAL);
+    if (e != cudaSuccess) { rsa_set_error("pw_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
+    configured = true;
+  }
+  pw_wgrad_kernel<KA, KB, NB><<<grid, NTHREADS, Cfg::TOTAL, st>>>(tmX, tmDY, p);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+}  // namespace
+
+/* dw[k*ldw + co] (fp32, zeroed by the caller once per step) += sum_pix x[n, h*s, w*s, k] * dz[n,h,w,co] for a 1x1
+ * convolution source with Cin channels (power of two >= 16) and Cout in {16,32,64,128k}; x bf16 [N,H*s,W*s,Cin],
+ * dz bf16 [N,H,W,Cout].  Replaces the Conv2D 1x1 backward-filter behind model2.py:37,84,92,101-111. */
+extern "C" int rsa_pw_wgrad_tc(const void* x, const void* dz, float* dw, int ldw, int N, int H, int W, int Cin,
+                               int Cout, int in_stride, void* stream) {
+  RSA_REQUIRE(x && dz && dw, RSA_ERR_SHAPE, "pw_wgrad_tc: null pointer");
+  auto p2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  RSA_REQUIRE(H == W && p2(W) && W >= 4 && p2(Cin) && Cin >= 16 && Cin <= 1024 && p2(Cout) && Cout >= 16 && Cout <= 1024 &&
+                  (in_stride == 1 || in_stride == 2), RSA_ERR_SHAPE,
+              "pw_wgrad_tc: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d stride=%d", N, H, W, Cin, Cout, in_stride);
+  EncodeTiledFn enc = get_encode();
+  RSA_REQUIRE(enc, RSA_ERR_CUDA, "pw_wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
+  PwWgradParams p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.in_stride = in_stride; p.ldw = ldw; p.dw = dw;
+  p.TW = W < 16 ? W : 16;
+  p.TH = H < 64 / p.TW ? H : 64 / p.TW;
+  p.TN = 64 / (p.TW * p.TH);
+  p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
+  p.ntiles = p.tiles_w * p.tiles_h * ((N + p.TN - 1) / p.TN);
+  const int KA = Cin >= 64 ? 64 : Cin;
+  const int NB = Cout >= 128 ? 128 : Cout;
+  const int KB = NB >= 64 ? 64 : NB;
+  p.ncob = Cout / NB; p.ncib = Cin >= 128 ? Cin / 128 : 1;
+  const int ygroups = p.ncob * p.ncib;
+  int want = (2 * rsa_num_sms() + ygroups - 1) / ygroups;
+  int maxsplit = (p.ntiles + 3) / 4;
+  int split = want > maxsplit ? maxsplit : want;
+  if (split < 1) split = 1;
+  p.tiles_per_cta = (p.ntiles + split - 1) / split;
+  split = (p.ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  auto swz = [](int kc) { return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); };
+  auto encode = [&](CUtensorMap* tm, const void* base, int C, int KC, int s) -> CUresult {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W * s, (cuuint64_t)H * s, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * s * C * 2, (cuuint64_t)H * s * W * s * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.TW * s), (cuuint32_t)(p.TH * s), (cuuint32_t)p.TN};
+    cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUtensorMap tmX, tmDY;
+  CUresult r = encode(&tmX, x, Cin, KA, in_stride);
+  RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "pw_wgrad_tc: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+  r = encode(&tmDY, dz, Cout, KB, 1);
+  RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "pw_wgrad_tc: cuTensorMapEncodeTiled(dz) failed (%d)", (int)r);
+  dim3 grid((unsigned)split, (unsigned)ygroups);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PW_CASE(ka, kb, nb) if (KA == ka && KB == kb && NB == nb) return launch_pw<ka, kb, nb>(tmX, tmDY, p, grid, st);
+  PW_CASE(16, 16, 16) PW_CASE(16, 32, 32) PW_CASE(16, 64, 64) PW_CASE(16, 64, 128)
+  PW_CASE(32, 16, 16) PW_CASE(32, 32, 32) PW_CASE(32, 64, 64) PW_CASE(32, 64, 128)
+  PW_CASE(64, 16, 16) PW_CASE(64, 32, 32) PW_CASE(64, 64, 64) PW_CASE(64, 64, 128)
+#undef PW_CASE
+  RSA_REQUIRE(false, RSA_ERR_SHAPE, "pw_wgrad_tc: no kernel for KA=%d KB=%d NB=%d", KA, KB, NB);
 }
 
 namespace {

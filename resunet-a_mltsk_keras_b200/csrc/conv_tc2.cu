@@ -28,6 +28,7 @@ struct ConvTc2Params {
   int Cout;               // true output channels (stores / bias / stats bounded by it)
   int nsrc, kch0, kch1;   // K chunks (of KC channels) per source
   int taps, dil, in_stride;
+  int k_base, out_stride;   // first K element inside wt's K dimension; pixel stride of the stores (transposed stride-2 conv)
   int TW, TH, TN, tiles_w, tiles_h, mtiles, ntn, total;
   const float* bias;
   void* out;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_cons
               uint8_t* sa = smem + stage * L::STAGE_BYTES;
               mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
               tma_load_4d(sa, tm, &full_bar[stage], kc * KC, cw, ch, n0);
-              tma_load_3d(sa + L::A_BYTES, &tmB, &full_bar[stage], kglob * KC, nb * BN, tap);
+              tma_load_3d(sa + L::A_BYTES, &tmB, &full_bar[stage], p.k_base + kglob * KC, nb * BN, tap);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_cons
       const int ph = h0 + (r / p.TW) % p.TH;
       const int pn = n0 + r / (p.TW * p.TH);
       const bool valid = pn < p.N && ph < p.H && pw < p.W;
-      const size_t pix = ((size_t)pn * p.H + ph) * p.W + pw;
+      const size_t pix = (((size_t)pn * p.H * p.out_stride + (size_t)ph * p.out_stride) * (size_t)(p.W * p.out_stride)) + (size_t)pw * p.out_stride;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -325,16 +326,20 @@ extern "C" int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int C
  * wt: bf16 [taps][CoutP][C0+C1] with CoutP = Cout rounded up to the N tile (zero rows beyond Cout);
  * in_stride 1 or 2 (Conv2D strides=2 'valid' samples [0::2, 0::2], model2.py:103-111);
  * q_u: bf16 [N, H>>shift, W>>shift, Cout] low-resolution addends (nearest up-sampling, model2.py:55-60,91);
- * out bf16 or fp32 (out_f32), other epilogue flags as rsa_igemm_fwd.  Replaces the cuDNN / Eigen kernels behind
+ * k_base / k_total: the sources use columns [k_base, k_base+C0+C1) of a [taps][CoutP][k_total] weight matrix
+ * (k_total = 0 means C0+C1); out_stride 2 stores pixel (h,w) at (2h,2w) of a (2H,2W) tensor — the data gradient of a
+ * stride-2 convolution; out bf16 or fp32 (out_f32), other epilogue flags as rsa_igemm_fwd.  Replaces the cuDNN / Eigen kernels behind
  * keras Conv2D at model2.py:19-24,37,84,92,101-111,153-187 in bf16 mode. */
 extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void* wt, int CoutP,
                                 const float* bias, void* out, int out_f32, const void* residual, const void* mask,
                                 double* stats, int N, int H, int W, int Cout, int taps, int dil, int in_stride,
-                                int nup, const void* const* up_ptrs, const int* up_shifts, int accumulate, int relu,
-                                void* stream) {
+                                int nup, const void* const* up_ptrs, const int* up_shifts, int k_base, int k_total,
+                                int out_stride, int accumulate, int relu, void* stream) {
   RSA_REQUIRE(x0 && wt && out, RSA_ERR_SHAPE, "conv_tc2_fwd: null pointer");
   RSA_REQUIRE((taps == 9 && !x1 && in_stride == 1) || taps == 1, RSA_ERR_SHAPE, "conv_tc2_fwd: taps/sources combination");
   RSA_REQUIRE(in_stride == 1 || in_stride == 2, RSA_ERR_SHAPE, "conv_tc2_fwd: in_stride must be 1 or 2");
+  RSA_REQUIRE((out_stride == 1 || out_stride == 2) && k_base >= 0 && !(out_stride == 2 && (nup || stats)), RSA_ERR_SHAPE,
+              "conv_tc2_fwd: bad out_stride / k_base");
   RSA_REQUIRE(rsa_conv_tc2_supported(N, H, W, C0, x1 ? C1 : 0, Cout), RSA_ERR_SHAPE,
               "conv_tc2_fwd: unsupported shape N=%d H=%d W=%d C0=%d C1=%d Cout=%d", N, H, W, C0, C1, Cout);
   RSA_REQUIRE(nup >= 0 && nup <= 4 && Cout <= 1024, RSA_ERR_SHAPE, "conv_tc2_fwd: nup/Cout out of range");
@@ -347,6 +352,7 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   p.N = N; p.H = H; p.W = W; p.Cout = Cout;
   p.nsrc = x1 ? 2 : 1; p.kch0 = C0 / KC; p.kch1 = C1 / KC;
   p.taps = taps; p.dil = dil; p.in_stride = in_stride;
+  p.k_base = k_base; p.out_stride = out_stride;
   p.TW = W < 16 ? W : 16;
   p.TH = H < TILE_M / p.TW ? H : TILE_M / p.TW;
   p.TN = TILE_M / (p.TW * p.TH);
@@ -387,7 +393,7 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
     tmA1 = tmA0;
   }
   {
-    const int Kt = C0 + C1;
+    const int Kt = k_total > 0 ? k_total : C0 + C1;
     cuuint64_t gdim[3] = {(cuuint64_t)Kt, (cuuint64_t)CoutP, (cuuint64_t)taps};
     cuuint64_t gstr[2] = {(cuuint64_t)Kt * 2, (cuuint64_t)CoutP * Kt * 2};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};

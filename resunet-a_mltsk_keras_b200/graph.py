@@ -248,10 +248,11 @@ class Plan:
     # ---------------------------------------------------------------------------------------------
     # generic 1x1 convolution over gathered / concatenated inputs
     # ---------------------------------------------------------------------------------------------
-    def conv1x1(self, inputs, cout, name, stats=False, out_dtype=None, bias_grad=True):
+    def conv1x1(self, inputs, cout, name, stats=False, out_dtype=None, bias_grad=True, relu=False):
         """inputs: list of (T, mode, relu_in); mode = 'plain' | 's2' | ('up', s).
         keras: Conv2D(cout,(1,1)) on Concatenate/UpSampling2D/strides=2 inputs
-        (model2.py:37,84,92,101-111,159-187)."""
+        (model2.py:37,84,92,101-111,159-187).  relu=True fuses the consumer's Activation('relu') into the
+        epilogue (ReLU commutes with nearest up-sampling)."""
         k_total = sum(t.C for t, _, _ in inputs)
         self._reg_conv(name, 1, k_total, cout)
         t0, m0, _ = inputs[0]
@@ -266,9 +267,14 @@ class Plan:
             return out
         if stats:
             self._new_stats(out, out.M)
+        out.relu_masked = relu
         lib, N = self.lib, self.N
         W_ = self.P(name + "/kernel")
         b_ = self.P(name + "/bias")
+        pw = self._pw_classify(inputs, cout, name, out)
+        if pw is not None:
+            self._conv1x1_tc(inputs, pw, cout, name, out, stats, bias_grad, relu)
+            return out
         segs, koff = [], 0
         for t, mode, relu_in in inputs:
             if mode == "plain":
@@ -283,10 +289,135 @@ class Plan:
             koff += t.C
         st = out.stats
         self.fwd.append(self._late(lambda: lib.igemm_fwd(segs, W_, cout, False, b_, out.data, N, Ho, Wo, cout,
-                                                          stats=st[0] if st else None)))
+                                                          stats=st[0] if st else None, relu=relu)))
         if self.training:
             self.tape.append(lambda: self._conv1x1_bwd(inputs, segs, out, name, cout, bias_grad))
         return out
+
+    # ---------------------------------------------------------------------------------------------
+    # tensor-core path of the 1x1 convolutions (bf16 mode)
+    # ---------------------------------------------------------------------------------------------
+    def _pw_classify(self, inputs, cout, name, out):
+        """Split the sources of a 1x1 conv into `mains` (K-concatenated through TMA by conv_tc2) and `sides`
+        (evaluated as their own small conv at the source resolution and added in the epilogue, using
+        Conv1x1(Up(v)) == Up(Conv1x1(v))).  None -> CUDA-core implicit GEMM."""
+        ent = self.net.tc.get(name)
+        if ent is None or ent["taps"] != 1 or self.adt != torch.bfloat16:
+            return None
+        if out.H != out.W or out.W < 4 or (out.W & (out.W - 1)) or cout > 1024:
+            return None
+        mains, sides, koff = [], [], 0
+        for t, mode, relu_in in inputs:
+            if relu_in or t.dtype != torch.bfloat16:
+                return None
+            if mode in ("plain", "s2") and t.C % 16 == 0 and len(mains) < 2 and \
+                    (not mains or (mains[-1][1] == mode == "plain" and mains[-1][2] + mains[-1][0].C == koff)):
+                mains.append((t, mode, koff))
+            elif mode == "s2":
+                return None
+            else:
+                sides.append((t, 0 if mode == "plain" else mode[1], koff))
+            koff += t.C
+        if not mains or (mains[0][1] == "s2" and (sides or len(mains) > 1)):
+            return None
+        if sum(1 for _, sh, _ in sides if sh == 0) > 1 or sum(1 for _, sh, _ in sides if sh > 0) > 4:
+            return None
+        if out.dtype == torch.float32 and any(sh == 0 for _, sh, _ in sides):
+            return None
+        return mains, sides, koff
+
+    @staticmethod
+    def _tc_spatial_ok(H, W):
+        return H == W and W >= 4 and (W & (W - 1)) == 0
+
+    def _pw_fwd_one(self, src, koff, K, cout, name, out, Hq, Wq):
+        """q = W[koff:koff+C] . src at the source's own resolution (no bias)."""
+        lib, N = self.lib, self.N
+        ent = self.net.tc[name]
+        if src.C % 16 == 0 and self._tc_spatial_ok(Hq, Wq):
+            wt = self.net.shadow[ent["fwd"]:ent["fwd"] + ent["coutp"] * K]
+            return lib.conv_tc2_fwd(src.data, None, wt, ent["coutp"], None, out, N, Hq, Wq, cout, k_base=koff, k_total=K)
+        W_ = self.P(name + "/kernel")
+        return lib.igemm_fwd([Seg(src.data, src.C, Hq, Wq, w_off=koff * cout)], W_, cout, False, None, out, N, Hq, Wq, cout)
+
+    def _conv1x1_tc(self, inputs, pw, cout, name, out, stats, bias_grad, relu):
+        lib, N = self.lib, self.N
+        mains, sides, K = pw
+        ent = self.net.tc[name]
+        b_ = self.P(name + "/bias")
+        wt = self.net.shadow[ent["fwd"]:ent["fwd"] + ent["coutp"] * K]
+        qs = []
+        for t, sh, koff in sides:
+            q = self.alloc((N, t.H, t.W, cout), torch.bfloat16)
+            self.fwd.append(self._pw_fwd_one(t, koff, K, cout, name, q, t.H, t.W))
+            qs.append((t, sh, koff, q))
+        ups = [(q, sh) for _, sh, _, q in qs if sh > 0]
+        res = next((q for _, sh, _, q in qs if sh == 0), None)
+        x0 = mains[0][0]
+        x1 = mains[1][0] if len(mains) > 1 else None
+        stride = 2 if mains[0][1] == "s2" else 1
+        st = out.stats
+        self.fwd.append(self._late(lambda: lib.conv_tc2_fwd(
+            x0.data, x1.data if x1 is not None else None, wt, ent["coutp"], b_, out.data, N, out.H, out.W, cout,
+            in_stride=stride, ups=ups, residual=res, stats=st[0] if st else None, relu=relu, k_base=mains[0][2],
+            k_total=K)))
+        if not self.training:
+            return
+
+        def bwd():
+            if out.grad is None:
+                return
+            dz = out.grad
+            dW = self.G(name + "/kernel")
+            W_ = self.P(name + "/kernel")
+            wb = self.net.shadow[ent["bwd"]:ent["bwd"] + K * cout]
+            bf = dz.dtype == torch.bfloat16
+            p2 = lambda v: v >= 16 and (v & (v - 1)) == 0
+            db_simt = [None]
+            if bias_grad:
+                if cout % 8 == 0 and bf:
+                    self.bwd.append(lib.bias_grad(dz, out.M, cout, [self.G(name + "/bias")]))
+                else:   # fp32 head logits / odd channel counts: folded into the CUDA-core wgrad of the first main
+                    db_simt[0] = self.G(name + "/bias")
+            sp = {}
+
+            def one_source(t, koff, dq, Hq, Wq, in_stride):
+                """weight + data gradient of one source given the gradient dq at the conv's own resolution."""
+                sp_ok = self._tc_spatial_ok(Hq, Wq)
+                if bf and p2(t.C) and p2(cout) and sp_ok:
+                    self.bwd.append(lib.pw_wgrad_tc(t.data, dq, dW[koff * cout:], cout, N, Hq, Wq, t.C, cout, in_stride))
+                else:
+                    seg = Seg(t.data, t.C, t.H, t.W, mult=in_stride, w_off=koff * cout)
+                    db, db_simt[0] = (db_simt[0], None) if dq is dz else (None, db_simt[0])
+                    self.bwd.append(lib.igemm_wgrad([seg], dq, dW, cout, db, N, Hq, Wq, cout))
+                if not t.needs_grad:
+                    return
+                g, acc = self.gacc(t)
+                mask = t.data if t.relu_masked else None
+                if bf and cout % 16 == 0 and t.C % 16 == 0 and sp_ok:
+                    wsl = wb[koff * cout:(koff + t.C) * cout]
+                    if in_stride == 2 and not acc:
+                        self.bwd.append(lambda s_, g=g: g.zero_())      # odd pixels receive no gradient
+                    self.bwd.append(lib.conv_tc2_fwd(dq, None, wsl, t.C, None, g, N, Hq, Wq, t.C, mask=mask,
+                                                     accumulate=acc or in_stride == 2, out_stride=in_stride))
+                else:
+                    if in_stride == 2:
+                        sg = [Seg(dq, cout, Hq, Wq, shift=1, aligned=True, w_off=koff * cout)]
+                    else:
+                        sg = [Seg(dq, cout, Hq, Wq, w_off=koff * cout)]
+                    self.bwd.append(lib.igemm_fwd(sg, W_, cout, True, None, g, N, t.H, t.W, t.C, mask=mask, accumulate=acc))
+
+            for i, (t, mode, koff) in enumerate(mains):
+                one_source(t, koff, dz, out.H, out.W, 2 if mode == "s2" else 1)
+            need = sorted({sh for _, sh, _, _ in qs if sh > 0})
+            if need:   # adjoint of nearest up-sampling: window sums of dz, all levels in one pass
+                sp = {sh: self.alloc((N, out.H >> sh, out.W >> sh, cout), dz.dtype) for sh in need}
+                self.bwd.append(lib.sumpool_pyr(dz, N, out.H, out.W, cout, sp.get(1), sp.get(2), sp.get(3)))
+            for t, sh, koff, q in qs:
+                one_source(t, koff, dz if sh == 0 else sp[sh], t.H, t.W, 1)
+            assert db_simt[0] is None, "bias gradient was not emitted"
+            self._ready(name + "/kernel", name + "/bias")
+        self.tape.append(bwd)
 
     def _late(self, make):
         """Bind a launch lazily: scratch views (statistics) only exist after _finalize_scratch()."""
@@ -358,8 +489,8 @@ class Plan:
         flops = 2.0 * N * H * W * 9 * C * cout
         tcw = self.net.tc_weights(name, N, H, W)
         if tcw is not None:
-            self.fwd.append(self._tag(self._late(lambda: lib.conv_tc_fwd(
-                x.data, tcw[0], b_, out.data, N, H, W, C, cout, 9, dil, residual=res,
+            self.fwd.append(self._tag(self._late(lambda: lib.conv_tc2_fwd(
+                x.data, None, tcw[0], cout, b_, out.data, N, H, W, cout, taps=9, dil=dil, residual=res,
                 stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
         else:
             self.fwd.append(self._tag(self._late(lambda: lib.igemm_fwd(
@@ -387,8 +518,9 @@ class Plan:
                               w_off=(ky * 3 + kx) * C * cout) for ky in range(3) for kx in range(3)]
                     mask = x.data if x.relu_masked else None
                     if tcw is not None:
-                        self.bwd.append(self._tag(lib.conv_tc_fwd(dy, tcw[1], None, g, N, H, W, cout, C, 9, -dil,
-                                                                  mask=mask, accumulate=acc), "conv3x3_dgrad", flops))
+                        self.bwd.append(self._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9,
+                                                                   dil=-dil, mask=mask, accumulate=acc),
+                                                  "conv3x3_dgrad", flops))
                     else:
                         self.bwd.append(self._tag(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask,
                                                                 accumulate=acc), "conv3x3_dgrad", flops))
@@ -608,7 +740,7 @@ class Plan:
 # ------------------------------------------------------------------------------------------------------
 # network definition (shared by the spec pass and every plan)
 # ------------------------------------------------------------------------------------------------------
-def _resblock(pl, x, f, dils, identity):
+def _resblock(pl, x, f, dils, identity, relu_out=False):
     """ResBlock-a: x + Σ_d Conv3x3_d(ReLU(BN(Conv3x3_d(ReLU(BN_d(x)))))) (model2.py:15-34);
     model.py:15-33 has no identity term."""
     names = [(pl.name_bn(), pl.name_conv(), pl.name_bn(), pl.name_conv()) for _ in dils]
@@ -625,11 +757,16 @@ def _resblock(pl, x, f, dils, identity):
     for i, d in enumerate(dils):
         y1 = pl.conv3x3(a1[i], f, d, names[i][1], stats=True, bias_grad=False)   # bias before BN: zero gradient
         a2 = pl.bn(y1, [names[i][2]], relu=True)[0]
-        _conv_into(pl, a2, f, d, names[i][3], out, first=(i == 0), residual=x if identity else None)
+        _conv_into(pl, a2, f, d, names[i][3], out, first=(i == 0), residual=x if identity else None,
+                   relu=relu_out and i == len(dils) - 1)
+    if relu_out:
+        # the block's only consumer applies Activation('relu') (combine, model2.py:82): fused into the last
+        # branch's epilogue; the stored tensor is relu(out) and gradients written to it are masked with it
+        out.relu_masked = True
     return out
 
 
-def _conv_into(pl, a, f, d, name, out, first, residual):
+def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
     """Second conv of a branch: writes (first) or accumulates into the block output; the first one
     also adds the identity input so that the branch sum + identity never exist as separate tensors."""
     pl._reg_conv(name, 3, a.C, f)
@@ -644,11 +781,11 @@ def _conv_into(pl, a, f, d, name, out, first, residual):
     flops = 2.0 * N * H * W * 9 * C * f
     tcw = pl.net.tc_weights(name, N, H, W)
     if tcw is not None:
-        pl.fwd.append(pl._tag(lib.conv_tc_fwd(a.data, tcw[0], b_, out.data, N, H, W, C, f, 9, d, residual=res,
-                                              accumulate=not first), "conv3x3_fwd", flops))
+        pl.fwd.append(pl._tag(lib.conv_tc2_fwd(a.data, None, tcw[0], f, b_, out.data, N, H, W, f, taps=9, dil=d,
+                                               residual=res, accumulate=not first, relu=relu), "conv3x3_fwd", flops))
     else:
         pl.fwd.append(pl._tag(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res,
-                                            accumulate=not first), "conv3x3_fwd", flops))
+                                            accumulate=not first, relu=relu), "conv3x3_fwd", flops))
     if pl.training:
         def bwd():
             if out.grad is None:
@@ -666,8 +803,8 @@ def _conv_into(pl, a, f, d, name, out, first, residual):
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
                   for ky in range(3) for kx in range(3)]
             if tcw is not None:
-                pl.bwd.append(pl._tag(lib.conv_tc_fwd(dy, tcw[1], None, g, N, H, W, f, C, 9, -d, accumulate=acc),
-                                      "conv3x3_dgrad", flops))
+                pl.bwd.append(pl._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9, dil=-d,
+                                                       accumulate=acc), "conv3x3_dgrad", flops))
             else:
                 pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
                                       "conv3x3_dgrad", flops))
@@ -723,11 +860,12 @@ def define_network(pl):
                            bias_grad=False)
             t = pl.bn(z, [pl.name_bn()], relu=False, derive=True)[0]
         else:
-            u = pl.conv1x1([(t, "plain", False)], f, pl.name_conv())                # model.py:93-94
-            t = pl.conv1x1([(u, ("up", 1), True), (skip, "plain", False)], f, pl.name_conv(), stats=True)
-        t = _resblock(pl, t, f, dils, identity=v2)
-    xc = pl.conv1x1([(t, "plain", True), (skips[0], "plain", False)], 32, pl.name_conv(), stats=v2,
-                    bias_grad=not v2)                                               # model2.py:140
+            # model.py:93-94 Conv1x1(f) -> UpSampling2D; combine's ReLU (model.py:67) fused into this conv
+            u = pl.conv1x1([(t, "plain", False)], f, pl.name_conv(), relu=True)
+            t = pl.conv1x1([(u, ("up", 1), False), (skip, "plain", False)], f, pl.name_conv(), stats=True)
+        t = _resblock(pl, t, f, dils, identity=v2, relu_out=(lvl == 0))
+    xc = pl.conv1x1([(t, "plain", False), (skips[0], "plain", False)], 32, pl.name_conv(), stats=v2,
+                    bias_grad=not v2)                                               # model2.py:140 (ReLU fused above)
     if v2:
         x_comb = pl.bn(xc, [pl.name_bn()], relu=False)[0]
     else:
@@ -799,16 +937,26 @@ class Net:
         okc = lambda c: c == 32 or (c >= 64 and c % 64 == 0)
         off, table, max_elems = 0, b"", 0
         for name, (shape, _, _) in self.params.spec.items():
-            if not name.endswith("/kernel") or shape[0] != 3:
+            if not name.endswith("/kernel"):
                 continue
-            _, _, cin, cout = shape
-            if not (okc(cin) and okc(cout)):
-                continue
-            n = 9 * cin * cout
-            self.tc[name[:-len("/kernel")]] = (off, off + n, cin, cout)
-            table += struct.pack("<qqqiiii", self.params.off[name], off, off + n, 9, cin, cout, 0)
-            off += 2 * n
-            max_elems = max(max_elems, n)
+            k, _, cin, cout = shape
+            if k == 3:
+                if not (okc(cin) and okc(cout)):
+                    continue
+                coutp = cout
+            else:
+                if cin < 16:
+                    continue       # stem (3 or 14 input channels): CUDA-core path
+                bn = 128 if cout >= 128 else (64 if cout >= 64 else (32 if cout >= 32 else 16))
+                coutp = (cout + bn - 1) // bn * bn
+            taps = k * k
+            nf, nb = taps * coutp * cin, taps * cin * cout
+            off = (off + 127) // 128 * 128
+            self.tc[name[:-len("/kernel")]] = dict(fwd=off, bwd=off + nf, taps=taps, cin=cin, cout=cout, coutp=coutp)
+            table += struct.pack("<qqqiiii", self.params.off[name], off, off + nf, taps, cin, cout, coutp)
+            off += nf + nb
+            off = (off + 127) // 128 * 128
+            max_elems = max(max_elems, taps * cin * cout)
         if not self.tc:
             self.conv_engine = "igemm_simt"
             return
@@ -816,15 +964,15 @@ class Net:
         self._pack_table = torch.frombuffer(bytearray(table), dtype=torch.uint8).to(self.device)
         self.pack_launch = self.lib.pack_weights_tc(self.params.data, self.shadow, self._pack_table, len(self.tc),
                                                     max_elems)
-        self.conv_engine = "tcgen05 fwd+dgrad / simt wgrad"
+        self.conv_engine = "tcgen05 (3x3 fwd/dgrad/wgrad persistent TMA kernels; 1x1 on tensor cores where K,N % 16 == 0)"
 
     def tc_weights(self, name, N, H, W):
         """(fwd copy, dgrad copy) bf16 views if the tensor-core kernel handles this layer at this size."""
         ent = self.tc.get(name)
-        if ent is None or not self.lib.conv_tc_supported(N, H, W, ent[2], ent[3]):
+        if ent is None or ent["taps"] != 9 or not self.lib.conv_tc_supported(N, H, W, ent["cin"], ent["cout"]):
             return None
-        n = 9 * ent[2] * ent[3]
-        return self.shadow[ent[0]:ent[0] + n], self.shadow[ent[1]:ent[1] + n]
+        n = 9 * ent["cin"] * ent["cout"]
+        return self.shadow[ent["fwd"]:ent["fwd"] + n], self.shadow[ent["bwd"]:ent["bwd"] + n]
 
     def ensure_shadow(self, stream):
         if self.pack_launch is not None and self.shadow_dirty:

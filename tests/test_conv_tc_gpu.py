@@ -202,3 +202,48 @@ def test_conv_tc2_pointwise_modes(lib, N, H, C0, C1, Co, stride, ups, f32):
     scale = out.float().abs().max().item()
     assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100
     np.testing.assert_allclose(d_stats.cpu().numpy(), stats.numpy(), rtol=2e-2, atol=2e-2 * N * H * H ** 0.5)
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,stride", [(2, 64, 32, 32, 1), (2, 32, 32, 64, 2), (2, 32, 16, 32, 1), (2, 32, 64, 16, 1),
+                                                  (3, 16, 256, 512, 1), (2, 8, 1024, 256, 1), (16, 4, 512, 1024, 2),
+                                                  (4, 64, 64, 128, 1), (2, 64, 128, 32, 1)])
+def test_pw_wgrad_tc(lib, N, H, Cin, Cout, stride):
+    dt = torch.bfloat16
+    Hs = H * stride
+    x = rnd((N, Hs, Hs, Cin), dt, 1)
+    dz = rnd((N, H, H, Cout), dt, 2)
+    ldw = Cout + 16                     # a row-slice of a wider [K_total, ldw] gradient matrix
+    dw = torch.zeros(Cin * ldw, dtype=torch.float32)
+    EMU.igemm_wgrad([Seg(x, Cin, Hs, Hs, mult=stride, w_off=0)], dz, dw, ldw, None, N, H, H, Cout)(0)
+    d_dw = torch.zeros(Cin * ldw, dtype=torch.float32).cuda()
+    lib.pw_wgrad_tc(x.cuda(), dz.cuda(), d_dw, ldw, N, H, H, Cin, Cout, stride)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    scale = dw.abs().max().item()
+    assert (d_dw.cpu() - dw).abs().max().item() <= 2e-3 * scale
+
+
+def test_conv_tc2_k_base_and_strided_store(lib):
+    """A K sub-range of a wider weight matrix (q-convs of the decoder) and the transposed stride-2 store."""
+    dt = torch.bfloat16
+    N, H, C, Co, Kt, kb = 2, 32, 32, 64, 96, 64
+    x = rnd((N, H, H, C), dt, 1)
+    wfull = rnd((Kt * Co,), torch.float32, 2, 0.1).to(dt).float()          # [Kt][Co]
+    wt = wfull.view(Kt, Co).t().contiguous().to(dt).view(1, Co, Kt)
+    out = torch.zeros((N, H, H, Co), dtype=dt)
+    EMU.igemm_fwd([Seg(x, C, H, H, w_off=kb * Co)], wfull, Co, False, None, out, N, H, H, Co)(0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_out = torch.zeros_like(out).cuda()
+    lib.conv_tc2_fwd(x.cuda(), None, wt.cuda(), Co, None, d_out, N, H, H, Co, k_base=kb, k_total=Kt)(st)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().float() - out.float()).abs().max().item() <= out.float().abs().max().item() / 100
+    # data gradient of a stride-2 conv: dx[2h,2w] += W^T dz[h,w], other pixels untouched
+    dz = rnd((N, H, H, Co), dt, 3)
+    wb = wfull.view(Kt, Co)[:C].contiguous().to(dt).view(1, C, Co)        # [N=C][K=Co]
+    dx = rnd((N, 2 * H, 2 * H, C), dt, 4)
+    ref = dx.clone()
+    EMU.igemm_fwd([Seg(dz, Co, H, H, shift=1, aligned=True, w_off=0)], wfull, Co, True, None, ref, N, 2 * H, 2 * H, C,
+                  accumulate=True)(0)
+    d_dx = dx.clone().cuda()
+    lib.conv_tc2_fwd(dz.cuda(), None, wb.cuda(), C, None, d_dx, N, H, H, C, out_stride=2, accumulate=True)(st)
+    torch.cuda.synchronize()
+    assert (d_dx.cpu().float() - ref.float()).abs().max().item() <= ref.float().abs().max().item() / 100
