@@ -334,6 +334,10 @@ namespace {
 // whose duplicate rows are ignored by the epilogue.  The pixel dimension is split across CTAs; partial
 // sums are added to the fp32 gradient with atomics (the buffer is zeroed once per step).
 // =====================================================================================================
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 struct WgradTcParams {
   int N, H, W, Cin, Cout, dil;
   int TW, TH, TN, tiles_w, tiles_h, ntiles;   // 64-pixel tiles
@@ -489,7 +493,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_wgrad_kernel(const __grid_co
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * NB + c0), v);
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                         __uint_as_float(v[j + 3]));
           }
         }
       }
@@ -541,7 +547,7 @@ extern "C" int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N
   const int KA = CC >= 64 ? 64 : 32, KB = NB >= 64 ? 64 : 32;
   const int ygroups = (CC == 128 ? 3 * (Cin / 128) : 1) * (Cout / NB);
   // split the pixel reduction so that ~2 CTAs per SM exist, but keep >= 4 tiles per CTA
-  int want = (2 * rsa_num_sms() + ygroups - 1) / ygroups;
+  int want = ygroups >= 96 ? 1 : (2 * rsa_num_sms() + ygroups - 1) / ygroups;   // deep levels: enough (ci,co,tap) groups already
   int maxsplit = (p.ntiles + 3) / 4;
   int split = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
   if (split < 1) split = 1;
@@ -691,8 +697,10 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const __grid_constan
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < ncol) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < ncol)      // ncol is a multiple of 16
+              red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                         __uint_as_float(v[j + 3]));
         }
       }
     }

@@ -47,16 +47,15 @@ struct Smem2 {
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING = STAGES * STAGE_BYTES;
-  static constexpr int TR_BYTES = 4 * 32 * 33 * 4;        // per-epilogue-warp transpose tile
   static constexpr int CS_BYTES = 2 * 1024 * 4;           // per-CTA channel sums (Cout <= 1024)
-  static constexpr int BAR_OFF = RING + TR_BYTES + CS_BYTES;
+  static constexpr int BAR_OFF = RING + CS_BYTES;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
   static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // power of two (BN in 16..256)
 };
 
 template <int BN, int KC, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                const __grid_constant__ CUtensorMap tmA1,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const ConvTc2Params p) {
@@ -64,8 +63,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_cons
   constexpr int SWZ = KC * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* tr_base = reinterpret_cast<float*>(smem + L::RING);
-  float* csum = reinterpret_cast<float*>(smem + L::RING + L::TR_BYTES);
+  float* csum = reinterpret_cast<float*>(smem + L::RING);
   float* csq = csum + 1024;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -165,7 +163,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_cons
   } else {
     // ===== epilogue warps 2..5 =====
     const int q = warp & 3;
-    float* tr = tr_base + (warp - 2) * 32 * 33;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
       const int nb = tile % p.ntn;
@@ -255,17 +252,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc2_kernel(const __grid_cons
           }
         }
         if (p.stats) {
+          // per-channel sums over this warp's 32 pixels: butterfly reduce-scatter, lane l ends with channel l
+          float s[32], sq[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = valid ? f[j] : 0.f;
-          __syncwarp();
-          if (lane < nval) {
-            float s = 0.f, sq = 0.f;
+          for (int j = 0; j < 32; ++j) { s[j] = valid ? f[j] : 0.f; sq[j] = s[j] * s[j]; }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { float t = tr[i * 33 + lane]; s += t; sq += t * t; }
-            atomicAdd(&csum[co + lane], s);
-            atomicAdd(&csq[co + lane], sq);
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send_s = upper ? s[i] : s[i + off], keep_s = upper ? s[i + off] : s[i];
+              const float send_q = upper ? sq[i] : sq[i + off], keep_q = upper ? sq[i + off] : sq[i];
+              s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
           }
-          __syncwarp();
+          if (lane < nval) {
+            atomicAdd(&csum[co + lane], s[0]);
+            atomicAdd(&csq[co + lane], sq[0]);
+          }
         }
       }
       // this warp is done reading the accumulator stage
@@ -302,7 +307,8 @@ int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, 
     if (e != cudaSuccess) { rsa_set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
-  int grid = p.total < rsa_num_sms() ? p.total : rsa_num_sms();
+  const int per_sm = (227 * 1024) / L::TOTAL >= 2 ? 2 : 1;       // co-resident persistent CTAs overlap their epilogues
+  int grid = p.total < per_sm * rsa_num_sms() ? p.total : per_sm * rsa_num_sms();
   conv_tc2_kernel<BN, KC, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(a0, a1, b, p);
   RSA_CHECK_LAUNCH();
   return RSA_OK;
@@ -404,16 +410,16 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (KC == 64) {
-    if (BN == 128) return launch2<128, 64, 5>(tmA0, tmA1, tmB, p, st);
-    if (BN == 64) return launch2<64, 64, 7>(tmA0, tmA1, tmB, p, st);
-    if (BN == 32) return launch2<32, 64, 8>(tmA0, tmA1, tmB, p, st);
-    return launch2<16, 64, 8>(tmA0, tmA1, tmB, p, st);
+    if (BN == 128) return launch2<128, 64, 3>(tmA0, tmA1, tmB, p, st);
+    if (BN == 64) return launch2<64, 64, 4>(tmA0, tmA1, tmB, p, st);
+    if (BN == 32) return launch2<32, 64, 5>(tmA0, tmA1, tmB, p, st);
+    return launch2<16, 64, 5>(tmA0, tmA1, tmB, p, st);
   }
   if (KC == 32) {
-    if (BN == 128) return launch2<128, 32, 8>(tmA0, tmA1, tmB, p, st);
-    if (BN == 64) return launch2<64, 32, 10>(tmA0, tmA1, tmB, p, st);
-    if (BN == 32) return launch2<32, 32, 14>(tmA0, tmA1, tmB, p, st);
-    return launch2<16, 32, 14>(tmA0, tmA1, tmB, p, st);
+    if (BN == 128) return launch2<128, 32, 6>(tmA0, tmA1, tmB, p, st);
+    if (BN == 64) return launch2<64, 32, 8>(tmA0, tmA1, tmB, p, st);
+    if (BN == 32) return launch2<32, 32, 9>(tmA0, tmA1, tmB, p, st);
+    return launch2<16, 32, 10>(tmA0, tmA1, tmB, p, st);
   }
   if (BN == 128) return launch2<128, 16, 8>(tmA0, tmA1, tmB, p, st);
   if (BN == 64) return launch2<64, 16, 10>(tmA0, tmA1, tmB, p, st);
