@@ -85,6 +85,17 @@ int rsa_bn_bwd_reduce(const void* dy, const void* x, const void* act, int dtype,
 int rsa_bn_bwd_apply(const void* dy, const void* x, const void* act, int dtype, int64_t M, int C,
                      const double* stats, double count, float eps, const float* gamma, const double* red,
                      void* dx, int accumulate, float* dgamma, float* dbeta, void* stream);
+/* Backward of k <= 4 BatchNormalization(+ReLU) layers that share their input x — the ResBlock-a branches all
+ * normalise the same tensor (model2.py:17-18).  The ReLU mask is recomputed from x (bn_b(x) > 0).
+ * reduce: reds[b][2C] (double, zeroed) += { sum g_b, sum g_b*xhat };
+ * apply : dx (=|+=) sum_b gamma_b*invstd*(g_b - reds[b][0]/count - xhat*reds[b][1]/count), dgamma_b, dbeta_b. */
+int rsa_bn_bwd_reduce_multi(const void* const* dys, const void* x, int dtype, int64_t M, int C, int k,
+                            const double* stats, double count, float eps, const float* const* gammas,
+                            const float* const* betas, int relu, double* const* reds, void* stream);
+int rsa_bn_bwd_apply_multi(const void* const* dys, const void* x, int dtype, int64_t M, int C, int k,
+                           const double* stats, double count, float eps, const float* const* gammas,
+                           const float* const* betas, int relu, double* const* reds, void* dx, int accumulate,
+                           float* const* dgammas, float* const* dbetas, void* stream);
 /* statistics of y = gamma*xhat+beta derived analytically from the statistics of x */
 int rsa_bn_derive_stats(const double* src_stats, double count, const float* gamma, const float* beta,
                         float eps, double* dst_stats, double dst_count, int C, void* stream);

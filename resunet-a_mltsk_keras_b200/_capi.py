@@ -74,6 +74,13 @@ _SIGS = {
     "rsa_bn_bwd_apply": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_double,
                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                          C.c_void_p],
+    "rsa_bn_bwd_reduce_multi": [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                C.c_double, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                                C.POINTER(C.c_void_p), C.c_void_p],
+    "rsa_bn_bwd_apply_multi": [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                               C.c_double, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                               C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_void_p), C.c_void_p],
     "rsa_bn_derive_stats": [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_double,
                             C.c_int, C.c_void_p],
     "rsa_bn_update_moving": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p],
@@ -170,6 +177,7 @@ class Lib:
             if rc:
                 raise RuntimeError(f"{name} failed ({rc}): {dll.rsa_last_error().decode()}")
         launch.kernel = name
+        launch.ints = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool))
         return launch
 
     @staticmethod
@@ -227,6 +235,18 @@ class Lib:
         return self._bind("rsa_bn_bwd_apply", _p(dy), _p(x), _p(act), dtype_code(x), M, C_, _p(stats),
                           float(count), float(eps), _p(gamma), _p(red), _p(dx), int(accumulate), _p(dgamma),
                           _p(dbeta), keep=(dy, x, act, stats, gamma, red, dx, dgamma, dbeta))
+
+    def bn_bwd_reduce_multi(self, dys, x, M, C_, stats, count, eps, gammas, betas, relu, reds):
+        return self._bind("rsa_bn_bwd_reduce_multi", self._ptr_array(dys), _p(x), dtype_code(x), M, C_, len(dys),
+                          _p(stats), float(count), float(eps), self._ptr_array(gammas), self._ptr_array(betas),
+                          int(relu), self._ptr_array(reds), keep=(dys, x, stats, gammas, betas, reds))
+
+    def bn_bwd_apply_multi(self, dys, x, M, C_, stats, count, eps, gammas, betas, relu, reds, dx, accumulate, dgammas,
+                           dbetas):
+        return self._bind("rsa_bn_bwd_apply_multi", self._ptr_array(dys), _p(x), dtype_code(x), M, C_, len(dys),
+                          _p(stats), float(count), float(eps), self._ptr_array(gammas), self._ptr_array(betas),
+                          int(relu), self._ptr_array(reds), _p(dx), int(accumulate), self._ptr_array(dgammas),
+                          self._ptr_array(dbetas), keep=(dys, x, stats, gammas, betas, reds, dx, dgammas, dbetas))
 
     def bn_derive_stats(self, src_stats, count, gamma, beta, eps, dst_stats, dst_count, C_):
         return self._bind("rsa_bn_derive_stats", _p(src_stats), float(count), _p(gamma), _p(beta), float(eps),

@@ -62,34 +62,43 @@ struct ApplyParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(NT) bn_apply_kernel(const T* __restrict__ x, int64_t nvec, int C,
-                                                      const ApplyParams ap, const double* __restrict__ stats,
-                                                      double count, float eps, int relu) {
+__global__ void __launch_bounds__(NT) bn_apply_kernel(const T* __restrict__ x, int64_t M, int C, const ApplyParams ap,
+                                                      const double* __restrict__ stats, double count, float eps,
+                                                      int relu, int rows_per_block) {
+  // each thread owns one fixed group of V channels: scale/shift live in registers, rows are walked with
+  // 16-byte loads/stores (one read of x feeds all nout branch outputs)
   constexpr int V = Vec16<T>::N;
-  extern __shared__ float sm[];   // [nout][2][C]: scale, shift
-  for (int i = threadIdx.x; i < ap.nout * C; i += NT) {
-    int k = i / C, c = i % C;
-    float mean, invstd;
-    bn_mean_invstd(stats, count, C, c, eps, ap.mmean[k], ap.mvar[k], mean, invstd);
-    float sc = ap.gamma[k][c] * invstd;
-    sm[(k * 2) * C + c] = sc;
-    sm[(k * 2 + 1) * C + c] = ap.beta[k][c] - mean * sc;
-  }
-  __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * NT) {
-    float v[V];
-    ldv<T>(x + i * V, v);
-    int c0 = (int)((i * V) % C);
-    for (int k = 0; k < ap.nout; ++k) {
-      const float* sc = sm + (k * 2) * C + c0;
-      const float* sh = sm + (k * 2 + 1) * C + c0;
-      float o[V];
+  const int tpr = C / V, rpi = NT / tpr, tid = threadIdx.x;
+  const int cg = tid % tpr, r0 = tid / tpr;
+  float sc[MAX_OUT][V], sh[MAX_OUT][V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float t = fmaf(v[j], sc[j], sh[j]);
-        o[j] = relu ? fmaxf(t, 0.f) : t;
+  for (int k = 0; k < MAX_OUT; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (k < ap.nout) {
+        float mean, invstd;
+        bn_mean_invstd(stats, count, C, cg * V + j, eps, ap.mmean[k], ap.mvar[k], mean, invstd);
+        sc[k][j] = ap.gamma[k][cg * V + j] * invstd;
+        sh[k][j] = ap.beta[k][cg * V + j] - mean * sc[k][j];
+      } else { sc[k][j] = 0.f; sh[k][j] = 0.f; }
+    }
+  const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t rend = min(M, rbeg + rows_per_block);
+  for (int64_t r = rbeg + r0; r < rend; r += rpi) {
+    const int64_t o = r * C + cg * V;
+    float v[V];
+    ldv<T>(x + o, v);
+#pragma unroll
+    for (int k = 0; k < MAX_OUT; ++k) {
+      if (k < ap.nout) {
+        float out[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float t = fmaf(v[j], sc[k][j], sh[k][j]);
+          out[j] = relu ? fmaxf(t, 0.f) : t;
+        }
+        stv<T>(reinterpret_cast<T*>(ap.out[k]) + o, out);
       }
-      stv<T>(reinterpret_cast<T*>(ap.out[k]) + i * V, o);
     }
   }
 }
@@ -232,6 +241,148 @@ __global__ void bn_update_moving_kernel(const double* __restrict__ stats_base, f
   }
 }
 
+// ---- multi-branch backward with recomputed ReLU masks ---------------------------------------------------
+// The k branches of a ResBlock-a normalise the SAME input x (model2.py:17), so their BatchNorm backward
+// shares every read of x and produces ONE dx:  dx (=|+=) sum_k gamma_k*inv*(g_k - mean(g_k) - xhat*mean(g_k xhat)).
+// The ReLU mask is recomputed from x with the forward's own scale/shift (fmaf(x, sc, sh) > 0) instead of
+// re-reading the activated tensor.  Each thread owns 4 fixed channels (coefficients live in registers) and
+// walks rows; HBM traffic per element: reduce (1+k) reads, apply (1+k) reads + 1 write (+1 read to accumulate).
+constexpr int MAXK = 4;
+constexpr int VM = 4;
+
+struct BwdMultiParams {
+  const void* dy[MAXK];
+  const float* gamma[MAXK];
+  const float* beta[MAXK];
+  double* red[MAXK];
+  float* dgamma[MAXK];
+  float* dbeta[MAXK];
+  int k;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT) bn_bwd_reduce_multi_kernel(const T* __restrict__ x, int64_t M, int C,
+                                                                 const BwdMultiParams bp, const double* __restrict__ stats,
+                                                                 double count, float eps, int relu, int rows_per_block) {
+  extern __shared__ float sm[];    // [NT][2*VM] per branch pass
+  const int tpr = C / VM, rpi = NT / tpr, tid = threadIdx.x;
+  const int cg = tid % tpr, r0 = tid / tpr;
+  float mean[VM], inv[VM];
+#pragma unroll
+  for (int i = 0; i < VM; ++i) bn_mean_invstd(stats, count, C, cg * VM + i, eps, nullptr, nullptr, mean[i], inv[i]);
+  float sc[MAXK][VM], sh[MAXK][VM], s[MAXK][VM], q[MAXK][VM];
+#pragma unroll
+  for (int b = 0; b < MAXK; ++b)
+#pragma unroll
+    for (int i = 0; i < VM; ++i) {
+      s[b][i] = 0.f; q[b][i] = 0.f;
+      if (b < bp.k) {
+        sc[b][i] = bp.gamma[b][cg * VM + i] * inv[i];
+        sh[b][i] = bp.beta[b][cg * VM + i] - mean[i] * sc[b][i];
+      } else { sc[b][i] = 0.f; sh[b][i] = 0.f; }
+    }
+  const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t rend = min(M, rbeg + rows_per_block);
+  for (int64_t r = rbeg + r0; r < rend; r += rpi) {
+    const int64_t o = r * C + cg * VM;
+    float xv[VM];
+    ld4<T>(x + o, xv);
+#pragma unroll
+    for (int b = 0; b < MAXK; ++b) {
+      if (b < bp.k) {
+        float g[VM];
+        ld4<T>(reinterpret_cast<const T*>(bp.dy[b]) + o, g);
+#pragma unroll
+        for (int i = 0; i < VM; ++i) {
+          const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[i] : 0.f;
+          s[b][i] += gg;
+          q[b][i] += gg * (xv[i] - mean[i]) * inv[i];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAXK; ++b) {
+    if (b >= bp.k) break;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VM; ++i) { sm[tid * 2 * VM + i] = s[b][i]; sm[tid * 2 * VM + VM + i] = q[b][i]; }
+    __syncthreads();
+    for (int c = tid; c < C; c += NT) {
+      const int g = c / VM, i = c % VM;
+      double a = 0, d = 0;
+      for (int r = 0; r < rpi; ++r) {
+        a += sm[(r * tpr + g) * 2 * VM + i];
+        d += sm[(r * tpr + g) * 2 * VM + VM + i];
+      }
+      atomicAdd(bp.red[b] + c, a);
+      atomicAdd(bp.red[b] + C + c, d);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) bn_bwd_apply_multi_kernel(const T* __restrict__ x, int64_t M, int C,
+                                                                const BwdMultiParams bp, const double* __restrict__ stats,
+                                                                double count, float eps, int relu, T* __restrict__ dx,
+                                                                int accumulate, int rows_per_block) {
+  const int tpr = C / VM, rpi = NT / tpr, tid = threadIdx.x;
+  const int cg = tid % tpr, r0 = tid / tpr;
+  float mean[VM], inv[VM], Bsum[VM], Dsum[VM];
+  float A[MAXK][VM], sc[MAXK][VM], sh[MAXK][VM];
+#pragma unroll
+  for (int i = 0; i < VM; ++i) {
+    bn_mean_invstd(stats, count, C, cg * VM + i, eps, nullptr, nullptr, mean[i], inv[i]);
+    Bsum[i] = 0.f; Dsum[i] = 0.f;
+  }
+#pragma unroll
+  for (int b = 0; b < MAXK; ++b)
+#pragma unroll
+    for (int i = 0; i < VM; ++i) {
+      if (b < bp.k) {
+        const int c = cg * VM + i;
+        const float gam = bp.gamma[b][c];
+        sc[b][i] = gam * inv[i];
+        sh[b][i] = bp.beta[b][c] - mean[i] * sc[b][i];
+        A[b][i] = sc[b][i];
+        Bsum[i] += A[b][i] * (float)(bp.red[b][c] / count);
+        Dsum[i] += A[b][i] * (float)(bp.red[b][C + c] / count);
+        if (blockIdx.x == 0 && r0 == 0) {
+          if (bp.dgamma[b]) bp.dgamma[b][c] = (float)bp.red[b][C + c];
+          if (bp.dbeta[b]) bp.dbeta[b][c] = (float)bp.red[b][c];
+        }
+      } else { A[b][i] = 0.f; sc[b][i] = 0.f; sh[b][i] = 0.f; }
+    }
+  const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t rend = min(M, rbeg + rows_per_block);
+  for (int64_t r = rbeg + r0; r < rend; r += rpi) {
+    const int64_t o = r * C + cg * VM;
+    float xv[VM], acc[VM];
+    ld4<T>(x + o, xv);
+    if (accumulate) ld4<T>(dx + o, acc);
+#pragma unroll
+    for (int i = 0; i < VM; ++i) {
+      const float base = -Bsum[i] - (xv[i] - mean[i]) * inv[i] * Dsum[i];
+      acc[i] = accumulate ? acc[i] + base : base;
+    }
+#pragma unroll
+    for (int b = 0; b < MAXK; ++b) {
+      if (b < bp.k) {
+        float g[VM];
+        ld4<T>(reinterpret_cast<const T*>(bp.dy[b]) + o, g);
+#pragma unroll
+        for (int i = 0; i < VM; ++i) {
+          const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[i] : 0.f;
+          acc[i] = fmaf(A[b][i], gg, acc[i]);
+        }
+      }
+    }
+    st4<T>(dx + o, acc);
+  }
+}
+
+inline bool multi_shape_ok(int C) { return C >= VM && C % VM == 0 && (C / VM) <= NT && NT % (C / VM) == 0; }
+
 template <typename T> bool bn_shape_ok(int C) {
   constexpr int V = Vec16<T>::N;
   if (C < V || C % V) return false;
@@ -282,15 +433,20 @@ extern "C" int rsa_bn_apply(const void* x, int dtype, int64_t M, int C, int nout
     ap.mvar[k] = moving_vars ? moving_vars[kk] : nullptr;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  size_t smem = (size_t)nout * 2 * C * sizeof(float);
   if (dtype == RSA_F32) {
-    RSA_REQUIRE(C % 4 == 0, RSA_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 4", C);
-    int64_t nvec = M * C / 4;
-    bn_apply_kernel<float><<<grid_for(nvec), NT, smem, st>>>((const float*)x, nvec, C, ap, stats, count, eps, relu);
+    RSA_REQUIRE(bn_shape_ok<float>(C), RSA_ERR_SHAPE, "bn_apply: C=%d unsupported", C);
+    const int rpi = NT / (C / 4);
+    int rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 8);
+    rows = (rows + rpi - 1) / rpi * rpi;
+    if (rows < 4 * rpi) rows = 4 * rpi;
+    bn_apply_kernel<float><<<(int)ceil_div64(M, rows), NT, 0, st>>>((const float*)x, M, C, ap, stats, count, eps, relu, rows);
   } else if (dtype == RSA_BF16) {
-    RSA_REQUIRE(C % 8 == 0, RSA_ERR_SHAPE, "bn_apply: C=%d must be a multiple of 8", C);
-    int64_t nvec = M * C / 8;
-    bn_apply_kernel<bf16><<<grid_for(nvec), NT, smem, st>>>((const bf16*)x, nvec, C, ap, stats, count, eps, relu);
+    RSA_REQUIRE(bn_shape_ok<bf16>(C), RSA_ERR_SHAPE, "bn_apply: C=%d unsupported", C);
+    const int rpi = NT / (C / 8);
+    int rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 8);
+    rows = (rows + rpi - 1) / rpi * rpi;
+    if (rows < 4 * rpi) rows = 4 * rpi;
+    bn_apply_kernel<bf16><<<(int)ceil_div64(M, rows), NT, 0, st>>>((const bf16*)x, M, C, ap, stats, count, eps, relu, rows);
   } else {
     RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_apply: bad dtype");
   }
@@ -359,6 +515,69 @@ extern "C" int rsa_bn_update_moving(const double* stats_base, float* param_base,
               "bn_update_moving: bad args");
   bn_update_moving_kernel<<<nlayers, 128, 0, (cudaStream_t)stream>>>(stats_base, param_base, table, counts,
                                                                      nlayers, momentum);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+
+namespace {
+int fill_multi(BwdMultiParams& bp, int k, const void* const* dys, const float* const* gammas, const float* const* betas,
+               double* const* reds, float* const* dgammas, float* const* dbetas) {
+  RSA_REQUIRE(k >= 1 && k <= MAXK && dys && gammas && betas && reds, RSA_ERR_SHAPE, "bn_bwd_multi: bad branch arguments");
+  bp.k = k;
+  for (int b = 0; b < MAXK; ++b) {
+    const int bb = b < k ? b : 0;
+    bp.dy[b] = dys[bb]; bp.gamma[b] = gammas[bb]; bp.beta[b] = betas[bb]; bp.red[b] = reds[bb];
+    bp.dgamma[b] = dgammas ? dgammas[bb] : nullptr;
+    bp.dbeta[b] = dbetas ? dbetas[bb] : nullptr;
+    RSA_REQUIRE(bp.dy[b] && bp.gamma[b] && bp.beta[b] && bp.red[b], RSA_ERR_SHAPE, "bn_bwd_multi: null branch pointer");
+  }
+  return RSA_OK;
+}
+inline void multi_grid(int64_t M, int C, int& rows, int& grid) {
+  const int rpi = NT / (C / VM);
+  rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 6);
+  rows = (rows + rpi - 1) / rpi * rpi;
+  if (rows < rpi * 4) rows = rpi * 4;
+  grid = (int)ceil_div64(M, rows);
+}
+}  // namespace
+
+/* Backward of k <= 4 BatchNormalization(+ReLU) layers that share their input x (the ResBlock-a branches,
+ * model2.py:17-18): reds[b][2C] (double, zeroed) += { sum g_b, sum g_b*xhat }, g_b = dy_b * (relu ? bn_b(x) > 0 : 1). */
+extern "C" int rsa_bn_bwd_reduce_multi(const void* const* dys, const void* x, int dtype, int64_t M, int C, int k,
+                                       const double* stats, double count, float eps, const float* const* gammas,
+                                       const float* const* betas, int relu, double* const* reds, void* stream) {
+  RSA_REQUIRE(x && stats && M > 0 && multi_shape_ok(C), RSA_ERR_SHAPE, "bn_bwd_reduce_multi: bad args (C=%d)", C);
+  BwdMultiParams bp;
+  int rc = fill_multi(bp, k, dys, gammas, betas, reds, nullptr, nullptr);
+  if (rc) return rc;
+  int rows, grid;
+  multi_grid(M, C, rows, grid);
+  const size_t smem = (size_t)NT * 2 * VM * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RSA_F32) bn_bwd_reduce_multi_kernel<float><<<grid, NT, smem, st>>>((const float*)x, M, C, bp, stats, count, eps, relu, rows);
+  else if (dtype == RSA_BF16) bn_bwd_reduce_multi_kernel<bf16><<<grid, NT, smem, st>>>((const bf16*)x, M, C, bp, stats, count, eps, relu, rows);
+  else RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_bwd_reduce_multi: bad dtype");
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+/* dx (=|+=) sum_b gamma_b*invstd*(g_b - red_b[0]/count - xhat*red_b[1]/count); dgamma_b = red_b[1], dbeta_b = red_b[0]. */
+extern "C" int rsa_bn_bwd_apply_multi(const void* const* dys, const void* x, int dtype, int64_t M, int C, int k,
+                                      const double* stats, double count, float eps, const float* const* gammas,
+                                      const float* const* betas, int relu, double* const* reds, void* dx, int accumulate,
+                                      float* const* dgammas, float* const* dbetas, void* stream) {
+  RSA_REQUIRE(x && dx && stats && M > 0 && multi_shape_ok(C), RSA_ERR_SHAPE, "bn_bwd_apply_multi: bad args (C=%d)", C);
+  BwdMultiParams bp;
+  int rc = fill_multi(bp, k, dys, gammas, betas, reds, dgammas, dbetas);
+  if (rc) return rc;
+  int rows, grid;
+  multi_grid(M, C, rows, grid);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RSA_F32) bn_bwd_apply_multi_kernel<float><<<grid, NT, 0, st>>>((const float*)x, M, C, bp, stats, count, eps, relu, (float*)dx, accumulate, rows);
+  else if (dtype == RSA_BF16) bn_bwd_apply_multi_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)x, M, C, bp, stats, count, eps, relu, (bf16*)dx, accumulate, rows);
+  else RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_bwd_apply_multi: bad dtype");
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }

@@ -560,18 +560,19 @@ class Plan:
             reds = [self.zeroed(2 * C) for _ in names]
 
             def bwd():
-                for k, o in enumerate(outs):
-                    if o.grad is None:
-                        continue
-                    act = o.data if relu else None
-                    self.bwd.append(self._late(lambda k=k, o=o, act=act: lib.bn_bwd_reduce(
-                        o.grad, x.data, act, M, C, xs[0], cnt, BN_EPS, reds[k][0])))
-                    if x.needs_grad:
-                        g, acc = self.gacc(x)
-                        self.bwd.append(self._late(lambda k=k, o=o, act=act, g=g, acc=acc: lib.bn_bwd_apply(
-                            o.grad, x.data, act, M, C, xs[0], cnt, BN_EPS, gam[k], reds[k][0], g, acc,
-                            self.G(names[k] + "/gamma"), self.G(names[k] + "/beta"))))
-                        self._ready(names[k] + "/gamma", names[k] + "/beta")
+                live = [k for k, o in enumerate(outs) if o.grad is not None]
+                if not live:
+                    return
+                dys = [outs[k].grad for k in live]
+                gl, bl, rl = [gam[k] for k in live], [bet[k] for k in live], [reds[k] for k in live]
+                self.bwd.append(self._late(lambda: lib.bn_bwd_reduce_multi(
+                    dys, x.data, M, C, xs[0], cnt, BN_EPS, gl, bl, relu, [r[0] for r in rl])))
+                if x.needs_grad:
+                    g, acc = self.gacc(x)
+                    self.bwd.append(self._late(lambda: lib.bn_bwd_apply_multi(
+                        dys, x.data, M, C, xs[0], cnt, BN_EPS, gl, bl, relu, [r[0] for r in rl], g, acc,
+                        [self.G(names[k] + "/gamma") for k in live], [self.G(names[k] + "/beta") for k in live])))
+                    self._ready(*[names[k] + sfx for k in live for sfx in ("/gamma", "/beta")])
             self.tape.append(bwd)
         else:
             self.fwd.append(lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, None, 1.0, mm, mv, BN_EPS,

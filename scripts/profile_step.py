@@ -39,15 +39,18 @@ for phase, op, e0, e1 in evs:
     ms = e0.elapsed_time(e1)
     k = (phase, name)
     c, t = agg.get(k, (0, 0.0)); agg[k] = (c + 1, t + ms)
-    rows.append((phase, name, ms, getattr(op, "flops", 0.0)))
+    rows.append((phase, name, ms, getattr(op, "flops", 0.0), getattr(getattr(op, "cell", [op])[0] if getattr(op, "cell", None) else op, "ints", ())))
 tot = sum(t for _, t in agg.values())
 lines = [f"step (eager, event-timed): {t0.elapsed_time(t1):.2f} ms wall, {tot:.2f} ms summed kernels; plan bytes {pl.bytes/2**30:.2f} GiB"]
 for (phase, name), (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"{phase:4s} {name:44s} n={c:4d} {t:9.3f} ms {100*t/tot:5.1f}%")
 if a.detail:
     lines.append("---- conv launches (ms, TFLOP/s)")
-    for phase, name, ms, fl in rows:
+    for phase, name, ms, fl, ints in rows:
         if fl: lines.append(f"{phase} {name:40s} {ms:8.3f} ms {fl/ms/1e9:8.1f} TF")
+    lines.append("---- non-conv launches over 40 us")
+    for phase, name, ms, fl, ints in sorted(rows, key=lambda r: -r[2]):
+        if not fl and ms > 0.04: lines.append(f"{phase} {name:28s} {ms:8.3f} ms  args={ints}")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", "step_breakdown.txt"), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines[:40]))

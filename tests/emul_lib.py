@@ -150,6 +150,42 @@ class EmulLib:
                 dbeta.copy_(red[:C].to(torch.float32))
         return self._wrap(run, "rsa_bn_bwd_apply")
 
+    def bn_bwd_reduce_multi(self, dys, x, M, C, stats, count, eps, gammas, betas, relu, reds):
+        def run():
+            mu, inv = _mean_inv(stats, count, C, eps)
+            xv = x.reshape(M, C).to(F64)
+            xh = (xv - mu) * inv
+            for dy, ga, be, red in zip(dys, gammas, betas, reds):
+                g = dy.reshape(M, C).to(F64)
+                if relu:
+                    sc = (ga.to(torch.float32) * inv.to(torch.float32)).to(F64)
+                    sh = (be.to(torch.float32) - mu.to(torch.float32) * sc.to(torch.float32)).to(F64)
+                    g = g * ((xv * sc + sh) > 0)
+                red[:C] += g.sum(0)
+                red[C:2 * C] += (g * xh).sum(0)
+        return self._wrap(run, "rsa_bn_bwd_reduce_multi")
+
+    def bn_bwd_apply_multi(self, dys, x, M, C, stats, count, eps, gammas, betas, relu, reds, dx, accumulate, dgammas,
+                           dbetas):
+        def run():
+            mu, inv = _mean_inv(stats, count, C, eps)
+            xv = x.reshape(M, C).to(F64)
+            xh = (xv - mu) * inv
+            tot = dx.reshape(M, C).to(F64).clone() if accumulate else torch.zeros(M, C, dtype=F64)
+            for b, (dy, ga, be, red) in enumerate(zip(dys, gammas, betas, reds)):
+                g = dy.reshape(M, C).to(F64)
+                if relu:
+                    sc = (ga.to(torch.float32) * inv.to(torch.float32)).to(F64)
+                    sh = (be.to(torch.float32) - mu.to(torch.float32) * sc.to(torch.float32)).to(F64)
+                    g = g * ((xv * sc + sh) > 0)
+                tot += ga.to(F64) * inv * (g - red[:C] / count - xh * red[C:2 * C] / count)
+                if dgammas is not None and dgammas[b] is not None:
+                    dgammas[b].copy_(red[C:2 * C].to(torch.float32))
+                if dbetas is not None and dbetas[b] is not None:
+                    dbetas[b].copy_(red[:C].to(torch.float32))
+            _store(dx, tot)
+        return self._wrap(run, "rsa_bn_bwd_apply_multi")
+
     def bn_derive_stats(self, src_stats, count, gamma, beta, eps, dst_stats, dst_count, C):
         def run():
             mu = src_stats[:C] / count

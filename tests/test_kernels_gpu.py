@@ -280,3 +280,25 @@ def test_optimizers_axpy_cast(lib):
     src = rnd((n,), torch.float32, 7)
     dst = torch.zeros(n, dtype=torch.bfloat16)
     run_pair(lib, "cast", [src, dst, n], {}, [1], 0.0)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("C,k,relu", [(32, 4, True), (8, 1, False), (256, 3, True), (1024, 1, True), (64, 2, False)])
+def test_bn_backward_multi_branch(lib, dt, C, k, relu):
+    M = 1300
+    x = rnd((M, C), dt, 1) * 2 + 0.5
+    stats = torch.zeros(2 * C, dtype=torch.float64)
+    EMU.bn_stats(x, M, C, stats)(0)
+    dys = [rnd((M, C), dt, 10 + b) for b in range(k)]
+    gam = [rnd((C,), torch.float32, 20 + b) for b in range(k)]
+    bet = [rnd((C,), torch.float32, 30 + b) for b in range(k)]
+    reds = [torch.zeros(2 * C, dtype=torch.float64) for _ in range(k)]
+    run_pair(lib, "bn_bwd_reduce_multi", [dys, x, M, C, stats, float(M), 1e-3, gam, bet, relu, reds], {}, [10], 2e-3 if dt == torch.bfloat16 else 1e-4, 3.0)   # atol: one borderline ReLU-mask flip moves a sum by |dy|
+    for r in reds:
+        r.zero_()
+    EMU.bn_bwd_reduce_multi(dys, x, M, C, stats, float(M), 1e-3, gam, bet, relu, reds)(0)
+    dx = rnd((M, C), dt, 40)
+    dg = [torch.zeros(C) for _ in range(k)]
+    db = [torch.zeros(C) for _ in range(k)]
+    run_pair(lib, "bn_bwd_apply_multi", [dys, x, M, C, stats, float(M), 1e-3, gam, bet, relu, reds, dx, True, dg, db], {},
+             [11, 13, 14], TOL[dt] * 4, 1e-2)
