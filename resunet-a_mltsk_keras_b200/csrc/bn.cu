@@ -61,43 +61,49 @@ struct ApplyParams {
   int nout;
 };
 
-template <typename T>
+template <typename T, int NOUT>
 __global__ void __launch_bounds__(NT) bn_apply_kernel(const T* __restrict__ x, int64_t M, int C, const ApplyParams ap,
                                                       const double* __restrict__ stats, double count, float eps,
                                                       int relu, int rows_per_block) {
-  // each thread owns one fixed group of V channels: scale/shift live in registers, rows are walked with
-  // 16-byte loads/stores (one read of x feeds all nout branch outputs)
+  // each thread owns one fixed group of V channels: scale/shift are computed once per block (fp64 -> smem),
+  // copied to registers, and the rows are walked with 16-byte loads/stores, two rows in flight per thread
+  // (one read of x feeds all NOUT branch outputs)
   constexpr int V = Vec16<T>::N;
+  extern __shared__ float tab[];          // [NOUT][2][C]
+  for (int i = threadIdx.x; i < NOUT * C; i += NT) {
+    const int k = i / C, c = i % C;
+    float mean, invstd;
+    bn_mean_invstd(stats, count, C, c, eps, ap.mmean[k], ap.mvar[k], mean, invstd);
+    const float scv = ap.gamma[k][c] * invstd;
+    tab[(2 * k) * C + c] = scv;
+    tab[(2 * k + 1) * C + c] = ap.beta[k][c] - mean * scv;
+  }
+  __syncthreads();
   const int tpr = C / V, rpi = NT / tpr, tid = threadIdx.x;
   const int cg = tid % tpr, r0 = tid / tpr;
-  float sc[MAX_OUT][V], sh[MAX_OUT][V];
+  float sc[NOUT][V], sh[NOUT][V];
 #pragma unroll
-  for (int k = 0; k < MAX_OUT; ++k)
+  for (int k = 0; k < NOUT; ++k)
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      if (k < ap.nout) {
-        float mean, invstd;
-        bn_mean_invstd(stats, count, C, cg * V + j, eps, ap.mmean[k], ap.mvar[k], mean, invstd);
-        sc[k][j] = ap.gamma[k][cg * V + j] * invstd;
-        sh[k][j] = ap.beta[k][cg * V + j] - mean * sc[k][j];
-      } else { sc[k][j] = 0.f; sh[k][j] = 0.f; }
-    }
+    for (int j = 0; j < V; ++j) { sc[k][j] = tab[(2 * k) * C + cg * V + j]; sh[k][j] = tab[(2 * k + 1) * C + cg * V + j]; }
   const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
   const int64_t rend = min(M, rbeg + rows_per_block);
-  for (int64_t r = rbeg + r0; r < rend; r += rpi) {
-    const int64_t o = r * C + cg * V;
-    float v[V];
-    ldv<T>(x + o, v);
+  for (int64_t r = rbeg + r0; r < rend; r += 2 * rpi) {
+    const int64_t o0 = r * C + cg * V, o1 = (r + rpi) * C + cg * V;
+    const bool two = r + rpi < rend;
+    float v0[V], v1[V];
+    ldv<T>(x + o0, v0);
+    if (two) ldv<T>(x + o1, v1);
 #pragma unroll
-    for (int k = 0; k < MAX_OUT; ++k) {
-      if (k < ap.nout) {
-        float out[V];
+    for (int k = 0; k < NOUT; ++k) {
+      float out[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const float t = fmaf(v[j], sc[k][j], sh[k][j]);
-          out[j] = relu ? fmaxf(t, 0.f) : t;
-        }
-        stv<T>(reinterpret_cast<T*>(ap.out[k]) + o, out);
+      for (int j = 0; j < V; ++j) { const float t = fmaf(v0[j], sc[k][j], sh[k][j]); out[j] = relu ? fmaxf(t, 0.f) : t; }
+      stv<T>(reinterpret_cast<T*>(ap.out[k]) + o0, out);
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { const float t = fmaf(v1[j], sc[k][j], sh[k][j]); out[j] = relu ? fmaxf(t, 0.f) : t; }
+        stv<T>(reinterpret_cast<T*>(ap.out[k]) + o1, out);
       }
     }
   }
@@ -248,7 +254,6 @@ __global__ void bn_update_moving_kernel(const double* __restrict__ stats_base, f
 // re-reading the activated tensor.  Each thread owns 4 fixed channels (coefficients live in registers) and
 // walks rows; HBM traffic per element: reduce (1+k) reads, apply (1+k) reads + 1 write (+1 read to accumulate).
 constexpr int MAXK = 4;
-constexpr int VM = 4;
 
 struct BwdMultiParams {
   const void* dy[MAXK];
@@ -260,60 +265,87 @@ struct BwdMultiParams {
   int k;
 };
 
-template <typename T>
+// VM channels per thread: 8 (one 16-byte bf16 vector) for a single branch, 4 for several (register budget)
+template <typename T, int K> struct MultiV { static constexpr int V = (K == 1 && sizeof(T) == 2) ? 8 : 4; };
+
+template <typename T, int V> __device__ __forceinline__ void ldm(const T* p, float* v) {
+  if constexpr (V == 8) ldv<T>(p, v);
+  else { float t[4]; ld4<T>(p, t); v[0] = t[0]; v[1] = t[1]; v[2] = t[2]; v[3] = t[3]; }
+}
+template <typename T, int V> __device__ __forceinline__ void stm(T* p, const float* v) {
+  if constexpr (V == 8) stv<T>(p, v);
+  else { float t[4] = {v[0], v[1], v[2], v[3]}; st4<T>(p, t); }
+}
+
+// smem table [2 + 2K][C]: mean, invstd, then per branch scale = gamma*invstd and shift = beta - mean*scale
+template <int K>
+__device__ __forceinline__ void stage_coeffs(float* tab, int C, const BwdMultiParams& bp, const double* stats, double count,
+                                             float eps) {
+  for (int c = threadIdx.x; c < C; c += NT) {
+    float mean, inv;
+    bn_mean_invstd(stats, count, C, c, eps, nullptr, nullptr, mean, inv);
+    tab[c] = mean;
+    tab[C + c] = inv;
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+      const float scv = bp.gamma[b][c] * inv;
+      tab[(2 + 2 * b) * C + c] = scv;
+      tab[(3 + 2 * b) * C + c] = bp.beta[b][c] - mean * scv;
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T, int K>
 __global__ void __launch_bounds__(NT) bn_bwd_reduce_multi_kernel(const T* __restrict__ x, int64_t M, int C,
                                                                  const BwdMultiParams bp, const double* __restrict__ stats,
                                                                  double count, float eps, int relu, int rows_per_block) {
-  extern __shared__ float sm[];    // [NT][2*VM] per branch pass
-  const int tpr = C / VM, rpi = NT / tpr, tid = threadIdx.x;
+  constexpr int V = MultiV<T, K>::V;
+  extern __shared__ float tab[];    // coefficient table, reused for the block reduction
+  stage_coeffs<K>(tab, C, bp, stats, count, eps);
+  const int tpr = C / V, rpi = NT / tpr, tid = threadIdx.x;
   const int cg = tid % tpr, r0 = tid / tpr;
-  float mean[VM], inv[VM];
+  float mean[V], inv[V], sc[K][V], sh[K][V], s[K][V], q[K][V];
 #pragma unroll
-  for (int i = 0; i < VM; ++i) bn_mean_invstd(stats, count, C, cg * VM + i, eps, nullptr, nullptr, mean[i], inv[i]);
-  float sc[MAXK][VM], sh[MAXK][VM], s[MAXK][VM], q[MAXK][VM];
+  for (int i = 0; i < V; ++i) {
+    mean[i] = tab[cg * V + i];
+    inv[i] = tab[C + cg * V + i];
 #pragma unroll
-  for (int b = 0; b < MAXK; ++b)
-#pragma unroll
-    for (int i = 0; i < VM; ++i) {
+    for (int b = 0; b < K; ++b) {
+      sc[b][i] = tab[(2 + 2 * b) * C + cg * V + i];
+      sh[b][i] = tab[(3 + 2 * b) * C + cg * V + i];
       s[b][i] = 0.f; q[b][i] = 0.f;
-      if (b < bp.k) {
-        sc[b][i] = bp.gamma[b][cg * VM + i] * inv[i];
-        sh[b][i] = bp.beta[b][cg * VM + i] - mean[i] * sc[b][i];
-      } else { sc[b][i] = 0.f; sh[b][i] = 0.f; }
     }
+  }
   const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
   const int64_t rend = min(M, rbeg + rows_per_block);
   for (int64_t r = rbeg + r0; r < rend; r += rpi) {
-    const int64_t o = r * C + cg * VM;
-    float xv[VM];
-    ld4<T>(x + o, xv);
+    const int64_t o = r * C + cg * V;
+    float xv[V], g[K][V];
+    ldm<T, V>(x + o, xv);
 #pragma unroll
-    for (int b = 0; b < MAXK; ++b) {
-      if (b < bp.k) {
-        float g[VM];
-        ld4<T>(reinterpret_cast<const T*>(bp.dy[b]) + o, g);
+    for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[b]);
 #pragma unroll
-        for (int i = 0; i < VM; ++i) {
-          const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[i] : 0.f;
-          s[b][i] += gg;
-          q[b][i] += gg * (xv[i] - mean[i]) * inv[i];
-        }
+    for (int b = 0; b < K; ++b)
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[b][i] : 0.f;
+        s[b][i] += gg;
+        q[b][i] = fmaf(gg, (xv[i] - mean[i]) * inv[i], q[b][i]);
       }
-    }
   }
 #pragma unroll
-  for (int b = 0; b < MAXK; ++b) {
-    if (b >= bp.k) break;
+  for (int b = 0; b < K; ++b) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < VM; ++i) { sm[tid * 2 * VM + i] = s[b][i]; sm[tid * 2 * VM + VM + i] = q[b][i]; }
+    for (int i = 0; i < V; ++i) { tab[tid * 2 * V + i] = s[b][i]; tab[tid * 2 * V + V + i] = q[b][i]; }
     __syncthreads();
     for (int c = tid; c < C; c += NT) {
-      const int g = c / VM, i = c % VM;
+      const int g = c / V, i = c % V;
       double a = 0, d = 0;
       for (int r = 0; r < rpi; ++r) {
-        a += sm[(r * tpr + g) * 2 * VM + i];
-        d += sm[(r * tpr + g) * 2 * VM + VM + i];
+        a += tab[(r * tpr + g) * 2 * V + i];
+        d += tab[(r * tpr + g) * 2 * V + V + i];
       }
       atomicAdd(bp.red[b] + c, a);
       atomicAdd(bp.red[b] + C + c, d);
@@ -321,67 +353,61 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_multi_kernel(const T* __rest
   }
 }
 
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(NT) bn_bwd_apply_multi_kernel(const T* __restrict__ x, int64_t M, int C,
                                                                 const BwdMultiParams bp, const double* __restrict__ stats,
                                                                 double count, float eps, int relu, T* __restrict__ dx,
                                                                 int accumulate, int rows_per_block) {
-  const int tpr = C / VM, rpi = NT / tpr, tid = threadIdx.x;
+  constexpr int V = MultiV<T, K>::V;
+  extern __shared__ float tab[];
+  stage_coeffs<K>(tab, C, bp, stats, count, eps);
+  const int tpr = C / V, rpi = NT / tpr, tid = threadIdx.x;
   const int cg = tid % tpr, r0 = tid / tpr;
-  float mean[VM], inv[VM], Bsum[VM], Dsum[VM];
-  float A[MAXK][VM], sc[MAXK][VM], sh[MAXK][VM];
+  float mean[V], inv[V], Bsum[V], Dsum[V], sc[K][V], sh[K][V];
 #pragma unroll
-  for (int i = 0; i < VM; ++i) {
-    bn_mean_invstd(stats, count, C, cg * VM + i, eps, nullptr, nullptr, mean[i], inv[i]);
+  for (int i = 0; i < V; ++i) {
+    const int c = cg * V + i;
+    mean[i] = tab[c];
+    inv[i] = tab[C + c];
     Bsum[i] = 0.f; Dsum[i] = 0.f;
-  }
 #pragma unroll
-  for (int b = 0; b < MAXK; ++b)
-#pragma unroll
-    for (int i = 0; i < VM; ++i) {
-      if (b < bp.k) {
-        const int c = cg * VM + i;
-        const float gam = bp.gamma[b][c];
-        sc[b][i] = gam * inv[i];
-        sh[b][i] = bp.beta[b][c] - mean[i] * sc[b][i];
-        A[b][i] = sc[b][i];
-        Bsum[i] += A[b][i] * (float)(bp.red[b][c] / count);
-        Dsum[i] += A[b][i] * (float)(bp.red[b][C + c] / count);
-        if (blockIdx.x == 0 && r0 == 0) {
-          if (bp.dgamma[b]) bp.dgamma[b][c] = (float)bp.red[b][C + c];
-          if (bp.dbeta[b]) bp.dbeta[b][c] = (float)bp.red[b][c];
-        }
-      } else { A[b][i] = 0.f; sc[b][i] = 0.f; sh[b][i] = 0.f; }
+    for (int b = 0; b < K; ++b) {
+      sc[b][i] = tab[(2 + 2 * b) * C + c];
+      sh[b][i] = tab[(3 + 2 * b) * C + c];
+      Bsum[i] += sc[b][i] * (float)(bp.red[b][c] / count);
+      Dsum[i] += sc[b][i] * (float)(bp.red[b][C + c] / count);
+      if (blockIdx.x == 0 && r0 == 0) {
+        if (bp.dgamma[b]) bp.dgamma[b][c] = (float)bp.red[b][C + c];
+        if (bp.dbeta[b]) bp.dbeta[b][c] = (float)bp.red[b][c];
+      }
     }
+  }
   const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
   const int64_t rend = min(M, rbeg + rows_per_block);
   for (int64_t r = rbeg + r0; r < rend; r += rpi) {
-    const int64_t o = r * C + cg * VM;
-    float xv[VM], acc[VM];
-    ld4<T>(x + o, xv);
-    if (accumulate) ld4<T>(dx + o, acc);
+    const int64_t o = r * C + cg * V;
+    float xv[V], acc[V], g[K][V];
+    ldm<T, V>(x + o, xv);
 #pragma unroll
-    for (int i = 0; i < VM; ++i) {
+    for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[b]);
+    if (accumulate) ldm<T, V>(dx + o, acc);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
       const float base = -Bsum[i] - (xv[i] - mean[i]) * inv[i] * Dsum[i];
       acc[i] = accumulate ? acc[i] + base : base;
     }
 #pragma unroll
-    for (int b = 0; b < MAXK; ++b) {
-      if (b < bp.k) {
-        float g[VM];
-        ld4<T>(reinterpret_cast<const T*>(bp.dy[b]) + o, g);
+    for (int b = 0; b < K; ++b)
 #pragma unroll
-        for (int i = 0; i < VM; ++i) {
-          const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[i] : 0.f;
-          acc[i] = fmaf(A[b][i], gg, acc[i]);
-        }
+      for (int i = 0; i < V; ++i) {
+        const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[b][i] : 0.f;
+        acc[i] = fmaf(sc[b][i], gg, acc[i]);
       }
-    }
-    st4<T>(dx + o, acc);
+    stm<T, V>(dx + o, acc);
   }
 }
 
-inline bool multi_shape_ok(int C) { return C >= VM && C % VM == 0 && (C / VM) <= NT && NT % (C / VM) == 0; }
+inline bool multi_shape_ok(int C) { return C >= 8 && (C & (C - 1)) == 0 && C <= 1024; }
 
 template <typename T> bool bn_shape_ok(int C) {
   constexpr int V = Vec16<T>::N;
@@ -437,16 +463,30 @@ extern "C" int rsa_bn_apply(const void* x, int dtype, int64_t M, int C, int nout
     RSA_REQUIRE(bn_shape_ok<float>(C), RSA_ERR_SHAPE, "bn_apply: C=%d unsupported", C);
     const int rpi = NT / (C / 4);
     int rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 8);
-    rows = (rows + rpi - 1) / rpi * rpi;
+    rows = (rows + 2 * rpi - 1) / (2 * rpi) * (2 * rpi);
     if (rows < 4 * rpi) rows = 4 * rpi;
-    bn_apply_kernel<float><<<(int)ceil_div64(M, rows), NT, 0, st>>>((const float*)x, M, C, ap, stats, count, eps, relu, rows);
+    const size_t sm = (size_t)nout * 2 * C * sizeof(float);
+    const int gr = (int)ceil_div64(M, rows);
+    switch (nout) {
+      case 1: bn_apply_kernel<float, 1><<<gr, NT, sm, st>>>((const float*)x, M, C, ap, stats, count, eps, relu, rows); break;
+      case 2: bn_apply_kernel<float, 2><<<gr, NT, sm, st>>>((const float*)x, M, C, ap, stats, count, eps, relu, rows); break;
+      case 3: bn_apply_kernel<float, 3><<<gr, NT, sm, st>>>((const float*)x, M, C, ap, stats, count, eps, relu, rows); break;
+      default: bn_apply_kernel<float, 4><<<gr, NT, sm, st>>>((const float*)x, M, C, ap, stats, count, eps, relu, rows); break;
+    }
   } else if (dtype == RSA_BF16) {
     RSA_REQUIRE(bn_shape_ok<bf16>(C), RSA_ERR_SHAPE, "bn_apply: C=%d unsupported", C);
     const int rpi = NT / (C / 8);
     int rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 8);
-    rows = (rows + rpi - 1) / rpi * rpi;
+    rows = (rows + 2 * rpi - 1) / (2 * rpi) * (2 * rpi);
     if (rows < 4 * rpi) rows = 4 * rpi;
-    bn_apply_kernel<bf16><<<(int)ceil_div64(M, rows), NT, 0, st>>>((const bf16*)x, M, C, ap, stats, count, eps, relu, rows);
+    const size_t sm = (size_t)nout * 2 * C * sizeof(float);
+    const int gr = (int)ceil_div64(M, rows);
+    switch (nout) {
+      case 1: bn_apply_kernel<bf16, 1><<<gr, NT, sm, st>>>((const bf16*)x, M, C, ap, stats, count, eps, relu, rows); break;
+      case 2: bn_apply_kernel<bf16, 2><<<gr, NT, sm, st>>>((const bf16*)x, M, C, ap, stats, count, eps, relu, rows); break;
+      case 3: bn_apply_kernel<bf16, 3><<<gr, NT, sm, st>>>((const bf16*)x, M, C, ap, stats, count, eps, relu, rows); break;
+      default: bn_apply_kernel<bf16, 4><<<gr, NT, sm, st>>>((const bf16*)x, M, C, ap, stats, count, eps, relu, rows); break;
+    }
   } else {
     RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_apply: bad dtype");
   }
@@ -534,12 +574,34 @@ int fill_multi(BwdMultiParams& bp, int k, const void* const* dys, const float* c
   }
   return RSA_OK;
 }
-inline void multi_grid(int64_t M, int C, int& rows, int& grid) {
-  const int rpi = NT / (C / VM);
-  rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 6);
+inline void multi_grid(int64_t M, int C, int V, int& rows, int& grid) {
+  const int rpi = NT / (C / V);
+  rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 8);
   rows = (rows + rpi - 1) / rpi * rpi;
   if (rows < rpi * 4) rows = rpi * 4;
   grid = (int)ceil_div64(M, rows);
+}
+inline size_t multi_smem(int C, int k, int V) {
+  size_t a = (size_t)(2 + 2 * k) * C * sizeof(float), b = (size_t)NT * 2 * V * sizeof(float);
+  return a > b ? a : b;
+}
+
+template <typename T, int K>
+void launch_reduce(const void* x, int64_t M, int C, const BwdMultiParams& bp, const double* stats, double count, float eps,
+                   int relu, cudaStream_t st) {
+  constexpr int V = MultiV<T, K>::V;
+  int rows, grid;
+  multi_grid(M, C, V, rows, grid);
+  bn_bwd_reduce_multi_kernel<T, K><<<grid, NT, multi_smem(C, K, V), st>>>((const T*)x, M, C, bp, stats, count, eps, relu, rows);
+}
+template <typename T, int K>
+void launch_apply(const void* x, int64_t M, int C, const BwdMultiParams& bp, const double* stats, double count, float eps,
+                  int relu, void* dx, int accumulate, cudaStream_t st) {
+  constexpr int V = MultiV<T, K>::V;
+  int rows, grid;
+  multi_grid(M, C, V, rows, grid);
+  bn_bwd_apply_multi_kernel<T, K><<<grid, NT, multi_smem(C, K, V), st>>>((const T*)x, M, C, bp, stats, count, eps, relu,
+                                                                       (T*)dx, accumulate, rows);
 }
 }  // namespace
 
@@ -552,13 +614,12 @@ extern "C" int rsa_bn_bwd_reduce_multi(const void* const* dys, const void* x, in
   BwdMultiParams bp;
   int rc = fill_multi(bp, k, dys, gammas, betas, reds, nullptr, nullptr);
   if (rc) return rc;
-  int rows, grid;
-  multi_grid(M, C, rows, grid);
-  const size_t smem = (size_t)NT * 2 * VM * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == RSA_F32) bn_bwd_reduce_multi_kernel<float><<<grid, NT, smem, st>>>((const float*)x, M, C, bp, stats, count, eps, relu, rows);
-  else if (dtype == RSA_BF16) bn_bwd_reduce_multi_kernel<bf16><<<grid, NT, smem, st>>>((const bf16*)x, M, C, bp, stats, count, eps, relu, rows);
-  else RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_bwd_reduce_multi: bad dtype");
+  RSA_REQUIRE(dtype == RSA_F32 || dtype == RSA_BF16, RSA_ERR_DTYPE, "bn_bwd_reduce_multi: bad dtype");
+#define RED_CASE(KK) case KK: if (dtype == RSA_F32) launch_reduce<float, KK>(x, M, C, bp, stats, count, eps, relu, st); \
+                              else launch_reduce<bf16, KK>(x, M, C, bp, stats, count, eps, relu, st); break;
+  switch (k) { RED_CASE(1) RED_CASE(2) RED_CASE(3) RED_CASE(4) }
+#undef RED_CASE
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
@@ -572,12 +633,12 @@ extern "C" int rsa_bn_bwd_apply_multi(const void* const* dys, const void* x, int
   BwdMultiParams bp;
   int rc = fill_multi(bp, k, dys, gammas, betas, reds, dgammas, dbetas);
   if (rc) return rc;
-  int rows, grid;
-  multi_grid(M, C, rows, grid);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == RSA_F32) bn_bwd_apply_multi_kernel<float><<<grid, NT, 0, st>>>((const float*)x, M, C, bp, stats, count, eps, relu, (float*)dx, accumulate, rows);
-  else if (dtype == RSA_BF16) bn_bwd_apply_multi_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)x, M, C, bp, stats, count, eps, relu, (bf16*)dx, accumulate, rows);
-  else RSA_REQUIRE(false, RSA_ERR_DTYPE, "bn_bwd_apply_multi: bad dtype");
+  RSA_REQUIRE(dtype == RSA_F32 || dtype == RSA_BF16, RSA_ERR_DTYPE, "bn_bwd_apply_multi: bad dtype");
+#define APP_CASE(KK) case KK: if (dtype == RSA_F32) launch_apply<float, KK>(x, M, C, bp, stats, count, eps, relu, dx, accumulate, st); \
+                              else launch_apply<bf16, KK>(x, M, C, bp, stats, count, eps, relu, dx, accumulate, st); break;
+  switch (k) { APP_CASE(1) APP_CASE(2) APP_CASE(3) APP_CASE(4) }
+#undef APP_CASE
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
