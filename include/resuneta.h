@@ -203,6 +203,16 @@ int rsa_bias_grad(const void* dy, int dtype, long long M, int C, float* db0, flo
 int rsa_pack_weights_tc(const float* params, void* shadow, const void* table, int nlayers, long long max_elems,
                         void* stream);
 
+/* ---- thin 1x1 convolutions: one side <= 16 channels, the other exactly 32 (thin.cu) --------------------------------
+ * Stem Conv2D(32,(1,1)) on the raw n-band input (model2.py:101): out[m,0:32] = x[m,0:n].w[n][32] + b, optional BatchNorm
+ * statistics of the output (double[64]); its weight/bias gradient; and the backward of a head's final 1x1 convolution
+ * (model2.py:159,168,180,186) from the fp32 logits gradient dz: dh (=|+=) mask(h>0)*dz.w^T, dw[32][n] += h^T dz, db += sum dz. */
+int rsa_stem_fwd(const void* x, int x_dtype, const float* w, const float* b, void* out, int out_dtype, int64_t M, int n,
+                 double* stats, void* stream);
+int rsa_stem_wgrad(const void* x, const void* dy, int dtype, int64_t M, int n, float* dw, float* db, void* stream);
+int rsa_head_bwd(const void* h, int h_dtype, const float* dz, const float* w, int64_t M, int n, void* dh, int accumulate,
+                 int relu_mask, float* dw, float* db, void* stream);
+
 /* dst (=|+=) src, identity branch of the ResBlock-a backward (Add, model2.py:31) */
 int rsa_axpy(void* dst, const void* src, int dtype, int64_t n, int accumulate, void* stream);
 

@@ -109,6 +109,11 @@ _SIGS = {
                      C.c_void_p],
     "rsa_argmax_confusion": [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                              C.c_void_p],
+    "rsa_stem_fwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
+                     C.c_void_p],
+    "rsa_stem_wgrad": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+    "rsa_head_bwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                     C.c_void_p, C.c_void_p, C.c_void_p],
     "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
     "rsa_conv_tc_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
@@ -358,6 +363,19 @@ class Lib:
     def pack_weights_tc(self, params, shadow, table, nlayers, max_elems):
         return self._bind("rsa_pack_weights_tc", _p(params), _p(shadow), _p(table), nlayers, max_elems,
                           keep=(params, shadow, table))
+
+    # -- thin 1x1 convolutions ---------------------------------------------------------------------
+    def stem_fwd(self, x, w, b, out, M, n, stats):
+        return self._bind("rsa_stem_fwd", _p(x), dtype_code(x), _p(w), _p(b), _p(out), dtype_code(out), M, n, _p(stats),
+                          keep=(x, w, b, out, stats))
+
+    def stem_wgrad(self, x, dy, M, n, dw, db):
+        return self._bind("rsa_stem_wgrad", _p(x), _p(dy), dtype_code(x), M, n, _p(dw), _p(db), keep=(x, dy, dw, db))
+
+    def head_bwd(self, h, dz, w, M, n, dh, accumulate, relu_mask, dw, db):
+        assert dz.dtype == torch.float32
+        return self._bind("rsa_head_bwd", _p(h), dtype_code(h), _p(dz), _p(w), M, n, _p(dh), int(accumulate),
+                          int(relu_mask), _p(dw), _p(db), keep=(h, dz, w, dh, dw, db))
 
     # -- optimizers / misc ----------------------------------------------------------------------
     def adam_step(self, param, grad, m, v, n, lr_dev, b1, b2, eps, grad_scale):

@@ -226,18 +226,38 @@ struct PackEntry { long long src_off, fwd_off, bwd_off; int taps, Cin, Cout, pad
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ params, bf16* __restrict__ shadow,
                                                            const PackEntry* __restrict__ table) {
+  // 32x32 tiles through shared memory: reads (HWIO, co contiguous) and both writes ([ci][co] copy and the
+  // transposed [co][ci] copy) are coalesced
+  __shared__ float tile[32][33];
   const PackEntry e = table[blockIdx.y];
-  const long long n = (long long)e.taps * e.Cin * e.Cout;
+  const int coutp = e.pad > 0 ? e.pad : e.Cout;
+  const int tci = (e.Cin + 31) / 32, tco = (e.Cout + 31) / 32;
+  const int ntiles = e.taps * tci * tco;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   const float* src = params + e.src_off;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    float v = src[i];                       // HWIO: i = (tap*Cin + ci)*Cout + co
-    int co = (int)(i % e.Cout);
-    long long t = i / e.Cout;
-    int ci = (int)(t % e.Cin);
-    int tap = (int)(t / e.Cin);
-    bf16 b = __float2bfloat16_rn(v);
-    shadow[e.bwd_off + i] = b;
-    shadow[e.fwd_off + ((long long)tap * (e.pad > 0 ? e.pad : e.Cout) + co) * e.Cin + ci] = b;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tap = t / (tci * tco);
+    const int r = t % (tci * tco);
+    const int ci0 = (r / tco) * 32, co0 = (r % tco) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ci = ci0 + ty + 8 * i, co = co0 + tx;
+      float v = 0.f;
+      if (ci < e.Cin && co < e.Cout) {
+        const long long idx = ((long long)tap * e.Cin + ci) * e.Cout + co;
+        v = src[idx];
+        shadow[e.bwd_off + idx] = __float2bfloat16_rn(v);
+      }
+      tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int co = co0 + ty + 8 * i, ci = ci0 + tx;
+      if (ci < e.Cin && co < e.Cout)
+        shadow[e.fwd_off + ((long long)tap * coutp + co) * e.Cin + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+    __syncthreads();
   }
 }
 
@@ -845,9 +865,9 @@ extern "C" int rsa_bias_grad(const void* dy, int dtype, long long M, int C, floa
 extern "C" int rsa_pack_weights_tc(const float* params, void* shadow, const void* table, int nlayers,
                                    long long max_elems, void* stream) {
   RSA_REQUIRE(params && shadow && table && nlayers > 0, RSA_ERR_SHAPE, "pack_weights_tc: bad args");
-  int gx = (int)ceil_div64(max_elems, 256 * 8);
+  int gx = (int)ceil_div64(max_elems, 1024 * 4);     // 32x32 tiles, a few per block for the largest layer
   if (gx < 1) gx = 1;
-  if (gx > 2048) gx = 2048;
+  if (gx > 1024) gx = 1024;
   pack_weights_kernel<<<dim3(gx, nlayers), 256, 0, (cudaStream_t)stream>>>(params, (bf16*)shadow,
                                                                           (const PackEntry*)table);
   RSA_CHECK_LAUNCH();

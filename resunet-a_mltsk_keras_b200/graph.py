@@ -271,6 +271,8 @@ class Plan:
         lib, N = self.lib, self.N
         W_ = self.P(name + "/kernel")
         b_ = self.P(name + "/bias")
+        if self._thin_stem(inputs, cout, name, out, stats, bias_grad, relu):
+            return out
         pw = self._pw_classify(inputs, cout, name, out)
         if pw is not None:
             self._conv1x1_tc(inputs, pw, cout, name, out, stats, bias_grad, relu)
@@ -293,6 +295,42 @@ class Plan:
         if self.training:
             self.tape.append(lambda: self._conv1x1_bwd(inputs, segs, out, name, cout, bias_grad))
         return out
+
+    def _thin_stem(self, inputs, cout, name, out, stats, bias_grad, relu):
+        """Stem Conv2D(32,(1,1)) on the raw (<= 16 band) input, model2.py:101: streaming thin kernel."""
+        if len(inputs) != 1 or relu or cout != 32:
+            return False
+        t, mode, relu_in = inputs[0]
+        if mode != "plain" or relu_in or t.C > 16 or t.dtype != out.dtype or not hasattr(self.lib, "stem_fwd"):
+            return False
+        lib, M, n = self.lib, out.M, t.C
+        W_, b_ = self.P(name + "/kernel"), self.P(name + "/bias")
+        st = out.stats
+        self.fwd.append(self._late(lambda: lib.stem_fwd(t.data, W_, b_, out.data, M, n, st[0] if st else None)))
+        if self.training:
+            def bwd():
+                if out.grad is None:
+                    return
+                assert not t.needs_grad, "the stem input carries no gradient"
+                self.bwd.append(lib.stem_wgrad(t.data, out.grad, M, n, self.G(name + "/kernel"),
+                                               self.G(name + "/bias") if bias_grad else None))
+                self._ready(name + "/kernel", name + "/bias")
+            self.tape.append(bwd)
+        return True
+
+    def _head_bwd(self, inputs, out, name, cout, bias_grad):
+        """Backward of a head's last 1x1 conv (32 -> n classes, fp32 logits): one fused streaming kernel."""
+        if len(inputs) != 1 or out.dtype != torch.float32 or cout > 16 or not hasattr(self.lib, "head_bwd"):
+            return False
+        t, mode, relu_in = inputs[0]
+        if mode != "plain" or relu_in or t.C != 32:
+            return False
+        g, acc = self.gacc(t) if t.needs_grad else (None, False)
+        self.bwd.append(self.lib.head_bwd(t.data, out.grad, self.P(name + "/kernel"), out.M, cout, g, acc,
+                                          t.relu_masked, self.G(name + "/kernel"),
+                                          self.G(name + "/bias") if bias_grad else None))
+        self._ready(name + "/kernel", name + "/bias")
+        return True
 
     # ---------------------------------------------------------------------------------------------
     # tensor-core path of the 1x1 convolutions (bf16 mode)
@@ -367,6 +405,8 @@ class Plan:
         def bwd():
             if out.grad is None:
                 return
+            if self._head_bwd(inputs, out, name, cout, bias_grad):
+                return
             dz = out.grad
             dW = self.G(name + "/kernel")
             W_ = self.P(name + "/kernel")
@@ -435,6 +475,8 @@ class Plan:
         lib, N = self.lib, self.N
         if out.grad is None:
             return   # nothing consumed this output
+        if self._head_bwd(inputs, out, name, cout, bias_grad):
+            return
         dy = out.grad
         W_ = self.P(name + "/kernel")
         dW = self.G(name + "/kernel")

@@ -361,6 +361,43 @@ class EmulLib:
                 cm.add_(torch.bincount(idx, minlength=K * K))
         return self._wrap(run, "rsa_argmax_confusion")
 
+    # -- thin 1x1 convolutions --------------------------------------------------------------------------
+    def stem_fwd(self, x, w, b, out, M, n, stats):
+        def run():
+            v = x.reshape(M, n).to(F64) @ w[:n * 32].reshape(n, 32).to(F64)
+            if b is not None:
+                v = v + b.to(F64)
+            _store(out, v)
+            if stats is not None:
+                vv = v.to(torch.float32).to(F64)
+                stats[:32] += vv.sum(0)
+                stats[32:64] += (vv * vv).sum(0)
+        return self._wrap(run, "rsa_stem_fwd")
+
+    def stem_wgrad(self, x, dy, M, n, dw, db):
+        def run():
+            g = dy.reshape(M, 32).to(F64)
+            dw[:n * 32] += (x.reshape(M, n).to(F64).T @ g).reshape(-1).to(torch.float32)
+            if db is not None:
+                db.add_(g.sum(0).to(torch.float32))
+        return self._wrap(run, "rsa_stem_wgrad")
+
+    def head_bwd(self, h, dz, w, M, n, dh, accumulate, relu_mask, dw, db):
+        def run():
+            hv = h.reshape(M, 32).to(F64)
+            z = dz.reshape(M, n).to(F64)
+            if dh is not None:
+                d = z @ w[:32 * n].reshape(32, n).to(F64).T
+                if relu_mask:
+                    d = d * (hv > 0)
+                if accumulate:
+                    d = d + dh.reshape(M, 32).to(F64)
+                _store(dh, d)
+            dw[:32 * n] += (hv.T @ z).reshape(-1).to(torch.float32)
+            if db is not None:
+                db.add_(z.sum(0).to(torch.float32))
+        return self._wrap(run, "rsa_head_bwd")
+
     # -- optim / misc -----------------------------------------------------------------------------------
     def adam_step(self, param, grad, m, v, n, lr_dev, b1, b2, eps, grad_scale):
         def run():

@@ -302,3 +302,30 @@ def test_bn_backward_multi_branch(lib, dt, C, k, relu):
     db = [torch.zeros(C) for _ in range(k)]
     run_pair(lib, "bn_bwd_apply_multi", [dys, x, M, C, stats, float(M), 1e-3, gam, bet, relu, reds, dx, True, dg, db], {},
              [11, 13, 14], TOL[dt] * 4, 1e-2)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n", [3, 14])
+def test_stem_thin_kernels(lib, dt, n):
+    M = 40000
+    x = rnd((M, n), dt, 1)
+    w = rnd((n * 32,), torch.float32, 2, 0.3)
+    b = rnd((32,), torch.float32, 3)
+    out = torch.zeros((M, 32), dtype=dt)
+    stats = torch.zeros(64, dtype=torch.float64)
+    run_pair(lib, "stem_fwd", [x, w, b, out, M, n, stats], {}, [3, 6], TOL[dt], 1e-2)
+    dy = rnd((M, 32), dt, 4)
+    dw, db = torch.zeros(n * 32), torch.zeros(32)
+    run_pair(lib, "stem_wgrad", [x, dy, M, n, dw, db], {}, [4, 5], 1e-4, 1e-3)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("n,acc,mask", [(6, False, True), (3, True, False), (6, True, True)])
+def test_head_bwd_thin_kernel(lib, dt, n, acc, mask):
+    M = 30000
+    h = rnd((M, 32), dt, 1)
+    dz = rnd((M, n), torch.float32, 2)
+    w = rnd((32 * n,), torch.float32, 3, 0.3)
+    dh = rnd((M, 32), dt, 4)
+    dw, db = torch.zeros(32 * n), torch.zeros(n)
+    run_pair(lib, "head_bwd", [h, dz, w, M, n, dh, acc, mask, dw, db], {}, [5, 8, 9], max(TOL[dt], 1e-4), 1e-3)
