@@ -28,14 +28,20 @@ __global__ void __launch_bounds__(NT) stem_fwd_kernel(const TX* __restrict__ x, 
   for (int j = 0; j < MAXN; ++j) wr[j] = j < n ? w[j * 32 + lane] : 0.f;
   const float bias = b ? b[lane] : 0.f;
   float s = 0.f, sq = 0.f;
-  for (int64_t p = warp; p < M; p += nwarps) {
-    const TX* xp = x + p * n;
-    float acc = bias;
+  for (int64_t p0 = warp; p0 < M; p0 += 4 * nwarps) {
 #pragma unroll
-    for (int j = 0; j < MAXN; ++j)
-      if (j < n) acc = fmaf(ldf<TX>(xp + j), wr[j], acc);
-    stf<TO>(out + p * 32 + lane, acc);
-    s += acc; sq += acc * acc;
+    for (int u = 0; u < 4; ++u) {
+      const int64_t p = p0 + u * nwarps;
+      if (p < M) {
+        const TX* xp = x + p * n;
+        float acc = bias;
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j)
+          if (j < n) acc = fmaf(ldf<TX>(xp + j), wr[j], acc);
+        stf<TO>(out + p * 32 + lane, acc);
+        s += acc; sq += acc * acc;
+      }
+    }
   }
   if (stats) {
     __shared__ float sh[2][NT];
@@ -59,19 +65,31 @@ __global__ void __launch_bounds__(NT) stem_wgrad_kernel(const TX* __restrict__ x
   float acc[MAXN], bs = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXN; ++j) acc[j] = 0.f;
-  for (int64_t p = warp; p < M; p += nwarps) {
-    const float g = ldf<TG>(dy + p * 32 + lane);
-    const TX* xp = x + p * n;
-    bs += g;
+  constexpr int U = 4;                       // pixels in flight per warp
+  for (int64_t p0 = warp; p0 < M; p0 += U * nwarps) {
+    float g[U];
 #pragma unroll
-    for (int j = 0; j < MAXN; ++j)
-      if (j < n) acc[j] = fmaf(ldf<TX>(xp + j), g, acc[j]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * nwarps;
+      g[u] = p < M ? ldf<TG>(dy + p * 32 + lane) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * nwarps;
+      if (p < M) {
+        const TX* xp = x + p * n;
+        bs += g[u];
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j)
+          if (j < n) acc[j] = fmaf(ldf<TX>(xp + j), g[u], acc[j]);
+      }
+    }
   }
   __shared__ float sh[NT / 32][32];
   for (int j = 0; j <= n; ++j) {           // j == n: bias gradient
     float v = bs;
 #pragma unroll
-    for (int t = 0; t < MAXN; ++t) if (t == j) v = acc[t];
+    for (int t = 0; t < MAXN; ++t) if (t == j && j < n) v = acc[t];
     __syncthreads();
     sh[threadIdx.x >> 5][lane] = v;
     __syncthreads();
@@ -97,22 +115,34 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(const TH* __restrict__ h, 
   float wr[MAXN], acc[MAXN], bsum[MAXN];
 #pragma unroll
   for (int j = 0; j < MAXN; ++j) { wr[j] = j < n ? w[lane * n + j] : 0.f; acc[j] = 0.f; bsum[j] = 0.f; }
-  for (int64_t p = warp; p < M; p += nwarps) {
-    const float hv = ldf<TH>(h + p * 32 + lane);
-    const float* zp = dz + p * n;
-    float d = 0.f;
+  constexpr int U = 4;                       // pixels in flight per warp
+  for (int64_t p0 = warp; p0 < M; p0 += U * nwarps) {
+    float hv[U], old[U];
 #pragma unroll
-    for (int j = 0; j < MAXN; ++j)
-      if (j < n) {
-        const float z = __ldg(zp + j);
-        d = fmaf(z, wr[j], d);
-        acc[j] = fmaf(hv, z, acc[j]);
-        bsum[j] += z;
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * nwarps;
+      hv[u] = p < M ? ldf<TH>(h + p * 32 + lane) : 0.f;
+      old[u] = (p < M && dh && accumulate) ? ldf<TH>(dh + p * 32 + lane) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * nwarps;
+      if (p < M) {
+        const float* zp = dz + p * n;
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j)
+          if (j < n) {
+            const float z = __ldg(zp + j);
+            d = fmaf(z, wr[j], d);
+            acc[j] = fmaf(hv[u], z, acc[j]);
+            bsum[j] += z;
+          }
+        if (dh) {
+          if (relu_mask && !(hv[u] > 0.f)) d = 0.f;
+          stf<TH>(dh + p * 32 + lane, d + old[u]);
+        }
       }
-    if (dh) {
-      if (relu_mask && !(hv > 0.f)) d = 0.f;
-      if (accumulate) d += ldf<TH>(dh + p * 32 + lane);
-      stf<TH>(dh + p * 32 + lane, d);
     }
   }
   __shared__ float sh[NT / 32][32];
