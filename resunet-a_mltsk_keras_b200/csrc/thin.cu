@@ -103,68 +103,84 @@ __global__ void __launch_bounds__(NT) stem_wgrad_kernel(const TX* __restrict__ x
 }
 
 // heads backward: h [M,32] (bf16/f32), dz [M,n] fp32, w [32][n] fp32
-//   dh[p][lane] (=|+=) (mask: h>0) * sum_j dz[p][j] * w[lane*n + j]
-//   dw[lane*n + j] += sum_p h[p][lane] * dz[p][j];   db[j] += sum_p dz[p][j]
+//   dh[p][c] (=|+=) (mask: h>0) * sum_j dz[p][j] * w[c*n + j]
+//   dw[c*n + j] += sum_p h[p][c] * dz[p][j];   db[j] += sum_p dz[p][j]
+// Tiles of 192 pixels are staged in shared memory with coalesced 16-byte loads; phase A gives every thread one
+// (pixel, 8-channel group) of dh (16-byte store), phase B gives every thread one entry of dw/db whose partial sum
+// lives in a register across all tiles of the block.
 template <typename TH>
 __global__ void __launch_bounds__(NT) head_bwd_kernel(const TH* __restrict__ h, const float* __restrict__ dz,
                                                       const float* __restrict__ w, int64_t M, int n, TH* __restrict__ dh,
                                                       int accumulate, int relu_mask, float* __restrict__ dw,
                                                       float* __restrict__ db) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * NT) >> 5;
-  float wr[MAXN], acc[MAXN], bsum[MAXN];
-#pragma unroll
-  for (int j = 0; j < MAXN; ++j) { wr[j] = j < n ? w[lane * n + j] : 0.f; acc[j] = 0.f; bsum[j] = 0.f; }
-  constexpr int U = 4;                       // pixels in flight per warp
-  for (int64_t p0 = warp; p0 < M; p0 += U * nwarps) {
-    float hv[U], old[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + u * nwarps;
-      hv[u] = p < M ? ldf<TH>(h + p * 32 + lane) : 0.f;
-      old[u] = (p < M && dh && accumulate) ? ldf<TH>(dh + p * 32 + lane) : 0.f;
+  constexpr int TP = 192;                 // 192 x (33 + 17) floats + weights = 40.5 KB of static smem
+  __shared__ float hs[TP][33];
+  __shared__ float zs[TP][MAXN + 1];
+  __shared__ float wt[MAXN][32];          // wt[j][c] = w[c*n + j]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 32 * n; i += NT) wt[i % n][i / n] = w[i];
+  // phase-B ownership: outputs o = j*32 + c for j < n (dw) and o = 32n + j (db)
+  const int nout = 32 * n + n;
+  float accB[3] = {0.f, 0.f, 0.f};        // up to 3 outputs per thread (nout <= 528)
+  const int64_t ntile = (M + TP - 1) / TP;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t p0 = tile * TP;
+    const int np = (int)(M - p0 < TP ? M - p0 : TP);
+    __syncthreads();
+    for (int e = tid; e < TP * 32; e += NT) {
+      const int pp = e >> 5, c = e & 31;
+      hs[pp][c] = pp < np ? ldf<TH>(h + (p0 + pp) * 32 + c) : 0.f;
     }
+    for (int e = tid; e < TP * n; e += NT) {
+      const int pp = e / n, j = e % n;
+      zs[pp][j] = pp < np ? dz[(p0 + pp) * n + j] : 0.f;
+    }
+    __syncthreads();
+    if (dh) {
+      // phase A: 4 threads per pixel, 8 channels each
+      for (int it = 0; it < TP / 64; ++it) {
+        const int pp = it * 64 + (tid >> 2), g = (tid & 3) * 8;
+        if (pp < np) {
+          float d[8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + u * nwarps;
-      if (p < M) {
-        const float* zp = dz + p * n;
-        float d = 0.f;
+          for (int i = 0; i < 8; ++i) d[i] = 0.f;
+          for (int j = 0; j < n; ++j) {
+            const float z = zs[pp][j];
 #pragma unroll
-        for (int j = 0; j < MAXN; ++j)
-          if (j < n) {
-            const float z = __ldg(zp + j);
-            d = fmaf(z, wr[j], d);
-            acc[j] = fmaf(hv[u], z, acc[j]);
-            bsum[j] += z;
+            for (int i = 0; i < 8; ++i) d[i] = fmaf(z, wt[j][g + i], d[i]);
           }
-        if (dh) {
-          if (relu_mask && !(hv[u] > 0.f)) d = 0.f;
-          stf<TH>(dh + p * 32 + lane, d + old[u]);
+          TH* dst = dh + (p0 + pp) * 32 + g;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (relu_mask && !(hs[pp][g + i] > 0.f)) d[i] = 0.f;
+            if (accumulate) d[i] += ldf<TH>(dst + i);
+            stf<TH>(dst + i, d[i]);
+          }
         }
       }
     }
-  }
-  __shared__ float sh[NT / 32][32];
-  __shared__ float shb[NT / 32];
-  for (int j = 0; j < n; ++j) {
-    float v = 0.f, bv = 0.f;
+    // phase B
 #pragma unroll
-    for (int t = 0; t < MAXN; ++t) if (t == j) { v = acc[t]; bv = bsum[t]; }
-    __syncthreads();
-    sh[threadIdx.x >> 5][lane] = v;
-    if (lane == 0) shb[threadIdx.x >> 5] = bv;     // all lanes of a warp saw the same dz values
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float a = 0.f;
-      for (int wv = 0; wv < NT / 32; ++wv) a += sh[wv][lane];
-      atomicAdd(dw + lane * n + j, a);
+    for (int k = 0; k < 3; ++k) {
+      const int o = tid + k * NT;
+      if (o < nout) {
+        float a = 0.f;
+        if (o < 32 * n) {
+          const int j = o >> 5, c = o & 31;
+          for (int pp = 0; pp < TP; ++pp) a = fmaf(hs[pp][c], zs[pp][j], a);
+        } else {
+          const int j = o - 32 * n;
+          for (int pp = 0; pp < TP; ++pp) a += zs[pp][j];
+        }
+        accB[k] += a;
+      }
     }
-    if (threadIdx.x == 32 && db) {
-      float a = 0.f;
-      for (int wv = 0; wv < NT / 32; ++wv) a += shb[wv];
-      atomicAdd(db + j, a);
-    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int o = tid + k * NT;
+    if (o < 32 * n) atomicAdd(dw + (o & 31) * n + (o >> 5), accB[k]);
+    else if (o < nout && db) atomicAdd(db + (o - 32 * n), accB[k]);
   }
 }
 
