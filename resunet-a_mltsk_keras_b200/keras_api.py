@@ -264,7 +264,7 @@ class Model:
         if st is None:
             st = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
             self._staging[(key, a.shape)] = st
-        st.numpy()[...] = a
+        st.copy_(torch.from_numpy(a))          # multi-threaded host copy into the pinned staging buffer
         dst.copy_(st, non_blocking=True)
         return a.nbytes
 
