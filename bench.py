@@ -236,7 +236,9 @@ def run_ours(args):
                                          f"{args.hw}x{args.hw}x3, {args.classes} classes, batch {args.batch}/GPU",
                                 global_batch=args.batch * world, parallelism=f"dp{world}",
                                 l2="working set per step (>8 GB of activations) is far larger than the 126 MB L2",
-                                cuda_graph=bool(model.use_cuda_graph and world == 1),
+                                cuda_graph=bool(model.use_cuda_graph),
+                                dp_mode=("graph fwd+bwd, one all-reduce, graph optimizer" if world > 1 and not strat.dp.overlap
+                                         else ("eager, bucketed all-reduce overlapped with backward" if world > 1 else None)),
                                 conv_engine=getattr(model.net, "conv_engine", "igemm_simt")),
                     e2e=dict(value=e2e, unit="patches/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=ops_per_step * args.steps, launches_per_step=ops_per_step,

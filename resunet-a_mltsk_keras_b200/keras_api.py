@@ -326,7 +326,7 @@ class Model:
         self._lr_dev.copy_(self._lr_host[slot:slot + 1], non_blocking=True)
 
     # -- the step itself ----------------------------------------------------------------------------------------
-    def _run_train_ops(self, pl, stream):
+    def _run_fwd_bwd(self, pl, stream):
         pl.scratch.zero_()
         self.net.params.grad.zero_()
         if self.net.pack_launch is not None:      # refresh the bf16 weight copies of the tensor-core path
@@ -335,11 +335,11 @@ class Model:
             op(stream)
         if pl.bn_update is not None:
             pl.bn_update(stream)
-        if self.dp is not None and self.dp.world_size > 1:
-            self.dp.run_backward(pl, stream)
-        else:
-            for op in pl.bwd:
-                op(stream)
+        for op in pl.bwd:
+            op(stream)
+
+    def _run_train_ops(self, pl, stream):
+        self._run_fwd_bwd(pl, stream)
         self._opt_launch(stream)
 
     def _run_eval_ops(self, pl, stream):
@@ -347,31 +347,54 @@ class Model:
         for op in pl.fwd:
             op(stream)
 
+    def _graph(self, key, fn):
+        """Capture `fn` (allocation-free pre-bound launches) once and replay it afterwards."""
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                fn(torch.cuda.current_stream().cuda_stream)
+            self._graphs[key] = g
+        g.replay()
+
     def _execute(self, pl, train):
         if train:
             self.net.shadow_dirty = True      # parameters change: bf16 copies are refreshed lazily for eval
         stream = self._stream()
-        run = self._run_train_ops if train else self._run_eval_ops
-        can_graph = (self.use_cuda_graph and self.net.device.type == "cuda"
-                     and not (train and self.dp is not None and self.dp.world_size > 1))
-        if not can_graph:
-            if not train:
-                self.net.ensure_shadow(stream)
-            run(pl, stream)
-            return
+        on_gpu = self.net.device.type == "cuda"
+        dp = train and self.dp is not None and self.dp.world_size > 1
         if not train:
             self.net.ensure_shadow(stream)
-        key = (id(pl), train)
-        g = self._graphs.get(key)
-        if g is None:
-            # one eager warm-up step is NOT possible for training (it would apply an update), so the
-            # graph is captured directly; all launches are pre-bound and allocation-free
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                run(pl, torch.cuda.current_stream().cuda_stream)
-            self._graphs[key] = g
-        g.replay()
+        if not (self.use_cuda_graph and on_gpu):
+            if dp and self.dp.overlap:
+                # eager launches: bucket all-reduces are issued as their gradients complete (distribute.py)
+                pl.scratch.zero_()
+                self.net.params.grad.zero_()
+                if self.net.pack_launch is not None:
+                    self.net.pack_launch(stream)
+                for op in pl.fwd:
+                    op(stream)
+                if pl.bn_update is not None:
+                    pl.bn_update(stream)
+                self.dp.run_backward(pl, stream)
+                self._opt_launch(stream)
+            elif dp:
+                self._run_fwd_bwd(pl, stream)
+                self.dp.all_reduce_sum_(self.net.params.grad)
+                self._opt_launch(stream)
+            else:
+                (self._run_train_ops if train else self._run_eval_ops)(pl, stream)
+            return
+        if not train:
+            self._graph((id(pl), "eval"), lambda s: self._run_eval_ops(pl, s))
+        elif dp:
+            # data parallel: replayed graph for fwd+bwd, one NCCL sum over the flat gradient buffer, replayed optimizer
+            self._graph((id(pl), "fwdbwd"), lambda s: self._run_fwd_bwd(pl, s))
+            self.dp.all_reduce_sum_(self.net.params.grad)
+            self._graph((id(pl), "opt"), lambda s: self._opt_launch(s))
+        else:
+            self._graph((id(pl), "train"), lambda s: self._run_train_ops(pl, s))
 
     def _collect(self, pl):
         """Device -> host read of the step results; returns the keras metrics list."""

@@ -14,7 +14,7 @@ N_CLS, HW = 4, 64
 LW = dict(seg=1.0, bound=0.5, dist=1.0, color=1.0)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     from resuneta_b200.builder import build_model
     from resuneta_b200.distribute import MirroredStrategy
     _capi.set_lib(EmulLib())
-    strat = MirroredStrategy(backend="gloo", n_buckets=5)
+    strat = MirroredStrategy(backend="gloo", n_buckets=5, overlap=overlap)
     assert strat.num_replicas_in_sync == world
     with strat.scope():
         # different seeds per rank: compile() must broadcast rank 0's parameters
@@ -53,12 +53,13 @@ def _free_port():
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_data_parallel_step_matches_oracle_average():
+@pytest.mark.parametrize("overlap", [True, False])
+def test_two_rank_data_parallel_step_matches_oracle_average(overlap):
     from oracle import resuneta_oracle as O
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=500) for _ in procs], key=lambda t: t[0])

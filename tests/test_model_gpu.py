@@ -200,3 +200,59 @@ def test_single_task_256_forward_config1_shape():
     ref = O.forward(p, torch.from_numpy(x), False, 6, False, "v2").numpy()
     assert out.shape == (1, 256, 256, 6)
     assert rel_l2(out, ref) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_amazon_shape_config3_train_step(dtype, tol):
+    """BASELINE config 3: 128x128, 14 bands (two dates x 7), 3 classes, weighted CE [tot/n0, tot/n1, 0] on seg,
+    BCE on bound, MSE on dist/color (amazon_py/main_tcc.py:82-84,190; train_ISPRS.py:426-428); PSP levels {1,2,4}."""
+    n, hw, cin = 3, 128, 14
+    p = rand_params("v2", hw, cin, n, seed=9)
+    m = build_model((hw, hw, cin), n, True, "v2", dtype=dtype)
+    m.net.set_weights(p)
+    w = [1.1, 9.0, 0.0]
+    m.compile(optimizer=SGD(lr=1e-2, momentum=0.8),
+              loss=dict(seg=weighted_categorical_crossentropy(w), bound=BinaryCrossentropy(), dist=MeanSquaredError(),
+                        color=MeanSquaredError()), loss_weights=LW)
+    rng = np.random.RandomState(0)
+    x = rng.randn(4, hw, hw, cin).astype(np.float32)
+    _, y = O.synth_batch(4, hw, 3, n, seed=4, block=16)
+    res = m.train_on_batch(x, y)
+    theirs = dict(seg=O.weighted_categorical_crossentropy(w), bound=O.binary_crossentropy, dist=O.mean_squared_error,
+                  color=O.mean_squared_error)
+    p64 = {k: v.double() for k, v in p.items()}
+    y64 = {k: torch.from_numpy(v).double() for k, v in y.items()}
+    tot, per, out, grads, _ = O.loss_and_grads(p64, torch.from_numpy(x).double(), y64, theirs, LW, n, True, "v2", True)
+    assert abs(res[0] - tot.item()) <= tol * abs(tot.item())
+    for a, b in zip(res[1:5], per):
+        assert abs(a - b.item()) <= tol * max(abs(b.item()), 1e-2)
+    if dtype == "fp32":
+        gmax = max(g.norm().item() for g in grads.values())
+        for k, g in grads.items():
+            err = (m.net.params.gview(k).double().cpu() - g).norm().item()
+            assert err <= 1e-2 * g.norm().item() + 2e-5 * gmax, (k, err, g.norm().item())
+
+
+def test_scene_inference_config5_reduced():
+    """Config 5 at reduced size: a 600x800 scene -> 2x3 patches of 256 (88/32-pixel border dropped), batches of 4 + 2,
+    argmax + confusion on the device vs numpy/sklearn on the same probabilities (bit-exact), reconstruction."""
+    from sklearn.metrics import confusion_matrix
+    n = 6
+    m = build_model((256, 256, 3), n, True, "v2", dtype="bf16", seed=11)
+    rng = np.random.RandomState(7)
+    scene = rng.rand(600, 800, 3).astype(np.float32)
+    ref = rng.randint(0, n, size=(600, 800))
+    r = inference.predict_scene(m, scene, ref, patch_size=256, batch_size=4, num_classes=n)
+    patches = inference.extract_patches(scene, 256)
+    assert patches.shape == (6, 256, 256, 3) and r["seg_pred"].shape == (6, 256, 256)
+    prob = m.predict(patches, batch_size=4)["seg"]
+    pr = prob.argmax(-1)
+    np.testing.assert_array_equal(r["seg_pred"], pr)
+    tl = inference.extract_patches(ref, 256)
+    np.testing.assert_array_equal(r["confusion"], confusion_matrix(tl.ravel(), pr.ravel()))
+    assert r["confusion"].sum() == 6 * 256 * 256
+    assert r["reconstructed"].shape == (600, 800) and (r["reconstructed"][512:] == 0).all() and (r["reconstructed"][:, 768:] == 0).all()
+    np.testing.assert_array_equal(r["reconstructed"][:512, :768], O.pred_reconstruction(256, pr, (512, 768)))
+    acc, f1, rec, prec = r["metrics"]
+    a2, f2, r2, p2 = O.metrics_from_confusion(r["confusion"])
+    assert acc == a2 and np.array_equal(f1, f2)
