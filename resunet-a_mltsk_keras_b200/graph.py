@@ -1028,6 +1028,7 @@ class Net:
         if key not in self.plans:
             pl = Plan(self, N, training, with_loss=loss_spec is not None)
             define_network(pl)
+            pl.n_fwd_net = len(pl.fwd)      # forward launches before this index need only x (labels may still be in flight)
             if loss_spec is not None:
                 for head, kind, weight, cw in loss_spec:
                     pl.attach_loss(head, pl.outputs[head], kind, weight, cw)

@@ -269,6 +269,9 @@ class Model:
         return a.nbytes
 
     def _load_inputs(self, pl, x, y):
+        return self._load_x(pl, x) + self._load_labels(pl, y)
+
+    def _load_x(self, pl, x):
         nb = 0
         if pl.input.dtype == torch.float32:
             nb += self._stage("x", x, pl.input.data)
@@ -279,6 +282,10 @@ class Model:
                 pl._x_cast = self.net.lib.cast(xf, pl.input.data, xf.numel())
             nb += self._stage("x", x, xf)
             pl._x_cast(self._stream())
+        return nb
+
+    def _load_labels(self, pl, y):
+        nb = 0
         if y is not None:
             if not isinstance(y, dict):
                 y = {self.output_names[0]: y}
@@ -396,6 +403,47 @@ class Model:
         else:
             self._graph((id(pl), "train"), lambda s: self._run_train_ops(pl, s))
 
+    def _train_step_overlapped(self, pl, x, y):
+        """Graph-replayed training step whose label upload hides behind the forward pass: the network part of the
+        forward only needs x, so the (much larger) one-hot label tensors are staged and copied on a second stream
+        while the GPU already runs, and the loss/backward/optimizer graph waits for that copy's event."""
+        self.net.shadow_dirty = True
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        nb = self._load_x(pl, x)
+        self._push_lr()
+        k = pl.n_fwd_net
+
+        def part_a(st):
+            pl.scratch.zero_()
+            self.net.params.grad.zero_()
+            if self.net.pack_launch is not None:
+                self.net.pack_launch(st)
+            for op in pl.fwd[:k]:
+                op(st)
+
+        def part_b(st):
+            for op in pl.fwd[k:]:
+                op(st)
+            if pl.bn_update is not None:
+                pl.bn_update(st)
+            for op in pl.bwd:
+                op(st)
+
+        self._graph((id(pl), "A"), part_a)
+        with torch.cuda.stream(self._copy_stream):
+            nb += self._load_labels(pl, y)
+            ev = self._copy_stream.record_event()
+        main.wait_event(ev)
+        if self.dp is not None and self.dp.world_size > 1:
+            self._graph((id(pl), "B"), part_b)
+            self.dp.all_reduce_sum_(self.net.params.grad)
+            self._graph((id(pl), "opt"), lambda st: self._opt_launch(st))
+        else:
+            self._graph((id(pl), "B+opt"), lambda st: (part_b(st), self._opt_launch(st)))
+        return nb
+
     def _collect(self, pl):
         """Device -> host read of the step results; returns the keras metrics list."""
         if self.net.device.type == "cuda":
@@ -423,9 +471,12 @@ class Model:
         self._ensure_opt()
         N = int(np.shape(x)[0])
         pl = self.net.plan(N, True, self.loss_spec)
-        self.last_h2d_bytes = self._load_inputs(pl, x, y)
-        self._push_lr()
-        self._execute(pl, True)
+        if self.use_cuda_graph and self.net.device.type == "cuda" and not (self.dp is not None and self.dp.overlap):
+            self.last_h2d_bytes = self._train_step_overlapped(pl, x, y)
+        else:
+            self.last_h2d_bytes = self._load_inputs(pl, x, y)
+            self._push_lr()
+            self._execute(pl, True)
         res = self._collect(pl)
         self.last_d2h_bytes = 8 * 4 + 16 * 8
         if return_dict:
