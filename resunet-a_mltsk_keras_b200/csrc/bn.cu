@@ -319,20 +319,32 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_multi_kernel(const T* __rest
   }
   const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
   const int64_t rend = min(M, rbeg + rows_per_block);
-  for (int64_t r = rbeg + r0; r < rend; r += rpi) {
-    const int64_t o = r * C + cg * V;
-    float xv[V], g[K][V];
-    ldm<T, V>(x + o, xv);
+  constexpr int U = K <= 2 ? 2 : 1;            // rows in flight per thread (register budget)
+  for (int64_t r = rbeg + r0; r < rend; r += U * rpi) {
+    float xv[U][V], g[U][K][V];
 #pragma unroll
-    for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[b]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rpi;
+      if (rr < rend) {
+        const int64_t o = rr * C + cg * V;
+        ldm<T, V>(x + o, xv[u]);
 #pragma unroll
-    for (int b = 0; b < K; ++b)
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[b][i] : 0.f;
-        s[b][i] += gg;
-        q[b][i] = fmaf(gg, (xv[i] - mean[i]) * inv[i], q[b][i]);
+        for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[u][b]);
       }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u * rpi < rend) {
+#pragma unroll
+        for (int b = 0; b < K; ++b)
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float gg = (!relu || fmaf(xv[u][i], sc[b][i], sh[b][i]) > 0.f) ? g[u][b][i] : 0.f;
+            s[b][i] += gg;
+            q[b][i] = fmaf(gg, (xv[u][i] - mean[i]) * inv[i], q[b][i]);
+          }
+      }
+    }
   }
 #pragma unroll
   for (int b = 0; b < K; ++b) {
@@ -384,26 +396,39 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_multi_kernel(const T* __restr
   }
   const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
   const int64_t rend = min(M, rbeg + rows_per_block);
-  for (int64_t r = rbeg + r0; r < rend; r += rpi) {
-    const int64_t o = r * C + cg * V;
-    float xv[V], acc[V], g[K][V];
-    ldm<T, V>(x + o, xv);
+  constexpr int U = K <= 2 ? 2 : 1;
+  for (int64_t r = rbeg + r0; r < rend; r += U * rpi) {
+    float xv[U][V], acc[U][V], g[U][K][V];
 #pragma unroll
-    for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[b]);
-    if (accumulate) ldm<T, V>(dx + o, acc);
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rpi;
+      if (rr < rend) {
+        const int64_t o = rr * C + cg * V;
+        ldm<T, V>(x + o, xv[u]);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float base = -Bsum[i] - (xv[i] - mean[i]) * inv[i] * Dsum[i];
-      acc[i] = accumulate ? acc[i] + base : base;
+        for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[u][b]);
+        if (accumulate) ldm<T, V>(dx + o, acc[u]);
+      }
     }
 #pragma unroll
-    for (int b = 0; b < K; ++b)
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rpi;
+      if (rr < rend) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[b][i] : 0.f;
-        acc[i] = fmaf(sc[b][i], gg, acc[i]);
+        for (int i = 0; i < V; ++i) {
+          const float base = -Bsum[i] - (xv[u][i] - mean[i]) * inv[i] * Dsum[i];
+          acc[u][i] = accumulate ? acc[u][i] + base : base;
+        }
+#pragma unroll
+        for (int b = 0; b < K; ++b)
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float gg = (!relu || fmaf(xv[u][i], sc[b][i], sh[b][i]) > 0.f) ? g[u][b][i] : 0.f;
+            acc[u][i] = fmaf(sc[b][i], gg, acc[u][i]);
+          }
+        stm<T, V>(dx + rr * C + cg * V, acc[u]);
       }
-    stm<T, V>(dx + o, acc);
+    }
   }
 }
 

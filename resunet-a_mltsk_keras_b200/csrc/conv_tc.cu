@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const __grid_constan
   const int cob = blockIdx.y % p.ncob, cib = blockIdx.y / p.ncob;
   const int t_begin = blockIdx.x * p.tiles_per_cta;
   const int t_end = min(p.ntiles, t_begin + p.tiles_per_cta);
-  const int real_atoms = (p.Cin >= 128 ? 128 : p.Cin) / KA;      // 1 or 2 (Cin >= 128 -> KA = 64)
+  const int real_atoms = p.Cin >= 128 ? 2 : 1;                   // Cin >= 128 -> two 64-channel atoms, else one
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
@@ -756,7 +756,7 @@ extern "C" int rsa_pw_wgrad_tc(const void* x, const void* dz, float* dw, int ldw
                                int Cout, int in_stride, void* stream) {
   RSA_REQUIRE(x && dz && dw, RSA_ERR_SHAPE, "pw_wgrad_tc: null pointer");
   auto p2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
-  RSA_REQUIRE(H == W && p2(W) && W >= 4 && p2(Cin) && Cin >= 16 && Cin <= 1024 && p2(Cout) && Cout >= 16 && Cout <= 1024 &&
+  RSA_REQUIRE(p2(H) && p2(W) && W >= 4 && H >= 4 && p2(Cin) && Cin >= 8 && Cin <= 1024 && p2(Cout) && Cout >= 8 && Cout <= 1024 &&
                   (in_stride == 1 || in_stride == 2), RSA_ERR_SHAPE,
               "pw_wgrad_tc: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d stride=%d", N, H, W, Cin, Cout, in_stride);
   EncodeTiledFn enc = get_encode();
@@ -768,10 +768,11 @@ extern "C" int rsa_pw_wgrad_tc(const void* x, const void* dz, float* dw, int ldw
   p.TN = 64 / (p.TW * p.TH);
   p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
   p.ntiles = p.tiles_w * p.tiles_h * ((N + p.TN - 1) / p.TN);
-  const int KA = Cin >= 64 ? 64 : Cin;
-  const int NB = Cout >= 128 ? 128 : Cout;
+  // 8-channel tensors: a 16-channel TMA box whose upper half is out of bounds (zero filled)
+  const int KA = Cin >= 64 ? 64 : (Cin < 16 ? 16 : Cin);
+  const int NB = Cout >= 128 ? 128 : (Cout < 16 ? 16 : Cout);
   const int KB = NB >= 64 ? 64 : NB;
-  p.ncob = Cout / NB; p.ncib = Cin >= 128 ? Cin / 128 : 1;
+  p.ncob = (Cout + NB - 1) / NB; p.ncib = Cin >= 128 ? Cin / 128 : 1;
   const int ygroups = p.ncob * p.ncib;
   int want = (2 * rsa_num_sms() + ygroups - 1) / ygroups;
   int maxsplit = (p.ntiles + 3) / 4;

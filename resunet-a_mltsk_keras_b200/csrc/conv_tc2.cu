@@ -229,8 +229,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < 32; j += 8) stv<bf16>(reinterpret_cast<bf16*>(p.out) + o + j, f + j);
             }
+          } else if (!p.out_f32 && (nval & 7) == 0 && p.nup == 0 && !p.residual && !p.accumulate && !p.mask) {
+            // 8 / 16 / 24 valid channels (PSP branch and decoder up-convolutions): 16-byte stores
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < nval) {
+                if (p.relu) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[j + i] = fmaxf(f[j + i], 0.f);
+                }
+                stv<bf16>(reinterpret_cast<bf16*>(p.out) + o + j, f + j);
+              }
+            }
           } else {
-            // partial chunk (padded N: heads with 6/3 classes, 8/16-channel PSP / decoder convs): scalar path
+            // partial chunk (padded N: heads with 6/3 classes ...): scalar path
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < nval) {
@@ -318,10 +330,12 @@ bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace
 
-/* Shapes the persistent tensor-core convolution accepts: every source channel count a multiple of 16
- * (K chunk = 64 if all are multiples of 64, else 32, else 16), square power-of-two output side >= 4. */
+/* Shapes the persistent tensor-core convolution accepts: every source channel count a multiple of 16 (or exactly 8
+ * for a single source; K chunk = 64 if all are multiples of 64, else 32, else 16), power-of-two output sides >= 4. */
 extern "C" int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int Cout) {
-  if (H != W || !pow2(W) || W < 4 || N < 1) return 0;
+  if (!pow2(H) || !pow2(W) || W < 4 || H < 4 || N < 1) return 0;
+  // 8-channel tensors ride on TMA's zero fill of the out-of-bounds half of a 16-channel box (single source only)
+  if (C0 == 8 && C1 == 0) return Cout >= 1;
   if (C0 < 16 || C0 % 16 || (C1 && C1 % 16) || Cout < 1) return 0;
   return 1;
 }
@@ -356,7 +370,7 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   const int KC = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : ((C0 % 32 == 0 && C1 % 32 == 0) ? 32 : 16);
   ConvTc2Params p;
   p.N = N; p.H = H; p.W = W; p.Cout = Cout;
-  p.nsrc = x1 ? 2 : 1; p.kch0 = C0 / KC; p.kch1 = C1 / KC;
+  p.nsrc = x1 ? 2 : 1; p.kch0 = (C0 + KC - 1) / KC; p.kch1 = C1 / KC;
   p.taps = taps; p.dil = dil; p.in_stride = in_stride;
   p.k_base = k_base; p.out_stride = out_stride;
   p.TW = W < 16 ? W : 16;
@@ -400,8 +414,9 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   }
   {
     const int Kt = k_total > 0 ? k_total : C0 + C1;
-    cuuint64_t gdim[3] = {(cuuint64_t)Kt, (cuuint64_t)CoutP, (cuuint64_t)taps};
-    cuuint64_t gstr[2] = {(cuuint64_t)Kt * 2, (cuuint64_t)CoutP * Kt * 2};
+    // rows beyond the true Cout (padding of the N tile) are out of bounds for TMA and arrive as zeros
+    cuuint64_t gdim[3] = {(cuuint64_t)Kt, (cuuint64_t)Cout, (cuuint64_t)taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)Kt * 2, (cuuint64_t)(taps == 1 ? Cout : CoutP) * Kt * 2};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
     cuuint32_t es[3] = {1, 1, 1};
     r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wt), gdim, gstr, box, es,

@@ -372,7 +372,7 @@ class Plan:
         """q = W[koff:koff+C] . src at the source's own resolution (no bias)."""
         lib, N = self.lib, self.N
         ent = self.net.tc[name]
-        if src.C % 16 == 0 and self._tc_spatial_ok(Hq, Wq):
+        if (src.C % 16 == 0 or src.C == 8) and self._tc_spatial_ok(Hq, Wq):
             wt = self.net.shadow[ent["fwd"]:ent["fwd"] + ent["coutp"] * K]
             return lib.conv_tc2_fwd(src.data, None, wt, ent["coutp"], None, out, N, Hq, Wq, cout, k_base=koff, k_total=K)
         W_ = self.P(name + "/kernel")
@@ -412,7 +412,7 @@ class Plan:
             W_ = self.P(name + "/kernel")
             wb = self.net.shadow[ent["bwd"]:ent["bwd"] + K * cout]
             bf = dz.dtype == torch.bfloat16
-            p2 = lambda v: v >= 16 and (v & (v - 1)) == 0
+            p2 = lambda v: v >= 8 and (v & (v - 1)) == 0
             db_simt = [None]
             if bias_grad:
                 if cout % 8 == 0 and bf:
@@ -434,11 +434,12 @@ class Plan:
                     return
                 g, acc = self.gacc(t)
                 mask = t.data if t.relu_masked else None
-                if bf and cout % 16 == 0 and t.C % 16 == 0 and sp_ok:
+                ok8 = lambda v: v == 8 or v % 16 == 0
+                if bf and ok8(cout) and ok8(t.C) and sp_ok:
                     wsl = wb[koff * cout:(koff + t.C) * cout]
                     if in_stride == 2 and not acc:
                         self.bwd.append(lambda s_, g=g: g.zero_())      # odd pixels receive no gradient
-                    self.bwd.append(lib.conv_tc2_fwd(dq, None, wsl, t.C, None, g, N, Hq, Wq, t.C, mask=mask,
+                    self.bwd.append(lib.conv_tc2_fwd(dq, None, wsl, max(t.C, 16), None, g, N, Hq, Wq, t.C, mask=mask,
                                                      accumulate=acc or in_stride == 2, out_stride=in_stride))
                 else:
                     if in_stride == 2:

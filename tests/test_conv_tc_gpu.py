@@ -172,7 +172,9 @@ def test_conv_tc2_3x3_matches_emulation(lib, N, H, C, Co, d):
     (2, 32, 16, 0, 32, 1, (), False),             # K = 16 source (SWIZZLE_32B)
     (3, 8, 1024, 0, 256, 1, (), False),           # PSP mid branch
     (2, 16, 256, 512, 512, 1, (), False),         # wide two-source concat
-    (2, 32, 32, 0, 8, 1, (), False)])             # PSP out branch: 8 channels, partial-chunk stores
+    (2, 32, 32, 0, 8, 1, (), False),              # PSP out branch: 8 output channels
+    (2, 32, 8, 0, 32, 1, (), False),              # 8-channel source: 16-wide TMA box, upper half zero-filled
+    (2, 64, 8, 0, 32, 1, (), False)])
 def test_conv_tc2_pointwise_modes(lib, N, H, C0, C1, Co, stride, ups, f32):
     dt = torch.bfloat16
     Hs = H * stride
@@ -206,7 +208,8 @@ def test_conv_tc2_pointwise_modes(lib, N, H, C0, C1, Co, stride, ups, f32):
 
 @pytest.mark.parametrize("N,H,Cin,Cout,stride", [(2, 64, 32, 32, 1), (2, 32, 32, 64, 2), (2, 32, 16, 32, 1), (2, 32, 64, 16, 1),
                                                   (3, 16, 256, 512, 1), (2, 8, 1024, 256, 1), (16, 4, 512, 1024, 2),
-                                                  (4, 64, 64, 128, 1), (2, 64, 128, 32, 1)])
+                                                  (4, 64, 64, 128, 1), (2, 64, 128, 32, 1), (2, 64, 32, 8, 1), (2, 64, 8, 32, 1),
+                                                  (2, 32, 8, 8, 1)])
 def test_pw_wgrad_tc(lib, N, H, Cin, Cout, stride):
     dt = torch.bfloat16
     Hs = H * stride
