@@ -96,6 +96,8 @@ int rsa_bn_bwd_apply_multi(const void* const* dys, const void* x, int dtype, int
                            const double* stats, double count, float eps, const float* const* gammas,
                            const float* const* betas, int relu, double* const* reds, void* dx, int accumulate,
                            float* const* dgammas, float* const* dbetas, void* stream);
+/* out[2C] = {mean, invstd} in fp32 from the {sum, sumsq} statistics. */
+int rsa_bn_meaninv(const double* stats, double count, float eps, float* out, int C, void* stream);
 /* statistics of y = gamma*xhat+beta derived analytically from the statistics of x */
 int rsa_bn_derive_stats(const double* src_stats, double count, const float* gamma, const float* beta,
                         float eps, double* dst_stats, double dst_count, int C, void* stream);
@@ -177,13 +179,15 @@ int rsa_conv_tc_fwd(const void* x, const void* wt, const float* bias, void* out,
  * Conv2D strides=2 (model2.py:103-111); q_u bf16 [N, H>>shift, W>>shift, Cout] are low-resolution addends that are
  * nearest-up-sampled in the epilogue (UpSampling2D, model2.py:55-60,91); out bf16 or fp32.  The sources use columns
  * [k_base, k_base+C0+C1) of wt's K dimension of length k_total (0 = C0+C1); out_stride 2 scatters the result to the even
- * pixels of a (2H,2W) tensor (data gradient of the stride-2 convolutions). */
+ * pixels of a (2H,2W) tensor (data gradient of the stride-2 convolutions).  bnr_x / bnr_coef select the fused
+ * BatchNormalization-backward reduction epilogue: `stats` += {sum g, sum g*xhat}, xhat = (bnr_x - mean)*invstd with
+ * bnr_coef = rsa_bn_meaninv()'s [2][Cout] table (FusedBatchNormGrad's reductions, model2.py:17,21). */
 int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int Cout);
 int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void* wt, int CoutP, const float* bias,
                      void* out, int out_f32, const void* residual, const void* mask, double* stats, int N, int H,
                      int W, int Cout, int taps, int dil, int in_stride, int nup, const void* const* up_ptrs,
-                     const int* up_shifts, int k_base, int k_total, int out_stride, int accumulate, int relu,
-                     void* stream);
+                     const int* up_shifts, int k_base, int k_total, int out_stride, const void* bnr_x,
+                     const float* bnr_coef, int accumulate, int relu, void* stream);
 /* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co];
  * x, dy bf16 NHWC, Cin == Cout.  Replaces cuDNN's Conv2D backward-filter behind model2.py:19-24,153-178. */
 int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int dil,

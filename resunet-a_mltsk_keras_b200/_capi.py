@@ -81,6 +81,7 @@ _SIGS = {
                                C.c_double, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
                                C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
                                C.POINTER(C.c_void_p), C.c_void_p],
+    "rsa_bn_meaninv": [C.c_void_p, C.c_double, C.c_float, C.c_void_p, C.c_int, C.c_void_p],
     "rsa_bn_derive_stats": [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_double,
                             C.c_int, C.c_void_p],
     "rsa_bn_update_moving": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p],
@@ -119,8 +120,8 @@ _SIGS = {
                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc2_fwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                         C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
-                         C.c_int, C.c_void_p],
+                         C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                         C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_void_p],
     "rsa_pw_wgrad_tc": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -253,6 +254,9 @@ class Lib:
                           int(relu), self._ptr_array(reds), _p(dx), int(accumulate), self._ptr_array(dgammas),
                           self._ptr_array(dbetas), keep=(dys, x, stats, gammas, betas, reds, dx, dgammas, dbetas))
 
+    def bn_meaninv(self, stats, count, eps, out, C_):
+        return self._bind("rsa_bn_meaninv", _p(stats), float(count), float(eps), _p(out), C_, keep=(stats, out))
+
     def bn_derive_stats(self, src_stats, count, gamma, beta, eps, dst_stats, dst_count, C_):
         return self._bind("rsa_bn_derive_stats", _p(src_stats), float(count), _p(gamma), _p(beta), float(eps),
                           _p(dst_stats), float(dst_count), C_, keep=(src_stats, gamma, beta, dst_stats))
@@ -329,7 +333,7 @@ class Lib:
 
     def conv_tc2_fwd(self, x0, x1, wt, CoutP, bias, out, N, H, W, Cout, taps=1, dil=1, in_stride=1, ups=(),
                      residual=None, mask=None, stats=None, accumulate=False, relu=False, k_base=0, k_total=0,
-                     out_stride=1):
+                     out_stride=1, bnr_x=None, bnr_coef=None):
         """ups: sequence of (q tensor, shift).  x1 may be None.  out bf16 or fp32."""
         assert x0.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16
         C0 = x0.shape[-1]
@@ -343,8 +347,9 @@ class Lib:
             up_sh[i] = sft
         return self._bind("rsa_conv_tc2_fwd", _p(x0), C0, _p(x1), C1, _p(wt), CoutP, _p(bias), _p(out),
                           int(out.dtype == torch.float32), _p(residual), _p(mask), _p(stats), N, H, W, Cout, taps, dil,
-                          in_stride, nup, up_ptrs, up_sh, k_base, k_total, out_stride, int(accumulate), int(relu),
-                          keep=(x0, x1, wt, bias, out, residual, mask, stats, ups, up_ptrs, up_sh))
+                          in_stride, nup, up_ptrs, up_sh, k_base, k_total, out_stride, _p(bnr_x), _p(bnr_coef),
+                          int(accumulate), int(relu),
+                          keep=(x0, x1, wt, bias, out, residual, mask, stats, ups, up_ptrs, up_sh, bnr_x, bnr_coef))
 
     def conv_tc_wgrad(self, x, dy, dw, N, H, W, Cin, Cout, dil):
         assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32

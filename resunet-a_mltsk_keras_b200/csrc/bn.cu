@@ -212,6 +212,15 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_kernel(const T* __restrict__ 
   }
 }
 
+__global__ void bn_meaninv_kernel(const double* __restrict__ stats, double count, float eps, float* __restrict__ out, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, inv;
+  bn_mean_invstd(stats, count, C, c, eps, nullptr, nullptr, mean, inv);
+  out[c] = mean;
+  out[C + c] = inv;
+}
+
 __global__ void bn_derive_stats_kernel(const double* __restrict__ src, double count, const float* gamma,
                                        const float* beta, float eps, double* __restrict__ dst, double dcount,
                                        int C) {
@@ -664,6 +673,15 @@ extern "C" int rsa_bn_bwd_apply_multi(const void* const* dys, const void* x, int
                               else launch_apply<bf16, KK>(x, M, C, bp, stats, count, eps, relu, dx, accumulate, st); break;
   switch (k) { APP_CASE(1) APP_CASE(2) APP_CASE(3) APP_CASE(4) }
 #undef APP_CASE
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+/* out[2C] = {mean, invstd} (fp32) of a BatchNormalization from its {sum, sumsq} statistics — the coefficient table
+ * the fused BatchNorm-backward epilogue of rsa_conv_tc2_fwd reads. */
+extern "C" int rsa_bn_meaninv(const double* stats, double count, float eps, float* out, int C, void* stream) {
+  RSA_REQUIRE(stats && out && C > 0, RSA_ERR_SHAPE, "bn_meaninv: bad args");
+  bn_meaninv_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, count, eps, out, C);
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }

@@ -36,6 +36,8 @@ struct ConvTc2Params {
   const bf16* residual;
   const bf16* mask;
   double* stats;
+  const bf16* bnr_x;       // BatchNorm-backward reduction mode: stats += {sum g, sum g*xhat} with xhat from bnr_x
+  const float* bnr_coef;   // [2][Cout] mean, invstd of that BatchNorm
   int accumulate, relu;
   int nup;
   UpRes up[4];
@@ -266,8 +268,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
         if (p.stats) {
           // per-channel sums over this warp's 32 pixels: butterfly reduce-scatter, lane l ends with channel l
           float s[32], sq[32];
+          if (p.bnr_x) {
+            // BatchNorm backward fused into this data-gradient epilogue: the stored value is g = d(relu(bn(x)))
+            // already masked by the activated tensor (p.mask), so sum g and sum g*x are all the reduction needs;
+            // xhat's affine part is applied per channel after the 32-pixel reduce-scatter below
+            float xr[32];
+            if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { s[j] = valid ? f[j] : 0.f; sq[j] = s[j] * s[j]; }
+              for (int j = 0; j < 32; j += 8) ldv<bf16>(p.bnr_x + o + j, xr + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s[j] = valid ? f[j] : 0.f; sq[j] = valid ? f[j] * xr[j] : 0.f; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s[j] = valid ? f[j] : 0.f; sq[j] = s[j] * s[j]; }
+          }
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
             const bool upper = (lane & off) != 0;
@@ -280,8 +295,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
             }
           }
           if (lane < nval) {
+            float qv = sq[0];
+            if (p.bnr_x) qv = __ldg(p.bnr_coef + p.Cout + co + lane) * (qv - __ldg(p.bnr_coef + co + lane) * s[0]);
             atomicAdd(&csum[co + lane], s[0]);
-            atomicAdd(&csq[co + lane], sq[0]);
+            atomicAdd(&csq[co + lane], qv);
           }
         }
       }
@@ -348,13 +365,16 @@ extern "C" int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int C
  * q_u: bf16 [N, H>>shift, W>>shift, Cout] low-resolution addends (nearest up-sampling, model2.py:55-60,91);
  * k_base / k_total: the sources use columns [k_base, k_base+C0+C1) of a [taps][CoutP][k_total] weight matrix
  * (k_total = 0 means C0+C1); out_stride 2 stores pixel (h,w) at (2h,2w) of a (2H,2W) tensor — the data gradient of a
- * stride-2 convolution; out bf16 or fp32 (out_f32), other epilogue flags as rsa_igemm_fwd.  Replaces the cuDNN / Eigen kernels behind
+ * stride-2 convolution; out bf16 or fp32 (out_f32), other epilogue flags as rsa_igemm_fwd.
+ * bnr_x / bnr_coef: when set, `stats` receives the BatchNormalization-backward reductions {sum g, sum g*xhat} of the
+ * stored values g against xhat = (bnr_x - mean) * invstd (bnr_coef = [2][Cout] mean, invstd) instead of {sum, sumsq}.  Replaces the cuDNN / Eigen kernels behind
  * keras Conv2D at model2.py:19-24,37,84,92,101-111,153-187 in bf16 mode. */
 extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void* wt, int CoutP,
                                 const float* bias, void* out, int out_f32, const void* residual, const void* mask,
                                 double* stats, int N, int H, int W, int Cout, int taps, int dil, int in_stride,
                                 int nup, const void* const* up_ptrs, const int* up_shifts, int k_base, int k_total,
-                                int out_stride, int accumulate, int relu, void* stream) {
+                                int out_stride, const void* bnr_x, const float* bnr_coef, int accumulate, int relu,
+                                void* stream) {
   RSA_REQUIRE(x0 && wt && out, RSA_ERR_SHAPE, "conv_tc2_fwd: null pointer");
   RSA_REQUIRE((taps == 9 && !x1 && in_stride == 1) || taps == 1, RSA_ERR_SHAPE, "conv_tc2_fwd: taps/sources combination");
   RSA_REQUIRE(in_stride == 1 || in_stride == 2, RSA_ERR_SHAPE, "conv_tc2_fwd: in_stride must be 1 or 2");
@@ -386,6 +406,9 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   p.total = p.mtiles * p.ntn;
   p.bias = bias; p.out = out; p.out_f32 = out_f32; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.stats = stats; p.accumulate = accumulate; p.relu = relu; p.nup = nup;
+  p.bnr_x = (const bf16*)bnr_x; p.bnr_coef = bnr_coef;
+  RSA_REQUIRE(!bnr_x || (stats && bnr_coef && Cout % 32 == 0 && !out_f32 && out_stride == 1), RSA_ERR_SHAPE,
+              "conv_tc2_fwd: BatchNorm-backward epilogue needs stats, coefficients and Cout %% 32 == 0");
   for (int u = 0; u < 4; ++u) {
     if (u < nup) {
       RSA_REQUIRE(up_ptrs && up_shifts && up_ptrs[u] && up_shifts[u] >= 1 && up_shifts[u] <= 3, RSA_ERR_SHAPE, "conv_tc2_fwd: bad up-residual %d", u);
