@@ -124,6 +124,9 @@ _SIGS = {
                          C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_void_p],
+    "rsa_conv_tc3_fwd": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int,
+                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                         C.c_int, C.c_void_p],
     "rsa_pw_wgrad_tc": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                         C.c_int, C.c_void_p],
     "rsa_bias_grad": [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -133,7 +136,7 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported",
-                                "rsa_conv_tc2_supported"])
+                                "rsa_conv_tc2_supported", "rsa_conv_tc3_supported"])
 
 
 def load_cdll(path=LIB_PATH):
@@ -153,6 +156,8 @@ def load_cdll(path=LIB_PATH):
     dll.rsa_conv_tc_supported.restype = C.c_int
     dll.rsa_conv_tc2_supported.argtypes = [C.c_int] * 6
     dll.rsa_conv_tc2_supported.restype = C.c_int
+    dll.rsa_conv_tc3_supported.argtypes = [C.c_int] * 4
+    dll.rsa_conv_tc3_supported.restype = C.c_int
     return dll
 
 
@@ -350,6 +355,24 @@ class Lib:
                           in_stride, nup, up_ptrs, up_sh, k_base, k_total, out_stride, _p(bnr_x), _p(bnr_coef),
                           int(accumulate), int(relu),
                           keep=(x0, x1, wt, bias, out, residual, mask, stats, ups, up_ptrs, up_sh, bnr_x, bnr_coef))
+
+    def conv_tc3_supported(self, N, H, W, C_):
+        return bool(self.dll.rsa_conv_tc3_supported(N, H, W, C_))
+
+    def conv_tc3_fwd(self, xs, wts, biases, dils, out, N, H, W, C_, residual=None, mask=None, stats=None,
+                     accumulate=False, relu=False):
+        """Thin-layer 3x3 convolution; len(xs) branches accumulate into one tile (conv_tc3.cu)."""
+        nbr = len(xs)
+        assert nbr == len(wts) == len(dils) and 1 <= nbr <= 4
+        assert all(x.dtype == torch.bfloat16 for x in xs) and out.dtype == torch.bfloat16
+        xa, wa = self._ptr_array(xs), self._ptr_array(wts)
+        ba = (C.c_void_p * nbr)()
+        for i in range(nbr):
+            ba[i] = biases[i].data_ptr() if biases is not None and biases[i] is not None else None
+        da = (C.c_int * nbr)(*[int(d) for d in dils])
+        return self._bind("rsa_conv_tc3_fwd", xa, wa, ba, da, nbr, _p(out), _p(residual), _p(mask), _p(stats), N, H, W,
+                          C_, int(accumulate), int(relu),
+                          keep=(xs, wts, biases, out, residual, mask, stats, xa, wa, ba, da))
 
     def conv_tc_wgrad(self, x, dy, dw, N, H, W, Cin, Cout, dil):
         assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32

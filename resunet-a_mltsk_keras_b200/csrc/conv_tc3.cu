@@ -1,0 +1,479 @@
+// conv_tc3.cu — thin-layer (C = 32) dilated 3x3 'same' convolution on tcgen05, built around what the ncu captures
+// of conv_tc2 showed for these layers (profiles/r1b_*): the tensor pipe sat at 7 % because every 128-pixel tile paid
+// nine TMA round trips and a ~5.7k-cycle register epilogue on 4 warps; a first version of this kernel then showed
+// the single MMA-issuing thread (~100 cycles per 16-cycle N=32 MMA) and shared-memory operand bandwidth as the next
+// limits.  Hence:
+//
+//   * weights of all branches stay resident in shared memory for the life of the (persistent) CTA;
+//   * an item is 16 x (8*KT) pixels = KT accumulators; small dilations (|d| <= 3) load ONE halo box per item and
+//     form the nine taps as shifted UMMA descriptors into it (measured in scripts/exp_desc.cu: with base_offset = 0
+//     any row shift and any stride-byte-offset address a TMA-swizzled tile correctly); large dilations load one
+//     16 x (8*KT) box per tap.  Either way one stage feeds all KT sub-tiles;
+//   * KT warps issue the MMAs, one per sub-tile (independent accumulators), so the issue rate scales;
+//   * up to four branches (ResBlock-a: dilations 1/3/15/31, model2.py:23-31) accumulate into the same TMEM tiles,
+//     so the branch sum and the identity add happen once, in the epilogue;
+//   * the epilogue is spread over 8 warps, prefetches its bf16 side inputs one sub-tile ahead, stages the bf16
+//     tile in shared memory (swizzled, conflict free) and leaves the global write to a TMA store issued by a
+//     dedicated warp; BatchNorm statistics of the stored values are reduced with a 16-wide shuffle butterfly.
+//
+// Replaces cuDNN's Conv2D forward / backward-data behind keras Conv2D(32, 3, dilation_rate=d, padding='same') at
+// model2.py:19-24,153-178 for the C = 32 layers (enc1, dec1, heads).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int T3_THREADS = 512;   // warp 0 TMA, 1..4 MMA (one per sub-tile), 5 TMA store, 8..15 epilogue
+constexpr int T3_MAXBR = 4;
+constexpr int T3_C = 32;
+constexpr int T3_PITCH = T3_C * 2;            // bytes per pixel row = SWIZZLE_64B span
+constexpr int T3_BOXB = 128 * T3_PITCH;       // one 16x8-pixel sub-tile
+constexpr int T3_WBYTES = 9 * T3_C * T3_PITCH;
+constexpr int T3_NSB = 4;                     // staged output tiles
+
+struct Tc3Params {
+  int N, H, W;
+  int nbr;
+  int dil[T3_MAXBR];      // signed: negative = data gradient (taps mirrored)
+  int halo[T3_MAXBR];     // 1: one halo box per item, 0: one box per tap
+  int items, tiles_w, tiles_h;
+  int nstages, slot_bytes;
+  const float* bias[T3_MAXBR];
+  const bf16* residual;
+  const bf16* mask;
+  const bf16* prev;       // accumulate: previous contents of out
+  double* stats;
+  int relu;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* t) {
+  t[0] = __uint_as_float(q.x << 16); t[1] = __uint_as_float(q.x & 0xffff0000u);
+  t[2] = __uint_as_float(q.y << 16); t[3] = __uint_as_float(q.y & 0xffff0000u);
+  t[4] = __uint_as_float(q.z << 16); t[5] = __uint_as_float(q.z & 0xffff0000u);
+  t[6] = __uint_as_float(q.w << 16); t[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+// K-major SWIZZLE_64B descriptor split in halves: hi carries the stride byte offset (distance between 8-row groups)
+__device__ __forceinline__ uint32_t t3_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (4u << 29); }
+__device__ __forceinline__ uint64_t t3_desc(uint32_t hi, uint32_t saddr) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFF) | (1u << 16));
+}
+
+struct Tc3Maps { CUtensorMap a[T3_MAXBR]; CUtensorMap w[T3_MAXBR]; CUtensorMap out; };
+
+// shared-memory carve-up (offsets from the 1024-aligned base)
+struct Tc3Smem {
+  int w_off, st_off, ring_off, misc_off, bar_off, total;
+  __host__ __device__ Tc3Smem(int nbr, int nstages, int slot_bytes) {
+    w_off = 0;
+    st_off = (nbr * T3_WBYTES + 1023) & ~1023;
+    ring_off = st_off + T3_NSB * T3_BOXB;
+    misc_off = ring_off + nstages * slot_bytes;              // bias[32], csum[32], csq[32]
+    bar_off = misc_off + 3 * T3_C * 4;
+    total = bar_off + (2 * nstages + 2 * T3_NSB + 8) * 8 + 16 + 1024;
+  }
+};
+
+template <int KT>
+__global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
+  constexpr int C = T3_C, PITCH = T3_PITCH, BOXB = T3_BOXB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const Tc3Smem L(p.nbr, p.nstages, p.slot_bytes);
+  uint8_t* wsm = smem + L.w_off;
+  uint8_t* ysm = smem + L.st_off;
+  uint8_t* ring = smem + L.ring_off;
+  float* bias_s = reinterpret_cast<float*>(smem + L.misc_off);
+  float* csum = bias_s + C;
+  float* csq = csum + C;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty_bar = full_bar + p.nstages;
+  uint64_t* tfull = empty_bar + p.nstages;   // [2]
+  uint64_t* tempty = tfull + 2;              // [2]
+  uint64_t* sready = tempty + 2;             // [NSB] staged tile written by the 8 epilogue warps
+  uint64_t* sfree = sready + T3_NSB;         // [NSB] staged tile read by its TMA store
+  uint64_t* wbar = sfree + T3_NSB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_stats = p.stats != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < p.nbr; ++b) { prefetch_tmap(&maps.a[b]); prefetch_tmap(&maps.w[b]); }
+    prefetch_tmap(&maps.out);
+    for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], KT); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], KT); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < T3_NSB; ++s) { mbar_init(&sready[s], 8); mbar_init(&sfree[s], 1); }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (warp == 8) {
+    float b = 0.f;
+    for (int k = 0; k < p.nbr; ++k) if (p.bias[k]) b += __ldg(p.bias[k] + lane);
+    bias_s[lane] = b;
+    csum[lane] = 0.f;
+    csq[lane] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(wbar, p.nbr * T3_WBYTES);
+      for (int b = 0; b < p.nbr; ++b)
+        for (int t = 0; t < 9; ++t) tma_load_3d(wsm + b * T3_WBYTES + t * C * PITCH, &maps.w[b], wbar, 0, 0, t);
+      int stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int r = item;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int n = r, h0 = th * 16, w0 = tw * 8 * KT;
+        for (int b = 0; b < p.nbr; ++b) {
+          const int d = p.dil[b], ad = d < 0 ? -d : d;
+          if (p.halo[b]) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], (16 + 2 * ad) * (8 * KT + 2 * ad) * PITCH);
+            tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, w0 - ad, h0 - ad, n);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          } else {
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ch = h0 + (tap / 3 - 1) * d, cw = w0 + (tap % 3 - 1) * d;
+              if (ch + 16 <= 0 || ch >= p.H || cw + 8 * KT <= 0 || cw >= p.W) continue;
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], KT * BOXB);
+              tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, cw, ch, n);
+              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp <= KT) {
+    // ===== MMA issuers: warp 1+s owns sub-tile s of every item =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, C);
+      const int s = warp - 1;
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t bhi = t3_desc_hi(8 * PITCH);
+      int stage = 0, phase = 0, it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        int r = item;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h;
+        const int h0 = th * 16, w0 = tw * 8 * KT;
+        mbar_wait(&tempty[it & 1], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(((it & 1) * KT + s) * C);
+        uint32_t started = 0;
+        for (int b = 0; b < p.nbr; ++b) {
+          const int d = p.dil[b], ad = d < 0 ? -d : d;
+          const uint32_t wb = wbase + b * T3_WBYTES;
+          if (p.halo[b]) {
+            const int Wh = 8 * KT + 2 * ad;
+            const uint32_t ahi = t3_desc_hi(Wh * PITCH);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(ring + stage * p.slot_bytes) + (uint32_t)((ad * Wh + ad + 8 * s) * PITCH);
+            const int rowb = d * Wh * PITCH, colb = d * PITCH;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t adesc = t3_desc(ahi, sa + (tap / 3 - 1) * rowb + (tap % 3 - 1) * colb);
+              const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
+              umma_bf16(acc, adesc, bdesc, idesc, started | (tap > 0));
+              umma_bf16(acc, adesc + 2, bdesc + 2, idesc, 1);
+            }
+            started = 1;
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          } else {
+            const uint32_t ahi = t3_desc_hi(8 * KT * PITCH);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ch = h0 + (tap / 3 - 1) * d, cw = w0 + (tap % 3 - 1) * d;
+              if (ch + 16 <= 0 || ch >= p.H || cw + 8 * KT <= 0 || cw >= p.W) continue;
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint64_t adesc = t3_desc(ahi, smem_u32(ring + stage * p.slot_bytes) + 8 * s * PITCH);
+              const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
+              umma_bf16(acc, adesc, bdesc, idesc, started);
+              umma_bf16(acc, adesc + 2, bdesc + 2, idesc, 1);
+              started = 1;
+              umma_commit(&empty_bar[stage]);
+              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        umma_commit(&tfull[it & 1]);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== TMA store of the staged tiles =====
+    if (lane == 0) {
+      int seq = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int r = item;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int n = r, h0 = th * 16, w0 = tw * 8 * KT;
+        for (int s = 0; s < KT; ++s, ++seq) {
+          const int j = seq % T3_NSB;
+          mbar_wait(&sready[j], (seq / T3_NSB) & 1);
+          tma_store_4d(&maps.out, ysm + j * BOXB, 0, w0 + 8 * s, h0, n);
+          // the store issued two tiles ago has finished reading its buffer: hand that buffer back
+          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          if (seq >= 2) mbar_arrive(&sfree[(seq - 2) % T3_NSB]);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue warps 8..15: lane quarter q, column half hs =====
+    const int q = warp & 3, hs = (warp - 8) >> 2;
+    const int rrow = q * 32 + lane;                 // accumulator row = pixel of the 16x8 sub-tile
+    const int py = rrow >> 3, px = rrow & 7;
+    const uint32_t srow = (uint32_t)rrow * PITCH;
+    const uint32_t sw = (uint32_t)((rrow >> 1) & 3);
+    const uint32_t ch0 = ((uint32_t)(2 * hs) ^ sw) << 4, ch1 = ((uint32_t)(2 * hs + 1) ^ sw) << 4;
+    float bias_r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bias_r[j] = bias_s[hs * 16 + j];
+    const bool side = p.residual || p.prev || p.mask;
+    auto pix_off = [&](int item, int s) -> size_t {
+      int r = item;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      return (((size_t)r * p.H + (th * 16 + py)) * p.W + (tw * 8 * KT + 8 * s + px)) * C + hs * 16;
+    };
+    float acc_s[16], acc_q[16];                     // BatchNorm statistics of this thread's pixels (all its sub-tiles)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+    uint4 rq[2], pq[2], mq[2];                      // side inputs of the next sub-tile (bf16 x 16), prefetched
+    auto prefetch = [&](size_t o) {
+      if (p.residual) { rq[0] = __ldg(reinterpret_cast<const uint4*>(p.residual + o)); rq[1] = __ldg(reinterpret_cast<const uint4*>(p.residual + o + 8)); }
+      if (p.prev) { pq[0] = *reinterpret_cast<const uint4*>(p.prev + o); pq[1] = *reinterpret_cast<const uint4*>(p.prev + o + 8); }
+      if (p.mask) { mq[0] = __ldg(reinterpret_cast<const uint4*>(p.mask + o)); mq[1] = __ldg(reinterpret_cast<const uint4*>(p.mask + o + 8)); }
+    };
+    if (side && (int)blockIdx.x < p.items) prefetch(pix_off(blockIdx.x, 0));
+    int it = 0, seq = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      mbar_wait(&tfull[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int s = 0; s < KT; ++s, ++seq) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((it & 1) * KT + s) * C + hs * 16), v);
+        if (s == KT - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[it & 1]);
+        }
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bias_r[j];
+        if (side) {
+          float t[16];
+          if (p.residual) {
+            unpack8(rq[0], t); unpack8(rq[1], t + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += t[j];
+          }
+          if (p.prev) {
+            unpack8(pq[0], t); unpack8(pq[1], t + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += t[j];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.mask) {
+            unpack8(mq[0], t); unpack8(mq[1], t + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = t[j] > 0.f ? f[j] : 0.f;
+          }
+          // next sub-tile's side inputs: issued now, consumed one iteration later
+          const int nitem = s + 1 < KT ? item : item + (int)gridDim.x;
+          if (nitem < p.items) prefetch(pix_off(nitem, s + 1 < KT ? s + 1 : 0));
+        } else if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint4 lo, hi;
+        lo.x = pack_bf16x2(f[0], f[1]); lo.y = pack_bf16x2(f[2], f[3]); lo.z = pack_bf16x2(f[4], f[5]); lo.w = pack_bf16x2(f[6], f[7]);
+        hi.x = pack_bf16x2(f[8], f[9]); hi.y = pack_bf16x2(f[10], f[11]); hi.z = pack_bf16x2(f[12], f[13]); hi.w = pack_bf16x2(f[14], f[15]);
+        const int j = seq % T3_NSB;
+        if (lane == 0) mbar_wait(&sfree[j], ((seq / T3_NSB) & 1) ^ 1);
+        __syncwarp();
+        uint8_t* yb = ysm + j * BOXB + srow;
+        *reinterpret_cast<uint4*>(yb + ch0) = lo;
+        *reinterpret_cast<uint4*>(yb + ch1) = hi;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sready[j]);
+        if (has_stats) {
+          // per-thread partial sums of the stored (bf16-rounded) values; reduced across lanes once per CTA
+          float t[16];
+          unpack8(lo, t); unpack8(hi, t + 8);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { acc_s[i] += t[i]; acc_q[i] = fmaf(t[i], t[i], acc_q[i]); }
+        }
+      }
+    }
+    if (has_stats) {
+      // 16-wide butterfly reduce-scatter over the warp's 32 pixels: the lane pair (2m, 2m+1) ends with channel bitrev4(m)
+#pragma unroll
+      for (int off = 16, n = 8; n >= 1; off >>= 1, n >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          const float send_s = upper ? acc_s[i] : acc_s[i + n], keep_s = upper ? acc_s[i + n] : acc_s[i];
+          const float send_q = upper ? acc_q[i] : acc_q[i + n], keep_q = upper ? acc_q[i + n] : acc_q[i];
+          acc_s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+          acc_q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+        }
+      }
+      acc_s[0] += __shfl_xor_sync(0xffffffffu, acc_s[0], 1);
+      acc_q[0] += __shfl_xor_sync(0xffffffffu, acc_q[0], 1);
+      if ((lane & 1) == 0) {
+        const int ch = hs * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        atomicAdd(&csum[ch], acc_s[0]);
+        atomicAdd(&csq[ch], acc_q[0]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 8 && it > 0) {
+        atomicAdd(p.stats + lane, (double)csum[lane]);
+        atomicAdd(p.stats + C + lane, (double)csq[lane]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+template <int KT>
+int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { rsa_set_error("conv_tc3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
+    configured = true;
+  }
+  const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
+  conv_tc3_kernel<KT><<<grid, T3_THREADS, smem_bytes, st>>>(maps, p);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+}  // namespace
+
+/* Shapes the thin-layer kernel accepts: 32 channels in and out, H a multiple of 16, W a multiple of 32. */
+extern "C" int rsa_conv_tc3_supported(int N, int H, int W, int C) {
+  return C == T3_C && N >= 1 && H >= 16 && H % 16 == 0 && W >= 32 && W % 32 == 0;
+}
+
+/* out[n,h,w,:] = epi( sum_b sum_tap x_b[n, h+dy*dil_b, w+dx*dil_b, :] . wt_b[tap] + sum_b bias_b )
+ *   epi: + residual, + out (accumulate), ReLU, mask (keep where mask > 0), in that order; bf16 NHWC throughout.
+ * xs[b]: bf16 [N,H,W,32]; wts[b]: bf16 [9][32][32] K-major copies ([tap][co][ci] forward, [tap][ci][co] with a negative
+ * dilation for the data gradient, as rsa_conv_tc2_fwd); biases[b] fp32[32] or NULL; nbr <= 4 branches accumulate into
+ * one TMEM tile (ResBlock-a branch sum, model2.py:23-31).  stats (double[64], optional) += {sum, sum of squares} of
+ * the stored bf16 values (BatchNormalization batch statistics, model2.py:21). */
+extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float* const* biases,
+                                const int* dils, int nbr, void* out, const void* residual, const void* mask,
+                                double* stats, int N, int H, int W, int C, int accumulate, int relu, void* stream) {
+  RSA_REQUIRE(xs && wts && dils && out && nbr >= 1 && nbr <= T3_MAXBR, RSA_ERR_SHAPE, "conv_tc3_fwd: bad arguments");
+  RSA_REQUIRE(rsa_conv_tc3_supported(N, H, W, C), RSA_ERR_SHAPE, "conv_tc3_fwd: unsupported shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  EncodeTiledFn enc = get_encode();
+  RSA_REQUIRE(enc, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled not available from the driver");
+  Tc3Params p;
+  p.N = N; p.H = H; p.W = W; p.nbr = nbr;
+  int max_ad = 0, any_box = 0;
+  for (int b = 0; b < T3_MAXBR; ++b) {
+    if (b < nbr) {
+      RSA_REQUIRE(xs[b] && wts[b] && dils[b] != 0, RSA_ERR_SHAPE, "conv_tc3_fwd: branch %d: null pointer or zero dilation", b);
+      const int ad = dils[b] < 0 ? -dils[b] : dils[b];
+      p.dil[b] = dils[b];
+      p.halo[b] = ad <= 3;
+      if (p.halo[b]) max_ad = ad > max_ad ? ad : max_ad; else any_box = 1;
+      p.bias[b] = biases ? biases[b] : nullptr;
+    } else { p.dil[b] = 1; p.halo[b] = 1; p.bias[b] = nullptr; }
+  }
+  // item = 16 x (8*KT) pixels; wide items amortise the halo, narrow ones keep the ring deep when 4 branches are resident
+  const int KT = nbr > 1 ? 2 : 4;
+  p.tiles_w = W / (8 * KT); p.tiles_h = H / 16;
+  p.items = p.tiles_w * p.tiles_h * N;
+  int slot = any_box ? KT * T3_BOXB : 0;
+  if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * KT + 2 * max_ad) * T3_PITCH; slot = hb > slot ? hb : slot; }
+  slot = (slot + 1023) & ~1023;
+  p.slot_bytes = slot;
+  {
+    const Tc3Smem L0(nbr, 0, slot);
+    int ns = (227 * 1024 - L0.total - 256) / (slot + 16);
+    if (ns > 8) ns = 8;
+    RSA_REQUIRE(ns >= 2, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory budget allows only %d stage(s)", ns);
+    p.nstages = ns;
+  }
+  const Tc3Smem L(nbr, p.nstages, slot);
+  RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
+  p.residual = (const bf16*)residual; p.mask = (const bf16*)mask; p.prev = accumulate ? (const bf16*)out : nullptr;
+  p.stats = stats; p.relu = relu;
+  Tc3Maps maps;
+  for (int b = 0; b < nbr; ++b) {
+    const int ad = p.dil[b] < 0 ? -p.dil[b] : p.dil[b];
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(p.halo[b] ? 8 * KT + 2 * ad : 8 * KT), (cuuint32_t)(p.halo[b] ? 16 + 2 * ad : 16), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&maps.a[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[b]), gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(x%d) failed (%d)", b, (int)r);
+    cuuint64_t wdim[3] = {(cuuint64_t)C, (cuuint64_t)C, 9};
+    cuuint64_t wstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * C * 2};
+    cuuint32_t wbox[3] = {(cuuint32_t)C, (cuuint32_t)C, 1};
+    cuuint32_t wes[3] = {1, 1, 1};
+    r = enc(&maps.w[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wts[b]), wdim, wstr, wbox, wes,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(w%d) failed (%d)", b, (int)r);
+  }
+  for (int b = nbr; b < T3_MAXBR; ++b) { maps.a[b] = maps.a[0]; maps.w[b] = maps.w[0]; }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, 8, 16, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (KT == 2) return launch3<2>(maps, p, L.total, st);
+  return launch3<4>(maps, p, L.total, st);
+}

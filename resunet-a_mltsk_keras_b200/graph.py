@@ -531,7 +531,12 @@ class Plan:
         res = residual.data if residual is not None else None
         flops = 2.0 * N * H * W * 9 * C * cout
         tcw = self.net.tc_weights(name, N, H, W)
-        if tcw is not None:
+        thin = tcw is not None and self.net.thin_ok(N, H, W, C, cout)
+        if thin:
+            self.fwd.append(self._tag(self._late(lambda: lib.conv_tc3_fwd(
+                [x.data], [tcw[0]], [b_], [dil], out.data, N, H, W, C, residual=res,
+                stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
+        elif tcw is not None:
             self.fwd.append(self._tag(self._late(lambda: lib.conv_tc2_fwd(
                 x.data, None, tcw[0], cout, b_, out.data, N, H, W, cout, taps=9, dil=dil, residual=res,
                 stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
@@ -560,7 +565,10 @@ class Plan:
                     sg = [Seg(dy, cout, H, W, off_h=-(ky - 1) * dil, off_w=-(kx - 1) * dil,
                               w_off=(ky * 3 + kx) * C * cout) for ky in range(3) for kx in range(3)]
                     mask = x.data if x.relu_masked else None
-                    if tcw is not None:
+                    if thin:
+                        self.bwd.append(self._tag(lib.conv_tc3_fwd([dy], [tcw[1]], None, [-dil], g, N, H, W, C, mask=mask,
+                                                                   accumulate=acc), "conv3x3_dgrad", flops))
+                    elif tcw is not None:
                         self.bwd.append(self._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9,
                                                                    dil=-dil, mask=mask, accumulate=acc),
                                                   "conv3x3_dgrad", flops))
@@ -824,7 +832,11 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
     res = residual.data if (first and residual is not None) else None
     flops = 2.0 * N * H * W * 9 * C * f
     tcw = pl.net.tc_weights(name, N, H, W)
-    if tcw is not None:
+    thin = tcw is not None and pl.net.thin_ok(N, H, W, C, f)
+    if thin:
+        pl.fwd.append(pl._tag(lib.conv_tc3_fwd([a.data], [tcw[0]], [b_], [d], out.data, N, H, W, C, residual=res,
+                                               accumulate=not first, relu=relu), "conv3x3_fwd", flops))
+    elif tcw is not None:
         pl.fwd.append(pl._tag(lib.conv_tc2_fwd(a.data, None, tcw[0], f, b_, out.data, N, H, W, f, taps=9, dil=d,
                                                residual=res, accumulate=not first, relu=relu), "conv3x3_fwd", flops))
     else:
@@ -846,7 +858,10 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
             g, acc = pl.gacc(a)
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
                   for ky in range(3) for kx in range(3)]
-            if tcw is not None:
+            if thin:
+                pl.bwd.append(pl._tag(lib.conv_tc3_fwd([dy], [tcw[1]], None, [-d], g, N, H, W, C, accumulate=acc),
+                                      "conv3x3_dgrad", flops))
+            elif tcw is not None:
                 pl.bwd.append(pl._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9, dil=-d,
                                                        accumulate=acc), "conv3x3_dgrad", flops))
             else:
@@ -1017,6 +1032,12 @@ class Net:
             return None
         n = 9 * ent["cin"] * ent["cout"]
         return self.shadow[ent["fwd"]:ent["fwd"] + n], self.shadow[ent["bwd"]:ent["bwd"] + n]
+
+    def thin_ok(self, N, H, W, cin, cout):
+        """conv_tc3 (thin-layer kernel: halo tiles, resident weights) handles this 3x3 convolution."""
+        import os
+        return (cin == cout and hasattr(self.lib, "conv_tc3_supported") and os.environ.get("RSA_TC3", "1") != "0"
+                and self.lib.conv_tc3_supported(N, H, W, cin))
 
     def ensure_shadow(self, stream):
         if self.pack_launch is not None and self.shadow_dirty:

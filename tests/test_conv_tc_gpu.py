@@ -250,3 +250,80 @@ def test_conv_tc2_k_base_and_strided_store(lib):
     lib.conv_tc2_fwd(dz.cuda(), None, wb.cuda(), C, None, d_dx, N, H, H, C, out_stride=2, accumulate=True)(st)
     torch.cuda.synchronize()
     assert (d_dx.cpu().float() - ref.float()).abs().max().item() <= ref.float().abs().max().item() / 100
+
+
+# ---- thin-layer kernel (conv_tc3.cu): halo tiles, resident weights, fused branches, tensor-core statistics ----
+def _conv3_ref(x, w, C, d, N, H, W):
+    """fp64 'same' dilated 3x3 conv of bf16 operands; w flat HWIO."""
+    segs = [Seg(x, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * C)
+            for ky in range(3) for kx in range(3)]
+    o = torch.zeros((N, H, W, C), dtype=torch.float64)
+    EMU.igemm_fwd(segs, w, C, False, None, o, N, H, W, C)(0)
+    return o
+
+
+@pytest.mark.parametrize("N,H,W,d", [(2, 32, 32, 1), (1, 16, 64, 3), (2, 32, 32, 15), (2, 64, 64, 31), (3, 48, 96, 3),
+                                     (1, 32, 32, 31)])
+def test_conv_tc3_single_branch(lib, N, H, W, d):
+    C, dt = 32, torch.bfloat16
+    assert lib.conv_tc3_supported(N, H, W, C)
+    x = rnd((N, H, W, C), dt, 1)
+    w = rnd((9 * C * C,), torch.float32, 2, 1.0 / (3 * C ** 0.5)).to(dt).float()
+    b = rnd((C,), torch.float32, 3)
+    wf, wb = _pack(w, 9, C, C)
+    res, prev, mask = rnd((N, H, W, C), dt, 5), rnd((N, H, W, C), dt, 4), rnd((N, H, W, C), dt, 6)
+    st = torch.cuda.current_stream().cuda_stream
+    conv = _conv3_ref(x, w, C, d, N, H, W)
+    # bias + residual + accumulate + statistics
+    ref = conv + b.double() + res.double() + prev.double()
+    ref_b = ref.to(dt)
+    d_out, d_stats = prev.clone().cuda(), torch.zeros(2 * C, dtype=torch.float64).cuda()
+    lib.conv_tc3_fwd([x.cuda()], [wf.cuda()], [b.cuda()], [d], d_out, N, H, W, C, residual=res.cuda(), stats=d_stats,
+                     accumulate=True)(st)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (d_out.cpu().double() - ref).abs().max().item() <= scale / 100, "forward"
+    got = d_out.cpu().double().reshape(-1, C)
+    # the statistics are those of the stored (bf16) tensor
+    np.testing.assert_allclose(d_stats[:C].cpu().numpy(), got.sum(0).numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(d_stats[C:].cpu().numpy(), (got * got).sum(0).numpy(), rtol=1e-4, atol=1e-2)
+    # relu + mask, plain store
+    ref2 = (conv + b.double()).clamp_min(0) * (mask.double() > 0)
+    d_out2 = torch.zeros((N, H, W, C), dtype=dt).cuda()
+    lib.conv_tc3_fwd([x.cuda()], [wf.cuda()], [b.cuda()], [d], d_out2, N, H, W, C, mask=mask.cuda(), relu=True)(st)
+    torch.cuda.synchronize()
+    assert (d_out2.cpu().double() - ref2).abs().max().item() <= scale / 100, "relu/mask"
+    # data gradient: negated dilation with the [tap][ci][co] copy
+    dy = rnd((N, H, W, C), dt, 7)
+    sg = [Seg(dy, C, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * C)
+          for ky in range(3) for kx in range(3)]
+    dx = torch.zeros((N, H, W, C), dtype=torch.float64)
+    EMU.igemm_fwd(sg, w, C, True, None, dx, N, H, W, C)(0)
+    d_dx = torch.zeros((N, H, W, C), dtype=dt).cuda()
+    lib.conv_tc3_fwd([dy.cuda()], [wb.cuda()], None, [-d], d_dx, N, H, W, C)(st)
+    torch.cuda.synchronize()
+    assert (d_dx.cpu().double() - dx).abs().max().item() <= dx.abs().max().item() / 100, "dgrad"
+
+
+@pytest.mark.parametrize("N,H,W,dils", [(2, 64, 64, (1, 3, 15, 31)), (1, 32, 64, (1, 3, 15)), (2, 32, 32, (3, 31))])
+def test_conv_tc3_fused_branches(lib, N, H, W, dils):
+    """ResBlock-a branch sum + identity in one launch (model2.py:23-31)."""
+    C, dt = 32, torch.bfloat16
+    xs = [rnd((N, H, W, C), dt, 10 + i) for i in range(len(dils))]
+    ws = [rnd((9 * C * C,), torch.float32, 20 + i, 1.0 / (3 * C ** 0.5)).to(dt).float() for i in range(len(dils))]
+    bs = [rnd((C,), torch.float32, 30 + i) for i in range(len(dils))]
+    res = rnd((N, H, W, C), dt, 5)
+    ref = res.double()
+    for x, w, b, d in zip(xs, ws, bs, dils):
+        ref = ref + _conv3_ref(x, w, C, d, N, H, W) + b.double()
+    ref = ref.clamp_min(0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_out = torch.zeros((N, H, W, C), dtype=dt).cuda()
+    d_stats = torch.zeros(2 * C, dtype=torch.float64).cuda()
+    lib.conv_tc3_fwd([x.cuda() for x in xs], [_pack(w, 9, C, C)[0].cuda() for w in ws], [b.cuda() for b in bs], list(dils),
+                     d_out, N, H, W, C, residual=res.cuda(), relu=True, stats=d_stats)(st)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().double() - ref).abs().max().item() <= ref.abs().max().item() / 100
+    got = d_out.cpu().double().reshape(-1, C)
+    np.testing.assert_allclose(d_stats[:C].cpu().numpy(), got.sum(0).numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(d_stats[C:].cpu().numpy(), (got * got).sum(0).numpy(), rtol=1e-4, atol=1e-2)
