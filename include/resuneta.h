@@ -199,6 +199,9 @@ int rsa_conv_tc3_supported(int N, int H, int W, int C);
 int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float* const* biases, const int* dils, int nbr,
                      void* out, const void* residual, const void* mask, double* stats, int N, int H, int W, int C,
                      int accumulate, int relu, void* stream);
+/* Weight gradient of the thin layers: one x halo per 16x16 item, the three taps of a tap row are the M atoms of one
+ * MMA (conv_tc3.cu); same contract as rsa_conv_tc_wgrad, Cin == Cout == C == 32, dil > 0. */
+int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int dil, void* stream);
 /* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co];
  * x, dy bf16 NHWC, Cin == Cout.  Replaces cuDNN's Conv2D backward-filter behind model2.py:19-24,153-178. */
 int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int dil,

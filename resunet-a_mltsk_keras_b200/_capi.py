@@ -124,6 +124,7 @@ _SIGS = {
                          C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_void_p],
+    "rsa_conv_tc3_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc3_fwd": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int,
                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                          C.c_int, C.c_void_p],
@@ -373,6 +374,10 @@ class Lib:
         return self._bind("rsa_conv_tc3_fwd", xa, wa, ba, da, nbr, _p(out), _p(residual), _p(mask), _p(stats), N, H, W,
                           C_, int(accumulate), int(relu),
                           keep=(xs, wts, biases, out, residual, mask, stats, xa, wa, ba, da))
+
+    def conv_tc3_wgrad(self, x, dy, dw, N, H, W, C_, dil):
+        assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32
+        return self._bind("rsa_conv_tc3_wgrad", _p(x), _p(dy), _p(dw), N, H, W, C_, dil, keep=(x, dy, dw))
 
     def conv_tc_wgrad(self, x, dy, dw, N, H, W, Cin, Cout, dil):
         assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32

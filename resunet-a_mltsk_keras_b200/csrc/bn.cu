@@ -286,6 +286,27 @@ template <typename T, int V> __device__ __forceinline__ void stm(T* p, const flo
   else { float t[4] = {v[0], v[1], v[2], v[3]}; st4<T>(p, t); }
 }
 
+// raw (still packed) vectors: loads stay in flight as 8/16-byte registers and are unpacked at use, so that several
+// rows per thread can be outstanding without the fp32 copies eating the register file
+template <typename T, int V> struct RawV;
+template <> struct RawV<bf16, 8> { typedef uint4 type; };
+template <> struct RawV<bf16, 4> { typedef uint2 type; };
+template <> struct RawV<float, 4> { typedef float4 type; };
+template <typename T, int V> __device__ __forceinline__ typename RawV<T, V>::type ld_raw(const T* p) {
+  return __ldg(reinterpret_cast<const typename RawV<T, V>::type*>(p));
+}
+__device__ __forceinline__ void unpack_raw(const uint4& q, float* v) {
+  v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+  v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+  v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
+  v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+__device__ __forceinline__ void unpack_raw(const uint2& q, float* v) {
+  v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+  v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+}
+__device__ __forceinline__ void unpack_raw(const float4& q, float* v) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+
 // smem table [2 + 2K][C]: mean, invstd, then per branch scale = gamma*invstd and shift = beta - mean*scale
 template <int K>
 __device__ __forceinline__ void stage_coeffs(float* tab, int C, const BwdMultiParams& bp, const double* stats, double count,
@@ -328,30 +349,38 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_multi_kernel(const T* __rest
   }
   const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
   const int64_t rend = min(M, rbeg + rows_per_block);
-  constexpr int U = K <= 2 ? 2 : 1;            // rows in flight per thread (register budget)
+  constexpr int U = K == 1 ? 4 : 2;            // rows in flight per thread (loads stay packed)
+  typedef typename RawV<T, V>::type Raw;
   for (int64_t r = rbeg + r0; r < rend; r += U * rpi) {
-    float xv[U][V], g[U][K][V];
+    Raw xr[U], gr[U][K];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * rpi;
       if (rr < rend) {
         const int64_t o = rr * C + cg * V;
-        ldm<T, V>(x + o, xv[u]);
+        xr[u] = ld_raw<T, V>(x + o);
 #pragma unroll
-        for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[u][b]);
+        for (int b = 0; b < K; ++b) gr[u][b] = ld_raw<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (r + u * rpi < rend) {
+        float xv[V], xh[V];
+        unpack_raw(xr[u], xv);
 #pragma unroll
-        for (int b = 0; b < K; ++b)
+        for (int i = 0; i < V; ++i) xh[i] = (xv[i] - mean[i]) * inv[i];
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+          float g[V];
+          unpack_raw(gr[u][b], g);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float gg = (!relu || fmaf(xv[u][i], sc[b][i], sh[b][i]) > 0.f) ? g[u][b][i] : 0.f;
+            const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[i] : 0.f;
             s[b][i] += gg;
-            q[b][i] = fmaf(gg, (xv[u][i] - mean[i]) * inv[i], q[b][i]);
+            q[b][i] = fmaf(gg, xh[i], q[b][i]);
           }
+        }
       }
     }
   }
@@ -405,37 +434,44 @@ __global__ void __launch_bounds__(NT) bn_bwd_apply_multi_kernel(const T* __restr
   }
   const int64_t rbeg = (int64_t)blockIdx.x * rows_per_block;
   const int64_t rend = min(M, rbeg + rows_per_block);
-  constexpr int U = K <= 2 ? 2 : 1;
+  constexpr int U = K == 1 ? 4 : 2;
+  typedef typename RawV<T, V>::type Raw;
   for (int64_t r = rbeg + r0; r < rend; r += U * rpi) {
-    float xv[U][V], acc[U][V], g[U][K][V];
+    Raw xr[U], ar[U], gr[U][K];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * rpi;
       if (rr < rend) {
         const int64_t o = rr * C + cg * V;
-        ldm<T, V>(x + o, xv[u]);
+        xr[u] = ld_raw<T, V>(x + o);
 #pragma unroll
-        for (int b = 0; b < K; ++b) ldm<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o, g[u][b]);
-        if (accumulate) ldm<T, V>(dx + o, acc[u]);
+        for (int b = 0; b < K; ++b) gr[u][b] = ld_raw<T, V>(reinterpret_cast<const T*>(bp.dy[b]) + o);
+        if (accumulate) ar[u] = *reinterpret_cast<const Raw*>(dx + o);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * rpi;
       if (rr < rend) {
+        float xv[V], acc[V];
+        unpack_raw(xr[u], xv);
+        if (accumulate) unpack_raw(ar[u], acc);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          const float base = -Bsum[i] - (xv[u][i] - mean[i]) * inv[i] * Dsum[i];
-          acc[u][i] = accumulate ? acc[u][i] + base : base;
+          const float base = -Bsum[i] - (xv[i] - mean[i]) * inv[i] * Dsum[i];
+          acc[i] = accumulate ? acc[i] + base : base;
         }
 #pragma unroll
-        for (int b = 0; b < K; ++b)
+        for (int b = 0; b < K; ++b) {
+          float g[V];
+          unpack_raw(gr[u][b], g);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float gg = (!relu || fmaf(xv[u][i], sc[b][i], sh[b][i]) > 0.f) ? g[u][b][i] : 0.f;
-            acc[u][i] = fmaf(sc[b][i], gg, acc[u][i]);
+            const float gg = (!relu || fmaf(xv[i], sc[b][i], sh[b][i]) > 0.f) ? g[i] : 0.f;
+            acc[i] = fmaf(sc[b][i], gg, acc[i]);
           }
-        stm<T, V>(dx + rr * C + cg * V, acc[u]);
+        }
+        stm<T, V>(dx + rr * C + cg * V, acc);
       }
     }
   }
@@ -609,10 +645,11 @@ int fill_multi(BwdMultiParams& bp, int k, const void* const* dys, const float* c
   return RSA_OK;
 }
 inline void multi_grid(int64_t M, int C, int V, int& rows, int& grid) {
+  // one resident wave (2 blocks of 256 threads per SM at ~120 registers): the per-block prologue (coefficient table)
+  // and epilogue (block reduction + atomics) are paid once per SM slot instead of once per ~900 rows
   const int rpi = NT / (C / V);
-  rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 8);
-  rows = (rows + rpi - 1) / rpi * rpi;
-  if (rows < rpi * 4) rows = rpi * 4;
+  rows = (int)ceil_div64(M, (int64_t)rsa_num_sms() * 2);
+  rows = (rows + 4 * rpi - 1) / (4 * rpi) * (4 * rpi);
   grid = (int)ceil_div64(M, rows);
 }
 inline size_t multi_smem(int C, int k, int V) {

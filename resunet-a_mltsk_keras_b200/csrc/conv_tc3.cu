@@ -477,3 +477,219 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   if (KT == 2) return launch3<2>(maps, p, L.total, st);
   return launch3<4>(maps, p, L.total, st);
 }
+
+// =====================================================================================================
+// Weight gradient of the thin-layer 3x3 convolution.
+//   dW[tap][ci][co] += sum_pix x[pix + off(tap), ci] * dy[pix, co]          (Conv2D backward-filter, model2.py:19-24)
+// GEMM view: K = pixels, both operands MN-major (channels contiguous).  conv_tc.cu's kernel loads nine shifted copies of
+// every 64-pixel tile (655 MB of L2->SM traffic per launch, one issuing thread); here an item is a 16 x 16 pixel tile
+// whose x halo is loaded ONCE and the three taps of a tap row are the M atoms of one MMA: atom i starts i*d pixels
+// further (LBO = d pixels), so D_dy[128 x 32] = [tap(dy,-1) | tap(dy,0) | tap(dy,+1) | unused] and three warps (one per
+// tap row) issue independent accumulation chains that run for the whole life of the persistent CTA.  Large dilations
+// use nine 16 x 8 boxes per item with LBO = one box.  One red.global.add pass per CTA at the end.
+// =====================================================================================================
+namespace {
+
+constexpr int W3_THREADS = 256;   // warp 0 TMA, 1..3 MMA (tap row dy = warp - 1), 4..7 final reduction
+
+struct Wg3Params {
+  int N, H, W, dil, halo;
+  int IW;                 // item width in pixels: 16 (halo) or 8 (boxes); item height 16
+  int items, tiles_w, tiles_h;
+  int nstages, stage_bytes, a_bytes, a_tx;   // a_tx: bytes the halo box actually delivers
+  float* dw;
+};
+
+__device__ __forceinline__ uint64_t w3_mndesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                      // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void w3_red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                       const __grid_constant__ CUtensorMap tmDY,
+                                                                       const Wg3Params p) {
+  constexpr int C = T3_C, PITCH = T3_PITCH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.nstages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.nstages;
+  uint64_t* done_bar = empty_bar + p.nstages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = p.dil;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmDY);
+    for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 3); }
+    mbar_init(done_bar, 3);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nmine = ((int)blockIdx.x < p.items) ? (p.items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int r = item;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int n = r, h0 = th * 16, w0 = tw * p.IW;
+        uint8_t* sa = smem + stage * p.stage_bytes;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.halo) {
+          mbar_expect_tx(&full_bar[stage], p.a_tx + 16 * p.IW * PITCH);
+          tma_load_4d(sa, &tmX, &full_bar[stage], 0, w0 - d, h0 - d, n);
+        } else {
+          int nrow = 0;
+          for (int dyi = 0; dyi < 3; ++dyi) { const int ch = h0 + (dyi - 1) * d; nrow += !(ch + 16 <= 0 || ch >= p.H); }
+          mbar_expect_tx(&full_bar[stage], (3 * nrow + 1) * 16 * p.IW * PITCH);
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            const int ch = h0 + (dyi - 1) * d;
+            if (ch + 16 <= 0 || ch >= p.H) continue;
+            for (int dxi = 0; dxi < 3; ++dxi)
+              tma_load_4d(sa + (dyi * 3 + dxi) * 16 * p.IW * PITCH, &tmX, &full_bar[stage], 0, w0 + (dxi - 1) * d, ch, n);
+          }
+        }
+        tma_load_4d(sa + p.a_bytes, &tmDY, &full_bar[stage], 0, w0, h0, n);
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp <= 3) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, C) | (1u << 15) | (1u << 16);
+      const int dyi = warp - 1;
+      const uint32_t acc = tmem_base + (uint32_t)(dyi * C);
+      const int Wh = p.IW + 2 * d;                        // halo mode: region row pitch in pixels
+      const int ncb = p.IW / 8;                           // 8-pixel column blocks per item row
+      const uint32_t boxb = 16 * p.IW * PITCH;
+      int stage = 0, phase = 0;
+      uint32_t accum = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int r = item;
+        r /= p.tiles_w;
+        const int th = r % p.tiles_h;
+        const int ch = th * 16 + (dyi - 1) * d;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t sb = sa + p.a_bytes;
+        if (p.halo || !(ch + 16 <= 0 || ch >= p.H)) {
+          // A: atom i = tap (dy, dx = i - 1); two 8-pixel K groups per MMA = rows (2rp, 2rp+1), column block cb
+          const uint32_t a0 = p.halo ? sa + (uint32_t)((dyi * d * Wh) * PITCH) : sa + (uint32_t)(dyi * 3) * boxb;
+          const uint32_t arow = p.halo ? Wh * PITCH : p.IW * PITCH;
+          const uint32_t lbo = p.halo ? d * PITCH : boxb;
+          const uint32_t brow = p.IW * PITCH;
+#pragma unroll 1
+          for (int rp = 0; rp < 8; ++rp) {
+            for (int cb = 0; cb < ncb; ++cb) {
+              const uint64_t adesc = w3_mndesc(a0 + 2 * rp * arow + cb * 8 * PITCH, lbo, arow);
+              const uint64_t bdesc = w3_mndesc(sb + 2 * rp * brow + cb * 8 * PITCH, 0, brow);
+              umma_bf16(acc, adesc, bdesc, idesc, accum);
+              accum = 1;
+            }
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // ===== final reduction: lanes 32q.. of D_dy hold tap (dy, dx = q - 1), row = ci, columns = co =====
+    const int q = warp & 3;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (nmine > 0 && q < 3) {
+      for (int dyi = 0; dyi < 3; ++dyi) {
+        // a tap row that was out of range for every item of this CTA never initialised its accumulator
+        bool any = p.halo;
+        if (!any) {
+          for (int item = blockIdx.x; item < p.items && !any; item += gridDim.x) {
+            const int ch = ((item / p.tiles_w) % p.tiles_h) * 16 + (dyi - 1) * d;
+            any = !(ch + 16 <= 0 || ch >= p.H);
+          }
+        }
+        if (!any) continue;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dyi * C), v);
+        float* dst = p.dw + ((size_t)(dyi * 3 + q) * C + lane) * C;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          w3_red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+}  // namespace
+
+/* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co] for the
+ * thin (32-channel) layers; x, dy bf16 NHWC [N,H,W,32], dil > 0.  Same contract as rsa_conv_tc_wgrad. */
+extern "C" int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int dil, void* stream) {
+  RSA_REQUIRE(x && dy && dw && dil > 0, RSA_ERR_SHAPE, "conv_tc3_wgrad: bad arguments");
+  RSA_REQUIRE(rsa_conv_tc3_supported(N, H, W, C), RSA_ERR_SHAPE, "conv_tc3_wgrad: unsupported shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  EncodeTiledFn enc = get_encode();
+  RSA_REQUIRE(enc, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled not available from the driver");
+  Wg3Params p;
+  p.N = N; p.H = H; p.W = W; p.dil = dil; p.dw = dw;
+  p.halo = dil <= 3;
+  p.IW = p.halo ? 16 : 8;
+  p.tiles_w = W / p.IW; p.tiles_h = H / 16;
+  p.items = p.tiles_w * p.tiles_h * N;
+  // the unused fourth M atom reads up to 2*dil pixels (halo) / one box past the A region: keep that inside the stage
+  const int a_raw = p.halo ? (16 + 2 * dil) * (p.IW + 2 * dil) * T3_PITCH : 9 * 16 * p.IW * T3_PITCH;
+  p.a_tx = a_raw;
+  p.a_bytes = (a_raw + 2 * dil * T3_PITCH + 1023) & ~1023;
+  p.stage_bytes = p.a_bytes + 16 * p.IW * T3_PITCH;
+  p.stage_bytes = (p.stage_bytes + 1023) & ~1023;
+  int ns = (227 * 1024 - 2048) / p.stage_bytes;
+  if (ns > 6) ns = 6;
+  RSA_REQUIRE(ns >= 2, RSA_ERR_SHAPE, "conv_tc3_wgrad: stage of %d bytes leaves %d stage(s)", p.stage_bytes, ns);
+  p.nstages = ns;
+  const int smem_bytes = ns * p.stage_bytes + (2 * ns + 1) * 8 + 16 + 1024;
+  CUtensorMap tmX, tmDY;
+  auto encode = [&](CUtensorMap* tm, const void* base, int bw, int bh) -> CUresult {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = p.halo ? encode(&tmX, x, p.IW + 2 * dil, 16 + 2 * dil) : encode(&tmX, x, p.IW, 16);
+  RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+  r = encode(&tmDY, dy, p.IW, 16);
+  RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    RSA_REQUIRE(e == cudaSuccess, RSA_ERR_CUDA, "conv_tc3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
+  conv_tc3_wgrad_kernel<<<grid, W3_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmDY, p);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}

@@ -552,8 +552,11 @@ class Plan:
                 dW = self.G(name + "/kernel")
                 db = self.G(name + "/bias") if bias_grad else None
                 if tcw is not None and C == cout:
-                    self.bwd.append(self._tag(lib.conv_tc_wgrad(x.data, dy, dW, N, H, W, C, cout, dil),
-                                              "conv3x3_wgrad", flops))
+                    if thin:
+                        self.bwd.append(self._tag(lib.conv_tc3_wgrad(x.data, dy, dW, N, H, W, C, dil), "conv3x3_wgrad", flops))
+                    else:
+                        self.bwd.append(self._tag(lib.conv_tc_wgrad(x.data, dy, dW, N, H, W, C, cout, dil),
+                                                  "conv3x3_wgrad", flops))
                     if db is not None:
                         self.bwd.append(lib.bias_grad(dy, N * H * W, cout, [db]))
                 else:
@@ -849,8 +852,12 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
             dy = out.grad
             if tcw is not None and C == f:
                 # bias gradient: one column-sum of d(out) per block (block_bias_grad)
-                pl.bwd.append(pl._tag(lib.conv_tc_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, f, d),
-                                      "conv3x3_wgrad", flops))
+                if thin:
+                    pl.bwd.append(pl._tag(lib.conv_tc3_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, d),
+                                          "conv3x3_wgrad", flops))
+                else:
+                    pl.bwd.append(pl._tag(lib.conv_tc_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, f, d),
+                                          "conv3x3_wgrad", flops))
             else:
                 pl.bwd.append(pl._tag(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N,
                                                       H, W, f), "conv3x3_wgrad", flops))

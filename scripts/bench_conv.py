@@ -50,6 +50,7 @@ if lib.conv_tc3_supported(N, H, W, C):
     print(f"C={C} fused 4-branch (1,3,15,31) + identity: {t4:7.1f} us ({4*flops/t4/1e6:6.0f} TF)")
     xw = torch.randn(N, H, W, C, device="cuda").to(dt)
     dw = torch.zeros(9 * C * C, device="cuda")
-    for d in (1, 15):
+    for d in (1, 3, 15, 31):
         tw = timeit(lambda i: lib.conv_tc_wgrad(xs[i], outs[(i + 1) % NB], dw, N, H, W, C, C, d))
-        print(f"C={C} wgrad d={d}: {tw:7.1f} us ({flops/tw/1e6:6.0f} TF)")
+        tw3 = timeit(lambda i: lib.conv_tc3_wgrad(xs[i], outs[(i + 1) % NB], dw, N, H, W, C, d))
+        print(f"C={C} wgrad d={d}: {tw:7.1f} us ({flops/tw/1e6:6.0f} TF) | tc3 {tw3:7.1f} us ({flops/tw3/1e6:6.0f} TF)")

@@ -327,3 +327,21 @@ def test_conv_tc3_fused_branches(lib, N, H, W, dils):
     got = d_out.cpu().double().reshape(-1, C)
     np.testing.assert_allclose(d_stats[:C].cpu().numpy(), got.sum(0).numpy(), rtol=1e-4, atol=1e-2)
     np.testing.assert_allclose(d_stats[C:].cpu().numpy(), (got * got).sum(0).numpy(), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,H,W,d", [(2, 32, 32, 1), (1, 16, 64, 3), (2, 32, 32, 15), (2, 64, 64, 31), (16, 64, 64, 1),
+                                     (1, 32, 32, 31), (3, 48, 96, 3)])
+def test_conv_tc3_wgrad(lib, N, H, W, d):
+    C, dt = 32, torch.bfloat16
+    x = rnd((N, H, W, C), dt, 1)
+    dy = rnd((N, H, W, C), dt, 2)
+    segs = [Seg(x, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * C)
+            for ky in range(3) for kx in range(3)]
+    dw = torch.zeros(9 * C * C, dtype=torch.float32)
+    EMU.igemm_wgrad(segs, dy, dw, C, None, N, H, W, C)(0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_dw = torch.zeros(9 * C * C, dtype=torch.float32).cuda()
+    lib.conv_tc3_wgrad(x.cuda(), dy.cuda(), d_dw, N, H, W, C, d)(st)
+    torch.cuda.synchronize()
+    scale = dw.abs().max().item()
+    assert (d_dw.cpu() - dw).abs().max().item() <= scale * 2e-3
