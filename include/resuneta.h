@@ -221,6 +221,9 @@ int rsa_bias_grad(const void* dy, int dtype, long long M, int C, float* db0, flo
 int rsa_pack_weights_tc(const float* params, void* shadow, const void* table, int nlayers, long long max_elems,
                         void* stream);
 
+/* Head forward (bf16 mode): z[m, 0:n] fp32 = h[m, 0:32] bf16 . w[32][n] + b, n <= 8; the final Conv2D 1x1 of the
+ * heads, model2.py:159,168,180,186. */
+int rsa_head_fwd(const void* h, const float* w, const float* b, float* z, int64_t M, int n, void* stream);
 /* ---- thin 1x1 convolutions: one side <= 16 channels, the other exactly 32 (thin.cu) --------------------------------
  * Stem Conv2D(32,(1,1)) on the raw n-band input (model2.py:101): out[m,0:32] = x[m,0:n].w[n][32] + b, optional BatchNorm
  * statistics of the output (double[64]); its weight/bias gradient; and the backward of a head's final 1x1 convolution

@@ -115,6 +115,7 @@ _SIGS = {
     "rsa_stem_wgrad": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "rsa_head_bwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                      C.c_void_p, C.c_void_p, C.c_void_p],
+    "rsa_head_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p],
     "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
     "rsa_conv_tc_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
@@ -404,6 +405,10 @@ class Lib:
 
     def stem_wgrad(self, x, dy, M, n, dw, db):
         return self._bind("rsa_stem_wgrad", _p(x), _p(dy), dtype_code(x), M, n, _p(dw), _p(db), keep=(x, dy, dw, db))
+
+    def head_fwd(self, h, w, b, z, M, n):
+        assert h.dtype == torch.bfloat16 and z.dtype == torch.float32
+        return self._bind("rsa_head_fwd", _p(h), _p(w), _p(b), _p(z), M, n, keep=(h, w, b, z))
 
     def head_bwd(self, h, dz, w, M, n, dh, accumulate, relu_mask, dw, db):
         assert dz.dtype == torch.float32

@@ -348,9 +348,9 @@ bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 }  // namespace
 
 /* Shapes the persistent tensor-core convolution accepts: every source channel count a multiple of 16 (or exactly 8
- * for a single source; K chunk = 64 if all are multiples of 64, else 32, else 16), power-of-two output sides >= 4. */
+ * for a single source; K chunk = 64 if all are multiples of 64, else 32, else 16), power-of-two output sides. */
 extern "C" int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int Cout) {
-  if (!pow2(H) || !pow2(W) || W < 4 || H < 4 || N < 1) return 0;
+  if (!pow2(H) || !pow2(W) || N < 1) return 0;     // down to 1x1 maps: the 128-row tile then spans up to 128 images
   // 8-channel tensors ride on TMA's zero fill of the out-of-bounds half of a 16-channel box (single source only)
   if (C0 == 8 && C1 == 0) return Cout >= 1;
   if (C0 < 16 || C0 % 16 || (C1 && C1 % 16) || Cout < 1) return 0;

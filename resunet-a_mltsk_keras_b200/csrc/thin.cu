@@ -184,6 +184,252 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(const TH* __restrict__ h, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 fast paths: one thread owns (pixel, 8-channel group) so that every access to the 32-channel tensor is one
+// 16-byte vector (a warp covers 8 consecutive pixels = 512 contiguous bytes); per-channel reductions live in registers
+// for the whole grid-stride walk and leave the block through one shuffle/shared-memory reduction.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack_bf8(const uint4& q, float* v) {
+  v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+  v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+  v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
+  v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack_bf8(const float* v) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return t;
+}
+// sum over the 8 lanes of a warp that share (lane & 3), result valid in lanes 0..3
+__device__ __forceinline__ float quad_col_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+// stem, bf16: out[p][8g..8g+8) = x[p][0..NI) . w[:, 8g..] + b;  statistics of the stored values
+template <int NI>
+__global__ void __launch_bounds__(NT) stem_fwd_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, bf16* __restrict__ out, int64_t M,
+                                                           double* __restrict__ stats) {
+  const int g = threadIdx.x & 3;
+  float wr[NI][8], br[8], s[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    br[i] = b ? b[g * 8 + i] : 0.f; s[i] = 0.f; sq[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) wr[j][i] = w[j * 32 + g * 8 + i];
+  }
+  const int64_t stride = (int64_t)gridDim.x * (NT / 4);
+  for (int64_t p = (int64_t)blockIdx.x * (NT / 4) + (threadIdx.x >> 2); p < M; p += stride) {
+    float xv[NI];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) xv[j] = __bfloat162float(x[p * NI + j]);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = br[i];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) a = fmaf(xv[j], wr[j][i], a);
+      o[i] = a;
+    }
+    const uint4 pk = pack_bf8(o);
+    *reinterpret_cast<uint4*>(out + p * 32 + g * 8) = pk;
+    if (stats) {
+      float r[8];
+      unpack_bf8(pk, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += r[i]; sq[i] = fmaf(r[i], r[i], sq[i]); }
+    }
+  }
+  if (stats) {
+    __shared__ float sh[NT / 32][2][32];
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = quad_col_sum(s[i]), d = quad_col_sum(sq[i]);
+      if (lane < 4) { sh[wv][0][lane * 8 + i] = a; sh[wv][1][lane * 8 + i] = d; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int which = threadIdx.x >> 5, c = threadIdx.x & 31;
+      double a = 0;
+      for (int k = 0; k < NT / 32; ++k) a += sh[k][which][c];
+      atomicAdd(stats + which * 32 + c, a);
+    }
+  }
+}
+
+// stem weight gradient, bf16: dw[j][c] += sum_p x[p][j] dy[p][c];  db[c] += sum_p dy[p][c]
+template <int NI>
+__global__ void __launch_bounds__(NT) stem_wgrad_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, int64_t M,
+                                                             float* __restrict__ dw, float* __restrict__ db) {
+  const int g = threadIdx.x & 3;
+  float acc[NI + 1][8];
+#pragma unroll
+  for (int j = 0; j <= NI; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * (NT / 4);
+  for (int64_t p = (int64_t)blockIdx.x * (NT / 4) + (threadIdx.x >> 2); p < M; p += 2 * stride) {
+    uint4 q[2]; float xv[2][NI];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t pp = p + u * stride;
+      if (pp < M) {
+        q[u] = __ldg(reinterpret_cast<const uint4*>(dy + pp * 32 + g * 8));
+#pragma unroll
+        for (int j = 0; j < NI; ++j) xv[u][j] = __bfloat162float(x[pp * NI + j]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * stride < M) {
+        float gv[8];
+        unpack_bf8(q[u], gv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[NI][i] += gv[i];
+#pragma unroll
+          for (int j = 0; j < NI; ++j) acc[j][i] = fmaf(xv[u][j], gv[i], acc[j][i]);
+        }
+      }
+    }
+  }
+  __shared__ float sh[NT / 32][NI + 1][32];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j <= NI; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = quad_col_sum(acc[j][i]);
+      if (lane < 4) sh[wv][j][lane * 8 + i] = a;
+    }
+  __syncthreads();
+  for (int o = threadIdx.x; o < (NI + 1) * 32; o += NT) {
+    const int j = o >> 5, c = o & 31;
+    float a = 0.f;
+    for (int k = 0; k < NT / 32; ++k) a += sh[k][j][c];
+    if (j < NI) atomicAdd(dw + j * 32 + c, a);
+    else if (db) atomicAdd(db + c, a);
+  }
+}
+
+// head forward, bf16 features -> fp32 logits: z[p][j] = sum_c h[p][c] w[c*NO + j] + b[j]; one thread per pixel
+template <int NO>
+__global__ void __launch_bounds__(NT) head_fwd_bf16_kernel(const bf16* __restrict__ h, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float* __restrict__ z, int64_t M) {
+  __shared__ float ws[32 * NO];
+  for (int i = threadIdx.x; i < 32 * NO; i += NT) ws[i] = w[i];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t p = (int64_t)blockIdx.x * NT + threadIdx.x; p < M; p += stride) {
+    uint4 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = __ldg(reinterpret_cast<const uint4*>(h + p * 32) + k);
+    float a[NO];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) a[j] = b ? b[j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float hv[8];
+      unpack_bf8(q[k], hv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NO; ++j) a[j] = fmaf(hv[i], ws[(k * 8 + i) * NO + j], a[j]);
+    }
+    float* zp = z + p * NO;
+#pragma unroll
+    for (int j = 0; j < NO; ++j) zp[j] = a[j];
+  }
+}
+
+// head backward, bf16 features: thread = (pixel, 8-channel group g)
+//   dh[p][8g+i] (=|+=) mask(h>0) * sum_j dz[p][j] w[(8g+i)*NO + j];  dw[c*NO+j] += sum_p h[p][c] dz[p][j];  db[j] += sum_p dz[p][j]
+template <int NO>
+__global__ void __launch_bounds__(NT) head_bwd_bf16_kernel(const bf16* __restrict__ h, const float* __restrict__ dz,
+                                                           const float* __restrict__ w, int64_t M, bf16* __restrict__ dh,
+                                                           int accumulate, int relu_mask, float* __restrict__ dw,
+                                                           float* __restrict__ db) {
+  const int g = threadIdx.x & 3;
+  float wr[8][NO], acc[8][NO], accb[NO];
+#pragma unroll
+  for (int j = 0; j < NO; ++j) {
+    accb[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { wr[i][j] = w[(g * 8 + i) * NO + j]; acc[i][j] = 0.f; }
+  }
+  const int64_t stride = (int64_t)gridDim.x * (NT / 4);
+  for (int64_t p = (int64_t)blockIdx.x * (NT / 4) + (threadIdx.x >> 2); p < M; p += stride) {
+    const uint4 hq = __ldg(reinterpret_cast<const uint4*>(h + p * 32 + g * 8));
+    float zv[NO];
+#pragma unroll
+    for (int j = 0; j < NO; ++j) zv[j] = __ldg(dz + p * NO + j);
+    uint4 prev;
+    if (dh && accumulate) prev = *reinterpret_cast<const uint4*>(dh + p * 32 + g * 8);
+    float hv[8];
+    unpack_bf8(hq, hv);
+    if (dh) {
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) a = fmaf(zv[j], wr[i][j], a);
+        d[i] = (relu_mask && !(hv[i] > 0.f)) ? 0.f : a;
+      }
+      if (accumulate) {
+        float pv[8];
+        unpack_bf8(prev, pv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += pv[i];
+      }
+      *reinterpret_cast<uint4*>(dh + p * 32 + g * 8) = pack_bf8(d);
+    }
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+      accb[j] += zv[j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(hv[i], zv[j], acc[i][j]);
+    }
+  }
+  __shared__ float sh[NT / 32][33][NO];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NO; ++j) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = quad_col_sum(acc[i][j]);
+      if (lane < 4) sh[wv][lane * 8 + i][j] = a;
+    }
+    const float bsum = quad_col_sum(accb[j]);      // every quad lane saw the same dz: lane 0's copy is the pixel sum
+    if (lane == 0) sh[wv][32][j] = bsum;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 33 * NO; o += NT) {
+    const int c = o / NO, j = o % NO;
+    float a = 0.f;
+    for (int k = 0; k < NT / 32; ++k) a += sh[k][c][j];
+    if (c < 32) atomicAdd(dw + c * NO + j, a);
+    else if (db) atomicAdd(db + j, a);
+  }
+}
+
+template <int NO>
+void launch_head_bwd_bf16(const void* h, const float* dz, const float* w, int64_t M, void* dh, int accumulate, int relu_mask,
+                          float* dw, float* db, cudaStream_t st) {
+  head_bwd_bf16_kernel<NO><<<rsa_num_sms() * 4, NT, 0, st>>>((const bf16*)h, dz, w, M, (bf16*)dh, accumulate, relu_mask, dw, db);
+}
+template <int NO>
+void launch_head_fwd_bf16(const void* h, const float* w, const float* b, float* z, int64_t M, cudaStream_t st) {
+  head_fwd_bf16_kernel<NO><<<rsa_num_sms() * 8, NT, 0, st>>>((const bf16*)h, w, b, z, M);
+}
+
 }  // namespace
 
 /* Stem: out[m, 0:32] = x[m, 0:n] . w[n][32] + b, optional BatchNorm statistics of the output (double[64]).
@@ -193,7 +439,9 @@ extern "C" int rsa_stem_fwd(const void* x, int x_dtype, const float* w, const fl
   RSA_REQUIRE(x && w && out && M > 0 && n >= 1 && n <= MAXN, RSA_ERR_SHAPE, "stem_fwd: bad args (n=%d)", n);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = thin_grid();
-  if (x_dtype == RSA_BF16 && out_dtype == RSA_BF16) stem_fwd_kernel<bf16, bf16><<<grid, NT, 0, st>>>((const bf16*)x, w, b, (bf16*)out, M, n, stats);
+  if (x_dtype == RSA_BF16 && out_dtype == RSA_BF16 && n == 3) stem_fwd_bf16_kernel<3><<<grid, NT, 0, st>>>((const bf16*)x, w, b, (bf16*)out, M, stats);
+  else if (x_dtype == RSA_BF16 && out_dtype == RSA_BF16 && n == 4) stem_fwd_bf16_kernel<4><<<grid, NT, 0, st>>>((const bf16*)x, w, b, (bf16*)out, M, stats);
+  else if (x_dtype == RSA_BF16 && out_dtype == RSA_BF16) stem_fwd_kernel<bf16, bf16><<<grid, NT, 0, st>>>((const bf16*)x, w, b, (bf16*)out, M, n, stats);
   else if (x_dtype == RSA_F32 && out_dtype == RSA_F32) stem_fwd_kernel<float, float><<<grid, NT, 0, st>>>((const float*)x, w, b, (float*)out, M, n, stats);
   else RSA_REQUIRE(false, RSA_ERR_DTYPE, "stem_fwd: dtype combination");
   RSA_CHECK_LAUNCH();
@@ -205,7 +453,9 @@ extern "C" int rsa_stem_wgrad(const void* x, const void* dy, int dtype, int64_t 
   RSA_REQUIRE(x && dy && dw && M > 0 && n >= 1 && n <= MAXN, RSA_ERR_SHAPE, "stem_wgrad: bad args (n=%d)", n);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = thin_grid();
-  if (dtype == RSA_BF16) stem_wgrad_kernel<bf16, bf16><<<grid, NT, 0, st>>>((const bf16*)x, (const bf16*)dy, M, n, dw, db);
+  if (dtype == RSA_BF16 && n == 3) stem_wgrad_bf16_kernel<3><<<rsa_num_sms() * 4, NT, 0, st>>>((const bf16*)x, (const bf16*)dy, M, dw, db);
+  else if (dtype == RSA_BF16 && n == 4) stem_wgrad_bf16_kernel<4><<<rsa_num_sms() * 4, NT, 0, st>>>((const bf16*)x, (const bf16*)dy, M, dw, db);
+  else if (dtype == RSA_BF16) stem_wgrad_kernel<bf16, bf16><<<grid, NT, 0, st>>>((const bf16*)x, (const bf16*)dy, M, n, dw, db);
   else if (dtype == RSA_F32) stem_wgrad_kernel<float, float><<<grid, NT, 0, st>>>((const float*)x, (const float*)dy, M, n, dw, db);
   else RSA_REQUIRE(false, RSA_ERR_DTYPE, "stem_wgrad: bad dtype");
   RSA_CHECK_LAUNCH();
@@ -220,9 +470,29 @@ extern "C" int rsa_head_bwd(const void* h, int h_dtype, const float* dz, const f
   RSA_REQUIRE(h && dz && w && dw && M > 0 && n >= 1 && n <= MAXN, RSA_ERR_SHAPE, "head_bwd: bad args (n=%d)", n);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = thin_grid();
-  if (h_dtype == RSA_BF16) head_bwd_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)h, dz, w, M, n, (bf16*)dh, accumulate, relu_mask, dw, db);
+  if (h_dtype == RSA_BF16 && n <= 8) {
+    switch (n) {
+#define HB_CASE(NN) case NN: launch_head_bwd_bf16<NN>(h, dz, w, M, dh, accumulate, relu_mask, dw, db, st); break;
+      HB_CASE(1) HB_CASE(2) HB_CASE(3) HB_CASE(4) HB_CASE(5) HB_CASE(6) HB_CASE(7) HB_CASE(8)
+#undef HB_CASE
+    }
+  } else if (h_dtype == RSA_BF16) head_bwd_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)h, dz, w, M, n, (bf16*)dh, accumulate, relu_mask, dw, db);
   else if (h_dtype == RSA_F32) head_bwd_kernel<float><<<grid, NT, 0, st>>>((const float*)h, dz, w, M, n, (float*)dh, accumulate, relu_mask, dw, db);
   else RSA_REQUIRE(false, RSA_ERR_DTYPE, "head_bwd: bad dtype");
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+/* Head forward: z[m, 0:n] (fp32 logits) = h[m, 0:32] (bf16) . w[32][n] + b, n <= 8.  Replaces the final Conv2D 1x1 of the
+ * heads (model2.py:159,168,180,186) in bf16 mode: pure streaming, 64 B read + 4n B written per pixel. */
+extern "C" int rsa_head_fwd(const void* h, const float* w, const float* b, float* z, int64_t M, int n, void* stream) {
+  RSA_REQUIRE(h && w && z && M > 0 && n >= 1 && n <= 8, RSA_ERR_SHAPE, "head_fwd: bad args (n=%d)", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n) {
+#define HF_CASE(NN) case NN: launch_head_fwd_bf16<NN>(h, w, b, z, M, st); break;
+    HF_CASE(1) HF_CASE(2) HF_CASE(3) HF_CASE(4) HF_CASE(5) HF_CASE(6) HF_CASE(7) HF_CASE(8)
+#undef HF_CASE
+  }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }

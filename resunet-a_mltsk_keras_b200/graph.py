@@ -273,6 +273,8 @@ class Plan:
         b_ = self.P(name + "/bias")
         if self._thin_stem(inputs, cout, name, out, stats, bias_grad, relu):
             return out
+        if self._thin_head(inputs, cout, name, out, stats, bias_grad, relu):
+            return out
         pw = self._pw_classify(inputs, cout, name, out)
         if pw is not None:
             self._conv1x1_tc(inputs, pw, cout, name, out, stats, bias_grad, relu)
@@ -318,6 +320,24 @@ class Plan:
             self.tape.append(bwd)
         return True
 
+    def _thin_head(self, inputs, cout, name, out, stats, bias_grad, relu):
+        """Final Conv2D 1x1 of a head (32 -> n classes, fp32 logits, model2.py:159,168,180,186): streaming kernel."""
+        if len(inputs) != 1 or relu or stats or cout > 8 or out.dtype != torch.float32 or not hasattr(self.lib, "head_fwd"):
+            return False
+        t, mode, relu_in = inputs[0]
+        if mode != "plain" or relu_in or t.C != 32 or t.dtype != torch.bfloat16:
+            return False
+        W_, b_ = self.P(name + "/kernel"), self.P(name + "/bias")
+        self.fwd.append(self.lib.head_fwd(t.data, W_, b_, out.data, out.M, cout))
+        if self.training:
+            def bwd():
+                if out.grad is None:
+                    return
+                ok = self._head_bwd(inputs, out, name, cout, bias_grad)
+                assert ok, "head backward kernel unavailable"
+            self.tape.append(bwd)
+        return True
+
     def _head_bwd(self, inputs, out, name, cout, bias_grad):
         """Backward of a head's last 1x1 conv (32 -> n classes, fp32 logits): one fused streaming kernel."""
         if len(inputs) != 1 or out.dtype != torch.float32 or cout > 16 or not hasattr(self.lib, "head_bwd"):
@@ -342,7 +362,7 @@ class Plan:
         ent = self.net.tc.get(name)
         if ent is None or ent["taps"] != 1 or self.adt != torch.bfloat16:
             return None
-        if out.H != out.W or out.W < 4 or (out.W & (out.W - 1)) or cout > 1024:
+        if out.H != out.W or out.W < 1 or (out.W & (out.W - 1)) or cout > 1024:
             return None
         mains, sides, koff = [], [], 0
         for t, mode, relu_in in inputs:
@@ -365,8 +385,8 @@ class Plan:
         return mains, sides, koff
 
     @staticmethod
-    def _tc_spatial_ok(H, W):
-        return H == W and W >= 4 and (W & (W - 1)) == 0
+    def _tc_spatial_ok(H, W, min_side=1):
+        return H == W and W >= min_side and (W & (W - 1)) == 0
 
     def _pw_fwd_one(self, src, koff, K, cout, name, out, Hq, Wq):
         """q = W[koff:koff+C] . src at the source's own resolution (no bias)."""
@@ -424,7 +444,7 @@ class Plan:
             def one_source(t, koff, dq, Hq, Wq, in_stride):
                 """weight + data gradient of one source given the gradient dq at the conv's own resolution."""
                 sp_ok = self._tc_spatial_ok(Hq, Wq)
-                if bf and p2(t.C) and p2(cout) and sp_ok:
+                if bf and p2(t.C) and p2(cout) and self._tc_spatial_ok(Hq, Wq, 4):
                     self.bwd.append(lib.pw_wgrad_tc(t.data, dq, dW[koff * cout:], cout, N, Hq, Wq, t.C, cout, in_stride))
                 else:
                     seg = Seg(t.data, t.C, t.H, t.W, mult=in_stride, w_off=koff * cout)

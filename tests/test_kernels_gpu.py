@@ -329,3 +329,17 @@ def test_head_bwd_thin_kernel(lib, dt, n, acc, mask):
     dh = rnd((M, 32), dt, 4)
     dw, db = torch.zeros(32 * n), torch.zeros(n)
     run_pair(lib, "head_bwd", [h, dz, w, M, n, dh, acc, mask, dw, db], {}, [5, 8, 9], max(TOL[dt], 1e-4), 1e-3)
+
+
+@pytest.mark.parametrize("n", [6, 3, 8])
+def test_head_fwd_thin_kernel(lib, n):
+    """bf16 features -> fp32 logits (model2.py:159,168,180,186) against the fp64 product of the same operands."""
+    M = 30011
+    h = rnd((M, 32), torch.bfloat16, 1)
+    w = rnd((32 * n,), torch.float32, 2, 0.3)
+    b = rnd((n,), torch.float32, 3)
+    z = torch.zeros((M, n), dtype=torch.float32).cuda()
+    lib.head_fwd(h.cuda(), w.cuda(), b.cuda(), z, M, n)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = h.double() @ w.view(32, n).double() + b.double()
+    assert (z.cpu().double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
