@@ -188,7 +188,7 @@ int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void*
                      int W, int Cout, int taps, int dil, int in_stride, int nup, const void* const* up_ptrs,
                      const int* up_shifts, int k_base, int k_total, int out_stride, const void* bnr_x,
                      const float* bnr_coef, int accumulate, int relu, void* stream);
-/* Thin-layer (32-channel) dilated 3x3 'same' convolution (conv_tc3.cu): resident weights, halo tiles for |dil| <= 3,
+/* Thin-layer (32- / 64-channel) dilated 3x3 'same' convolution (conv_tc3.cu): resident weights, halo tiles for |dil| <= 3,
  * up to four branches accumulated in one TMEM tile (ResBlock-a branch sum, model2.py:23-31), TMA-stored output and
  * BatchNormalization statistics computed by the tensor core.
  *   out = epi( sum_b conv3x3(xs[b], wts[b], dils[b]) + sum_b biases[b] ), epi: + residual, + out (accumulate), ReLU,
@@ -200,7 +200,8 @@ int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float*
                      void* out, const void* residual, const void* mask, double* stats, int N, int H, int W, int C,
                      int accumulate, int relu, void* stream);
 /* Weight gradient of the thin layers: one x halo per 16x16 item, the three taps of a tap row are the M atoms of one
- * MMA (conv_tc3.cu); same contract as rsa_conv_tc_wgrad, Cin == Cout == C == 32, dil > 0. */
+ * MMA (conv_tc3.cu); same contract as rsa_conv_tc_wgrad, Cin == Cout == C in {32, 64}, dil > 0 (C = 64: dil <= 3). */
+int rsa_conv_tc3_wgrad_supported(int N, int H, int W, int C, int dil);
 int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int dil, void* stream);
 /* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co];
  * x, dy bf16 NHWC, Cin == Cout.  Replaces cuDNN's Conv2D backward-filter behind model2.py:19-24,153-178. */

@@ -138,7 +138,7 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported",
-                                "rsa_conv_tc2_supported", "rsa_conv_tc3_supported"])
+                                "rsa_conv_tc2_supported", "rsa_conv_tc3_supported", "rsa_conv_tc3_wgrad_supported"])
 
 
 def load_cdll(path=LIB_PATH):
@@ -160,6 +160,8 @@ def load_cdll(path=LIB_PATH):
     dll.rsa_conv_tc2_supported.restype = C.c_int
     dll.rsa_conv_tc3_supported.argtypes = [C.c_int] * 4
     dll.rsa_conv_tc3_supported.restype = C.c_int
+    dll.rsa_conv_tc3_wgrad_supported.argtypes = [C.c_int] * 5
+    dll.rsa_conv_tc3_wgrad_supported.restype = C.c_int
     return dll
 
 
@@ -375,6 +377,9 @@ class Lib:
         return self._bind("rsa_conv_tc3_fwd", xa, wa, ba, da, nbr, _p(out), _p(residual), _p(mask), _p(stats), N, H, W,
                           C_, int(accumulate), int(relu),
                           keep=(xs, wts, biases, out, residual, mask, stats, xa, wa, ba, da))
+
+    def conv_tc3_wgrad_supported(self, N, H, W, C_, dil):
+        return bool(self.dll.rsa_conv_tc3_wgrad_supported(N, H, W, C_, dil))
 
     def conv_tc3_wgrad(self, x, dy, dw, N, H, W, C_, dil):
         assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32

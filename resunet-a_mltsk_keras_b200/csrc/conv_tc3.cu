@@ -22,13 +22,23 @@
 
 namespace {
 
-constexpr int T3_THREADS = 512;   // warp 0 TMA, 1..4 MMA (one per sub-tile), 5 TMA store, 8..15 epilogue
 constexpr int T3_MAXBR = 4;
-constexpr int T3_C = 32;
-constexpr int T3_PITCH = T3_C * 2;            // bytes per pixel row = SWIZZLE_64B span
-constexpr int T3_BOXB = 128 * T3_PITCH;       // one 16x8-pixel sub-tile
-constexpr int T3_WBYTES = 9 * T3_C * T3_PITCH;
-constexpr int T3_NSB = 4;                     // staged output tiles
+constexpr int T3_MAXSB = 4;
+
+// compile-time geometry of one channel class (C = 32: SWIZZLE_64B rows, C = 64: SWIZZLE_128B rows)
+template <int C>
+struct T3 {
+  static constexpr int PITCH = C * 2;               // bytes per pixel = swizzle span
+  static constexpr int BOXB = 128 * PITCH;          // one 16x8-pixel sub-tile
+  static constexpr int WBYTES = 9 * C * PITCH;      // one branch's weights
+  static constexpr uint32_t LAYOUT = C == 32 ? 4u : 2u;   // UMMA layout code: SWIZZLE_64B / SWIZZLE_128B
+};
+// warp roles: 0 TMA producer, 1..KT MMA issuers (one per sub-tile), KT+1 TMA store, EPI0..EPI0+7 epilogue
+template <int KT> struct T3Warps {
+  static constexpr int STORE = KT + 1;
+  static constexpr int EPI0 = (KT + 2 + 3) / 4 * 4;
+  static constexpr int THREADS = (EPI0 + 8) * 32;
+};
 
 struct Tc3Params {
   int N, H, W;
@@ -36,11 +46,10 @@ struct Tc3Params {
   int dil[T3_MAXBR];      // signed: negative = data gradient (taps mirrored)
   int halo[T3_MAXBR];     // 1: one halo box per item, 0: one box per tap
   int items, tiles_w, tiles_h;
-  int nstages, slot_bytes;
+  int nstages, slot_bytes, nsb;
+  int nsb_log, nsi_log;         // nsb, nsi are powers of two
+  int nsi, has_add, has_mask;   // side-input ring: slots, addend present (residual or previous out), ReLU mask present
   const float* bias[T3_MAXBR];
-  const bf16* residual;
-  const bf16* mask;
-  const bf16* prev;       // accumulate: previous contents of out
   double* stats;
   int relu;
 };
@@ -69,35 +78,42 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* t) {
   t[4] = __uint_as_float(q.z << 16); t[5] = __uint_as_float(q.z & 0xffff0000u);
   t[6] = __uint_as_float(q.w << 16); t[7] = __uint_as_float(q.w & 0xffff0000u);
 }
-// K-major SWIZZLE_64B descriptor split in halves: hi carries the stride byte offset (distance between 8-row groups)
-__device__ __forceinline__ uint32_t t3_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (4u << 29); }
+// K-major swizzled descriptor split in halves: hi carries the stride byte offset (distance between 8-row groups)
+template <int C> __device__ __forceinline__ uint32_t t3_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (T3<C>::LAYOUT << 29);
+}
 __device__ __forceinline__ uint64_t t3_desc(uint32_t hi, uint32_t saddr) {
   return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFF) | (1u << 16));
 }
 
-struct Tc3Maps { CUtensorMap a[T3_MAXBR]; CUtensorMap w[T3_MAXBR]; CUtensorMap out; };
+struct Tc3Maps { CUtensorMap a[T3_MAXBR]; CUtensorMap w[T3_MAXBR]; CUtensorMap out; CUtensorMap add; CUtensorMap mask; };
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
 struct Tc3Smem {
-  int w_off, st_off, ring_off, misc_off, bar_off, total;
-  __host__ __device__ Tc3Smem(int nbr, int nstages, int slot_bytes) {
+  int w_off, st_off, side_off, ring_off, misc_off, bar_off, total;
+  __host__ __device__ Tc3Smem(int C, int nbr, int nsb, int nside, int nsi, int nstages, int slot_bytes) {
     w_off = 0;
-    st_off = (nbr * T3_WBYTES + 1023) & ~1023;
-    ring_off = st_off + T3_NSB * T3_BOXB;
-    misc_off = ring_off + nstages * slot_bytes;              // bias[32], csum[32], csq[32]
-    bar_off = misc_off + 3 * T3_C * 4;
-    total = bar_off + (2 * nstages + 2 * T3_NSB + 8) * 8 + 16 + 1024;
+    st_off = (nbr * 9 * C * C * 2 + 1023) & ~1023;
+    side_off = st_off + nsb * 128 * C * 2;                   // [nsi][nside] tiles of 128 pixels
+    ring_off = side_off + nsi * nside * 128 * C * 2;
+    misc_off = ring_off + nstages * slot_bytes;              // bias[C], csum[C], csq[C]
+    bar_off = misc_off + 3 * C * 4;
+    total = bar_off + (2 * nstages + 4 * T3_MAXSB + 8) * 8 + 16 + 1024;
   }
 };
 
-template <int KT>
-__global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
-  constexpr int C = T3_C, PITCH = T3_PITCH, BOXB = T3_BOXB;
+template <int C, int KT>
+__global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
+  constexpr int PITCH = T3<C>::PITCH, BOXB = T3<C>::BOXB, WBYTES = T3<C>::WBYTES;
+  constexpr int EPI0 = T3Warps<KT>::EPI0;
+  constexpr int NCT = C / 2;            // accumulator columns per epilogue thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const Tc3Smem L(p.nbr, p.nstages, p.slot_bytes);
+  const int nside = p.has_add + p.has_mask;
+  const Tc3Smem L(C, p.nbr, p.nsb, nside, p.nsi, p.nstages, p.slot_bytes);
   uint8_t* wsm = smem + L.w_off;
   uint8_t* ysm = smem + L.st_off;
+  uint8_t* sidesm = smem + L.side_off;
   uint8_t* ring = smem + L.ring_off;
   float* bias_s = reinterpret_cast<float*>(smem + L.misc_off);
   float* csum = bias_s + C;
@@ -106,32 +122,42 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
   uint64_t* empty_bar = full_bar + p.nstages;
   uint64_t* tfull = empty_bar + p.nstages;   // [2]
   uint64_t* tempty = tfull + 2;              // [2]
-  uint64_t* sready = tempty + 2;             // [NSB] staged tile written by the 8 epilogue warps
-  uint64_t* sfree = sready + T3_NSB;         // [NSB] staged tile read by its TMA store
-  uint64_t* wbar = sfree + T3_NSB;
+  uint64_t* sready = tempty + 2;             // [nsb] staged tile written by the 8 epilogue warps
+  uint64_t* sfree = sready + T3_MAXSB;       // [nsb] staged tile read by its TMA store
+  uint64_t* ifull = sfree + T3_MAXSB;        // [nsi] side-input tiles landed
+  uint64_t* iempty = ifull + T3_MAXSB;       // [nsi] side-input tiles consumed by the 8 epilogue warps
+  uint64_t* wbar = iempty + T3_MAXSB;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_stats = p.stats != nullptr;
+  constexpr uint32_t TMEM_COLS = 2 * KT * C <= 64 ? 64 : (2 * KT * C <= 128 ? 128 : 256);
+  static_assert(2 * KT * C <= 256, "accumulator ring exceeds the TMEM allocation");
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < p.nbr; ++b) { prefetch_tmap(&maps.a[b]); prefetch_tmap(&maps.w[b]); }
     prefetch_tmap(&maps.out);
+    if (p.has_add) prefetch_tmap(&maps.add);
+    if (p.has_mask) prefetch_tmap(&maps.mask);
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], KT); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], KT); mbar_init(&tempty[s], 8); }
-    for (int s = 0; s < T3_NSB; ++s) { mbar_init(&sready[s], 8); mbar_init(&sfree[s], 1); }
+    for (int s = 0; s < T3_MAXSB; ++s) {
+      mbar_init(&sready[s], 8); mbar_init(&sfree[s], 1);
+      mbar_init(&ifull[s], 1); mbar_init(&iempty[s], 8);
+    }
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  if (warp == 8) {
+  if (warp >= EPI0 && warp < EPI0 + C / 32) {
+    const int c = (warp - EPI0) * 32 + lane;
     float b = 0.f;
-    for (int k = 0; k < p.nbr; ++k) if (p.bias[k]) b += __ldg(p.bias[k] + lane);
-    bias_s[lane] = b;
-    csum[lane] = 0.f;
-    csq[lane] = 0.f;
+    for (int k = 0; k < p.nbr; ++k) if (p.bias[k]) b += __ldg(p.bias[k] + c);
+    bias_s[c] = b;
+    csum[c] = 0.f;
+    csq[c] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -141,10 +167,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(wbar, p.nbr * T3_WBYTES);
+      mbar_expect_tx(wbar, p.nbr * WBYTES);
       for (int b = 0; b < p.nbr; ++b)
-        for (int t = 0; t < 9; ++t) tma_load_3d(wsm + b * T3_WBYTES + t * C * PITCH, &maps.w[b], wbar, 0, 0, t);
-      int stage = 0, phase = 0;
+        for (int t = 0; t < 9; ++t) tma_load_3d(wsm + b * WBYTES + t * C * PITCH, &maps.w[b], wbar, 0, 0, t);
+      int stage = 0, phase = 0, iseq = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         int r = item;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
@@ -168,6 +194,18 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             }
           }
         }
+        // side inputs of this item's sub-tiles (addend, ReLU mask): same 16x8 boxes as the output tiles, landed several
+        // sub-tiles ahead of the epilogue that consumes them
+        if (nside) {
+          for (int s = 0; s < KT; ++s, ++iseq) {
+            const int k = iseq & (p.nsi - 1);
+            mbar_wait(&iempty[k], ((iseq >> p.nsi_log) & 1) ^ 1);
+            mbar_expect_tx(&ifull[k], nside * BOXB);
+            uint8_t* dst = sidesm + k * nside * BOXB;
+            if (p.has_add) tma_load_4d(dst, &maps.add, &ifull[k], 0, w0 + 8 * s, h0, n);
+            if (p.has_mask) tma_load_4d(dst + p.has_add * BOXB, &maps.mask, &ifull[k], 0, w0 + 8 * s, h0, n);
+          }
+        }
       }
     }
   } else if (warp <= KT) {
@@ -178,7 +216,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
       mbar_wait(wbar, 0);
       tc_fence_after();
       const uint32_t wbase = smem_u32(wsm);
-      const uint32_t bhi = t3_desc_hi(8 * PITCH);
+      const uint32_t bhi = t3_desc_hi<C>(8 * PITCH);
       int stage = 0, phase = 0, it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         int r = item;
@@ -191,10 +229,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         uint32_t started = 0;
         for (int b = 0; b < p.nbr; ++b) {
           const int d = p.dil[b], ad = d < 0 ? -d : d;
-          const uint32_t wb = wbase + b * T3_WBYTES;
+          const uint32_t wb = wbase + b * WBYTES;
           if (p.halo[b]) {
             const int Wh = 8 * KT + 2 * ad;
-            const uint32_t ahi = t3_desc_hi(Wh * PITCH);
+            const uint32_t ahi = t3_desc_hi<C>(Wh * PITCH);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(ring + stage * p.slot_bytes) + (uint32_t)((ad * Wh + ad + 8 * s) * PITCH);
@@ -203,14 +241,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
             for (int tap = 0; tap < 9; ++tap) {
               const uint64_t adesc = t3_desc(ahi, sa + (tap / 3 - 1) * rowb + (tap % 3 - 1) * colb);
               const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
-              umma_bf16(acc, adesc, bdesc, idesc, started | (tap > 0));
-              umma_bf16(acc, adesc + 2, bdesc + 2, idesc, 1);
+#pragma unroll
+              for (int k = 0; k < C / 16; ++k)
+                umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started | (tap > 0) | (k > 0));
             }
             started = 1;
             umma_commit(&empty_bar[stage]);
             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           } else {
-            const uint32_t ahi = t3_desc_hi(8 * KT * PITCH);
+            const uint32_t ahi = t3_desc_hi<C>(8 * KT * PITCH);
             for (int tap = 0; tap < 9; ++tap) {
               const int ch = h0 + (tap / 3 - 1) * d, cw = w0 + (tap % 3 - 1) * d;
               if (ch + 16 <= 0 || ch >= p.H || cw + 8 * KT <= 0 || cw >= p.W) continue;
@@ -218,8 +257,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
               tc_fence_after();
               const uint64_t adesc = t3_desc(ahi, smem_u32(ring + stage * p.slot_bytes) + 8 * s * PITCH);
               const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
-              umma_bf16(acc, adesc, bdesc, idesc, started);
-              umma_bf16(acc, adesc + 2, bdesc + 2, idesc, 1);
+#pragma unroll
+              for (int k = 0; k < C / 16; ++k)
+                umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started | (k > 0));
               started = 1;
               umma_commit(&empty_bar[stage]);
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
@@ -229,143 +269,150 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
         umma_commit(&tfull[it & 1]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == T3Warps<KT>::STORE) {
     // ===== TMA store of the staged tiles =====
     if (lane == 0) {
       int seq = 0;
+      const int lag = p.nsb >> 1;          // stores allowed in flight before a buffer is handed back
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         int r = item;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h; r /= p.tiles_h;
         const int n = r, h0 = th * 16, w0 = tw * 8 * KT;
         for (int s = 0; s < KT; ++s, ++seq) {
-          const int j = seq % T3_NSB;
-          mbar_wait(&sready[j], (seq / T3_NSB) & 1);
+          const int j = seq & (p.nsb - 1);
+          mbar_wait(&sready[j], (seq >> p.nsb_log) & 1);
           tma_store_4d(&maps.out, ysm + j * BOXB, 0, w0 + 8 * s, h0, n);
-          // the store issued two tiles ago has finished reading its buffer: hand that buffer back
-          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-          if (seq >= 2) mbar_arrive(&sfree[(seq - 2) % T3_NSB]);
+          // the store issued `lag` tiles ago has finished reading its buffer: hand that buffer back
+          if (lag == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (seq >= lag) mbar_arrive(&sfree[(seq - lag) & (p.nsb - 1)]);
         }
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-  } else if (warp >= 8) {
-    // ===== epilogue warps 8..15: lane quarter q, column half hs =====
-    const int q = warp & 3, hs = (warp - 8) >> 2;
+  } else if (warp >= EPI0) {
+    // ===== epilogue warps: lane quarter q, column half hs =====
+    const int q = warp & 3, hs = (warp - EPI0) >> 2;
     const int rrow = q * 32 + lane;                 // accumulator row = pixel of the 16x8 sub-tile
     const int py = rrow >> 3, px = rrow & 7;
     const uint32_t srow = (uint32_t)rrow * PITCH;
-    const uint32_t sw = (uint32_t)((rrow >> 1) & 3);
-    const uint32_t ch0 = ((uint32_t)(2 * hs) ^ sw) << 4, ch1 = ((uint32_t)(2 * hs + 1) ^ sw) << 4;
-    float bias_r[16];
+    const uint32_t sw = C == 32 ? (uint32_t)((rrow >> 1) & 3) : (uint32_t)(rrow & 7);   // swizzle phase of this row
+    float acc_s[NCT], acc_q[NCT];                   // BatchNorm statistics of this thread's pixels (all its sub-tiles)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) bias_r[j] = bias_s[hs * 16 + j];
-    const bool side = p.residual || p.prev || p.mask;
-    auto pix_off = [&](int item, int s) -> size_t {
-      int r = item;
-      const int tw = r % p.tiles_w; r /= p.tiles_w;
-      const int th = r % p.tiles_h; r /= p.tiles_h;
-      return (((size_t)r * p.H + (th * 16 + py)) * p.W + (tw * 8 * KT + 8 * s + px)) * C + hs * 16;
-    };
-    float acc_s[16], acc_q[16];                     // BatchNorm statistics of this thread's pixels (all its sub-tiles)
+    for (int j = 0; j < NCT; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+    float bias_r[C == 32 ? 16 : 1];                 // 32 channels: the thread's 16 biases live in registers
+    if constexpr (C == 32) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
-    uint4 rq[2], pq[2], mq[2];                      // side inputs of the next sub-tile (bf16 x 16), prefetched
-    auto prefetch = [&](size_t o) {
-      if (p.residual) { rq[0] = __ldg(reinterpret_cast<const uint4*>(p.residual + o)); rq[1] = __ldg(reinterpret_cast<const uint4*>(p.residual + o + 8)); }
-      if (p.prev) { pq[0] = *reinterpret_cast<const uint4*>(p.prev + o); pq[1] = *reinterpret_cast<const uint4*>(p.prev + o + 8); }
-      if (p.mask) { mq[0] = __ldg(reinterpret_cast<const uint4*>(p.mask + o)); mq[1] = __ldg(reinterpret_cast<const uint4*>(p.mask + o + 8)); }
-    };
-    if (side && (int)blockIdx.x < p.items) prefetch(pix_off(blockIdx.x, 0));
+      for (int j = 0; j < 16; ++j) bias_r[j] = bias_s[hs * 16 + j];
+    }
     int it = 0, seq = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       mbar_wait(&tfull[it & 1], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int s = 0; s < KT; ++s, ++seq) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((it & 1) * KT + s) * C + hs * 16), v);
-        if (s == KT - 1) {
-          tc_fence_before();
+        const int j = seq & (p.nsb - 1);
+        uint8_t* yb = ysm + j * BOXB + srow;
+        const int ks = nside ? (seq & (p.nsi - 1)) : 0;
+        const uint8_t* ib = sidesm + ks * nside * BOXB + srow;
+        if (nside) {
+          if (lane == 0) mbar_wait(&ifull[ks], (seq >> p.nsi_log) & 1);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[it & 1]);
         }
-        float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bias_r[j];
-        if (side) {
-          float t[16];
-          if (p.residual) {
-            unpack8(rq[0], t); unpack8(rq[1], t + 8);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += t[j];
+        for (int cc = 0; cc < NCT; cc += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((it & 1) * KT + s) * C + hs * NCT + cc), v);
+          if (s == KT - 1 && cc + 16 >= NCT) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[it & 1]);
           }
-          if (p.prev) {
-            unpack8(pq[0], t); unpack8(pq[1], t + 8);
+          float f[16];
+          if constexpr (C == 32) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += t[j];
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_r[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias_s + hs * NCT + cc + i);
+              f[i] = __uint_as_float(v[i]) + bv.x; f[i + 1] = __uint_as_float(v[i + 1]) + bv.y;
+              f[i + 2] = __uint_as_float(v[i + 2]) + bv.z; f[i + 3] = __uint_as_float(v[i + 3]) + bv.w;
+            }
+          }
+          const uint32_t c16 = (uint32_t)((hs * NCT + cc) >> 3);        // first 16-byte chunk of this group inside the row
+          const uint32_t o0 = (c16 ^ sw) << 4, o1 = ((c16 + 1) ^ sw) << 4;
+          if (p.has_add) {
+            float t[16];
+            unpack8(*reinterpret_cast<const uint4*>(ib + o0), t); unpack8(*reinterpret_cast<const uint4*>(ib + o1), t + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += t[i];
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (p.mask) {
-            unpack8(mq[0], t); unpack8(mq[1], t + 8);
+          if (p.has_mask) {
+            float t[16];
+            const uint8_t* mb = ib + p.has_add * BOXB;
+            unpack8(*reinterpret_cast<const uint4*>(mb + o0), t); unpack8(*reinterpret_cast<const uint4*>(mb + o1), t + 8);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = t[j] > 0.f ? f[j] : 0.f;
+            for (int i = 0; i < 16; ++i) f[i] = t[i] > 0.f ? f[i] : 0.f;
           }
-          // next sub-tile's side inputs: issued now, consumed one iteration later
-          const int nitem = s + 1 < KT ? item : item + (int)gridDim.x;
-          if (nitem < p.items) prefetch(pix_off(nitem, s + 1 < KT ? s + 1 : 0));
-        } else if (p.relu) {
+          uint4 lo, hi;
+          lo.x = pack_bf16x2(f[0], f[1]); lo.y = pack_bf16x2(f[2], f[3]); lo.z = pack_bf16x2(f[4], f[5]); lo.w = pack_bf16x2(f[6], f[7]);
+          hi.x = pack_bf16x2(f[8], f[9]); hi.y = pack_bf16x2(f[10], f[11]); hi.z = pack_bf16x2(f[12], f[13]); hi.w = pack_bf16x2(f[14], f[15]);
+          if (cc == 0) {
+            if (lane == 0) mbar_wait(&sfree[j], ((seq >> p.nsb_log) & 1) ^ 1);
+            __syncwarp();
+          }
+          *reinterpret_cast<uint4*>(yb + o0) = lo;
+          *reinterpret_cast<uint4*>(yb + o1) = hi;
+          if (has_stats) {
+            // per-thread partial sums of the stored (bf16-rounded) values; reduced across lanes once per CTA
+            float t[16];
+            unpack8(lo, t); unpack8(hi, t + 8);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int i = 0; i < 16; ++i) { acc_s[cc + i] += t[i]; acc_q[cc + i] = fmaf(t[i], t[i], acc_q[cc + i]); }
+          }
         }
-        uint4 lo, hi;
-        lo.x = pack_bf16x2(f[0], f[1]); lo.y = pack_bf16x2(f[2], f[3]); lo.z = pack_bf16x2(f[4], f[5]); lo.w = pack_bf16x2(f[6], f[7]);
-        hi.x = pack_bf16x2(f[8], f[9]); hi.y = pack_bf16x2(f[10], f[11]); hi.z = pack_bf16x2(f[12], f[13]); hi.w = pack_bf16x2(f[14], f[15]);
-        const int j = seq % T3_NSB;
-        if (lane == 0) mbar_wait(&sfree[j], ((seq / T3_NSB) & 1) ^ 1);
-        __syncwarp();
-        uint8_t* yb = ysm + j * BOXB + srow;
-        *reinterpret_cast<uint4*>(yb + ch0) = lo;
-        *reinterpret_cast<uint4*>(yb + ch1) = hi;
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sready[j]);
-        if (has_stats) {
-          // per-thread partial sums of the stored (bf16-rounded) values; reduced across lanes once per CTA
-          float t[16];
-          unpack8(lo, t); unpack8(hi, t + 8);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { acc_s[i] += t[i]; acc_q[i] = fmaf(t[i], t[i], acc_q[i]); }
+        if (lane == 0) {
+          mbar_arrive(&sready[j]);
+          if (nside) mbar_arrive(&iempty[ks]);
         }
       }
     }
     if (has_stats) {
       // 16-wide butterfly reduce-scatter over the warp's 32 pixels: the lane pair (2m, 2m+1) ends with channel bitrev4(m)
 #pragma unroll
-      for (int off = 16, n = 8; n >= 1; off >>= 1, n >>= 1) {
-        const bool upper = (lane & off) != 0;
+      for (int cc = 0; cc < NCT; cc += 16) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-          const float send_s = upper ? acc_s[i] : acc_s[i + n], keep_s = upper ? acc_s[i + n] : acc_s[i];
-          const float send_q = upper ? acc_q[i] : acc_q[i + n], keep_q = upper ? acc_q[i + n] : acc_q[i];
-          acc_s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-          acc_q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+        for (int off = 16, n = 8; n >= 1; off >>= 1, n >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const float send_s = upper ? acc_s[cc + i] : acc_s[cc + i + n], keep_s = upper ? acc_s[cc + i + n] : acc_s[cc + i];
+            const float send_q = upper ? acc_q[cc + i] : acc_q[cc + i + n], keep_q = upper ? acc_q[cc + i + n] : acc_q[cc + i];
+            acc_s[cc + i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+            acc_q[cc + i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+          }
+        }
+        acc_s[cc] += __shfl_xor_sync(0xffffffffu, acc_s[cc], 1);
+        acc_q[cc] += __shfl_xor_sync(0xffffffffu, acc_q[cc], 1);
+        if ((lane & 1) == 0) {
+          const int ch = hs * NCT + cc + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          atomicAdd(&csum[ch], acc_s[cc]);
+          atomicAdd(&csq[ch], acc_q[cc]);
         }
       }
-      acc_s[0] += __shfl_xor_sync(0xffffffffu, acc_s[0], 1);
-      acc_q[0] += __shfl_xor_sync(0xffffffffu, acc_q[0], 1);
-      if ((lane & 1) == 0) {
-        const int ch = hs * 16 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        atomicAdd(&csum[ch], acc_s[0]);
-        atomicAdd(&csq[ch], acc_q[0]);
-      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp == 8 && it > 0) {
-        atomicAdd(p.stats + lane, (double)csum[lane]);
-        atomicAdd(p.stats + C + lane, (double)csq[lane]);
+      if (it > 0 && warp < EPI0 + C / 32) {
+        const int c = (warp - EPI0) * 32 + lane;
+        atomicAdd(p.stats + c, (double)csum[c]);
+        atomicAdd(p.stats + C + c, (double)csq[c]);
       }
     }
     tc_fence_before();
@@ -373,44 +420,46 @@ __global__ void __launch_bounds__(T3_THREADS, 1) conv_tc3_kernel(const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
-template <int KT>
+template <int C, int KT>
 int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<C, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { rsa_set_error("conv_tc3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
   const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
-  conv_tc3_kernel<KT><<<grid, T3_THREADS, smem_bytes, st>>>(maps, p);
+  conv_tc3_kernel<C, KT><<<grid, T3Warps<KT>::THREADS, smem_bytes, st>>>(maps, p);
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
 
 }  // namespace
 
-/* Shapes the thin-layer kernel accepts: 32 channels in and out, H a multiple of 16, W a multiple of 32. */
+/* Shapes the thin-layer kernels accept: 32 or 64 channels in and out, H a multiple of 16, W a multiple of 32. */
 extern "C" int rsa_conv_tc3_supported(int N, int H, int W, int C) {
-  return C == T3_C && N >= 1 && H >= 16 && H % 16 == 0 && W >= 32 && W % 32 == 0;
+  return (C == 32 || C == 64) && N >= 1 && H >= 16 && H % 16 == 0 && W >= 32 && W % 32 == 0;
 }
 
 /* out[n,h,w,:] = epi( sum_b sum_tap x_b[n, h+dy*dil_b, w+dx*dil_b, :] . wt_b[tap] + sum_b bias_b )
  *   epi: + residual, + out (accumulate), ReLU, mask (keep where mask > 0), in that order; bf16 NHWC throughout.
- * xs[b]: bf16 [N,H,W,32]; wts[b]: bf16 [9][32][32] K-major copies ([tap][co][ci] forward, [tap][ci][co] with a negative
- * dilation for the data gradient, as rsa_conv_tc2_fwd); biases[b] fp32[32] or NULL; nbr <= 4 branches accumulate into
- * one TMEM tile (ResBlock-a branch sum, model2.py:23-31).  stats (double[64], optional) += {sum, sum of squares} of
- * the stored bf16 values (BatchNormalization batch statistics, model2.py:21). */
+ * xs[b]: bf16 [N,H,W,C]; wts[b]: bf16 [9][C][C] K-major copies ([tap][co][ci] forward, [tap][ci][co] with a negative
+ * dilation for the data gradient, as rsa_conv_tc2_fwd); biases[b] fp32[C] or NULL; nbr <= 4 branches (C = 32; one for
+ * C = 64) accumulate into one TMEM tile (ResBlock-a branch sum, model2.py:23-31).  stats (double[2C], optional) +=
+ * {sum, sum of squares} of the stored bf16 values (BatchNormalization batch statistics, model2.py:21). */
 extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float* const* biases,
                                 const int* dils, int nbr, void* out, const void* residual, const void* mask,
                                 double* stats, int N, int H, int W, int C, int accumulate, int relu, void* stream) {
   RSA_REQUIRE(xs && wts && dils && out && nbr >= 1 && nbr <= T3_MAXBR, RSA_ERR_SHAPE, "conv_tc3_fwd: bad arguments");
   RSA_REQUIRE(rsa_conv_tc3_supported(N, H, W, C), RSA_ERR_SHAPE, "conv_tc3_fwd: unsupported shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  RSA_REQUIRE(C == 32 || nbr == 1, RSA_ERR_SHAPE, "conv_tc3_fwd: fused branches need C = 32 (resident weights)");
   EncodeTiledFn enc = get_encode();
   RSA_REQUIRE(enc, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled not available from the driver");
+  const int PITCH = C * 2, BOXB = 128 * PITCH;
   Tc3Params p;
   p.N = N; p.H = H; p.W = W; p.nbr = nbr;
   int max_ad = 0, any_box = 0;
@@ -424,25 +473,35 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
       p.bias[b] = biases ? biases[b] : nullptr;
     } else { p.dil[b] = 1; p.halo[b] = 1; p.bias[b] = nullptr; }
   }
-  // item = 16 x (8*KT) pixels; wide items amortise the halo, narrow ones keep the ring deep when 4 branches are resident
-  const int KT = nbr > 1 ? 2 : 4;
+  // item = 16 x (8*KT) pixels; wide items amortise the halo, narrow ones keep the ring deep when shared memory is
+  // short (four resident branches, or 64 channels with a dilation-3 halo)
+  int KT = C == 32 ? (nbr > 1 ? 2 : 4) : (max_ad == 3 ? 1 : 2);
+  p.nsb = C == 32 ? 4 : 2;
+  // at most one addend: the identity input of the first branch (residual) or the running sum (accumulate)
+  RSA_REQUIRE(!(residual && accumulate), RSA_ERR_SHAPE, "conv_tc3_fwd: residual and accumulate are exclusive");
+  p.has_add = (residual || accumulate) ? 1 : 0;
+  p.has_mask = mask ? 1 : 0;
+  const int nside = p.has_add + p.has_mask;
+  p.nsb_log = p.nsb == 4 ? 2 : 1;
+  p.nsi = nside ? (C == 32 ? 4 : (nside == 2 ? 1 : 2)) : 0;     // 64 channels: shared memory is short, keep >= 2 A stages
+  p.nsi_log = p.nsi == 4 ? 2 : (p.nsi == 2 ? 1 : 0);
+  auto plan = [&](int kt) {
+    int slot = any_box ? kt * BOXB : 0;
+    if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * kt + 2 * max_ad) * PITCH; slot = hb > slot ? hb : slot; }
+    slot = (slot + 1023) & ~1023;
+    const Tc3Smem L0(C, nbr, p.nsb, nside, p.nsi, 0, slot);
+    int ns = (227 * 1024 - L0.total - 256) / (slot + 16);
+    p.slot_bytes = slot;
+    p.nstages = ns > 8 ? 8 : ns;
+  };
+  plan(KT);
+  RSA_REQUIRE(p.nstages >= 2, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory budget allows only %d stage(s)", p.nstages);
   p.tiles_w = W / (8 * KT); p.tiles_h = H / 16;
   p.items = p.tiles_w * p.tiles_h * N;
-  int slot = any_box ? KT * T3_BOXB : 0;
-  if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * KT + 2 * max_ad) * T3_PITCH; slot = hb > slot ? hb : slot; }
-  slot = (slot + 1023) & ~1023;
-  p.slot_bytes = slot;
-  {
-    const Tc3Smem L0(nbr, 0, slot);
-    int ns = (227 * 1024 - L0.total - 256) / (slot + 16);
-    if (ns > 8) ns = 8;
-    RSA_REQUIRE(ns >= 2, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory budget allows only %d stage(s)", ns);
-    p.nstages = ns;
-  }
-  const Tc3Smem L(nbr, p.nstages, slot);
+  const Tc3Smem L(C, nbr, p.nsb, nside, p.nsi, p.nstages, p.slot_bytes);
   RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
-  p.residual = (const bf16*)residual; p.mask = (const bf16*)mask; p.prev = accumulate ? (const bf16*)out : nullptr;
   p.stats = stats; p.relu = relu;
+  const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   Tc3Maps maps;
   for (int b = 0; b < nbr; ++b) {
     const int ad = p.dil[b] < 0 ? -p.dil[b] : p.dil[b];
@@ -451,42 +510,54 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
     cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(p.halo[b] ? 8 * KT + 2 * ad : 8 * KT), (cuuint32_t)(p.halo[b] ? 16 + 2 * ad : 16), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&maps.a[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[b]), gdim, gstr, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(x%d) failed (%d)", b, (int)r);
     cuuint64_t wdim[3] = {(cuuint64_t)C, (cuuint64_t)C, 9};
     cuuint64_t wstr[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * C * 2};
     cuuint32_t wbox[3] = {(cuuint32_t)C, (cuuint32_t)C, 1};
     cuuint32_t wes[3] = {1, 1, 1};
     r = enc(&maps.w[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wts[b]), wdim, wstr, wbox, wes,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(w%d) failed (%d)", b, (int)r);
   }
   for (int b = nbr; b < T3_MAXBR; ++b) { maps.a[b] = maps.a[0]; maps.w[b] = maps.w[0]; }
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)C, 8, 16, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // 16x8-pixel tiles: the TMA-stored output and the TMA-loaded epilogue side inputs share one box shape
+    auto enc_tile = [&](CUtensorMap* tm, const void* base) -> CUresult {
+      cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)C, 8, 16, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = enc_tile(&maps.out, out);
     RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
+    maps.add = maps.out; maps.mask = maps.out;
+    if (p.has_add) {
+      r = enc_tile(&maps.add, residual ? residual : out);
+      RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(addend) failed (%d)", (int)r);
+    }
+    if (p.has_mask) {
+      r = enc_tile(&maps.mask, mask);
+      RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(mask) failed (%d)", (int)r);
+    }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (KT == 2) return launch3<2>(maps, p, L.total, st);
-  return launch3<4>(maps, p, L.total, st);
+  if (C == 32) return KT == 2 ? launch3<32, 2>(maps, p, L.total, st) : launch3<32, 4>(maps, p, L.total, st);
+  return KT == 1 ? launch3<64, 1>(maps, p, L.total, st) : launch3<64, 2>(maps, p, L.total, st);
 }
 
 // =====================================================================================================
 // Weight gradient of the thin-layer 3x3 convolution.
 //   dW[tap][ci][co] += sum_pix x[pix + off(tap), ci] * dy[pix, co]          (Conv2D backward-filter, model2.py:19-24)
 // GEMM view: K = pixels, both operands MN-major (channels contiguous).  conv_tc.cu's kernel loads nine shifted copies of
-// every 64-pixel tile (655 MB of L2->SM traffic per launch, one issuing thread); here an item is a 16 x 16 pixel tile
-// whose x halo is loaded ONCE and the three taps of a tap row are the M atoms of one MMA: atom i starts i*d pixels
-// further (LBO = d pixels), so D_dy[128 x 32] = [tap(dy,-1) | tap(dy,0) | tap(dy,+1) | unused] and three warps (one per
-// tap row) issue independent accumulation chains that run for the whole life of the persistent CTA.  Large dilations
-// use nine 16 x 8 boxes per item with LBO = one box.  One red.global.add pass per CTA at the end.
+// every 64-pixel tile (655 MB of L2->SM traffic per launch at C = 32, one issuing thread); here an item is a 16 x 16
+// pixel tile whose x halo is loaded ONCE and the taps of a tap row are the M atoms of one MMA: atom i starts i*d pixels
+// further (LBO = d pixels).  C = 32: D_dy[128 x 32] = [tap(dy,-1) | tap(dy,0) | tap(dy,+1) | unused]; C = 64 (atoms of
+// 64 channels): D_dy,0 = [tap(dy,-1) | tap(dy,0)], D_dy,1 = [tap(dy,+1) | unused].  Three warps (one per tap row) issue
+// independent accumulation chains that run for the whole life of the persistent CTA; one red.global.add pass per CTA
+// at the end.  Large dilations (C = 32 only) use nine 16 x 8 boxes per item with LBO = one box.
 // =====================================================================================================
 namespace {
 
@@ -500,23 +571,27 @@ struct Wg3Params {
   float* dw;
 };
 
+template <int C>
 __device__ __forceinline__ uint64_t w3_mndesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                      // SWIZZLE_64B
+  d |= (uint64_t)T3<C>::LAYOUT << 61;
   return d;
 }
 __device__ __forceinline__ void w3_red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <int C>
 __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                        const __grid_constant__ CUtensorMap tmDY,
                                                                        const Wg3Params p) {
-  constexpr int C = T3_C, PITCH = T3_PITCH;
+  constexpr int PITCH = T3<C>::PITCH;
+  constexpr int NACC = C == 32 ? 1 : 2;              // accumulators (MMA chains) per tap row
+  constexpr uint32_t TMEM_COLS = C == 32 ? 128 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.nstages * p.stage_bytes);
@@ -533,7 +608,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -574,7 +649,7 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, C) | (1u << 15) | (1u << 16);
       const int dyi = warp - 1;
-      const uint32_t acc = tmem_base + (uint32_t)(dyi * C);
+      const uint32_t acc = tmem_base + (uint32_t)(dyi * NACC * C);
       const int Wh = p.IW + 2 * d;                        // halo mode: region row pitch in pixels
       const int ncb = p.IW / 8;                           // 8-pixel column blocks per item row
       const uint32_t boxb = 16 * p.IW * PITCH;
@@ -590,7 +665,8 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
         const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
         const uint32_t sb = sa + p.a_bytes;
         if (p.halo || !(ch + 16 <= 0 || ch >= p.H)) {
-          // A: atom i = tap (dy, dx = i - 1); two 8-pixel K groups per MMA = rows (2rp, 2rp+1), column block cb
+          // A: atom i = tap (dy, dx = i - 1) (C = 32: four atoms, C = 64: two per chain); two 8-pixel K groups per MMA
+          // = rows (2rp, 2rp+1), column block cb
           const uint32_t a0 = p.halo ? sa + (uint32_t)((dyi * d * Wh) * PITCH) : sa + (uint32_t)(dyi * 3) * boxb;
           const uint32_t arow = p.halo ? Wh * PITCH : p.IW * PITCH;
           const uint32_t lbo = p.halo ? d * PITCH : boxb;
@@ -598,9 +674,12 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
 #pragma unroll 1
           for (int rp = 0; rp < 8; ++rp) {
             for (int cb = 0; cb < ncb; ++cb) {
-              const uint64_t adesc = w3_mndesc(a0 + 2 * rp * arow + cb * 8 * PITCH, lbo, arow);
-              const uint64_t bdesc = w3_mndesc(sb + 2 * rp * brow + cb * 8 * PITCH, 0, brow);
-              umma_bf16(acc, adesc, bdesc, idesc, accum);
+              const uint64_t bdesc = w3_mndesc<C>(sb + 2 * rp * brow + cb * 8 * PITCH, 0, brow);
+#pragma unroll
+              for (int c = 0; c < NACC; ++c) {
+                const uint64_t adesc = w3_mndesc<C>(a0 + 2 * rp * arow + cb * 8 * PITCH + c * 2 * lbo, lbo, arow);
+                umma_bf16(acc + c * C, adesc, bdesc, idesc, accum);
+              }
               accum = 1;
             }
           }
@@ -611,11 +690,11 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
       umma_commit(done_bar);
     }
   } else {
-    // ===== final reduction: lanes 32q.. of D_dy hold tap (dy, dx = q - 1), row = ci, columns = co =====
+    // ===== final reduction: the lanes of D hold (tap, ci), the columns co =====
     const int q = warp & 3;
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    if (nmine > 0 && q < 3) {
+    if (nmine > 0) {
       for (int dyi = 0; dyi < 3; ++dyi) {
         // a tap row that was out of range for every item of this CTA never initialised its accumulator
         bool any = p.halo;
@@ -626,12 +705,23 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
           }
         }
         if (!any) continue;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dyi * C), v);
-        float* dst = p.dw + ((size_t)(dyi * 3 + q) * C + lane) * C;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          w3_red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int c = 0; c < NACC; ++c) {
+          // C = 32: lane quarter q = dx + 1 (q = 3 unused); C = 64: chain 0 holds dx = -1 (q < 2) and 0 (q >= 2), chain 1 dx = +1
+          int dxi, ci;
+          if (C == 32) { dxi = q; ci = lane; }
+          else { dxi = c == 0 ? (q >> 1) : 2; ci = (q & 1) * 32 + lane; }
+          if ((C == 32 && q == 3) || (C == 64 && c == 1 && q >= 2)) continue;
+          float* dst = p.dw + ((size_t)(dyi * 3 + dxi) * C + ci) * C;
+#pragma unroll
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((dyi * NACC + c) * C + c0), v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              w3_red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          }
+        }
       }
     }
     tc_fence_before();
@@ -639,36 +729,58 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
+}
+
+template <int C>
+int launch_wg3(const CUtensorMap& tmX, const CUtensorMap& tmDY, const Wg3Params& p, int smem_bytes, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_wgrad_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { rsa_set_error("conv_tc3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
+    configured = true;
+  }
+  const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
+  conv_tc3_wgrad_kernel<C><<<grid, W3_THREADS, smem_bytes, st>>>(tmX, tmDY, p);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
 }
 
 }  // namespace
 
+/* C = 32: any dilation; C = 64: dilations <= 3 (the nine boxes of a large dilation do not fit beside the dy tile). */
+extern "C" int rsa_conv_tc3_wgrad_supported(int N, int H, int W, int C, int dil) {
+  return rsa_conv_tc3_supported(N, H, W, C) && dil > 0 && (C == 32 || dil <= 3);
+}
+
 /* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co] for the
- * thin (32-channel) layers; x, dy bf16 NHWC [N,H,W,32], dil > 0.  Same contract as rsa_conv_tc_wgrad. */
+ * thin (32- / 64-channel) layers; x, dy bf16 NHWC [N,H,W,C], dil > 0.  Same contract as rsa_conv_tc_wgrad. */
 extern "C" int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int dil, void* stream) {
   RSA_REQUIRE(x && dy && dw && dil > 0, RSA_ERR_SHAPE, "conv_tc3_wgrad: bad arguments");
-  RSA_REQUIRE(rsa_conv_tc3_supported(N, H, W, C), RSA_ERR_SHAPE, "conv_tc3_wgrad: unsupported shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  RSA_REQUIRE(rsa_conv_tc3_wgrad_supported(N, H, W, C, dil), RSA_ERR_SHAPE,
+              "conv_tc3_wgrad: unsupported shape N=%d H=%d W=%d C=%d dil=%d", N, H, W, C, dil);
   EncodeTiledFn enc = get_encode();
   RSA_REQUIRE(enc, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled not available from the driver");
+  const int PITCH = C * 2;
   Wg3Params p;
   p.N = N; p.H = H; p.W = W; p.dil = dil; p.dw = dw;
   p.halo = dil <= 3;
   p.IW = p.halo ? 16 : 8;
   p.tiles_w = W / p.IW; p.tiles_h = H / 16;
   p.items = p.tiles_w * p.tiles_h * N;
-  // the unused fourth M atom reads up to 2*dil pixels (halo) / one box past the A region: keep that inside the stage
-  const int a_raw = p.halo ? (16 + 2 * dil) * (p.IW + 2 * dil) * T3_PITCH : 9 * 16 * p.IW * T3_PITCH;
+  // the unused trailing M atom reads up to 2*dil pixels (halo) / one box past the A region: keep that inside the stage
+  const int a_raw = p.halo ? (16 + 2 * dil) * (p.IW + 2 * dil) * PITCH : 9 * 16 * p.IW * PITCH;
   p.a_tx = a_raw;
-  p.a_bytes = (a_raw + 2 * dil * T3_PITCH + 1023) & ~1023;
-  p.stage_bytes = p.a_bytes + 16 * p.IW * T3_PITCH;
+  p.a_bytes = (a_raw + 2 * dil * PITCH + 1023) & ~1023;
+  p.stage_bytes = p.a_bytes + 16 * p.IW * PITCH;
   p.stage_bytes = (p.stage_bytes + 1023) & ~1023;
   int ns = (227 * 1024 - 2048) / p.stage_bytes;
   if (ns > 6) ns = 6;
   RSA_REQUIRE(ns >= 2, RSA_ERR_SHAPE, "conv_tc3_wgrad: stage of %d bytes leaves %d stage(s)", p.stage_bytes, ns);
   p.nstages = ns;
   const int smem_bytes = ns * p.stage_bytes + (2 * ns + 1) * 8 + 16 + 1024;
+  const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUtensorMap tmX, tmDY;
   auto encode = [&](CUtensorMap* tm, const void* base, int bw, int bh) -> CUresult {
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -676,20 +788,12 @@ extern "C" int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int 
     cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
   CUresult r = p.halo ? encode(&tmX, x, p.IW + 2 * dil, 16 + 2 * dil) : encode(&tmX, x, p.IW, 16);
   RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
   r = encode(&tmDY, dy, p.IW, 16);
   RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    RSA_REQUIRE(e == cudaSuccess, RSA_ERR_CUDA, "conv_tc3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
-  conv_tc3_wgrad_kernel<<<grid, W3_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmX, tmDY, p);
-  RSA_CHECK_LAUNCH();
-  return RSA_OK;
+  if (C == 32) return launch_wg3<32>(tmX, tmDY, p, smem_bytes, (cudaStream_t)stream);
+  return launch_wg3<64>(tmX, tmDY, p, smem_bytes, (cudaStream_t)stream);
 }

@@ -572,7 +572,7 @@ class Plan:
                 dW = self.G(name + "/kernel")
                 db = self.G(name + "/bias") if bias_grad else None
                 if tcw is not None and C == cout:
-                    if thin:
+                    if thin and lib.conv_tc3_wgrad_supported(N, H, W, C, dil):
                         self.bwd.append(self._tag(lib.conv_tc3_wgrad(x.data, dy, dW, N, H, W, C, dil), "conv3x3_wgrad", flops))
                     else:
                         self.bwd.append(self._tag(lib.conv_tc_wgrad(x.data, dy, dW, N, H, W, C, cout, dil),
@@ -872,7 +872,7 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
             dy = out.grad
             if tcw is not None and C == f:
                 # bias gradient: one column-sum of d(out) per block (block_bias_grad)
-                if thin:
+                if thin and lib.conv_tc3_wgrad_supported(N, H, W, C, d):
                     pl.bwd.append(pl._tag(lib.conv_tc3_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, d),
                                           "conv3x3_wgrad", flops))
                 else:

@@ -40,17 +40,20 @@ for d in (1, 3, 15, 31):
     if lib.conv_tc3_supported(N, H, W, C):
         t3 = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [bias[0]], [d], outs[i], N, H, W, C, stats=stats))
         t3p = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [bias[0]], [d], outs[i], N, H, W, C))
-        t3r = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [bias[0]], [d], outs[i], N, H, W, C, residual=xs[(i + 1) % NB], accumulate=True))
-        line += f" | tc3 stats {t3:7.1f} us ({flops/t3/1e6:6.0f} TF)  plain {t3p:7.1f} us  res+acc {t3r:7.1f} us"
+        t3r = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [bias[0]], [d], outs[i], N, H, W, C, accumulate=True))
+        line += f" | tc3 stats {t3:7.1f} us ({flops/t3/1e6:6.0f} TF)  plain {t3p:7.1f} us  accum {t3r:7.1f} us"
     print(line, flush=True)
-if lib.conv_tc3_supported(N, H, W, C):
+if lib.conv_tc3_supported(N, H, W, C) and C == 32:
     dils = [1, 3, 15, 31]
     t4 = timeit(lambda i: lib.conv_tc3_fwd([xs[(i + k) % NB] for k in range(4)], [w.view(-1) for w in wt], bias, dils, outs[i], N, H, W, C,
                                            residual=xs[i], relu=True))
     print(f"C={C} fused 4-branch (1,3,15,31) + identity: {t4:7.1f} us ({4*flops/t4/1e6:6.0f} TF)")
+if lib.conv_tc3_supported(N, H, W, C):
     xw = torch.randn(N, H, W, C, device="cuda").to(dt)
     dw = torch.zeros(9 * C * C, device="cuda")
     for d in (1, 3, 15, 31):
         tw = timeit(lambda i: lib.conv_tc_wgrad(xs[i], outs[(i + 1) % NB], dw, N, H, W, C, C, d))
+        if not lib.conv_tc3_wgrad_supported(N, H, W, C, d):
+            print(f"C={C} wgrad d={d}: {tw:7.1f} us ({flops/tw/1e6:6.0f} TF)"); continue
         tw3 = timeit(lambda i: lib.conv_tc3_wgrad(xs[i], outs[(i + 1) % NB], dw, N, H, W, C, d))
         print(f"C={C} wgrad d={d}: {tw:7.1f} us ({flops/tw/1e6:6.0f} TF) | tc3 {tw3:7.1f} us ({flops/tw3/1e6:6.0f} TF)")

@@ -262,10 +262,11 @@ def _conv3_ref(x, w, C, d, N, H, W):
     return o
 
 
+@pytest.mark.parametrize("C", [32, 64])
 @pytest.mark.parametrize("N,H,W,d", [(2, 32, 32, 1), (1, 16, 64, 3), (2, 32, 32, 15), (2, 64, 64, 31), (3, 48, 96, 3),
                                      (1, 32, 32, 31)])
-def test_conv_tc3_single_branch(lib, N, H, W, d):
-    C, dt = 32, torch.bfloat16
+def test_conv_tc3_single_branch(lib, N, H, W, d, C):
+    dt = torch.bfloat16
     assert lib.conv_tc3_supported(N, H, W, C)
     x = rnd((N, H, W, C), dt, 1)
     w = rnd((9 * C * C,), torch.float32, 2, 1.0 / (3 * C ** 0.5)).to(dt).float()
@@ -274,19 +275,23 @@ def test_conv_tc3_single_branch(lib, N, H, W, d):
     res, prev, mask = rnd((N, H, W, C), dt, 5), rnd((N, H, W, C), dt, 4), rnd((N, H, W, C), dt, 6)
     st = torch.cuda.current_stream().cuda_stream
     conv = _conv3_ref(x, w, C, d, N, H, W)
-    # bias + residual + accumulate + statistics
-    ref = conv + b.double() + res.double() + prev.double()
-    ref_b = ref.to(dt)
-    d_out, d_stats = prev.clone().cuda(), torch.zeros(2 * C, dtype=torch.float64).cuda()
-    lib.conv_tc3_fwd([x.cuda()], [wf.cuda()], [b.cuda()], [d], d_out, N, H, W, C, residual=res.cuda(), stats=d_stats,
-                     accumulate=True)(st)
+    # bias + identity input (first branch of a ResBlock-a) + statistics
+    ref = conv + b.double() + res.double()
+    d_out, d_stats = torch.zeros((N, H, W, C), dtype=dt).cuda(), torch.zeros(2 * C, dtype=torch.float64).cuda()
+    lib.conv_tc3_fwd([x.cuda()], [wf.cuda()], [b.cuda()], [d], d_out, N, H, W, C, residual=res.cuda(), stats=d_stats)(st)
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
-    assert (d_out.cpu().double() - ref).abs().max().item() <= scale / 100, "forward"
+    assert (d_out.cpu().double() - ref).abs().max().item() <= scale / 100, "forward + residual"
     got = d_out.cpu().double().reshape(-1, C)
     # the statistics are those of the stored (bf16) tensor
     np.testing.assert_allclose(d_stats[:C].cpu().numpy(), got.sum(0).numpy(), rtol=1e-4, atol=1e-2)
     np.testing.assert_allclose(d_stats[C:].cpu().numpy(), (got * got).sum(0).numpy(), rtol=1e-4, atol=1e-2)
+    # bias + running branch sum (accumulate into out) + ReLU
+    ref1 = (conv + b.double() + prev.double()).clamp_min(0)
+    d_out1 = prev.clone().cuda()
+    lib.conv_tc3_fwd([x.cuda()], [wf.cuda()], [b.cuda()], [d], d_out1, N, H, W, C, accumulate=True, relu=True)(st)
+    torch.cuda.synchronize()
+    assert (d_out1.cpu().double() - ref1).abs().max().item() <= scale / 100, "forward + accumulate"
     # relu + mask, plain store
     ref2 = (conv + b.double()).clamp_min(0) * (mask.double() > 0)
     d_out2 = torch.zeros((N, H, W, C), dtype=dt).cuda()
@@ -303,6 +308,13 @@ def test_conv_tc3_single_branch(lib, N, H, W, d):
     lib.conv_tc3_fwd([dy.cuda()], [wb.cuda()], None, [-d], d_dx, N, H, W, C)(st)
     torch.cuda.synchronize()
     assert (d_dx.cpu().double() - dx).abs().max().item() <= dx.abs().max().item() / 100, "dgrad"
+    # masked and accumulated (second consumer of a ReLU'd tensor)
+    ref3 = prev.double() + dx * (mask.double() > 0)        # mask applies to the sum in the kernel's order: (+prev), then mask
+    ref3 = (prev.double() + dx) * (mask.double() > 0)
+    d_dx3 = prev.clone().cuda()
+    lib.conv_tc3_fwd([dy.cuda()], [wb.cuda()], None, [-d], d_dx3, N, H, W, C, mask=mask.cuda(), accumulate=True)(st)
+    torch.cuda.synchronize()
+    assert (d_dx3.cpu().double() - ref3).abs().max().item() <= ref3.abs().max().item() / 100, "dgrad mask+acc"
 
 
 @pytest.mark.parametrize("N,H,W,dils", [(2, 64, 64, (1, 3, 15, 31)), (1, 32, 64, (1, 3, 15)), (2, 32, 32, (3, 31))])
@@ -331,8 +343,11 @@ def test_conv_tc3_fused_branches(lib, N, H, W, dils):
 
 @pytest.mark.parametrize("N,H,W,d", [(2, 32, 32, 1), (1, 16, 64, 3), (2, 32, 32, 15), (2, 64, 64, 31), (16, 64, 64, 1),
                                      (1, 32, 32, 31), (3, 48, 96, 3)])
-def test_conv_tc3_wgrad(lib, N, H, W, d):
-    C, dt = 32, torch.bfloat16
+@pytest.mark.parametrize("C", [32, 64])
+def test_conv_tc3_wgrad(lib, N, H, W, d, C):
+    dt = torch.bfloat16
+    if not lib.conv_tc3_wgrad_supported(N, H, W, C, d):
+        pytest.skip("large dilations at 64 channels stay on conv_tc_wgrad")
     x = rnd((N, H, W, C), dt, 1)
     dy = rnd((N, H, W, C), dt, 2)
     segs = [Seg(x, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * C)
