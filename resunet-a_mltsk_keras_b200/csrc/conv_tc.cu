@@ -402,8 +402,10 @@ struct WgradCfg {
   }
 };
 
+constexpr int WG_THREADS = 384;   // warp 0 TMA, warps 1..NSLOT MMA issuers (one accumulator slot each), warps 8..11 epilogue
+
 template <int CC, int NB>
-__global__ void __launch_bounds__(NTHREADS) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(WG_THREADS) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                  const __grid_constant__ CUtensorMap tmDY,
                                                                  const WgradTcParams p) {
   using Cfg = WgradCfg<CC, NB>;
@@ -429,8 +431,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_wgrad_kernel(const __grid_co
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmDY);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], Cfg::NSLOT); }
+    mbar_init(tmem_full, Cfg::NSLOT);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -467,9 +469,11 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_wgrad_kernel(const __grid_co
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= Cfg::NSLOT) {
+    // one issuing thread per accumulator slot: the single-thread issue rate (~100 cycles per MMA) was the limit
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_mn(128, NB);
+      const int s = warp - 1;
       int stage = 0, phase = 0;
       uint32_t accum = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -480,12 +484,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_wgrad_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < Cfg::TP / 16; ++k) {
           const uint64_t bdesc = make_mnmajor_desc(sb + k * 16 * Cfg::KB * 2, Cfg::KB * 2, Cfg::B_SUB);
-#pragma unroll
-          for (int s = 0; s < Cfg::NSLOT; ++s) {
-            const uint64_t adesc = make_mnmajor_desc(sa + Cfg::slot_sub(s) * Cfg::A_SUB + k * 16 * Cfg::KA * 2,
-                                                     Cfg::KA * 2, Cfg::A_SUB);
-            umma_bf16(tmem_base + (uint32_t)(s * NB), adesc, bdesc, idesc, accum);
-          }
+          const uint64_t adesc = make_mnmajor_desc(sa + Cfg::slot_sub(s) * Cfg::A_SUB + k * 16 * Cfg::KA * 2,
+                                                   Cfg::KA * 2, Cfg::A_SUB);
+          umma_bf16(tmem_base + (uint32_t)(s * NB), adesc, bdesc, idesc, accum);
           accum = 1;
         }
         umma_commit(&empty_bar[stage]);
@@ -493,6 +494,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_wgrad_kernel(const __grid_co
       }
       umma_commit(tmem_full);
     }
+  } else if (warp < 8) {
+    // idle warps (role slots up to 7 MMA issuers)
   } else {
     const int q = warp & 3;
     mbar_wait(tmem_full, 0);
@@ -538,7 +541,7 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradTcP
     if (e != cudaSuccess) { rsa_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
-  conv_tc_wgrad_kernel<CC, NB><<<grid, NTHREADS, Cfg::TOTAL, st>>>(tmX, tmDY, p);
+  conv_tc_wgrad_kernel<CC, NB><<<grid, WG_THREADS, Cfg::TOTAL, st>>>(tmX, tmDY, p);
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
@@ -566,8 +569,8 @@ extern "C" int rsa_conv_tc_wgrad(const void* x, const void* dy, float* dw, int N
   const int NB = Cout >= 128 ? 128 : Cout;
   const int KA = CC >= 64 ? 64 : 32, KB = NB >= 64 ? 64 : 32;
   const int ygroups = (CC == 128 ? 3 * (Cin / 128) : 1) * (Cout / NB);
-  // split the pixel reduction so that ~2 CTAs per SM exist, but keep >= 4 tiles per CTA
-  int want = ygroups >= 96 ? 1 : (2 * rsa_num_sms() + ygroups - 1) / ygroups;   // deep levels: enough (ci,co,tap) groups already
+  // split the pixel reduction into ONE resident wave (a CTA owns an SM: ~190 KB of shared memory), keep >= 4 tiles per CTA
+  int want = ygroups >= 96 ? 1 : rsa_num_sms() / ygroups;   // deep levels: enough (ci,co,tap) groups already
   int maxsplit = (p.ntiles + 3) / 4;
   int split = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
   if (split < 1) split = 1;
