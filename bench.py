@@ -214,8 +214,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         conv_ms = sum(a.elapsed_time(b) for a, b in evs)
         achieved = flops / (conv_ms / 1e3) / 1e12
+        # DRAM bytes per launch of this kernel family from the committed ncu capture (profiles/, per launch like `achieved`)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1b_conv_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("mean_dram_bytes_per_launch"), tj.get("source")
         roof = dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s", frac=achieved / pk["tf_sust"],
-                    traffic=None, kernel="3x3 conv fwd+dgrad+wgrad (ResBlock-a + heads)", launches=nconv,
+                    traffic=traffic, traffic_source=traffic_src, kernel="3x3 conv fwd+dgrad+wgrad (ResBlock-a + heads)", launches=nconv,
                     avg_launch_ms=conv_ms / max(nconv, 1), conv_ms_per_step=conv_ms,
                     conv_share_of_step=conv_ms / (ms_total / args.steps), frac_of_burst=achieved / pk["tf_burst"],
                     peak_source=pk["src"] + " (sustained: timed inside a long step)",

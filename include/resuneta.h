@@ -193,12 +193,15 @@ int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void*
  * BatchNormalization statistics computed by the tensor core.
  *   out = epi( sum_b conv3x3(xs[b], wts[b], dils[b]) + sum_b biases[b] ), epi: + residual, + out (accumulate), ReLU,
  *   mask (keep where mask > 0);  xs[b] bf16 [N,H,W,32]; wts[b] bf16 [9][32][32] as rsa_conv_tc2_fwd (negative dilation
- *   with the [tap][ci][co] copy = data gradient); stats double[64] += {sum, sumsq} of the stored values.
+ *   with the [tap][ci][co] copy = data gradient); stats double[2C] += {sum, sumsq} of the stored values;
+ *   bnr_x != NULL (data gradient into a = [relu](BatchNorm(bnr_x))): the BatchNormalization backward reductions are fused:
+ *   out = d(a) * relu-mask recomputed from bnr_x, stats += {sum g, sum g*xhat} (residual/accumulate still allowed, no mask).
  * Replaces cuDNN's Conv2D forward / backward-data behind model2.py:19-24,153-178 for the C = 32 layers. */
 int rsa_conv_tc3_supported(int N, int H, int W, int C);
 int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float* const* biases, const int* dils, int nbr,
                      void* out, const void* residual, const void* mask, double* stats, int N, int H, int W, int C,
-                     int accumulate, int relu, void* stream);
+                     int accumulate, int relu, const void* bnr_x, const double* bnr_stats, double bnr_count, float bnr_eps,
+                     const float* bnr_gamma, const float* bnr_beta, int bnr_relu, void* stream);
 /* Weight gradient of the thin layers: one x halo per 16x16 item, the three taps of a tap row are the M atoms of one
  * MMA (conv_tc3.cu); same contract as rsa_conv_tc_wgrad, Cin == Cout == C in {32, 64}, dil > 0 (C = 64: dil <= 3). */
 int rsa_conv_tc3_wgrad_supported(int N, int H, int W, int C, int dil);

@@ -128,7 +128,7 @@ _SIGS = {
     "rsa_conv_tc3_wgrad": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc3_fwd": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int,
                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                         C.c_int, C.c_void_p],
+                         C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p],
     "rsa_pw_wgrad_tc": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                         C.c_int, C.c_void_p],
     "rsa_bias_grad": [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -364,8 +364,9 @@ class Lib:
         return bool(self.dll.rsa_conv_tc3_supported(N, H, W, C_))
 
     def conv_tc3_fwd(self, xs, wts, biases, dils, out, N, H, W, C_, residual=None, mask=None, stats=None,
-                     accumulate=False, relu=False):
-        """Thin-layer 3x3 convolution; len(xs) branches accumulate into one tile (conv_tc3.cu)."""
+                     accumulate=False, relu=False, bnr=None):
+        """Thin-layer 3x3 convolution; len(xs) branches accumulate into one tile (conv_tc3.cu).
+        bnr = (x, fwd_stats, count, eps, gamma, beta, relu): fuse that BatchNorm's backward reductions (stats = output)."""
         nbr = len(xs)
         assert nbr == len(wts) == len(dils) and 1 <= nbr <= 4
         assert all(x.dtype == torch.bfloat16 for x in xs) and out.dtype == torch.bfloat16
@@ -374,9 +375,10 @@ class Lib:
         for i in range(nbr):
             ba[i] = biases[i].data_ptr() if biases is not None and biases[i] is not None else None
         da = (C.c_int * nbr)(*[int(d) for d in dils])
+        bx, bst, bcnt, beps, bg, bb, brelu = bnr if bnr is not None else (None, None, 0.0, 0.0, None, None, 0)
         return self._bind("rsa_conv_tc3_fwd", xa, wa, ba, da, nbr, _p(out), _p(residual), _p(mask), _p(stats), N, H, W,
-                          C_, int(accumulate), int(relu),
-                          keep=(xs, wts, biases, out, residual, mask, stats, xa, wa, ba, da))
+                          C_, int(accumulate), int(relu), _p(bx), _p(bst), float(bcnt), float(beps), _p(bg), _p(bb),
+                          int(brelu), keep=(xs, wts, biases, out, residual, mask, stats, xa, wa, ba, da, bnr))
 
     def conv_tc3_wgrad_supported(self, N, H, W, C_, dil):
         return bool(self.dll.rsa_conv_tc3_wgrad_supported(N, H, W, C_, dil))

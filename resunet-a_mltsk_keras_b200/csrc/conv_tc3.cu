@@ -49,6 +49,12 @@ struct Tc3Params {
   int nstages, slot_bytes, nsb;
   int nsb_log, nsi_log;         // nsb, nsi are powers of two
   int nsi, has_add, has_mask;   // side-input ring: slots, addend present (residual or previous out), ReLU mask present
+  int has_bnx, bnr_relu;        // fused BatchNorm backward: BN input tile in the side ring; the BN was followed by ReLU
+  const double* bnr_stats;      // {sum, sumsq} of the BN input (forward statistics)
+  double bnr_count;
+  float bnr_eps;
+  const float* bnr_gamma;
+  const float* bnr_beta;
   const float* bias[T3_MAXBR];
   double* stats;
   int relu;
@@ -86,7 +92,7 @@ __device__ __forceinline__ uint64_t t3_desc(uint32_t hi, uint32_t saddr) {
   return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFF) | (1u << 16));
 }
 
-struct Tc3Maps { CUtensorMap a[T3_MAXBR]; CUtensorMap w[T3_MAXBR]; CUtensorMap out; CUtensorMap add; CUtensorMap mask; };
+struct Tc3Maps { CUtensorMap a[T3_MAXBR]; CUtensorMap w[T3_MAXBR]; CUtensorMap out; CUtensorMap add; CUtensorMap mask; CUtensorMap bnx; };
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
 struct Tc3Smem {
@@ -96,8 +102,8 @@ struct Tc3Smem {
     st_off = (nbr * 9 * C * C * 2 + 1023) & ~1023;
     side_off = st_off + nsb * 128 * C * 2;                   // [nsi][nside] tiles of 128 pixels
     ring_off = side_off + nsi * nside * 128 * C * 2;
-    misc_off = ring_off + nstages * slot_bytes;              // bias[C], csum[C], csq[C]
-    bar_off = misc_off + 3 * C * 4;
+    misc_off = ring_off + nstages * slot_bytes;              // bias[C], csum[C], csq[C], BN coefficients [4][C]
+    bar_off = misc_off + 7 * C * 4;
     total = bar_off + (2 * nstages + 4 * T3_MAXSB + 8) * 8 + 16 + 1024;
   }
 };
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
   constexpr int NCT = C / 2;            // accumulator columns per epilogue thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nside = p.has_add + p.has_mask;
+  const int nside = p.has_add + p.has_mask + p.has_bnx;
   const Tc3Smem L(C, p.nbr, p.nsb, nside, p.nsi, p.nstages, p.slot_bytes);
   uint8_t* wsm = smem + L.w_off;
   uint8_t* ysm = smem + L.st_off;
@@ -118,6 +124,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
   float* bias_s = reinterpret_cast<float*>(smem + L.misc_off);
   float* csum = bias_s + C;
   float* csq = csum + C;
+  float* bnc = csq + C;                      // [4][C]: invstd, -mean*invstd, gamma, beta of the fused BatchNorm backward
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + p.nstages;
   uint64_t* tfull = empty_bar + p.nstages;   // [2]
@@ -138,6 +145,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
     prefetch_tmap(&maps.out);
     if (p.has_add) prefetch_tmap(&maps.add);
     if (p.has_mask) prefetch_tmap(&maps.mask);
+    if (p.has_bnx) prefetch_tmap(&maps.bnx);
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], KT); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], KT); mbar_init(&tempty[s], 8); }
     for (int s = 0; s < T3_MAXSB; ++s) {
@@ -158,6 +166,11 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
     bias_s[c] = b;
     csum[c] = 0.f;
     csq[c] = 0.f;
+    if (p.has_bnx) {
+      float mean, inv;
+      bn_mean_invstd(p.bnr_stats, p.bnr_count, C, c, p.bnr_eps, nullptr, nullptr, mean, inv);
+      bnc[c] = inv; bnc[C + c] = -mean * inv; bnc[2 * C + c] = p.bnr_gamma[c]; bnc[3 * C + c] = p.bnr_beta[c];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -204,6 +217,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
             uint8_t* dst = sidesm + k * nside * BOXB;
             if (p.has_add) tma_load_4d(dst, &maps.add, &ifull[k], 0, w0 + 8 * s, h0, n);
             if (p.has_mask) tma_load_4d(dst + p.has_add * BOXB, &maps.mask, &ifull[k], 0, w0 + 8 * s, h0, n);
+            if (p.has_bnx) tma_load_4d(dst + (p.has_add + p.has_mask) * BOXB, &maps.bnx, &ifull[k], 0, w0 + 8 * s, h0, n);
           }
         }
       }
@@ -360,6 +374,27 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = t[i] > 0.f ? f[i] : 0.f;
           }
+          if (p.has_bnx) {
+            // fused BatchNorm(+ReLU) backward reductions: f is d(relu(bn(x))); recompute the ReLU mask from x like the
+            // forward did, keep g = f * mask as the stored value and accumulate {sum g, sum g*xhat} below
+            const uint8_t* xb = ib + (p.has_add + p.has_mask) * BOXB;
+            float xv[16], xh[4];
+            unpack8(*reinterpret_cast<const uint4*>(xb + o0), xv); unpack8(*reinterpret_cast<const uint4*>(xb + o1), xv + 8);
+            const float* cf = bnc + hs * NCT + cc;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 ca = *reinterpret_cast<const float4*>(cf + i), cb = *reinterpret_cast<const float4*>(cf + C + i);
+              const float4 cg = *reinterpret_cast<const float4*>(cf + 2 * C + i), ct = *reinterpret_cast<const float4*>(cf + 3 * C + i);
+              xh[0] = fmaf(xv[i], ca.x, cb.x); xh[1] = fmaf(xv[i + 1], ca.y, cb.y);
+              xh[2] = fmaf(xv[i + 2], ca.z, cb.z); xh[3] = fmaf(xv[i + 3], ca.w, cb.w);
+              if (p.bnr_relu) {
+                f[i] = fmaf(cg.x, xh[0], ct.x) > 0.f ? f[i] : 0.f; f[i + 1] = fmaf(cg.y, xh[1], ct.y) > 0.f ? f[i + 1] : 0.f;
+                f[i + 2] = fmaf(cg.z, xh[2], ct.z) > 0.f ? f[i + 2] : 0.f; f[i + 3] = fmaf(cg.w, xh[3], ct.w) > 0.f ? f[i + 3] : 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { acc_s[cc + i + e] += f[i + e]; acc_q[cc + i + e] = fmaf(f[i + e], xh[e], acc_q[cc + i + e]); }
+            }
+          }
           uint4 lo, hi;
           lo.x = pack_bf16x2(f[0], f[1]); lo.y = pack_bf16x2(f[2], f[3]); lo.z = pack_bf16x2(f[4], f[5]); lo.w = pack_bf16x2(f[6], f[7]);
           hi.x = pack_bf16x2(f[8], f[9]); hi.y = pack_bf16x2(f[10], f[11]); hi.z = pack_bf16x2(f[12], f[13]); hi.w = pack_bf16x2(f[14], f[15]);
@@ -369,7 +404,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
           }
           *reinterpret_cast<uint4*>(yb + o0) = lo;
           *reinterpret_cast<uint4*>(yb + o1) = hi;
-          if (has_stats) {
+          if (has_stats && !p.has_bnx) {
             // per-thread partial sums of the stored (bf16-rounded) values; reduced across lanes once per CTA
             float t[16];
             unpack8(lo, t); unpack8(hi, t + 8);
@@ -450,10 +485,16 @@ extern "C" int rsa_conv_tc3_supported(int N, int H, int W, int C) {
  * xs[b]: bf16 [N,H,W,C]; wts[b]: bf16 [9][C][C] K-major copies ([tap][co][ci] forward, [tap][ci][co] with a negative
  * dilation for the data gradient, as rsa_conv_tc2_fwd); biases[b] fp32[C] or NULL; nbr <= 4 branches (C = 32; one for
  * C = 64) accumulate into one TMEM tile (ResBlock-a branch sum, model2.py:23-31).  stats (double[2C], optional) +=
- * {sum, sum of squares} of the stored bf16 values (BatchNormalization batch statistics, model2.py:21). */
+ * {sum, sum of squares} of the stored bf16 values (BatchNormalization batch statistics, model2.py:21).
+ * bnr_x (optional, data-gradient use): the launch computes d(a) for a = [relu](BatchNorm(bnr_x)) and fuses that
+ * BatchNormalization's backward reductions (FusedBatchNormGrad behind model2.py:17,21): the ReLU mask is recomputed from
+ * bnr_x with the forward statistics bnr_stats/count/eps and gamma/beta, out receives g = d(a) * mask and `stats`
+ * (double[2C], zeroed) += {sum g, sum g * xhat}. */
 extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float* const* biases,
                                 const int* dils, int nbr, void* out, const void* residual, const void* mask,
-                                double* stats, int N, int H, int W, int C, int accumulate, int relu, void* stream) {
+                                double* stats, int N, int H, int W, int C, int accumulate, int relu, const void* bnr_x,
+                                const double* bnr_stats, double bnr_count, float bnr_eps, const float* bnr_gamma,
+                                const float* bnr_beta, int bnr_relu, void* stream) {
   RSA_REQUIRE(xs && wts && dils && out && nbr >= 1 && nbr <= T3_MAXBR, RSA_ERR_SHAPE, "conv_tc3_fwd: bad arguments");
   RSA_REQUIRE(rsa_conv_tc3_supported(N, H, W, C), RSA_ERR_SHAPE, "conv_tc3_fwd: unsupported shape N=%d H=%d W=%d C=%d", N, H, W, C);
   RSA_REQUIRE(C == 32 || nbr == 1, RSA_ERR_SHAPE, "conv_tc3_fwd: fused branches need C = 32 (resident weights)");
@@ -481,7 +522,12 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   RSA_REQUIRE(!(residual && accumulate), RSA_ERR_SHAPE, "conv_tc3_fwd: residual and accumulate are exclusive");
   p.has_add = (residual || accumulate) ? 1 : 0;
   p.has_mask = mask ? 1 : 0;
-  const int nside = p.has_add + p.has_mask;
+  p.has_bnx = bnr_x ? 1 : 0;
+  RSA_REQUIRE(!bnr_x || (stats && bnr_stats && bnr_gamma && bnr_beta && !mask && bnr_count > 0), RSA_ERR_SHAPE,
+              "conv_tc3_fwd: the fused BatchNorm backward needs stats (reduction output), forward statistics, gamma, beta and no mask");
+  p.bnr_stats = bnr_stats; p.bnr_count = bnr_count; p.bnr_eps = bnr_eps; p.bnr_gamma = bnr_gamma; p.bnr_beta = bnr_beta;
+  p.bnr_relu = bnr_relu;
+  const int nside = p.has_add + p.has_mask + p.has_bnx;
   p.nsb_log = p.nsb == 4 ? 2 : 1;
   p.nsi = nside ? (C == 32 ? 4 : (nside == 2 ? 1 : 2)) : 0;     // 64 channels: shared memory is short, keep >= 2 A stages
   p.nsi_log = p.nsi == 4 ? 2 : (p.nsi == 2 ? 1 : 0);
@@ -533,7 +579,11 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
     };
     CUresult r = enc_tile(&maps.out, out);
     RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
-    maps.add = maps.out; maps.mask = maps.out;
+    maps.add = maps.out; maps.mask = maps.out; maps.bnx = maps.out;
+    if (p.has_bnx) {
+      r = enc_tile(&maps.bnx, bnr_x);
+      RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(bnr_x) failed (%d)", (int)r);
+    }
     if (p.has_add) {
       r = enc_tile(&maps.add, residual ? residual : out);
       RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(addend) failed (%d)", (int)r);

@@ -46,7 +46,7 @@ def psp_levels(img_width):
 class T:
     """Activation tensor handle (NHWC, dense)."""
     __slots__ = ("name", "N", "H", "W", "C", "dtype", "data", "grad", "grad_written", "needs_grad",
-                 "relu_masked", "stats", "count")
+                 "relu_masked", "stats", "count", "bn_src")
 
     def __init__(self, name, N, H, W, C, dtype):
         self.name, self.N, self.H, self.W, self.C, self.dtype = name, N, H, W, C, dtype
@@ -57,6 +57,7 @@ class T:
         self.relu_masked = False   # value went through a fused ReLU: writers of .grad mask with data>0
         self.stats = None          # double[2C] {sum, sumsq} view, valid after the producer ran
         self.count = 0.0           # elements per channel behind .stats
+        self.bn_src = None         # this tensor is [relu](BatchNorm(x)): what a fused backward reduction needs
 
     @property
     def M(self):
@@ -480,6 +481,20 @@ class Plan:
             self._ready(name + "/kernel", name + "/bias")
         self.tape.append(bwd)
 
+    def _thin_dgrad(self, src, dy, wt, g, acc, mask, dil, N, H, W, C):
+        """conv_tc3 data gradient into `src`; when src = [relu](BatchNorm(x)) and this launch is the only writer of
+        d(src), the BatchNormalization backward reductions ride in its epilogue (no separate reduction pass)."""
+        lib = self.lib
+        b = src.bn_src
+        import os
+        if (b is not None and not acc and mask is None and b["x"].dtype == torch.bfloat16 and b["x"].shape == src.shape
+                and os.environ.get("RSA_BNR", "1") != "0"):
+            b["fused"] = True
+            return self._late(lambda: lib.conv_tc3_fwd(
+                [dy], [wt], None, [-dil], g, N, H, W, C, stats=b["red"][0],
+                bnr=(b["x"].data, b["xs"][0], b["cnt"], BN_EPS, b["gamma"], b["beta"], b["relu"])))
+        return lib.conv_tc3_fwd([dy], [wt], None, [-dil], g, N, H, W, C, mask=mask, accumulate=acc)
+
     def _late(self, make):
         """Bind a launch lazily: scratch views (statistics) only exist after _finalize_scratch()."""
         cell = []
@@ -589,8 +604,8 @@ class Plan:
                               w_off=(ky * 3 + kx) * C * cout) for ky in range(3) for kx in range(3)]
                     mask = x.data if x.relu_masked else None
                     if thin:
-                        self.bwd.append(self._tag(lib.conv_tc3_fwd([dy], [tcw[1]], None, [-dil], g, N, H, W, C, mask=mask,
-                                                                   accumulate=acc), "conv3x3_dgrad", flops))
+                        self.bwd.append(self._tag(self._thin_dgrad(x, dy, tcw[1], g, acc, mask, dil, N, H, W, C),
+                                                  "conv3x3_dgrad", flops))
                     elif tcw is not None:
                         self.bwd.append(self._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9,
                                                                    dil=-dil, mask=mask, accumulate=acc),
@@ -632,6 +647,8 @@ class Plan:
                 self.fwd.append(self._late(lambda: lib.bn_derive_stats(xs[0], cnt, gam[0], bet[0], BN_EPS, os_[0],
                                                                         float(o.M), C)))
             reds = [self.zeroed(2 * C) for _ in names]
+            for k, o in enumerate(outs):
+                o.bn_src = dict(x=x, xs=xs, cnt=cnt, gamma=gam[k], beta=bet[k], relu=relu, red=reds[k], fused=False)
 
             def bwd():
                 live = [k for k, o in enumerate(outs) if o.grad is not None]
@@ -639,8 +656,12 @@ class Plan:
                     return
                 dys = [outs[k].grad for k in live]
                 gl, bl, rl = [gam[k] for k in live], [bet[k] for k in live], [reds[k] for k in live]
-                self.bwd.append(self._late(lambda: lib.bn_bwd_reduce_multi(
-                    dys, x.data, M, C, xs[0], cnt, BN_EPS, gl, bl, relu, [r[0] for r in rl])))
+                # branches whose data-gradient kernel already produced {sum g, sum g*xhat} (conv_tc3 epilogue) are skipped
+                unf = [i for i, k in enumerate(live) if not outs[k].bn_src["fused"]]
+                if unf:
+                    self.bwd.append(self._late(lambda: lib.bn_bwd_reduce_multi(
+                        [dys[i] for i in unf], x.data, M, C, xs[0], cnt, BN_EPS, [gl[i] for i in unf], [bl[i] for i in unf],
+                        relu, [rl[i][0] for i in unf])))
                 if x.needs_grad:
                     g, acc = self.gacc(x)
                     self.bwd.append(self._late(lambda: lib.bn_bwd_apply_multi(
@@ -886,8 +907,7 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
                   for ky in range(3) for kx in range(3)]
             if thin:
-                pl.bwd.append(pl._tag(lib.conv_tc3_fwd([dy], [tcw[1]], None, [-d], g, N, H, W, C, accumulate=acc),
-                                      "conv3x3_dgrad", flops))
+                pl.bwd.append(pl._tag(pl._thin_dgrad(a, dy, tcw[1], g, acc, None, d, N, H, W, C), "conv3x3_dgrad", flops))
             elif tcw is not None:
                 pl.bwd.append(pl._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9, dil=-d,
                                                        accumulate=acc), "conv3x3_dgrad", flops))

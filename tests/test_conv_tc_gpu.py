@@ -360,3 +360,43 @@ def test_conv_tc3_wgrad(lib, N, H, W, d, C):
     torch.cuda.synchronize()
     scale = dw.abs().max().item()
     assert (d_dw.cpu() - dw).abs().max().item() <= scale * 2e-3
+
+
+@pytest.mark.parametrize("C", [32, 64])
+@pytest.mark.parametrize("N,H,W,d,relu", [(2, 32, 32, 1, True), (2, 32, 64, 15, True), (1, 32, 32, 3, False)])
+def test_conv_tc3_fused_bn_backward_reductions(lib, N, H, W, d, relu, C):
+    """Data gradient into a = [relu](BN(x)) with FusedBatchNormGrad's reductions {sum g, sum g*xhat} in the epilogue."""
+    dt, eps = torch.bfloat16, 1e-3
+    dy = rnd((N, H, W, C), dt, 7)
+    w = rnd((9 * C * C,), torch.float32, 2, 1.0 / (3 * C ** 0.5)).to(dt).float()
+    _, wb = _pack(w, 9, C, C)
+    x = (rnd((N, H, W, C), torch.float32, 8) * 1.5 + 0.3).to(dt)
+    gamma, beta = rnd((C,), torch.float32, 9) * 0.5 + 1.0, rnd((C,), torch.float32, 10) * 0.3
+    xd = x.double().reshape(-1, C)
+    cnt = float(xd.shape[0])
+    fstats = torch.cat([xd.sum(0), (xd * xd).sum(0)])
+    mean = fstats[:C] / cnt
+    var = (fstats[C:] / cnt - mean * mean).clamp_min(0)
+    xhat = (xd - mean) / torch.sqrt(var + eps)
+    sg = [Seg(dy, C, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * C)
+          for ky in range(3) for kx in range(3)]
+    da = torch.zeros((N, H, W, C), dtype=torch.float64)
+    EMU.igemm_fwd(sg, w, C, True, None, da, N, H, W, C)(0)
+    g = da.reshape(-1, C)
+    if relu:
+        g = g * ((gamma.double() * xhat + beta.double()) > 0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_out = torch.zeros((N, H, W, C), dtype=dt).cuda()
+    d_red = torch.zeros(2 * C, dtype=torch.float64).cuda()
+    lib.conv_tc3_fwd([dy.cuda()], [wb.cuda()], None, [-d], d_out, N, H, W, C, stats=d_red,
+                     bnr=(x.cuda(), fstats.cuda(), cnt, eps, gamma.cuda(), beta.cuda(), relu))(st)
+    torch.cuda.synchronize()
+    scale = g.abs().max().item()
+    # elements whose pre-activation sits within rounding of zero may flip their mask between fp32 and fp64
+    near = ((gamma.double() * xhat + beta.double()).abs() < 1e-3).reshape(N, H, W, C)
+    diff = (d_out.cpu().double() - g.reshape(N, H, W, C)).abs()
+    assert diff[~near].max().item() <= scale / 100
+    ref_s, ref_q = g.sum(0), (g * xhat).sum(0)
+    tol = 2e-2 * (g.abs().sum(0).max().item() / 10 + 1)
+    np.testing.assert_allclose(d_red[:C].cpu().numpy(), ref_s.numpy(), atol=tol)
+    np.testing.assert_allclose(d_red[C:].cpu().numpy(), ref_q.numpy(), atol=tol)
