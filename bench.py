@@ -155,6 +155,12 @@ def run_ours(args):
         last = model.train_on_batch(x, y)
     pl = model.net.plan(args.batch, True, model.loss_spec)
     ops_per_step = len(pl.fwd) + len(pl.bwd) + 2      # + bn_update_moving + optimizer (memsets not counted)
+    # device-resident warm-up: the first replays on a fresh box run 2-3 ms slower (power state / first-touch effects
+    # measured run to run); these untimed steps are counted in the reported `warmup`
+    extra_warm = 10
+    for _ in range(extra_warm):
+        model._push_lr()
+        model._execute(pl, True)
 
     # ---- device-resident timed region --------------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -236,7 +242,7 @@ def run_ours(args):
                           f"(stand-in for the reference's TF-CPU path)")
     if rank == 0:
         line = dict(metric="train patches/s (256^2, multitask fwd+bwd)", value=value, unit="patches/s", n_gpus=world,
-                    steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps,
+                    steps=args.steps, warmup=max(args.warmup, 3) + extra_warm, ms_per_step=ms_total / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
                     config=dict(workload="config2: ResUnet-a d6 model2 multitask fwd+bwd+Adam, Tanimoto dual x4, "
                                          f"{args.hw}x{args.hw}x3, {args.classes} classes, batch {args.batch}/GPU",
