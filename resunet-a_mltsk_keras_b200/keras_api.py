@@ -253,7 +253,14 @@ class Model:
         return 0 if self.net.device.type == "cpu" else torch.cuda.current_stream().cuda_stream
 
     def _stage(self, key, arr, dst):
-        """host numpy (any float) -> pinned fp32 staging -> device tensor `dst` (fp32) asynchronously."""
+        """host numpy (any float) -> pinned fp32 staging -> device tensor `dst` (fp32) asynchronously.  A float32 torch
+        tensor that already lives in pinned memory (data.PatchBatchLoader) is copied from directly."""
+        if isinstance(arr, torch.Tensor):
+            if (arr.dtype == torch.float32 and arr.is_contiguous() and tuple(arr.shape) == tuple(dst.shape)
+                    and arr.device.type == "cpu" and self.net.device.type != "cpu" and arr.is_pinned()):
+                dst.copy_(arr, non_blocking=True)
+                return arr.numel() * 4
+            arr = arr.detach().cpu().numpy()
         a = np.ascontiguousarray(arr, dtype=np.float32)
         if tuple(a.shape) != tuple(dst.shape):
             raise ValueError(f"{key}: expected shape {tuple(dst.shape)}, got {tuple(a.shape)}")

@@ -256,3 +256,33 @@ def test_scene_inference_config5_reduced():
     acc, f1, rec, prec = r["metrics"]
     a2, f2, r2, p2 = O.metrics_from_confusion(r["confusion"])
     assert acc == a2 and np.array_equal(f1, f2)
+
+
+def test_patch_loader_feeds_train_on_batch_from_pinned_memory(tmp_path):
+    """§8f rank 1: batches read by data.PatchBatchLoader (pinned tensors, no staging copy) give exactly the step results
+    of the reference-style loop that np.load()s every file into numpy batch buffers (train_ISPRS.py:115-148)."""
+    from resuneta_b200 import data as D
+    hw, n, B = 64, 4, 2
+    x, y = O.synth_batch(6, hw, 3, n, seed=3, block=16)
+    D.save_patch_dataset(str(tmp_path), x, y)
+    xp, yp = D.list_patch_dataset(str(tmp_path))
+    p = rand_params("v2", hw, 3, n)
+    res = []
+    for mode in ("loader", "numpy"):
+        m = build_model((hw, hw, 3), n, True, "v2", dtype="fp32")
+        m.net.set_weights(p)
+        m.compile(optimizer=SGD(lr=1e-2, momentum=0.8), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+        out = []
+        if mode == "loader":
+            ld = D.PatchBatchLoader(xp, yp, B, workers=4)
+            for xb, yb in ld:
+                assert xb.is_pinned() and all(v.is_pinned() for v in yb.values())
+                out.append(m.train_on_batch(xb, yb))
+        else:
+            for b in range(len(xp) // B):
+                xb = np.stack([np.load(f) for f in xp[b * B:(b + 1) * B]])
+                yb = {h: np.stack([np.load(f).astype(np.float32) for f in yp[h][b * B:(b + 1) * B]]) for h in yp}
+                out.append(m.train_on_batch(xb, yb))
+        res.append(np.array(out))
+    assert res[0].shape == (3, 10)
+    np.testing.assert_array_equal(res[0], res[1])
