@@ -285,5 +285,4 @@ def test_patch_loader_feeds_train_on_batch_from_pinned_memory(tmp_path):
                 out.append(m.train_on_batch(xb, yb))
         res.append(np.array(out))
     assert res[0].shape == (3, 10)
-    np.testing.assert_array_equal(res[0][0], res[1][0])      # same inputs, same weights: the first step is identical
-    np.testing.assert_allclose(res[0], res[1], rtol=1e-5)    # later steps: atomics reorder fp32 gradient sums
+    np.testing.assert_allclose(res[0], res[1], rtol=1e-5)    # atomics reorder the fp32 / double partial sums run to run
