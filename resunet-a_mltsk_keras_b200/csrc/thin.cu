@@ -351,54 +351,74 @@ __global__ void __launch_bounds__(NT) head_fwd_bf16_kernel(const bf16* __restric
 
 // head backward, bf16 features: thread = (pixel, 8-channel group g)
 //   dh[p][8g+i] (=|+=) mask(h>0) * sum_j dz[p][j] w[(8g+i)*NO + j];  dw[c*NO+j] += sum_p h[p][c] dz[p][j];  db[j] += sum_p dz[p][j]
+// The weights are read from shared memory (the eight lanes that share g read the same words: broadcast), so that the
+// 8 x NO weight-gradient accumulators are the only per-thread state and two blocks fit an SM; two pixels per thread are
+// in flight.
 template <int NO>
-__global__ void __launch_bounds__(NT) head_bwd_bf16_kernel(const bf16* __restrict__ h, const float* __restrict__ dz,
-                                                           const float* __restrict__ w, int64_t M, bf16* __restrict__ dh,
-                                                           int accumulate, int relu_mask, float* __restrict__ dw,
-                                                           float* __restrict__ db) {
+__global__ void __launch_bounds__(NT, 2) head_bwd_bf16_kernel(const bf16* __restrict__ h, const float* __restrict__ dz,
+                                                              const float* __restrict__ w, int64_t M, bf16* __restrict__ dh,
+                                                              int accumulate, int relu_mask, float* __restrict__ dw,
+                                                              float* __restrict__ db) {
+  __shared__ float ws[32 * NO];
+  __shared__ float sh[NT / 32][33][NO];
+  for (int i = threadIdx.x; i < 32 * NO; i += NT) ws[i] = w[i];
+  __syncthreads();
   const int g = threadIdx.x & 3;
-  float wr[8][NO], acc[8][NO], accb[NO];
+  const float* wg = ws + g * 8 * NO;
+  float acc[8][NO], accb[NO];
 #pragma unroll
   for (int j = 0; j < NO; ++j) {
     accb[j] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { wr[i][j] = w[(g * 8 + i) * NO + j]; acc[i][j] = 0.f; }
+    for (int i = 0; i < 8; ++i) acc[i][j] = 0.f;
   }
+  constexpr int U = 2;
   const int64_t stride = (int64_t)gridDim.x * (NT / 4);
-  for (int64_t p = (int64_t)blockIdx.x * (NT / 4) + (threadIdx.x >> 2); p < M; p += stride) {
-    const uint4 hq = __ldg(reinterpret_cast<const uint4*>(h + p * 32 + g * 8));
-    float zv[NO];
+  for (int64_t p0 = (int64_t)blockIdx.x * (NT / 4) + (threadIdx.x >> 2); p0 < M; p0 += U * stride) {
+    uint4 hq[U], prev[U];
+    float zv[U][NO];
 #pragma unroll
-    for (int j = 0; j < NO; ++j) zv[j] = __ldg(dz + p * NO + j);
-    uint4 prev;
-    if (dh && accumulate) prev = *reinterpret_cast<const uint4*>(dh + p * 32 + g * 8);
-    float hv[8];
-    unpack_bf8(hq, hv);
-    if (dh) {
-      float d[8];
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * stride;
+      if (p < M) {
+        hq[u] = __ldg(reinterpret_cast<const uint4*>(h + p * 32 + g * 8));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float a = 0.f;
-#pragma unroll
-        for (int j = 0; j < NO; ++j) a = fmaf(zv[j], wr[i][j], a);
-        d[i] = (relu_mask && !(hv[i] > 0.f)) ? 0.f : a;
+        for (int j = 0; j < NO; ++j) zv[u][j] = __ldg(dz + p * NO + j);
+        if (dh && accumulate) prev[u] = *reinterpret_cast<const uint4*>(dh + p * 32 + g * 8);
       }
-      if (accumulate) {
-        float pv[8];
-        unpack_bf8(prev, pv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] += pv[i];
-      }
-      *reinterpret_cast<uint4*>(dh + p * 32 + g * 8) = pack_bf8(d);
     }
 #pragma unroll
-    for (int j = 0; j < NO; ++j) {
-      accb[j] += zv[j];
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * stride;
+      if (p < M) {
+        float hv[8];
+        unpack_bf8(hq[u], hv);
+        if (dh) {
+          float d[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(hv[i], zv[j], acc[i][j]);
+          for (int i = 0; i < 8; ++i) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < NO; ++j) a = fmaf(zv[u][j], wg[i * NO + j], a);
+            d[i] = (relu_mask && !(hv[i] > 0.f)) ? 0.f : a;
+          }
+          if (accumulate) {
+            float pv[8];
+            unpack_bf8(prev[u], pv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] += pv[i];
+          }
+          *reinterpret_cast<uint4*>(dh + p * 32 + g * 8) = pack_bf8(d);
+        }
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+          accb[j] += zv[u][j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(hv[i], zv[u][j], acc[i][j]);
+        }
+      }
     }
   }
-  __shared__ float sh[NT / 32][33][NO];
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < NO; ++j) {
