@@ -244,6 +244,14 @@ int rsa_axpy(void* dst, const void* src, int dtype, int64_t n, int accumulate, v
 /* dtype conversion helper (host tensors arrive as fp32, train_ISPRS.py:122-141) */
 int rsa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 
+/* ---- multitask label generation (labels.cu; reference: OpenCV calls in multitasking_utils.py:6-34 and
+ * preprocess_save_patches_ISPRS.py:89-94,224-228).  label / bound / dist: fp32 [N,H,W,C]; workspace:
+ * rsa_label_workspace_bytes(N,H,W,C) bytes of device memory; rgb: uint8 [npix,3], color: fp32 [npix,3]. */
+int64_t rsa_label_workspace_bytes(int N, int H, int W, int C);
+int rsa_label_boundary(const float* label, float* bound, void* workspace, int N, int H, int W, int C, void* stream);
+int rsa_label_distance(const float* label, float* dist, void* workspace, int N, int H, int W, int C, void* stream);
+int rsa_label_hsv(const uint8_t* rgb, float* color, int64_t npix, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

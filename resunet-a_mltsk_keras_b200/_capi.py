@@ -115,6 +115,9 @@ _SIGS = {
     "rsa_stem_wgrad": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "rsa_head_bwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                      C.c_void_p, C.c_void_p, C.c_void_p],
+    "rsa_label_boundary": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "rsa_label_distance": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "rsa_label_hsv": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
     "rsa_head_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p],
     "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
     "rsa_conv_tc_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -138,7 +141,8 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported",
-                                "rsa_conv_tc2_supported", "rsa_conv_tc3_supported", "rsa_conv_tc3_wgrad_supported"])
+                                "rsa_conv_tc2_supported", "rsa_conv_tc3_supported", "rsa_conv_tc3_wgrad_supported",
+                                "rsa_label_workspace_bytes"])
 
 
 def load_cdll(path=LIB_PATH):
@@ -162,6 +166,8 @@ def load_cdll(path=LIB_PATH):
     dll.rsa_conv_tc3_supported.restype = C.c_int
     dll.rsa_conv_tc3_wgrad_supported.argtypes = [C.c_int] * 5
     dll.rsa_conv_tc3_wgrad_supported.restype = C.c_int
+    dll.rsa_label_workspace_bytes.argtypes = [C.c_int] * 4
+    dll.rsa_label_workspace_bytes.restype = C.c_int64
     return dll
 
 
@@ -412,6 +418,22 @@ class Lib:
 
     def stem_wgrad(self, x, dy, M, n, dw, db):
         return self._bind("rsa_stem_wgrad", _p(x), _p(dy), dtype_code(x), M, n, _p(dw), _p(db), keep=(x, dy, dw, db))
+
+    # -- multitask label generation (labels.cu) ------------------------------------------------------
+    def label_workspace_bytes(self, N, H, W, C_):
+        return int(self.dll.rsa_label_workspace_bytes(N, H, W, C_))
+
+    def label_boundary(self, label, out, ws, N, H, W, C_):
+        assert label.dtype == torch.float32 and out.dtype == torch.float32 and ws.dtype == torch.uint8
+        return self._bind("rsa_label_boundary", _p(label), _p(out), _p(ws), N, H, W, C_, keep=(label, out, ws))
+
+    def label_distance(self, label, out, ws, N, H, W, C_):
+        assert label.dtype == torch.float32 and out.dtype == torch.float32 and ws.dtype == torch.uint8
+        return self._bind("rsa_label_distance", _p(label), _p(out), _p(ws), N, H, W, C_, keep=(label, out, ws))
+
+    def label_hsv(self, rgb, out, npix):
+        assert rgb.dtype == torch.uint8 and out.dtype == torch.float32
+        return self._bind("rsa_label_hsv", _p(rgb), _p(out), npix, keep=(rgb, out))
 
     def head_fwd(self, h, w, b, z, M, n):
         assert h.dtype == torch.bfloat16 and z.dtype == torch.float32
