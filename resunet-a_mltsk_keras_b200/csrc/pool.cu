@@ -201,6 +201,154 @@ __global__ void __launch_bounds__(NT) sumpool_pyr_kernel(const T* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 fast paths for the full 8x8 pyramid (psp_out at 256^2 is the case that matters: 67 MB tensors): one thread owns
+// an 8x8 window of a channel PAIR, so every access is a 4-byte bf16x2 word and a warp touches 128 contiguous bytes
+// (the scalar kernels above move 64).  Same arithmetic and the same first-maximum convention.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ld_bf2(const bf16* p) {
+  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(p);
+  return make_float2(__low2float(h), __high2float(h));
+}
+// same load, opaque to common-subexpression elimination: the second pass of the backward kernel must RE-load x (from
+// L1/L2) instead of keeping all 64 values of the first pass in registers
+__device__ __forceinline__ float2 ld_bf2_again(const bf16* p) {
+  uint32_t w;
+  asm volatile("ld.global.b32 %0, [%1];" : "=r"(w) : "l"(p));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ void st_bf2(bf16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+__global__ void __launch_bounds__(NT) sumpool_pyr8_bf16x2_kernel(const bf16* __restrict__ x, int N, int H, int W, int C,
+                                                                 bf16* __restrict__ s2, bf16* __restrict__ s4,
+                                                                 bf16* __restrict__ s8) {
+  const int HB = H / 8, WB = W / 8, CP = C / 2;
+  const int64_t total = (int64_t)N * HB * WB * CP;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    const int c = (int)(idx % CP) * 2;
+    int64_t t = idx / CP;
+    const int wb = (int)(t % WB); t /= WB;
+    const int hb = (int)(t % HB);
+    const int n = (int)(t / HB);
+    const bf16* xp = x + (((int64_t)n * H + hb * 8) * W + wb * 8) * C + c;
+    float2 m2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = ld_bf2(xp + ((int64_t)(2 * i) * W + 2 * j) * C), b = ld_bf2(xp + ((int64_t)(2 * i) * W + 2 * j + 1) * C);
+        const float2 cc = ld_bf2(xp + ((int64_t)(2 * i + 1) * W + 2 * j) * C), d = ld_bf2(xp + ((int64_t)(2 * i + 1) * W + 2 * j + 1) * C);
+        m2[i][j] = make_float2((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y));
+      }
+    if (s2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_bf2(s2 + (((int64_t)n * (H / 2) + hb * 4 + i) * (W / 2) + wb * 4 + j) * C + c, m2[i][j].x, m2[i][j].y);
+    }
+    float2 m4[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        m4[i][j] = make_float2((m2[2 * i][2 * j].x + m2[2 * i][2 * j + 1].x) + (m2[2 * i + 1][2 * j].x + m2[2 * i + 1][2 * j + 1].x),
+                               (m2[2 * i][2 * j].y + m2[2 * i][2 * j + 1].y) + (m2[2 * i + 1][2 * j].y + m2[2 * i + 1][2 * j + 1].y));
+    if (s4) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          st_bf2(s4 + (((int64_t)n * (H / 4) + hb * 2 + i) * (W / 4) + wb * 2 + j) * C + c, m4[i][j].x, m4[i][j].y);
+    }
+    if (s8)
+      st_bf2(s8 + (((int64_t)n * (H / 8) + hb) * (W / 8) + wb) * C + c, (m4[0][0].x + m4[0][1].x) + (m4[1][0].x + m4[1][1].x),
+             (m4[0][0].y + m4[0][1].y) + (m4[1][0].y + m4[1][1].y));
+  }
+}
+
+// backward in two passes over the window: (1) window maxima of every level, (2) each element receives the pooled gradients
+// of the windows whose FIRST maximum (row-major scan) it is — one "taken" bit per (window, channel)
+__global__ void __launch_bounds__(NT, 2) maxpool_pyr8_bwd_bf16x2_kernel(const bf16* __restrict__ x, int N, int H, int W, int C,
+                                                                     const bf16* __restrict__ dp2, const bf16* __restrict__ dp4,
+                                                                     const bf16* __restrict__ dp8, bf16* __restrict__ dx,
+                                                                     int accumulate) {
+  const int HB = H / 8, WB = W / 8, CP = C / 2;
+  const int64_t total = (int64_t)N * HB * WB * CP;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    const int c = (int)(idx % CP) * 2;
+    int64_t t = idx / CP;
+    const int wb = (int)(t % WB); t /= WB;
+    const int hb = (int)(t % HB);
+    const int n = (int)(t / HB);
+    const int64_t base = (((int64_t)n * H + hb * 8) * W + wb * 8) * C + c;
+    // pass 1 in the packed bf16x2 domain (max is exact): one register per loaded word
+    __nv_bfloat162 p2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(x + base + ((int64_t)(2 * i) * W + 2 * j) * C);
+        const __nv_bfloat162 bq = *reinterpret_cast<const __nv_bfloat162*>(x + base + ((int64_t)(2 * i) * W + 2 * j + 1) * C);
+        const __nv_bfloat162 cc = *reinterpret_cast<const __nv_bfloat162*>(x + base + ((int64_t)(2 * i + 1) * W + 2 * j) * C);
+        const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(x + base + ((int64_t)(2 * i + 1) * W + 2 * j + 1) * C);
+        p2[i][j] = __hmax2(__hmax2(a, bq), __hmax2(cc, d));
+      }
+      asm volatile("" ::: "memory");
+    }
+    // window maxima and pooled gradients stay PACKED (one register per channel pair) and are unpacked at use
+    __nv_bfloat162 p4[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        p4[i][j] = __hmax2(__hmax2(p2[2 * i][2 * j], p2[2 * i][2 * j + 1]), __hmax2(p2[2 * i + 1][2 * j], p2[2 * i + 1][2 * j + 1]));
+    const __nv_bfloat162 p8 = __hmax2(__hmax2(p4[0][0], p4[0][1]), __hmax2(p4[1][0], p4[1][1]));
+    const float2 m8 = make_float2(__low2float(p8), __high2float(p8));
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+    __nv_bfloat162 q2[4][4], q4[2][2], q8 = zero2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        q2[i][j] = dp2 ? *reinterpret_cast<const __nv_bfloat162*>(dp2 + (((int64_t)n * (H / 2) + hb * 4 + i) * (W / 2) + wb * 4 + j) * C + c) : zero2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        q4[i][j] = dp4 ? *reinterpret_cast<const __nv_bfloat162*>(dp4 + (((int64_t)n * (H / 4) + hb * 2 + i) * (W / 4) + wb * 2 + j) * C + c) : zero2;
+    if (dp8) q8 = *reinterpret_cast<const __nv_bfloat162*>(dp8 + (((int64_t)n * (H / 8) + hb) * (W / 8) + wb) * C + c);
+    const float2 g8 = make_float2(__low2float(q8), __high2float(q8));
+    uint32_t t2x = 0, t2y = 0, t4x = 0, t4y = 0, t8x = 0, t8y = 0;      // taken bits
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t o = base + ((int64_t)i * W + j) * C;
+        const float2 v = ld_bf2_again(x + o);
+        float2 g = accumulate ? ld_bf2_again(dx + o) : make_float2(0.f, 0.f);
+        const int w2 = (i >> 1) * 4 + (j >> 1), w4 = (i >> 2) * 2 + (j >> 2);
+        // level 2
+        const __nv_bfloat162 pm2 = p2[i >> 1][j >> 1], pg2 = q2[i >> 1][j >> 1], pm4 = p4[i >> 2][j >> 2], pg4 = q4[i >> 2][j >> 2];
+        bool hx = !((t2x >> w2) & 1) && v.x == __low2float(pm2), hy = !((t2y >> w2) & 1) && v.y == __high2float(pm2);
+        g.x += hx ? __low2float(pg2) : 0.f; g.y += hy ? __high2float(pg2) : 0.f;
+        t2x |= (uint32_t)hx << w2; t2y |= (uint32_t)hy << w2;
+        // level 4
+        hx = !((t4x >> w4) & 1) && v.x == __low2float(pm4); hy = !((t4y >> w4) & 1) && v.y == __high2float(pm4);
+        g.x += hx ? __low2float(pg4) : 0.f; g.y += hy ? __high2float(pg4) : 0.f;
+        t4x |= (uint32_t)hx << w4; t4y |= (uint32_t)hy << w4;
+        // level 8
+        hx = !t8x && v.x == m8.x; hy = !t8y && v.y == m8.y;
+        g.x += hx ? g8.x : 0.f; g.y += hy ? g8.y : 0.f;
+        t8x |= (uint32_t)hx; t8y |= (uint32_t)hy;
+        st_bf2(dx + o, g.x, g.y);
+        if (j == 7 && (i & 1)) __threadfence_block();   // two rows of loads in flight, not all 64 (ptxas would hoist them all)
+      }
+  }
+}
+
 inline int pyr_bs(const void* a2, const void* a4, const void* a8) { return a8 ? 8 : (a4 ? 4 : 2); }
 inline int pyr_grid(int64_t total) {
   int64_t b = ceil_div64(total, NT);
@@ -238,7 +386,11 @@ extern "C" int rsa_maxpool_pyr_bwd(const void* x, int dtype, int N, int H, int W
               "maxpool_pyr_bwd: H=%d W=%d must be multiples of %d", H, W, bs);
   cudaStream_t st = (cudaStream_t)stream;
   int grid = pyr_grid((int64_t)N * (H / bs) * (W / bs) * C);
-  if (dtype == RSA_F32) PYR_DISPATCH(maxpool_pyr_bwd_kernel, float, (const float*)x, N, H, W, C, (const float*)dp2, (const float*)dp4, (const float*)dp8, (float*)dx, accumulate);
+  if (dtype == RSA_BF16 && bs == 8 && C % 2 == 0) {
+    const int g2 = pyr_grid((int64_t)N * (H / 8) * (W / 8) * (C / 2));
+    maxpool_pyr8_bwd_bf16x2_kernel<<<g2, NT, 0, st>>>((const bf16*)x, N, H, W, C, (const bf16*)dp2, (const bf16*)dp4,
+                                                      (const bf16*)dp8, (bf16*)dx, accumulate);
+  } else if (dtype == RSA_F32) PYR_DISPATCH(maxpool_pyr_bwd_kernel, float, (const float*)x, N, H, W, C, (const float*)dp2, (const float*)dp4, (const float*)dp8, (float*)dx, accumulate);
   else if (dtype == RSA_BF16) PYR_DISPATCH(maxpool_pyr_bwd_kernel, bf16, (const bf16*)x, N, H, W, C, (const bf16*)dp2, (const bf16*)dp4, (const bf16*)dp8, (bf16*)dx, accumulate);
   else RSA_REQUIRE(false, RSA_ERR_DTYPE, "maxpool_pyr_bwd: bad dtype");
   RSA_CHECK_LAUNCH();
@@ -252,7 +404,10 @@ extern "C" int rsa_sumpool_pyr(const void* x, int dtype, int N, int H, int W, in
               "sumpool_pyr: H=%d W=%d must be multiples of %d", H, W, bs);
   cudaStream_t st = (cudaStream_t)stream;
   int grid = pyr_grid((int64_t)N * (H / bs) * (W / bs) * C);
-  if (dtype == RSA_F32) PYR_DISPATCH(sumpool_pyr_kernel, float, (const float*)x, N, H, W, C, (float*)s2, (float*)s4, (float*)s8);
+  if (dtype == RSA_BF16 && bs == 8 && C % 2 == 0) {
+    const int g2 = pyr_grid((int64_t)N * (H / 8) * (W / 8) * (C / 2));
+    sumpool_pyr8_bf16x2_kernel<<<g2, NT, 0, st>>>((const bf16*)x, N, H, W, C, (bf16*)s2, (bf16*)s4, (bf16*)s8);
+  } else if (dtype == RSA_F32) PYR_DISPATCH(sumpool_pyr_kernel, float, (const float*)x, N, H, W, C, (float*)s2, (float*)s4, (float*)s8);
   else if (dtype == RSA_BF16) PYR_DISPATCH(sumpool_pyr_kernel, bf16, (const bf16*)x, N, H, W, C, (bf16*)s2, (bf16*)s4, (bf16*)s8);
   else RSA_REQUIRE(false, RSA_ERR_DTYPE, "sumpool_pyr: bad dtype");
   RSA_CHECK_LAUNCH();
