@@ -28,6 +28,33 @@ void rsa_set_error(const char* fmt, ...);
   } while (0)
 
 static inline int rsa_num_sms() { return 148; }  // B200
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// A training step is ~560 short kernels replayed from a CUDA graph.  Launched with the programmatic-stream-serialization
+// attribute, a kernel's CTAs may be scheduled while the previous kernel drains: they run their private prologue (mbarrier
+// init, TMEM allocation, tensor-map prefetch), then block in pdl_wait() until every prerequisite grid has completed and
+// flushed, and only then touch global memory.  Kernels without pdl_wait() must NOT be launched through launch_pdl().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+static inline bool rsa_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RSA_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = rsa_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- scalar / vector element access, always computing in fp32 ------------------------------

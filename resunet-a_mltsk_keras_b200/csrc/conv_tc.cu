@@ -439,6 +439,8 @@ __global__ void __launch_bounds__(WG_THREADS) conv_tc_wgrad_kernel(const __grid_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -541,7 +543,8 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradTcP
     if (e != cudaSuccess) { rsa_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
-  conv_tc_wgrad_kernel<CC, NB><<<grid, WG_THREADS, Cfg::TOTAL, st>>>(tmX, tmDY, p);
+  cudaError_t le = launch_pdl(conv_tc_wgrad_kernel<CC, NB>, grid, dim3(WG_THREADS), (size_t)Cfg::TOTAL, st, tmX, tmDY, p);
+  if (le != cudaSuccess) { rsa_set_error("conv_tc_wgrad: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
@@ -655,6 +658,8 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const __grid_constan
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -746,7 +751,8 @@ int launch_pw(const CUtensorMap& tmX, const CUtensorMap& tmDY, const PwWgradPara
     if (e != cudaSuccess) { rsa_set_error("pw_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
-  pw_wgrad_kernel<KA, KB, NB><<<grid, NTHREADS, Cfg::TOTAL, st>>>(tmX, tmDY, p);
+  cudaError_t le = launch_pdl(pw_wgrad_kernel<KA, KB, NB>, grid, dim3(NTHREADS), (size_t)Cfg::TOTAL, st, tmX, tmDY, p);
+  if (le != cudaSuccess) { rsa_set_error("pw_wgrad: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }

@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
   if (p.stats && warp >= 2) {
     for (int i = threadIdx.x - 64; i < 2048; i += 128) csum[i] = 0.f;
   }
+  pdl_wait();                        // everything above is private to the CTA; global memory is touched only below
+  if (threadIdx.x == 0) pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -338,7 +340,8 @@ int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, 
   }
   const int per_sm = (227 * 1024) / L::TOTAL >= 2 ? 2 : 1;       // co-resident persistent CTAs overlap their epilogues
   int grid = p.total < per_sm * rsa_num_sms() ? p.total : per_sm * rsa_num_sms();
-  conv_tc2_kernel<BN, KC, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(a0, a1, b, p);
+  cudaError_t le = launch_pdl(conv_tc2_kernel<BN, KC, STAGES>, dim3(grid), dim3(NTHREADS), (size_t)L::TOTAL, st, a0, a1, b, p);
+  if (le != cudaSuccess) { rsa_set_error("conv_tc2: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }

@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  pdl_wait();                        // everything above is private to the CTA; global memory is touched only below
+  if (threadIdx.x == 0) pdl_launch_dependents();
   if (warp >= EPI0 && warp < EPI0 + C / 32) {
     const int c = (warp - EPI0) * 32 + lane;
     float b = 0.f;
@@ -468,7 +470,8 @@ int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_
     configured = true;
   }
   const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
-  conv_tc3_kernel<C, KT><<<grid, T3Warps<KT>::THREADS, smem_bytes, st>>>(maps, p);
+  cudaError_t le = launch_pdl(conv_tc3_kernel<C, KT>, dim3(grid), dim3(T3Warps<KT>::THREADS), (size_t)smem_bytes, st, maps, p);
+  if (le != cudaSuccess) { rsa_set_error("conv_tc3: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
@@ -661,6 +664,8 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -792,7 +797,8 @@ int launch_wg3(const CUtensorMap& tmX, const CUtensorMap& tmDY, const Wg3Params&
     configured = true;
   }
   const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
-  conv_tc3_wgrad_kernel<C><<<grid, W3_THREADS, smem_bytes, st>>>(tmX, tmDY, p);
+  cudaError_t le = launch_pdl(conv_tc3_wgrad_kernel<C>, dim3(grid), dim3(W3_THREADS), (size_t)smem_bytes, st, tmX, tmDY, p);
+  if (le != cudaSuccess) { rsa_set_error("conv_tc3_wgrad: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
