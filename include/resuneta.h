@@ -252,6 +252,13 @@ int rsa_label_boundary(const float* label, float* bound, void* workspace, int N,
 int rsa_label_distance(const float* label, float* dist, void* workspace, int N, int H, int W, int C, void* stream);
 int rsa_label_hsv(const uint8_t* rgb, float* color, int64_t npix, void* stream);
 
+/* ---- Amazon deforestation evaluation post-processing (postproc.cu; utils.py:505-548, utils2.py:312-356) ---- */
+/* out = skimage.morphology.area_opening(img, area_threshold, connectivity=1) of a binary uint8 [H,W] map; workspace 2*H*W int32 */
+int rsa_area_opening_binary(const uint8_t* img, uint8_t* out, int H, int W, int area_threshold, void* workspace, void* stream);
+/* mask pipeline + 3x3 confusion counts (int64[9], zeroed by the caller) over the pixels under consideration, utils.py:527-545 */
+int rsa_amazon_consider(const uint8_t* pred, const uint8_t* opened, const uint8_t* ref_clip, const uint8_t* clip_mask,
+                        uint8_t* ref_consider, uint8_t* pred_consider, uint8_t* selected, int64_t n, int64_t* cm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,9 @@ _SIGS = {
     "rsa_stem_wgrad": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "rsa_head_bwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                      C.c_void_p, C.c_void_p, C.c_void_p],
+    "rsa_area_opening_binary": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p],
+    "rsa_amazon_consider": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                            C.c_void_p, C.c_void_p],
     "rsa_label_boundary": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "rsa_label_distance": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "rsa_label_hsv": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
@@ -418,6 +421,17 @@ class Lib:
 
     def stem_wgrad(self, x, dy, M, n, dw, db):
         return self._bind("rsa_stem_wgrad", _p(x), _p(dy), dtype_code(x), M, n, _p(dw), _p(db), keep=(x, dy, dw, db))
+
+    # -- Amazon evaluation post-processing (postproc.cu) ----------------------------------------------
+    def area_opening_binary(self, img, out, H, W, area_threshold, ws):
+        assert img.dtype == torch.uint8 and out.dtype == torch.uint8 and ws.dtype == torch.int32 and ws.numel() >= 2 * H * W
+        return self._bind("rsa_area_opening_binary", _p(img), _p(out), H, W, int(area_threshold), _p(ws), keep=(img, out, ws))
+
+    def amazon_consider(self, pred, opened, ref_clip, clip_mask, ref_consider, pred_consider, selected, n, cm):
+        assert cm.dtype == torch.int64 and cm.numel() >= 9
+        return self._bind("rsa_amazon_consider", _p(pred), _p(opened), _p(ref_clip), _p(clip_mask), _p(ref_consider),
+                          _p(pred_consider), _p(selected), n, _p(cm),
+                          keep=(pred, opened, ref_clip, clip_mask, ref_consider, pred_consider, selected, cm))
 
     # -- multitask label generation (labels.cu) ------------------------------------------------------
     def label_workspace_bytes(self, N, H, W, C_):
