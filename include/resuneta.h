@@ -198,6 +198,8 @@ int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void*
  *   out = d(a) * relu-mask recomputed from bnr_x, stats += {sum g, sum g*xhat} (residual/accumulate still allowed, no mask).
  * Replaces cuDNN's Conv2D forward / backward-data behind model2.py:19-24,153-178 for the C = 32 layers. */
 int rsa_conv_tc3_supported(int N, int H, int W, int C);
+/* diagnostic: per-CTA barrier-wait cycle counters of the following rsa_conv_tc3_fwd launches (NULL switches it off) */
+int rsa_conv_tc3_set_trace(long long* buf);
 int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float* const* biases, const int* dils, int nbr,
                      void* out, const void* residual, const void* mask, double* stats, int N, int H, int W, int C,
                      int accumulate, int relu, const void* bnr_x, const double* bnr_stats, double bnr_count, float bnr_eps,

@@ -145,7 +145,7 @@ _SIGS = {
 
 EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported",
                                 "rsa_conv_tc2_supported", "rsa_conv_tc3_supported", "rsa_conv_tc3_wgrad_supported",
-                                "rsa_label_workspace_bytes"])
+                                "rsa_label_workspace_bytes", "rsa_conv_tc3_set_trace"])
 
 
 def load_cdll(path=LIB_PATH):
@@ -169,6 +169,8 @@ def load_cdll(path=LIB_PATH):
     dll.rsa_conv_tc3_supported.restype = C.c_int
     dll.rsa_conv_tc3_wgrad_supported.argtypes = [C.c_int] * 5
     dll.rsa_conv_tc3_wgrad_supported.restype = C.c_int
+    dll.rsa_conv_tc3_set_trace.argtypes = [C.c_void_p]
+    dll.rsa_conv_tc3_set_trace.restype = C.c_int
     dll.rsa_label_workspace_bytes.argtypes = [C.c_int] * 4
     dll.rsa_label_workspace_bytes.restype = C.c_int64
     return dll

@@ -16,6 +16,12 @@
 //     tile in shared memory (swizzled, conflict free) and leaves the global write to a TMA store issued by a
 //     dedicated warp; BatchNorm statistics of the stored values are reduced with a 16-wide shuffle butterfly.
 //
+// What bounds it now (scripts/exp_mma_rate.cu, scripts/trace_tc3.py): an SS-mode tcgen05.mma reads its operands from
+// shared memory at 128 B/clk, i.e. 32 cycles for the 128x16 A slice + N/4 for B: 40 cycles per N=32 MMA against a 16-cycle
+// tensor floor, whatever the swizzle.  A C=32 sub-tile (18 MMAs, 90 KB of operand reads) therefore cannot take less than
+// ~700 cycles = 19.7 us per launch at batch 16; an experiment with the stores / TMEM loads removed runs at 35 us, the
+// full kernel at 42-46 us.  (Direct global stores from the epilogue instead of the staged TMA store were measured slower.)
+//
 // Replaces cuDNN's Conv2D forward / backward-data behind keras Conv2D(32, 3, dilation_rate=d, padding='same') at
 // model2.py:19-24,153-178 for the C = 32 layers (enc1, dec1, heads).
 #include "tc_common.cuh"
@@ -58,7 +64,16 @@ struct Tc3Params {
   const float* bias[T3_MAXBR];
   double* stats;
   int relu;
+  long long* trace;       // diagnostic: per-CTA cycles spent waiting on each barrier family (rsa_conv_tc3_set_trace)
 };
+
+// timed mbarrier wait for the diagnostic trace (plain wait when tracing is off)
+__device__ __forceinline__ void twait(uint64_t* bar, uint32_t parity, long long* tr, int slot) {
+  if (!tr) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  tr[slot] += clock64() - t0;
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -137,6 +152,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_stats = p.stats != nullptr;
+  long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
   constexpr uint32_t TMEM_COLS = 2 * KT * C <= 64 ? 64 : (2 * KT * C <= 128 ? 128 : 256);
   static_assert(2 * KT * C <= 256, "accumulator ring exceeds the TMEM allocation");
 
@@ -194,7 +210,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         for (int b = 0; b < p.nbr; ++b) {
           const int d = p.dil[b], ad = d < 0 ? -d : d;
           if (p.halo[b]) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            twait(&empty_bar[stage], phase ^ 1, tr, 0);
             mbar_expect_tx(&full_bar[stage], (16 + 2 * ad) * (8 * KT + 2 * ad) * PITCH);
             tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, w0 - ad, h0 - ad, n);
             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
@@ -202,7 +218,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
             for (int tap = 0; tap < 9; ++tap) {
               const int ch = h0 + (tap / 3 - 1) * d, cw = w0 + (tap % 3 - 1) * d;
               if (ch + 16 <= 0 || ch >= p.H || cw + 8 * KT <= 0 || cw >= p.W) continue;
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+              twait(&empty_bar[stage], phase ^ 1, tr, 0);
               mbar_expect_tx(&full_bar[stage], KT * BOXB);
               tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, cw, ch, n);
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         if (nside) {
           for (int s = 0; s < KT; ++s, ++iseq) {
             const int k = iseq & (p.nsi - 1);
-            mbar_wait(&iempty[k], ((iseq >> p.nsi_log) & 1) ^ 1);
+            twait(&iempty[k], ((iseq >> p.nsi_log) & 1) ^ 1, tr, 1);
             mbar_expect_tx(&ifull[k], nside * BOXB);
             uint8_t* dst = sidesm + k * nside * BOXB;
             if (p.has_add) tma_load_4d(dst, &maps.add, &ifull[k], 0, w0 + 8 * s, h0, n);
@@ -239,7 +255,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h;
         const int h0 = th * 16, w0 = tw * 8 * KT;
-        mbar_wait(&tempty[it & 1], ((it >> 1) & 1) ^ 1);
+        twait(&tempty[it & 1], ((it >> 1) & 1) ^ 1, s == 0 ? tr : nullptr, 2);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(((it & 1) * KT + s) * C);
         uint32_t started = 0;
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
           if (p.halo[b]) {
             const int Wh = 8 * KT + 2 * ad;
             const uint32_t ahi = t3_desc_hi<C>(Wh * PITCH);
-            mbar_wait(&full_bar[stage], phase);
+            twait(&full_bar[stage], phase, s == 0 ? tr : nullptr, 3);
             tc_fence_after();
             const uint32_t sa = smem_u32(ring + stage * p.slot_bytes) + (uint32_t)((ad * Wh + ad + 8 * s) * PITCH);
             const int rowb = d * Wh * PITCH, colb = d * PITCH;
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
             for (int tap = 0; tap < 9; ++tap) {
               const int ch = h0 + (tap / 3 - 1) * d, cw = w0 + (tap % 3 - 1) * d;
               if (ch + 16 <= 0 || ch >= p.H || cw + 8 * KT <= 0 || cw >= p.W) continue;
-              mbar_wait(&full_bar[stage], phase);
+              twait(&full_bar[stage], phase, s == 0 ? tr : nullptr, 3);
               tc_fence_after();
               const uint64_t adesc = t3_desc(ahi, smem_u32(ring + stage * p.slot_bytes) + 8 * s * PITCH);
               const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         const int n = r, h0 = th * 16, w0 = tw * 8 * KT;
         for (int s = 0; s < KT; ++s, ++seq) {
           const int j = seq & (p.nsb - 1);
-          mbar_wait(&sready[j], (seq >> p.nsb_log) & 1);
+          twait(&sready[j], (seq >> p.nsb_log) & 1, tr, 5);
           tma_store_4d(&maps.out, ysm + j * BOXB, 0, w0 + 8 * s, h0, n);
           // the store issued `lag` tiles ago has finished reading its buffer: hand that buffer back
           if (lag == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
@@ -323,8 +339,10 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
       for (int j = 0; j < 16; ++j) bias_r[j] = bias_s[hs * 16 + j];
     }
     int it = 0, seq = 0;
+    long long* etr = (warp == EPI0) ? tr : nullptr;
+    const long long e_t0 = clock64();
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      mbar_wait(&tfull[it & 1], (it >> 1) & 1);
+      if (lane == 0) twait(&tfull[it & 1], (it >> 1) & 1, etr, 6); else mbar_wait(&tfull[it & 1], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int s = 0; s < KT; ++s, ++seq) {
@@ -333,7 +351,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         const int ks = nside ? (seq & (p.nsi - 1)) : 0;
         const uint8_t* ib = sidesm + ks * nside * BOXB + srow;
         if (nside) {
-          if (lane == 0) mbar_wait(&ifull[ks], (seq >> p.nsi_log) & 1);
+          if (lane == 0) twait(&ifull[ks], (seq >> p.nsi_log) & 1, etr, 8);
           __syncwarp();
         }
 #pragma unroll
@@ -401,7 +419,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
           lo.x = pack_bf16x2(f[0], f[1]); lo.y = pack_bf16x2(f[2], f[3]); lo.z = pack_bf16x2(f[4], f[5]); lo.w = pack_bf16x2(f[6], f[7]);
           hi.x = pack_bf16x2(f[8], f[9]); hi.y = pack_bf16x2(f[10], f[11]); hi.z = pack_bf16x2(f[12], f[13]); hi.w = pack_bf16x2(f[14], f[15]);
           if (cc == 0) {
-            if (lane == 0) mbar_wait(&sfree[j], ((seq >> p.nsb_log) & 1) ^ 1);
+            if (lane == 0) twait(&sfree[j], ((seq >> p.nsb_log) & 1) ^ 1, etr, 7);
             __syncwarp();
           }
           *reinterpret_cast<uint4*>(yb + o0) = lo;
@@ -422,6 +440,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         }
       }
     }
+    if (etr && lane == 0) { etr[9] += clock64() - e_t0; etr[10] += seq; }
     if (has_stats) {
       // 16-wide butterfly reduce-scatter over the warp's 32 pixels: the lane pair (2m, 2m+1) ends with channel bitrev4(m)
 #pragma unroll
@@ -477,6 +496,14 @@ int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_
 }
 
 }  // namespace
+
+static long long* g_t3_trace = nullptr;
+/* Diagnostic hook: when buf != NULL (device memory, 148*16 int64, zeroed by the caller) every following rsa_conv_tc3_fwd
+ * launch adds, per CTA, the cycles its roles spent blocked: [0] producer on the A ring, [1] producer on the side ring,
+ * [2] MMA on the accumulators (epilogue behind), [3] MMA on A tiles (TMA behind), [5] store warp on staged tiles,
+ * [6] epilogue on accumulators (MMA behind), [7] epilogue on staging buffers, [8] epilogue on side tiles,
+ * [9] epilogue total cycles, [10] sub-tiles.  scripts/trace_tc3.py prints the breakdown. */
+extern "C" int rsa_conv_tc3_set_trace(long long* buf) { g_t3_trace = buf; return RSA_OK; }
 
 /* Shapes the thin-layer kernels accept: 32 or 64 channels in and out, H a multiple of 16, W a multiple of 32. */
 extern "C" int rsa_conv_tc3_supported(int N, int H, int W, int C) {
@@ -549,7 +576,7 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   p.items = p.tiles_w * p.tiles_h * N;
   const Tc3Smem L(C, nbr, p.nsb, nside, p.nsi, p.nstages, p.slot_bytes);
   RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
-  p.stats = stats; p.relu = relu;
+  p.stats = stats; p.relu = relu; p.trace = g_t3_trace;
   const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   Tc3Maps maps;
   for (int b = 0; b < nbr; ++b) {
