@@ -20,6 +20,52 @@ import torch
 from . import graph
 
 _COPY_POOL = None
+_HOST_REG = {}      # data pointer -> [nbytes, sightings, registered, weakref to the owning array]
+
+
+def _registered_view(a):
+    """Zero-copy path for host batches that are REUSED across steps (the reference refills the same x_train_b / y_*_b
+    buffers every step, train_ISPRS.py:71-92,121-141): the second time the same float32 buffer is seen it is page-locked
+    with cudaHostRegister, from then on the H2D copy reads the caller's memory directly and the staging memcpy disappears.
+    Returns a torch view that is_pinned(), or None (fresh / small / foreign memory: staging path).  The registration is
+    dropped when the owning array is garbage collected."""
+    import weakref
+    if os.environ.get("RSA_HOST_REGISTER", "1") == "0" or a.nbytes < (1 << 20) or not a.flags.owndata and a.base is None:
+        return None
+    owner = a
+    while isinstance(owner.base, np.ndarray):
+        owner = owner.base
+    if owner.base is not None or not owner.flags.owndata:
+        return None                               # memmap / foreign buffer: do not pin what we do not understand
+    ptr, nb = a.ctypes.data, a.nbytes
+    ent = _HOST_REG.get(ptr)
+    if ent is None or ent[0] != nb or ent[3]() is not owner:
+        if ent is not None and ent[2]:
+            torch.cuda.cudart().cudaHostUnregister(ptr)
+        _HOST_REG[ptr] = ent = [nb, 0, False, weakref.ref(owner)]
+    ent[1] += 1
+    if not ent[2]:
+        if ent[1] < 2:
+            return None
+        try:
+            rc = torch.cuda.cudart().cudaHostRegister(ptr, nb, 0)
+        except Exception:
+            rc = 1
+        if int(rc) != 0:
+            ent[1] = -(1 << 30)                   # never try this buffer again
+            return None
+        ent[2] = True
+
+        def _drop(_ptr=ptr):
+            e = _HOST_REG.pop(_ptr, None)
+            if e is not None and e[2]:
+                try:
+                    torch.cuda.cudart().cudaHostUnregister(_ptr)
+                except Exception:
+                    pass
+        weakref.finalize(owner, _drop)
+    t = torch.from_numpy(a)
+    return t if t.is_pinned() else None
 
 
 def _host_copy(dst_np, src_np, min_chunk=4 << 20):
@@ -289,6 +335,11 @@ class Model:
         if self.net.device.type == "cpu":
             dst.copy_(torch.from_numpy(a))
             return a.nbytes
+        if a is arr or (isinstance(arr, np.ndarray) and np.shares_memory(a, arr)):
+            rv = _registered_view(a)
+            if rv is not None:
+                dst.copy_(rv, non_blocking=True)
+                return a.nbytes
         st = self._staging.get((key, a.shape))
         if st is None:
             st = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)

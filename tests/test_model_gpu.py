@@ -286,3 +286,32 @@ def test_patch_loader_feeds_train_on_batch_from_pinned_memory(tmp_path):
         res.append(np.array(out))
     assert res[0].shape == (3, 10)
     np.testing.assert_allclose(res[0], res[1], rtol=1e-5)    # atomics reorder the fp32 / double partial sums run to run
+
+
+def test_reused_host_buffers_take_the_registered_zero_copy_path():
+    """The reference refills the same numpy batch buffers every step (train_ISPRS.py:71-92,121-141): from the second step on
+    they are page-locked in place and copied without staging; results must equal the staged path bit for bit (same device
+    work), including after the caller overwrites the buffers between steps."""
+    import os
+    from resuneta_b200 import keras_api as KA
+    hw, n, B = 64, 4, 8        # 8 x 64 x 64 x 4 floats = 512 KB per label tensor: raise above the 1 MB threshold with B
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["RSA_HOST_REGISTER"] = mode
+        m = build_model((hw, hw, 3), n, True, "v2", dtype="fp32")
+        m.net.set_weights(rand_params("v2", hw, 3, n))
+        m.compile(optimizer=SGD(lr=1e-2, momentum=0.8), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+        xb = np.zeros((64, hw, hw, 3), np.float32)             # 3 MB: above the registration threshold
+        yb = {h: np.zeros((64, hw, hw, c), np.float32) for h, c in (("seg", n), ("bound", n), ("dist", n), ("color", 3))}
+        out = []
+        for step in range(3):
+            x, y = O.synth_batch(64, hw, 3, n, seed=10 + step, block=16)
+            xb[...] = x
+            for h in yb:
+                yb[h][...] = y[h]
+            out.append(m.train_on_batch(xb, yb))
+        res[mode] = np.array(out)
+        if mode == "1":
+            assert any(e[2] for e in KA._HOST_REG.values()), "no buffer was registered"
+    os.environ.pop("RSA_HOST_REGISTER", None)
+    np.testing.assert_allclose(res["1"], res["0"], rtol=1e-5)
