@@ -285,7 +285,9 @@ def run_ours(args):
                                 global_batch=args.batch * world, parallelism=f"dp{world}",
                                 l2="working set per step (>8 GB of activations) is far larger than the 126 MB L2",
                                 cuda_graph=bool(model.use_cuda_graph),
-                                dp_mode=("graph fwd+bwd, one all-reduce, graph optimizer" if world > 1 and not strat.dp.overlap
+                                dp_mode=("graph replay; gradient all-reduce in two ranges, the parameter-heavy one overlapped with the rest of backward"
+                                         if world > 1 and not strat.dp.overlap and os.environ.get("RSA_DP_GRAPH_OVERLAP", "1") != "0"
+                                         else "graph fwd+bwd, one all-reduce, graph optimizer" if world > 1 and not strat.dp.overlap
                                          else ("eager, bucketed all-reduce overlapped with backward" if world > 1 else None)),
                                 conv_engine=getattr(model.net, "conv_engine", "igemm_simt")),
                     e2e=dict(value=e2e, unit="patches/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),

@@ -65,6 +65,39 @@ class DataParallel:
         self._sched[key] = buckets
         return buckets
 
+    def two_phase_split(self, pl, params, min_frac=0.6, max_pos=0.8):
+        """(k, o) for the graph-replayed overlapped step: after backward launch k every gradient element at flat offset
+        >= o is final, so `grad[o:]` (the deep, parameter-heavy levels: backward reaches them first and they sit at the
+        END of the creation-ordered buffer) can be all-reduced on NCCL's stream while backward launches k+1.. still run;
+        `grad[:o]` follows after the last launch.  None when no useful split exists."""
+        key = ("2p", id(pl))
+        if key in self._sched:
+            return self._sched[key]
+        n, nb = params.n_train, len(pl.bwd)
+        ready = torch.full((n,), -1, dtype=torch.int32)
+        for name, idx in pl.grad_ready.items():
+            o = params.off[name]
+            sz = 1
+            for d in params.spec[name][0]:
+                sz *= d
+            ready[o:o + sz] = idx
+        # suffix maximum: smax[o] = last launch that writes anything at or beyond offset o
+        smax = torch.flip(torch.cummax(torch.flip(ready, [0]), 0).values, [0])
+        best = None
+        for k in sorted(set(int(v) for v in torch.unique(ready).tolist())):
+            if k < 0 or k > max_pos * nb:
+                continue
+            ok = (smax <= k).nonzero()
+            if ok.numel() == 0:
+                continue
+            o = int(ok[0].item())
+            o = (o + 63) // 64 * 64                      # keep the two ranges 256-byte aligned
+            if n - o >= min_frac * n:
+                best = (k, o)
+                break
+        self._sched[key] = best
+        return best
+
     def run_backward(self, pl, stream, params=None):
         """Run the backward launches, issuing bucket all-reduces as their gradients complete."""
         params = params or pl.net.params
@@ -93,6 +126,11 @@ class DataParallel:
             tail = params.data[params.n_train:]
             dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group)
             tail.div_(self.world_size)
+
+    def all_reduce_async(self, t):
+        """Sum all-reduce on NCCL's stream (ordered after the work already enqueued on the current stream); the returned
+        handle's wait() makes the current stream wait for it."""
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def all_reduce_sum_(self, t):
         if self.world_size > 1:

@@ -476,9 +476,13 @@ class Model:
         if not train:
             self._graph((id(pl), "eval"), lambda s: self._run_eval_ops(pl, s))
         elif dp:
-            # data parallel: replayed graph for fwd+bwd, one NCCL sum over the flat gradient buffer, replayed optimizer
-            self._graph((id(pl), "fwdbwd"), lambda s: self._run_fwd_bwd(pl, s))
-            self.dp.all_reduce_sum_(self.net.params.grad)
+            # data parallel: replayed graphs for fwd+bwd with the gradient all-reduce overlapped, replayed optimizer
+            def head(st):
+                pl.scratch.zero_()
+                self.net.params.grad.zero_()
+                if self.net.pack_launch is not None:
+                    self.net.pack_launch(st)
+            self._dp_graph_backward(pl, 0, head, "X")
             self._graph((id(pl), "opt"), lambda s: self._opt_launch(s))
         else:
             self._graph((id(pl), "train"), lambda s: self._run_train_ops(pl, s))
@@ -517,12 +521,41 @@ class Model:
             ev = self._copy_stream.record_event()
         main.wait_event(ev)
         if self.dp is not None and self.dp.world_size > 1:
-            self._graph((id(pl), "B"), part_b)
-            self.dp.all_reduce_sum_(self.net.params.grad)
+            self._dp_graph_backward(pl, k, None, "B")
             self._graph((id(pl), "opt"), lambda st: self._opt_launch(st))
         else:
             self._graph((id(pl), "B+opt"), lambda st: (part_b(st), self._opt_launch(st)))
         return nb
+
+    def _dp_graph_backward(self, pl, fwd_from, head, tag):
+        """Forward launches [fwd_from:], BN moving statistics, backward and the NCCL gradient sum of a data-parallel step,
+        graph-replayed.  The all-reduce is overlapped with backward: the parameter-heavy deep levels are final after
+        backward launch ks (distribute.two_phase_split) and travel over NVLink on NCCL's stream while the shallow levels'
+        backward (a second graph) still runs; the small remainder follows.  RSA_DP_GRAPH_OVERLAP=0: one all-reduce after
+        the whole backward."""
+        split = self.dp.two_phase_split(pl, self.net.params) if os.environ.get("RSA_DP_GRAPH_OVERLAP", "1") != "0" else None
+        grad = self.net.params.grad
+        ks = split[0] if split else len(pl.bwd) - 1
+
+        def first(st):
+            if head is not None:
+                head(st)
+            for op in pl.fwd[fwd_from:]:
+                op(st)
+            if pl.bn_update is not None:
+                pl.bn_update(st)
+            for op in pl.bwd[:ks + 1]:
+                op(st)
+
+        self._graph((id(pl), tag + "1"), first)
+        if split is None:
+            self.dp.all_reduce_sum_(grad)
+            return
+        off = split[1]
+        h = self.dp.all_reduce_async(grad[off:])
+        self._graph((id(pl), tag + "2"), lambda st: [op(st) for op in pl.bwd[ks + 1:]])
+        self.dp.all_reduce_sum_(grad[:off])
+        h.wait()
 
     def _collect(self, pl):
         """Device -> host read of the step results; returns the keras metrics list."""
