@@ -39,11 +39,13 @@ struct T3 {
   static constexpr int WBYTES = 9 * C * PITCH;      // one branch's weights
   static constexpr uint32_t LAYOUT = C == 32 ? 4u : 2u;   // UMMA layout code: SWIZZLE_64B / SWIZZLE_128B
 };
-// warp roles: 0 TMA producer, 1..KT MMA issuers (one per sub-tile), KT+1 TMA store, EPI0..EPI0+7 epilogue
-template <int KT> struct T3Warps {
+// warp roles: 0 TMA producer, 1..KT MMA issuers (one per sub-tile), KT+1 TMA store + side loads, EPI0..EPI0+EW-1 epilogue.
+// The epilogue is a chain of dependent latencies per warp (tcgen05.ld, shared loads, proxy fence), so it is spread over
+// EW = 8 or 16 warps: lane quarter q = warp % 4 (the TMEM lanes a warp may read), column group (warp - EPI0) / 4.
+template <int KT, int EW> struct T3Warps {
   static constexpr int STORE = KT + 1;
   static constexpr int EPI0 = (KT + 2 + 3) / 4 * 4;
-  static constexpr int THREADS = (EPI0 + 8) * 32;
+  static constexpr int THREADS = (EPI0 + EW) * 32;
 };
 
 struct Tc3Params {
@@ -75,7 +77,15 @@ __device__ __forceinline__ void twait(uint64_t* bar, uint32_t parity, long long*
   tr[slot] += clock64() - t0;
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[N]);
+template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -123,11 +133,13 @@ struct Tc3Smem {
   }
 };
 
-template <int C, int KT>
-__global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
+template <int C, int KT, int EW>
+__global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
   constexpr int PITCH = T3<C>::PITCH, BOXB = T3<C>::BOXB, WBYTES = T3<C>::WBYTES;
-  constexpr int EPI0 = T3Warps<KT>::EPI0;
-  constexpr int NCT = C / 2;            // accumulator columns per epilogue thread
+  constexpr int EPI0 = T3Warps<KT, EW>::EPI0;
+  constexpr int NCT = C / (EW / 4);     // accumulator columns per epilogue thread
+  constexpr int CHK = NCT < 16 ? NCT : 16;   // columns per tcgen05.ld
+  static_assert(CHK == 8 || CHK == 16, "epilogue chunk");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nside = p.has_add + p.has_mask + p.has_bnx;
@@ -147,8 +159,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
   uint64_t* sready = tempty + 2;             // [nsb] staged tile written by the 8 epilogue warps
   uint64_t* sfree = sready + T3_MAXSB;       // [nsb] staged tile read by its TMA store
   uint64_t* ifull = sfree + T3_MAXSB;        // [nsi] side-input tiles landed
-  uint64_t* iempty = ifull + T3_MAXSB;       // [nsi] side-input tiles consumed by the 8 epilogue warps
-  uint64_t* wbar = iempty + T3_MAXSB;
+  uint64_t* wbar = ifull + T3_MAXSB;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_stats = p.stats != nullptr;
@@ -163,10 +174,10 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
     if (p.has_mask) prefetch_tmap(&maps.mask);
     if (p.has_bnx) prefetch_tmap(&maps.bnx);
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], KT); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], KT); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], KT); mbar_init(&tempty[s], EW); }
     for (int s = 0; s < T3_MAXSB; ++s) {
-      mbar_init(&sready[s], 8); mbar_init(&sfree[s], 1);
-      mbar_init(&ifull[s], 1); mbar_init(&iempty[s], 8);
+      mbar_init(&sready[s], EW); mbar_init(&sfree[s], 1);
+      mbar_init(&ifull[s], 1);
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
       mbar_expect_tx(wbar, p.nbr * WBYTES);
       for (int b = 0; b < p.nbr; ++b)
         for (int t = 0; t < 9; ++t) tma_load_3d(wsm + b * WBYTES + t * C * PITCH, &maps.w[b], wbar, 0, 0, t);
-      int stage = 0, phase = 0, iseq = 0;
+      int stage = 0, phase = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         int r = item;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
@@ -223,19 +234,6 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
               tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, cw, ch, n);
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
-          }
-        }
-        // side inputs of this item's sub-tiles (addend, ReLU mask): same 16x8 boxes as the output tiles, landed several
-        // sub-tiles ahead of the epilogue that consumes them
-        if (nside) {
-          for (int s = 0; s < KT; ++s, ++iseq) {
-            const int k = iseq & (p.nsi - 1);
-            twait(&iempty[k], ((iseq >> p.nsi_log) & 1) ^ 1, tr, 1);
-            mbar_expect_tx(&ifull[k], nside * BOXB);
-            uint8_t* dst = sidesm + k * nside * BOXB;
-            if (p.has_add) tma_load_4d(dst, &maps.add, &ifull[k], 0, w0 + 8 * s, h0, n);
-            if (p.has_mask) tma_load_4d(dst + p.has_add * BOXB, &maps.mask, &ifull[k], 0, w0 + 8 * s, h0, n);
-            if (p.has_bnx) tma_load_4d(dst + (p.has_add + p.has_mask) * BOXB, &maps.bnx, &ifull[k], 0, w0 + 8 * s, h0, n);
           }
         }
       }
@@ -301,9 +299,28 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         umma_commit(&tfull[it & 1]);
       }
     }
-  } else if (warp == T3Warps<KT>::STORE) {
-    // ===== TMA store of the staged tiles =====
+  } else if (warp == T3Warps<KT, EW>::STORE) {
+    // ===== TMA store of the staged tiles; the same thread keeps the side-input ring (addend, ReLU mask, BatchNorm
+    // input: 16x8 boxes like the output tiles) nsi sub-tiles ahead of the epilogue.  sready[j] completing for sub-tile
+    // `seq` also means the eight epilogue warps are done with that sub-tile's side slot, so the slot is refilled right
+    // there - the main operand pipeline (warp 0) never waits for the epilogue =====
     if (lane == 0) {
+      auto issue_side = [&](int sq) {
+        const int item = blockIdx.x + (sq / KT) * (int)gridDim.x;
+        if (item >= p.items) return;
+        int r = item;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; r /= p.tiles_h;
+        const int n = r, h0 = th * 16, w0 = tw * 8 * KT + 8 * (sq % KT);
+        const int k = sq & (p.nsi - 1);
+        mbar_expect_tx(&ifull[k], nside * BOXB);
+        uint8_t* dst = sidesm + k * nside * BOXB;
+        if (p.has_add) tma_load_4d(dst, &maps.add, &ifull[k], 0, w0, h0, n);
+        if (p.has_mask) tma_load_4d(dst + p.has_add * BOXB, &maps.mask, &ifull[k], 0, w0, h0, n);
+        if (p.has_bnx) tma_load_4d(dst + (p.has_add + p.has_mask) * BOXB, &maps.bnx, &ifull[k], 0, w0, h0, n);
+      };
+      if (nside)
+        for (int sq = 0; sq < p.nsi; ++sq) issue_side(sq);
       int seq = 0;
       const int lag = p.nsb >> 1;          // stores allowed in flight before a buffer is handed back
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -314,6 +331,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
         for (int s = 0; s < KT; ++s, ++seq) {
           const int j = seq & (p.nsb - 1);
           twait(&sready[j], (seq >> p.nsb_log) & 1, tr, 5);
+          if (nside) issue_side(seq + p.nsi);
           tma_store_4d(&maps.out, ysm + j * BOXB, 0, w0 + 8 * s, h0, n);
           // the store issued `lag` tiles ago has finished reading its buffer: hand that buffer back
           if (lag == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
@@ -324,19 +342,18 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp >= EPI0) {
-    // ===== epilogue warps: lane quarter q, column half hs =====
+    // ===== epilogue warps: lane quarter q, column group hs =====
     const int q = warp & 3, hs = (warp - EPI0) >> 2;
     const int rrow = q * 32 + lane;                 // accumulator row = pixel of the 16x8 sub-tile
-    const int py = rrow >> 3, px = rrow & 7;
     const uint32_t srow = (uint32_t)rrow * PITCH;
     const uint32_t sw = C == 32 ? (uint32_t)((rrow >> 1) & 3) : (uint32_t)(rrow & 7);   // swizzle phase of this row
     float acc_s[NCT], acc_q[NCT];                   // BatchNorm statistics of this thread's pixels (all its sub-tiles)
 #pragma unroll
     for (int j = 0; j < NCT; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
-    float bias_r[C == 32 ? 16 : 1];                 // 32 channels: the thread's 16 biases live in registers
+    float bias_r[C == 32 ? NCT : 1];                // 32 channels: the thread's biases live in registers
     if constexpr (C == 32) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) bias_r[j] = bias_s[hs * 16 + j];
+      for (int j = 0; j < NCT; ++j) bias_r[j] = bias_s[hs * NCT + j];
     }
     int it = 0, seq = 0;
     long long* etr = (warp == EPI0) ? tr : nullptr;
@@ -355,54 +372,60 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
           __syncwarp();
         }
 #pragma unroll
-        for (int cc = 0; cc < NCT; cc += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((it & 1) * KT + s) * C + hs * NCT + cc), v);
-          if (s == KT - 1 && cc + 16 >= NCT) {
+        for (int cc = 0; cc < NCT; cc += CHK) {
+          uint32_t v[CHK];
+          const long long tl0 = etr ? clock64() : 0;
+          tmem_ld<CHK>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((it & 1) * KT + s) * C + hs * NCT + cc), v);
+          if (etr && lane == 0) etr[11] += clock64() - tl0;
+          if (s == KT - 1 && cc + CHK >= NCT) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[it & 1]);
           }
-          float f[16];
+          float f[CHK];
           if constexpr (C == 32) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_r[i];
+            for (int i = 0; i < CHK; ++i) f[i] = __uint_as_float(v[i]) + bias_r[cc + i];
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
+            for (int i = 0; i < CHK; i += 4) {
               const float4 bv = *reinterpret_cast<const float4*>(bias_s + hs * NCT + cc + i);
               f[i] = __uint_as_float(v[i]) + bv.x; f[i + 1] = __uint_as_float(v[i + 1]) + bv.y;
               f[i + 2] = __uint_as_float(v[i + 2]) + bv.z; f[i + 3] = __uint_as_float(v[i + 3]) + bv.w;
             }
           }
           const uint32_t c16 = (uint32_t)((hs * NCT + cc) >> 3);        // first 16-byte chunk of this group inside the row
-          const uint32_t o0 = (c16 ^ sw) << 4, o1 = ((c16 + 1) ^ sw) << 4;
-          if (p.has_add) {
-            float t[16];
-            unpack8(*reinterpret_cast<const uint4*>(ib + o0), t); unpack8(*reinterpret_cast<const uint4*>(ib + o1), t + 8);
+          uint32_t o[CHK / 8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += t[i];
+          for (int k = 0; k < CHK / 8; ++k) o[k] = ((c16 + k) ^ sw) << 4;
+          auto ld_side = [&](const uint8_t* base, float* t) {
+#pragma unroll
+            for (int k = 0; k < CHK / 8; ++k) unpack8(*reinterpret_cast<const uint4*>(base + o[k]), t + 8 * k);
+          };
+          if (p.has_add) {
+            float t[CHK];
+            ld_side(ib, t);
+#pragma unroll
+            for (int i = 0; i < CHK; ++i) f[i] += t[i];
           }
           if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            for (int i = 0; i < CHK; ++i) f[i] = fmaxf(f[i], 0.f);
           }
           if (p.has_mask) {
-            float t[16];
-            const uint8_t* mb = ib + p.has_add * BOXB;
-            unpack8(*reinterpret_cast<const uint4*>(mb + o0), t); unpack8(*reinterpret_cast<const uint4*>(mb + o1), t + 8);
+            float t[CHK];
+            ld_side(ib + p.has_add * BOXB, t);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = t[i] > 0.f ? f[i] : 0.f;
+            for (int i = 0; i < CHK; ++i) f[i] = t[i] > 0.f ? f[i] : 0.f;
           }
           if (p.has_bnx) {
             // fused BatchNorm(+ReLU) backward reductions: f is d(relu(bn(x))); recompute the ReLU mask from x like the
             // forward did, keep g = f * mask as the stored value and accumulate {sum g, sum g*xhat} below
-            const uint8_t* xb = ib + (p.has_add + p.has_mask) * BOXB;
-            float xv[16], xh[4];
-            unpack8(*reinterpret_cast<const uint4*>(xb + o0), xv); unpack8(*reinterpret_cast<const uint4*>(xb + o1), xv + 8);
+            float xv[CHK], xh[4];
+            ld_side(ib + (p.has_add + p.has_mask) * BOXB, xv);
             const float* cf = bnc + hs * NCT + cc;
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
+            for (int i = 0; i < CHK; i += 4) {
               const float4 ca = *reinterpret_cast<const float4*>(cf + i), cb = *reinterpret_cast<const float4*>(cf + C + i);
               const float4 cg = *reinterpret_cast<const float4*>(cf + 2 * C + i), ct = *reinterpret_cast<const float4*>(cf + 3 * C + i);
               xh[0] = fmaf(xv[i], ca.x, cb.x); xh[1] = fmaf(xv[i + 1], ca.y, cb.y);
@@ -415,39 +438,45 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
               for (int e = 0; e < 4; ++e) { acc_s[cc + i + e] += f[i + e]; acc_q[cc + i + e] = fmaf(f[i + e], xh[e], acc_q[cc + i + e]); }
             }
           }
-          uint4 lo, hi;
-          lo.x = pack_bf16x2(f[0], f[1]); lo.y = pack_bf16x2(f[2], f[3]); lo.z = pack_bf16x2(f[4], f[5]); lo.w = pack_bf16x2(f[6], f[7]);
-          hi.x = pack_bf16x2(f[8], f[9]); hi.y = pack_bf16x2(f[10], f[11]); hi.z = pack_bf16x2(f[12], f[13]); hi.w = pack_bf16x2(f[14], f[15]);
+          uint4 pk[CHK / 8];
+#pragma unroll
+          for (int k = 0; k < CHK / 8; ++k) {
+            pk[k].x = pack_bf16x2(f[8 * k], f[8 * k + 1]); pk[k].y = pack_bf16x2(f[8 * k + 2], f[8 * k + 3]);
+            pk[k].z = pack_bf16x2(f[8 * k + 4], f[8 * k + 5]); pk[k].w = pack_bf16x2(f[8 * k + 6], f[8 * k + 7]);
+          }
           if (cc == 0) {
             if (lane == 0) twait(&sfree[j], ((seq >> p.nsb_log) & 1) ^ 1, etr, 7);
             __syncwarp();
           }
-          *reinterpret_cast<uint4*>(yb + o0) = lo;
-          *reinterpret_cast<uint4*>(yb + o1) = hi;
+#pragma unroll
+          for (int k = 0; k < CHK / 8; ++k) *reinterpret_cast<uint4*>(yb + o[k]) = pk[k];
           if (has_stats && !p.has_bnx) {
             // per-thread partial sums of the stored (bf16-rounded) values; reduced across lanes once per CTA
-            float t[16];
-            unpack8(lo, t); unpack8(hi, t + 8);
+            float t[CHK];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { acc_s[cc + i] += t[i]; acc_q[cc + i] = fmaf(t[i], t[i], acc_q[cc + i]); }
+            for (int k = 0; k < CHK / 8; ++k) unpack8(pk[k], t + 8 * k);
+#pragma unroll
+            for (int i = 0; i < CHK; ++i) { acc_s[cc + i] += t[i]; acc_q[cc + i] = fmaf(t[i], t[i], acc_q[cc + i]); }
           }
         }
+        const long long tf0 = etr ? clock64() : 0;
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&sready[j]);
-          if (nside) mbar_arrive(&iempty[ks]);
-        }
+        if (etr && lane == 0) etr[12] += clock64() - tf0;
+        if (lane == 0) mbar_arrive(&sready[j]);
       }
     }
     if (etr && lane == 0) { etr[9] += clock64() - e_t0; etr[10] += seq; }
     if (has_stats) {
-      // 16-wide butterfly reduce-scatter over the warp's 32 pixels: the lane pair (2m, 2m+1) ends with channel bitrev4(m)
+      // CHK-wide butterfly reduce-scatter over the warp's 32 pixels: after log2(CHK) halving exchanges every lane holds one
+      // channel's partial sum; the remaining xor steps finish the sum over the lanes that share that channel
 #pragma unroll
-      for (int cc = 0; cc < NCT; cc += 16) {
+      for (int cc = 0; cc < NCT; cc += CHK) {
+        int ch = 0;
 #pragma unroll
-        for (int off = 16, n = 8; n >= 1; off >>= 1, n >>= 1) {
+        for (int off = 16, n = CHK / 2; n >= 1; off >>= 1, n >>= 1) {
           const bool upper = (lane & off) != 0;
+          if (upper) ch += n;
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             const float send_s = upper ? acc_s[cc + i] : acc_s[cc + i + n], keep_s = upper ? acc_s[cc + i + n] : acc_s[cc + i];
@@ -456,15 +485,18 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
             acc_q[cc + i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
           }
         }
-        acc_s[cc] += __shfl_xor_sync(0xffffffffu, acc_s[cc], 1);
-        acc_q[cc] += __shfl_xor_sync(0xffffffffu, acc_q[cc], 1);
-        if ((lane & 1) == 0) {
-          const int ch = hs * NCT + cc + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          atomicAdd(&csum[ch], acc_s[cc]);
-          atomicAdd(&csq[ch], acc_q[cc]);
+        constexpr int REST = 32 / CHK;            // lanes sharing one channel: 2 (CHK 16) or 4 (CHK 8)
+#pragma unroll
+        for (int off = REST / 2; off >= 1; off >>= 1) {
+          acc_s[cc] += __shfl_xor_sync(0xffffffffu, acc_s[cc], off);
+          acc_q[cc] += __shfl_xor_sync(0xffffffffu, acc_q[cc], off);
+        }
+        if ((lane & (REST - 1)) == 0) {
+          atomicAdd(&csum[hs * NCT + cc + ch], acc_s[cc]);
+          atomicAdd(&csq[hs * NCT + cc + ch], acc_q[cc]);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       if (it > 0 && warp < EPI0 + C / 32) {
         const int c = (warp - EPI0) * 32 + lane;
         atomicAdd(p.stats + c, (double)csum[c]);
@@ -480,16 +512,16 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
   }
 }
 
-template <int C, int KT>
+template <int C, int KT, int EW>
 int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<C, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<C, KT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { rsa_set_error("conv_tc3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
   const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
-  cudaError_t le = launch_pdl(conv_tc3_kernel<C, KT>, dim3(grid), dim3(T3Warps<KT>::THREADS), (size_t)smem_bytes, st, maps, p);
+  cudaError_t le = launch_pdl(conv_tc3_kernel<C, KT, EW>, dim3(grid), dim3(T3Warps<KT, EW>::THREADS), (size_t)smem_bytes, st, maps, p);
   if (le != cudaSuccess) { rsa_set_error("conv_tc3: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
@@ -624,8 +656,10 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 32) return KT == 2 ? launch3<32, 2>(maps, p, L.total, st) : launch3<32, 4>(maps, p, L.total, st);
-  return KT == 1 ? launch3<64, 1>(maps, p, L.total, st) : launch3<64, 2>(maps, p, L.total, st);
+  // eight epilogue warps: sixteen (EW = 16) measured 5-15 % slower on every shape - the epilogue's shared-memory accesses
+  // queue behind the tensor core's operand reads, so more warps only add contention
+  if (C == 32) return KT == 2 ? launch3<32, 2, 8>(maps, p, L.total, st) : launch3<32, 4, 8>(maps, p, L.total, st);
+  return KT == 1 ? launch3<64, 1, 8>(maps, p, L.total, st) : launch3<64, 2, 8>(maps, p, L.total, st);
 }
 
 // =====================================================================================================

@@ -41,7 +41,13 @@ for d in (1, 3, 15, 31):
         t3 = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [bias[0]], [d], outs[i], N, H, W, C, stats=stats))
         t3p = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [bias[0]], [d], outs[i], N, H, W, C))
         t3r = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [bias[0]], [d], outs[i], N, H, W, C, accumulate=True))
-        line += f" | tc3 stats {t3:7.1f} us ({flops/t3/1e6:6.0f} TF)  plain {t3p:7.1f} us  accum {t3r:7.1f} us"
+        fst = torch.randn(2 * C, dtype=torch.float64, device="cuda").abs_() * (N * H * W) + 1.0
+        fst[C:] = fst[:C] ** 2 / (N * H * W) + (N * H * W)          # variance 1
+        bnr = (xs[(0 + 2) % NB], fst, float(N * H * W), 1e-3, bias[1], bias[2], 1)
+        t3b = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [None], [-d], outs[i], N, H, W, C, stats=stats,
+                                                bnr=(xs[(i + 2) % NB],) + bnr[1:]))
+        t3m = timeit(lambda i: lib.conv_tc3_fwd([xs[i]], [wt[0].view(-1)], [None], [-d], outs[i], N, H, W, C, mask=xs[(i + 2) % NB]))
+        line += f" | tc3 stats {t3:7.1f} us ({flops/t3/1e6:6.0f} TF)  plain {t3p:7.1f} us  accum {t3r:7.1f} us  dgrad+bnr {t3b:7.1f} us  dgrad+mask {t3m:7.1f} us"
     print(line, flush=True)
 if lib.conv_tc3_supported(N, H, W, C) and C == 32:
     dils = [1, 3, 15, 31]
