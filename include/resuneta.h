@@ -223,7 +223,8 @@ int rsa_bias_grad(const void* dy, int dtype, long long M, int C, float* db0, flo
                   void* stream);
 /* bf16 copies of the fp32 HWIO master kernels for the tensor-core path, all layers in one launch.
  * table (device): nlayers entries {int64 src_off, int64 fwd_off, int64 bwd_off, int32 taps, Cin, Cout, pad};
- * fwd copy is [tap][Cout][Cin], bwd copy is [tap][Cin][Cout]. */
+ * fwd copy is [tap][Cout][Cin], bwd copy is [tap][Cin][Cout].  nlayers <= 512; max_elems = elements of the largest layer
+ * (bounds the grid; the 32x32 tiles of all layers are walked as one flat list by a single wave of blocks). */
 int rsa_pack_weights_tc(const float* params, void* shadow, const void* table, int nlayers, long long max_elems,
                         void* stream);
 

@@ -224,18 +224,35 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
 // ---- weight packing: fp32 HWIO master -> bf16 [tap][Cout][Cin] (forward) and [tap][Cin][Cout] (dgrad) ----
 struct PackEntry { long long src_off, fwd_off, bwd_off; int taps, Cin, Cout, pad; };
 
+constexpr int PACK_MAXL = 512;
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ params, bf16* __restrict__ shadow,
-                                                           const PackEntry* __restrict__ table) {
+                                                           const PackEntry* __restrict__ table, int nlayers) {
   // 32x32 tiles through shared memory: reads (HWIO, co contiguous) and both writes ([ci][co] copy and the
-  // transposed [co][ci] copy) are coalesced
+  // transposed [co][ci] copy) are coalesced.  The tiles of all layers form one flat list (prefix sums rebuilt per
+  // block from the table) that a single wave of blocks walks with a grid stride - layer sizes differ by 1000x, so a
+  // (tiles, layer) grid would launch mostly empty blocks.
   __shared__ float tile[32][33];
-  const PackEntry e = table[blockIdx.y];
-  const int coutp = e.pad > 0 ? e.pad : e.Cout;
-  const int tci = (e.Cin + 31) / 32, tco = (e.Cout + 31) / 32;
-  const int ntiles = e.taps * tci * tco;
+  __shared__ int prefix[PACK_MAXL + 1];
+  for (int l = threadIdx.x; l < nlayers; l += 256) {
+    const PackEntry e = table[l];
+    prefix[l + 1] = e.taps * ((e.Cin + 31) / 32) * ((e.Cout + 31) / 32);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    prefix[0] = 0;
+    for (int l = 0; l < nlayers; ++l) prefix[l + 1] += prefix[l];
+  }
+  __syncthreads();
+  const int total = prefix[nlayers];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-  const float* src = params + e.src_off;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  int layer = 0;
+  for (int ft = blockIdx.x; ft < total; ft += gridDim.x) {
+    while (prefix[layer + 1] <= ft) ++layer;                   // flat ids only grow
+    const PackEntry e = table[layer];
+    const int coutp = e.pad > 0 ? e.pad : e.Cout;
+    const int tci = (e.Cin + 31) / 32, tco = (e.Cout + 31) / 32;
+    const float* src = params + e.src_off;
+    const int t = ft - prefix[layer];
     const int tap = t / (tci * tco);
     const int r = t % (tci * tco);
     const int ci0 = (r / tco) * 32, co0 = (r % tco) * 32;
@@ -875,11 +892,11 @@ extern "C" int rsa_bias_grad(const void* dy, int dtype, long long M, int C, floa
 extern "C" int rsa_pack_weights_tc(const float* params, void* shadow, const void* table, int nlayers,
                                    long long max_elems, void* stream) {
   RSA_REQUIRE(params && shadow && table && nlayers > 0, RSA_ERR_SHAPE, "pack_weights_tc: bad args");
-  int gx = (int)ceil_div64(max_elems, 1024 * 4);     // 32x32 tiles, a few per block for the largest layer
+  RSA_REQUIRE(nlayers <= PACK_MAXL, RSA_ERR_SHAPE, "pack_weights_tc: more than %d layers", PACK_MAXL);
+  int gx = (int)ceil_div64(max_elems, 1024);          // never more blocks than the largest layer has tiles
   if (gx < 1) gx = 1;
-  if (gx > 1024) gx = 1024;
-  pack_weights_kernel<<<dim3(gx, nlayers), 256, 0, (cudaStream_t)stream>>>(params, (bf16*)shadow,
-                                                                          (const PackEntry*)table);
+  if (gx > rsa_num_sms() * 8) gx = rsa_num_sms() * 8; // one resident wave
+  pack_weights_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(params, (bf16*)shadow, (const PackEntry*)table, nlayers);
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }

@@ -130,6 +130,24 @@ class ParamStore:
         return self.gflat(name).view(self.spec[name][0])
 
 
+class _BwdOps(list):
+    """Backward launch list.  Weight-gradient launches are tagged `side` (Plan._side): they only feed the optimizer, so
+    the executor may run them on a second stream next to the data-gradient chain.  The first main-stream launch that
+    writes a buffer a pending side launch still reads is tagged `join` (Plan.gacc notices the write)."""
+
+    def __init__(self, plan):
+        super().__init__()
+        self.plan = plan
+
+    def append(self, op):
+        pl = self.plan
+        if not getattr(op, "side", False) and pl._join_next:
+            op.join = True
+            pl._join_next = False
+            pl._side_reads.clear()
+        super().append(op)
+
+
 class Plan:
     """One walk of the network for a fixed batch size and mode.
 
@@ -147,7 +165,9 @@ class Plan:
         self._nconv = 0
         self._nbn = 0
         self.fwd = []        # launch(stream) callables
-        self.bwd = []
+        self.bwd = _BwdOps(self)
+        self._side_reads = set()   # buffers read by side launches emitted since the last join
+        self._join_next = False
         self.tape = []       # closures that emit backward launches (run reversed)
         self.bn_table = []   # (stats view, C, moving_mean name, moving_var name, count, count_full)
         self._scratch_chunks = []
@@ -210,7 +230,15 @@ class Plan:
             t.grad = self.alloc(t.shape, t.dtype)
         acc = t.grad_written
         t.grad_written = True
+        if self._side_reads and t.grad.data_ptr() in self._side_reads:
+            self._join_next = True     # the next main-stream launch overwrites what a side launch still reads
         return t.grad, acc
+
+    def _side(self, op, *bufs):
+        """Tag a weight/bias-gradient launch as runnable beside the main chain; bufs = the tensors it reads."""
+        op.side = True
+        self._side_reads.update(b.data_ptr() for b in bufs if b is not None)
+        return op
 
     @staticmethod
     def _tag(op, tag, flops):
@@ -437,7 +465,7 @@ class Plan:
             db_simt = [None]
             if bias_grad:
                 if cout % 8 == 0 and bf:
-                    self.bwd.append(lib.bias_grad(dz, out.M, cout, [self.G(name + "/bias")]))
+                    self.bwd.append(self._side(lib.bias_grad(dz, out.M, cout, [self.G(name + "/bias")]), dz))
                 else:   # fp32 head logits / odd channel counts: folded into the CUDA-core wgrad of the first main
                     db_simt[0] = self.G(name + "/bias")
             sp = {}
@@ -446,7 +474,8 @@ class Plan:
                 """weight + data gradient of one source given the gradient dq at the conv's own resolution."""
                 sp_ok = self._tc_spatial_ok(Hq, Wq)
                 if bf and p2(t.C) and p2(cout) and self._tc_spatial_ok(Hq, Wq, 4):
-                    self.bwd.append(lib.pw_wgrad_tc(t.data, dq, dW[koff * cout:], cout, N, Hq, Wq, t.C, cout, in_stride))
+                    self.bwd.append(self._side(lib.pw_wgrad_tc(t.data, dq, dW[koff * cout:], cout, N, Hq, Wq, t.C, cout,
+                                                               in_stride), t.data, dq))
                 else:
                     seg = Seg(t.data, t.C, t.H, t.W, mult=in_stride, w_off=koff * cout)
                     db, db_simt[0] = (db_simt[0], None) if dq is dz else (None, db_simt[0])
@@ -588,12 +617,13 @@ class Plan:
                 db = self.G(name + "/bias") if bias_grad else None
                 if tcw is not None and C == cout:
                     if thin and lib.conv_tc3_wgrad_supported(N, H, W, C, dil):
-                        self.bwd.append(self._tag(lib.conv_tc3_wgrad(x.data, dy, dW, N, H, W, C, dil), "conv3x3_wgrad", flops))
+                        self.bwd.append(self._side(self._tag(lib.conv_tc3_wgrad(x.data, dy, dW, N, H, W, C, dil),
+                                                             "conv3x3_wgrad", flops), x.data, dy))
                     else:
-                        self.bwd.append(self._tag(lib.conv_tc_wgrad(x.data, dy, dW, N, H, W, C, cout, dil),
-                                                  "conv3x3_wgrad", flops))
+                        self.bwd.append(self._side(self._tag(lib.conv_tc_wgrad(x.data, dy, dW, N, H, W, C, cout, dil),
+                                                             "conv3x3_wgrad", flops), x.data, dy))
                     if db is not None:
-                        self.bwd.append(lib.bias_grad(dy, N * H * W, cout, [db]))
+                        self.bwd.append(self._side(lib.bias_grad(dy, N * H * W, cout, [db]), dy))
                 else:
                     self.bwd.append(self._tag(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout),
                                               "conv3x3_wgrad", flops))
@@ -703,7 +733,7 @@ class Plan:
             if out.grad is None:
                 return
             dbs = [self.G(n + "/bias") for n in conv_names]
-            self.bwd.append(self.lib.bias_grad(out.grad, out.M, out.C, dbs))
+            self.bwd.append(self._side(self.lib.bias_grad(out.grad, out.M, out.C, dbs), out.grad))
             self._ready(*[n + "/bias" for n in conv_names])
         self.tape.append(bwd)
 
@@ -894,11 +924,11 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
             if tcw is not None and C == f:
                 # bias gradient: one column-sum of d(out) per block (block_bias_grad)
                 if thin and lib.conv_tc3_wgrad_supported(N, H, W, C, d):
-                    pl.bwd.append(pl._tag(lib.conv_tc3_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, d),
-                                          "conv3x3_wgrad", flops))
+                    pl.bwd.append(pl._side(pl._tag(lib.conv_tc3_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, d),
+                                                   "conv3x3_wgrad", flops), a.data, dy))
                 else:
-                    pl.bwd.append(pl._tag(lib.conv_tc_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, f, d),
-                                          "conv3x3_wgrad", flops))
+                    pl.bwd.append(pl._side(pl._tag(lib.conv_tc_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, f, d),
+                                                   "conv3x3_wgrad", flops), a.data, dy))
             else:
                 pl.bwd.append(pl._tag(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N,
                                                       H, W, f), "conv3x3_wgrad", flops))

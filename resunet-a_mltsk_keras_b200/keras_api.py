@@ -422,8 +422,35 @@ class Model:
             op(stream)
         if pl.bn_update is not None:
             pl.bn_update(stream)
-        for op in pl.bwd:
-            op(stream)
+        self._run_bwd(pl.bwd, stream)
+
+    def _run_bwd(self, ops, stream):
+        """Backward launches in tape order.  Weight/bias-gradient launches (tagged `side` by graph.Plan) only feed the
+        optimizer, so they go to a second stream behind an event of the main stream and run beside the data-gradient
+        chain - the bandwidth-bound BatchNorm / pooling kernels of that chain leave the tensor cores idle.  A launch
+        tagged `join` overwrites a buffer a pending side launch reads: the main stream waits for the side stream there,
+        and always at the end of the range.  RSA_WGRAD_STREAM=0 keeps everything on one stream."""
+        if self.net.device.type != "cuda" or os.environ.get("RSA_WGRAD_STREAM", "1") == "0":
+            for op in ops:
+                op(stream)
+            return
+        main = torch.cuda.current_stream()
+        if getattr(self, "_wg_stream", None) is None:
+            self._wg_stream = torch.cuda.Stream()
+        side = self._wg_stream
+        pending = False
+        for op in ops:
+            if getattr(op, "side", False):
+                side.wait_stream(main)
+                op(side.cuda_stream)
+                pending = True
+            else:
+                if pending and getattr(op, "join", False):
+                    main.wait_stream(side)
+                    pending = False
+                op(stream)
+        if pending:
+            main.wait_stream(side)
 
     def _run_train_ops(self, pl, stream):
         self._run_fwd_bwd(pl, stream)
@@ -512,8 +539,7 @@ class Model:
                 op(st)
             if pl.bn_update is not None:
                 pl.bn_update(st)
-            for op in pl.bwd:
-                op(st)
+            self._run_bwd(pl.bwd, st)
 
         self._graph((id(pl), "A"), part_a)
         with torch.cuda.stream(self._copy_stream):
@@ -544,8 +570,7 @@ class Model:
                 op(st)
             if pl.bn_update is not None:
                 pl.bn_update(st)
-            for op in pl.bwd[:ks + 1]:
-                op(st)
+            self._run_bwd(pl.bwd[:ks + 1], st)
 
         self._graph((id(pl), tag + "1"), first)
         if split is None:
@@ -553,7 +578,7 @@ class Model:
             return
         off = split[1]
         h = self.dp.all_reduce_async(grad[off:])
-        self._graph((id(pl), tag + "2"), lambda st: [op(st) for op in pl.bwd[ks + 1:]])
+        self._graph((id(pl), tag + "2"), lambda st: self._run_bwd(pl.bwd[ks + 1:], st))
         self.dp.all_reduce_sum_(grad[:off])
         h.wait()
 
