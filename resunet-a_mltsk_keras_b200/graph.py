@@ -19,6 +19,7 @@ consumer and accumulated by the others (``Plan.gacc``).
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from collections import OrderedDict
 
@@ -130,10 +131,13 @@ class ParamStore:
         return self.gflat(name).view(self.spec[name][0])
 
 
-class _BwdOps(list):
-    """Backward launch list.  Weight-gradient launches are tagged `side` (Plan._side): they only feed the optimizer, so
-    the executor may run them on a second stream next to the data-gradient chain.  The first main-stream launch that
-    writes a buffer a pending side launch still reads is tagged `join` (Plan.gacc notices the write)."""
+class _Ops(list):
+    """Launch list of a plan (forward or backward) carrying the hints the executor (keras_api._run_ops) schedules by:
+      side   weight/bias-gradient launches (Plan._side): they only feed the optimizer and may run on a second stream;
+      join   the first launch that overwrites a buffer a pending side launch still reads (Plan.gacc notices the write);
+      lane   launches of one ResBlock-a branch (Plan.lane): branches are independent chains, so alternating them over
+             two streams lets one branch's bandwidth-bound BatchNorm pass overlap the other's convolutions;
+      chain  launches that read-modify-write the same tensor across lanes (branch sum) and must keep their order."""
 
     def __init__(self, plan):
         super().__init__()
@@ -141,11 +145,35 @@ class _BwdOps(list):
 
     def append(self, op):
         pl = self.plan
+        if pl._lane is not None:
+            op.lane = pl._lane
         if not getattr(op, "side", False) and pl._join_next:
             op.join = True
             pl._join_next = False
             pl._side_reads.clear()
         super().append(op)
+
+
+class _Tape(list):
+    """Backward closures; one appended inside a Plan.lane() region emits its launches into that lane again."""
+
+    def __init__(self, plan):
+        super().__init__()
+        self.plan = plan
+
+    def append(self, fn):
+        pl, lane = self.plan, self.plan._lane
+        if lane is None:
+            super().append(fn)
+            return
+
+        def in_lane():
+            prev, pl._lane = pl._lane, lane
+            try:
+                fn()
+            finally:
+                pl._lane = prev
+        super().append(in_lane)
 
 
 class Plan:
@@ -164,11 +192,12 @@ class Plan:
         self.adt = net.act_dtype
         self._nconv = 0
         self._nbn = 0
-        self.fwd = []        # launch(stream) callables
-        self.bwd = _BwdOps(self)
         self._side_reads = set()   # buffers read by side launches emitted since the last join
         self._join_next = False
-        self.tape = []       # closures that emit backward launches (run reversed)
+        self._lane = None
+        self.fwd = _Ops(self)      # launch(stream) callables
+        self.bwd = _Ops(self)
+        self.tape = _Tape(self)    # closures that emit backward launches (run reversed)
         self.bn_table = []   # (stats view, C, moving_mean name, moving_var name, count, count_full)
         self._scratch_chunks = []
         self.scratch = None
@@ -233,6 +262,16 @@ class Plan:
         if self._side_reads and t.grad.data_ptr() in self._side_reads:
             self._join_next = True     # the next main-stream launch overwrites what a side launch still reads
         return t.grad, acc
+
+    @contextlib.contextmanager
+    def lane(self, k):
+        """Launches (and backward closures) emitted inside belong to branch k: an independent chain between the
+        surrounding launches, which act as barriers.  Anything shared across lanes must be read-only or `chain`ed."""
+        prev, self._lane = self._lane, k
+        try:
+            yield
+        finally:
+            self._lane = prev
 
     def _side(self, op, *bufs):
         """Tag a weight/bias-gradient launch as runnable beside the main chain; bufs = the tensors it reads."""
@@ -881,10 +920,11 @@ def _resblock(pl, x, f, dils, identity, relu_out=False):
     if identity:
         pl.identity_add(x, out)
     for i, d in enumerate(dils):
-        y1 = pl.conv3x3(a1[i], f, d, names[i][1], stats=True, bias_grad=False)   # bias before BN: zero gradient
-        a2 = pl.bn(y1, [names[i][2]], relu=True)[0]
-        _conv_into(pl, a2, f, d, names[i][3], out, first=(i == 0), residual=x if identity else None,
-                   relu=relu_out and i == len(dils) - 1)
+        with pl.lane(i if len(dils) > 1 else None):
+            y1 = pl.conv3x3(a1[i], f, d, names[i][1], stats=True, bias_grad=False)   # bias before BN: zero gradient
+            a2 = pl.bn(y1, [names[i][2]], relu=True)[0]
+            _conv_into(pl, a2, f, d, names[i][3], out, first=(i == 0), residual=x if identity else None,
+                       relu=relu_out and i == len(dils) - 1)
     if relu_out:
         # the block's only consumer applies Activation('relu') (combine, model2.py:82): fused into the last
         # branch's epilogue; the stored tensor is relu(out) and gradients written to it are masked with it
@@ -916,6 +956,7 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
     else:
         pl.fwd.append(pl._tag(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res,
                                             accumulate=not first, relu=relu), "conv3x3_fwd", flops))
+    pl.fwd[-1].chain = out.data.data_ptr()     # the branch sum is a read-modify-write sequence on `out`
     if pl.training:
         def bwd():
             if out.grad is None:

@@ -418,37 +418,69 @@ class Model:
         self.net.params.grad.zero_()
         if self.net.pack_launch is not None:      # refresh the bf16 weight copies of the tensor-core path
             self.net.pack_launch(stream)
-        for op in pl.fwd:
-            op(stream)
+        self._run_ops(pl.fwd, stream)
         if pl.bn_update is not None:
             pl.bn_update(stream)
-        self._run_bwd(pl.bwd, stream)
+        self._run_ops(pl.bwd, stream)
 
-    def _run_bwd(self, ops, stream):
-        """Backward launches in tape order.  Weight/bias-gradient launches (tagged `side` by graph.Plan) only feed the
-        optimizer, so they go to a second stream behind an event of the main stream and run beside the data-gradient
-        chain - the bandwidth-bound BatchNorm / pooling kernels of that chain leave the tensor cores idle.  A launch
-        tagged `join` overwrites a buffer a pending side launch reads: the main stream waits for the side stream there,
-        and always at the end of the range.  RSA_WGRAD_STREAM=0 keeps everything on one stream."""
-        if self.net.device.type != "cuda" or os.environ.get("RSA_WGRAD_STREAM", "1") == "0":
+    def _run_ops(self, ops, stream):
+        """Issue a range of plan launches with the concurrency the plan allows (hints: graph._Ops).
+        * `side` launches (weight / bias gradients) only feed the optimizer: they go to a second stream behind an event of
+          the stream they were emitted on and run beside the data-gradient chain, whose bandwidth-bound BatchNorm and
+          pooling kernels leave the tensor cores idle.  A launch tagged `join` overwrites a buffer a pending side launch
+          reads: its stream waits for the side stream first.
+        * `lane` launches belong to one ResBlock-a branch; branches alternate over RSA_LANES (default 2) streams, launches
+          without a lane are barriers for all of them, `chain` launches keep their order across lanes (branch sum).
+        Everything is joined into the calling stream at the end of the range, so ranges compose (graph capture, the
+        data-parallel split).  RSA_WGRAD_STREAM=0 / RSA_LANES=0 switch the two mechanisms off."""
+        use_side = os.environ.get("RSA_WGRAD_STREAM", "1") != "0"
+        nl = int(os.environ.get("RSA_LANES", "2"))
+        if self.net.device.type != "cuda" or not (use_side or nl > 0):
             for op in ops:
                 op(stream)
             return
         main = torch.cuda.current_stream()
         if getattr(self, "_wg_stream", None) is None:
             self._wg_stream = torch.cuda.Stream()
+            self._lane_streams = []
+        while len(self._lane_streams) < nl:
+            self._lane_streams.append(torch.cuda.Stream())
         side = self._wg_stream
-        pending = False
+        forked = set()       # lane streams carrying work since the last barrier
+        pending = False      # side launches not yet waited for
+        chain_ev = {}        # chain key -> (event, stream) of its last launch
         for op in ops:
-            if getattr(op, "side", False):
-                side.wait_stream(main)
+            ln = getattr(op, "lane", None)
+            in_lane = ln is not None and nl > 0
+            s = self._lane_streams[ln % nl] if in_lane else main
+            if getattr(op, "side", False) and use_side:
+                if in_lane and (ln % nl) not in forked:
+                    s = main                      # nothing of this lane is in flight: the data is final on main
+                side.wait_stream(s)
                 op(side.cuda_stream)
                 pending = True
+                continue
+            if in_lane:
+                if (ln % nl) not in forked:
+                    s.wait_stream(main)
+                    forked.add(ln % nl)
             else:
-                if pending and getattr(op, "join", False):
-                    main.wait_stream(side)
-                    pending = False
-                op(stream)
+                for k in forked:
+                    main.wait_stream(self._lane_streams[k])
+                forked.clear()
+            if pending and getattr(op, "join", False):
+                s.wait_stream(side)
+                pending = in_lane                 # only a wait on the main stream orders every later launch
+            ck = getattr(op, "chain", None)
+            if ck is not None and ck in chain_ev and chain_ev[ck][1] is not s:
+                s.wait_event(chain_ev[ck][0])
+            op(stream if s is main else s.cuda_stream)
+            if ck is not None and nl > 0:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                chain_ev[ck] = (ev, s)
+        for k in forked:
+            main.wait_stream(self._lane_streams[k])
         if pending:
             main.wait_stream(side)
 
@@ -458,8 +490,7 @@ class Model:
 
     def _run_eval_ops(self, pl, stream):
         pl.scratch.zero_()
-        for op in pl.fwd:
-            op(stream)
+        self._run_ops(pl.fwd, stream)
 
     def _graph(self, key, fn):
         """Capture `fn` (allocation-free pre-bound launches) once and replay it afterwards."""
@@ -487,8 +518,7 @@ class Model:
                 self.net.params.grad.zero_()
                 if self.net.pack_launch is not None:
                     self.net.pack_launch(stream)
-                for op in pl.fwd:
-                    op(stream)
+                self._run_ops(pl.fwd, stream)
                 if pl.bn_update is not None:
                     pl.bn_update(stream)
                 self.dp.run_backward(pl, stream)
@@ -531,15 +561,13 @@ class Model:
             self.net.params.grad.zero_()
             if self.net.pack_launch is not None:
                 self.net.pack_launch(st)
-            for op in pl.fwd[:k]:
-                op(st)
+            self._run_ops(pl.fwd[:k], st)
 
         def part_b(st):
-            for op in pl.fwd[k:]:
-                op(st)
+            self._run_ops(pl.fwd[k:], st)
             if pl.bn_update is not None:
                 pl.bn_update(st)
-            self._run_bwd(pl.bwd, st)
+            self._run_ops(pl.bwd, st)
 
         self._graph((id(pl), "A"), part_a)
         with torch.cuda.stream(self._copy_stream):
@@ -566,11 +594,10 @@ class Model:
         def first(st):
             if head is not None:
                 head(st)
-            for op in pl.fwd[fwd_from:]:
-                op(st)
+            self._run_ops(pl.fwd[fwd_from:], st)
             if pl.bn_update is not None:
                 pl.bn_update(st)
-            self._run_bwd(pl.bwd[:ks + 1], st)
+            self._run_ops(pl.bwd[:ks + 1], st)
 
         self._graph((id(pl), tag + "1"), first)
         if split is None:
@@ -578,7 +605,7 @@ class Model:
             return
         off = split[1]
         h = self.dp.all_reduce_async(grad[off:])
-        self._graph((id(pl), tag + "2"), lambda st: self._run_bwd(pl.bwd[ks + 1:], st))
+        self._graph((id(pl), tag + "2"), lambda st: self._run_ops(pl.bwd[ks + 1:], st))
         self.dp.all_reduce_sum_(grad[:off])
         h.wait()
 
