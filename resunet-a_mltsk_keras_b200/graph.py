@@ -147,6 +147,10 @@ class _Ops(list):
         pl = self.plan
         if pl._lane is not None:
             op.lane = pl._lane
+        if not getattr(op, "side", False) and pl._chain_next is not None:
+            if not hasattr(op, "chain"):
+                op.chain = pl._chain_next
+            pl._chain_next = None
         if not getattr(op, "side", False) and pl._join_next:
             op.join = True
             pl._join_next = False
@@ -194,6 +198,7 @@ class Plan:
         self._nbn = 0
         self._side_reads = set()   # buffers read by side launches emitted since the last join
         self._join_next = False
+        self._chain_next = None
         self._lane = None
         self.fwd = _Ops(self)      # launch(stream) callables
         self.bwd = _Ops(self)
@@ -261,6 +266,8 @@ class Plan:
         t.grad_written = True
         if self._side_reads and t.grad.data_ptr() in self._side_reads:
             self._join_next = True     # the next main-stream launch overwrites what a side launch still reads
+        if self._lane is not None:
+            self._chain_next = t.grad.data_ptr()   # write / accumulate order on a gradient shared across lanes
         return t.grad, acc
 
     @contextlib.contextmanager
@@ -1053,19 +1060,28 @@ def define_network(pl):
         z = pl.conv1x1([(x_psp, "plain", False)], n, pl.name_conv(), out_dtype=f32)
         pl.outputs["seg"] = pl.activation(z, "softmax")
         return
-    h = pl.conv3x3(x_psp, 32, 1, "seg1", relu=True)
-    h = pl.conv3x3(h, 32, 1, "seg2", relu=True)
-    z = pl.conv1x1([(h, "plain", False)], n, "seg3", out_dtype=f32)
-    pl.outputs["seg"] = pl.activation(z, "softmax")
-    h = pl.conv3x3(x_psp, 32, 1, pl.name_conv(), relu=True)
-    z = pl.conv1x1([(h, "plain", False)], n, pl.name_conv(), out_dtype=f32)
-    pl.outputs["bound"] = pl.activation(z, "sigmoid")
-    h = pl.conv3x3(x_comb, 32, 1, pl.name_conv(), relu=True)
-    h = pl.conv3x3(h, 32, 1, pl.name_conv(), relu=True)
-    z = pl.conv1x1([(h, "plain", False)], n, pl.name_conv(), out_dtype=f32)
-    pl.outputs["dist"] = pl.activation(z, "softmax")                                 # softmax, model2.py:182
-    z = pl.conv1x1([(x_comb, "plain", False)], 3, "color", out_dtype=f32)
-    pl.outputs["color"] = pl.activation(z, "sigmoid")
+    # the four heads are independent chains (shared inputs are read-only, the shared input gradients are `chain`ed):
+    # one lane each, like the ResBlock-a branches (HEAD_LANE is also used for their losses)
+    with pl.lane(HEAD_LANE["seg"]):
+        h = pl.conv3x3(x_psp, 32, 1, "seg1", relu=True)
+        h = pl.conv3x3(h, 32, 1, "seg2", relu=True)
+        z = pl.conv1x1([(h, "plain", False)], n, "seg3", out_dtype=f32)
+        pl.outputs["seg"] = pl.activation(z, "softmax")
+    with pl.lane(HEAD_LANE["bound"]):
+        h = pl.conv3x3(x_psp, 32, 1, pl.name_conv(), relu=True)
+        z = pl.conv1x1([(h, "plain", False)], n, pl.name_conv(), out_dtype=f32)
+        pl.outputs["bound"] = pl.activation(z, "sigmoid")
+    with pl.lane(HEAD_LANE["dist"]):
+        h = pl.conv3x3(x_comb, 32, 1, pl.name_conv(), relu=True)
+        h = pl.conv3x3(h, 32, 1, pl.name_conv(), relu=True)
+        z = pl.conv1x1([(h, "plain", False)], n, pl.name_conv(), out_dtype=f32)
+        pl.outputs["dist"] = pl.activation(z, "softmax")                                 # softmax, model2.py:182
+    with pl.lane(HEAD_LANE["color"]):
+        z = pl.conv1x1([(x_comb, "plain", False)], 3, "color", out_dtype=f32)
+        pl.outputs["color"] = pl.activation(z, "sigmoid")
+
+
+HEAD_LANE = {"seg": 0, "bound": 1, "dist": 2, "color": 3}
 
 
 class Net:
@@ -1171,7 +1187,8 @@ class Net:
             pl.n_fwd_net = len(pl.fwd)      # forward launches before this index need only x (labels may still be in flight)
             if loss_spec is not None:
                 for head, kind, weight, cw in loss_spec:
-                    pl.attach_loss(head, pl.outputs[head], kind, weight, cw)
+                    with pl.lane(HEAD_LANE.get(head) if self.multitask else None):
+                        pl.attach_loss(head, pl.outputs[head], kind, weight, cw)
                 pl.attach_seg_metrics(pl.outputs["seg"])
             pl.finish()
             self.plans[key] = pl

@@ -19,8 +19,10 @@ heads = ("seg", "bound", "dist", "color")
 hw, n, B = 64, 4, 4
 x, y = O.synth_batch(B, hw, 3, n, seed=100 + rank, block=16)
 res = {}
-for mode in ("1", "0", "0b"):      # "0b": the plain mode again = run-to-run noise floor (atomics reorder fp32 sums)
+for mode in ("1", "0", "0b", "0s"):   # "0b": the plain mode again = run-to-run noise floor (atomics reorder fp32 sums)
     os.environ["RSA_DP_GRAPH_OVERLAP"] = mode[0]
+    # "0s": everything on one stream (no weight-gradient side stream, no branch lanes) = the serial reference
+    os.environ["RSA_WGRAD_STREAM"], os.environ["RSA_LANES"] = ("0", "0") if mode == "0s" else ("1", "2")
     with strat.scope():
         m = build_model((hw, hw, 3), n, True, "v2", dtype="bf16", seed=7)
         m.compile(optimizer=SGD(lr=1e-2, momentum=0.5), loss={h: Tanimoto_dual_loss() for h in heads})
@@ -44,7 +46,11 @@ if rank == 0:
     print(f"max |loss diff| overlap-vs-plain {dl:.3e} (plain-vs-plain noise {noise_l:.3e}); checksum diff {dp_:.3e} (noise {noise_p:.3e})")
     loss_ok = dl <= 5 * noise_l + 1e-6
     par_ok = dp_ <= 5 * noise_p + 1e-6 * np.abs(b[1]).max()
+    sr = res["0s"]
+    ds_l = np.abs(sr[0] - b[0]).max(); ds_p = np.abs(sr[1] - b[1]).max()
+    ser_ok = ds_l <= 5 * noise_l + 1e-6 and ds_p <= 5 * noise_p + 1e-6 * np.abs(b[1]).max()
+    print(f"multi-stream vs single-stream launches: max |loss diff| {ds_l:.3e}, checksum diff {ds_p:.3e}: {ser_ok}")
     print("ranks hold identical parameters:", same_ranks, "| losses overlap vs plain:", loss_ok, "| parameter checksums:", par_ok)
     print("losses (overlap):", a[0][:, 0], "(plain):", b[0][:, 0])
-    print("DP CHECK", "PASS" if (same_ranks and loss_ok and par_ok and a[3] is not None) else "FAIL")
+    print("DP CHECK", "PASS" if (same_ranks and loss_ok and par_ok and ser_ok and a[3] is not None) else "FAIL")
 dist.barrier(); dist.destroy_process_group()

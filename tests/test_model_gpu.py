@@ -285,9 +285,9 @@ def test_patch_loader_feeds_train_on_batch_from_pinned_memory(tmp_path):
                 out.append(m.train_on_batch(xb, yb))
         res.append(np.array(out))
     assert res[0].shape == (3, 10)
-    # atomics reorder the fp32 / double partial sums run to run: losses to float accuracy, metric counts within a few pixels
-    np.testing.assert_allclose(res[0][:, :6], res[1][:, :6], rtol=1e-5)
-    np.testing.assert_allclose(res[0][:, 6:], res[1][:, 6:], rtol=1e-5, atol=3)
+    # atomics reorder the fp32 / double partial sums run to run: losses to 1e-4 (the noise grows over the three steps), metric counts within a few pixels
+    np.testing.assert_allclose(res[0][:, :6], res[1][:, :6], rtol=1e-4)
+    np.testing.assert_allclose(res[0][:, 6:], res[1][:, 6:], rtol=1e-4, atol=3)
 
 
 def test_reused_host_buffers_take_the_registered_zero_copy_path():
@@ -316,7 +316,7 @@ def test_reused_host_buffers_take_the_registered_zero_copy_path():
         if mode == "1":
             assert any(e[2] for e in KA._HOST_REG.values()), "no buffer was registered"
     os.environ.pop("RSA_HOST_REGISTER", None)
-    # losses to float accuracy; the integer metric counts (columns 6..) may move by a pixel or two between two runs because
+    # losses to 1e-4 (the noise grows over the three steps); the integer metric counts (columns 6..) may move by a pixel or two between two runs because
     # the weight-gradient atomics are unordered
-    np.testing.assert_allclose(res["1"][:, :6], res["0"][:, :6], rtol=1e-5)
-    np.testing.assert_allclose(res["1"][:, 6:], res["0"][:, 6:], rtol=1e-5, atol=3)
+    np.testing.assert_allclose(res["1"][:, :6], res["0"][:, :6], rtol=1e-4)
+    np.testing.assert_allclose(res["1"][:, 6:], res["0"][:, 6:], rtol=1e-4, atol=3)
