@@ -216,3 +216,80 @@ def test_fit_with_callbacks_runs():
     h = m.fit(x, y["seg"], batch_size=2, epochs=2, verbose=0, validation_data=(x, y["seg"]),
               callbacks=[EarlyStopping(monitor="val_loss", min_delta=1e-4, patience=10)])
     assert len(h.history["loss"]) == 2 and "val_loss" in h.history
+
+
+def _adversarial_run(ops, stream, nl=2):
+    """Issue `ops` in the most hostile order keras_api._run_ops' hints allow: launches without a lane are barriers;
+    between two barriers every stream (lane % nl) keeps its own order and `chain` launches keep their emission order,
+    but otherwise the HIGHEST stream always goes first.  Side launches are delayed to the next `join` / the end."""
+    i, n = 0, len(ops)
+    delayed = []
+    while i < n:
+        if getattr(ops[i], "lane", None) is None and not getattr(ops[i], "side", False):
+            if getattr(ops[i], "join", False):
+                for d in delayed:
+                    d(stream)
+                delayed.clear()
+            ops[i](stream)
+            i += 1
+            continue
+        j = i
+        while j < n and (getattr(ops[j], "lane", None) is not None or getattr(ops[j], "side", False)):
+            j += 1
+        region = ops[i:j]
+        queues = {}
+        for k, op in enumerate(region):
+            if getattr(op, "side", False):
+                delayed.append(op)
+            else:
+                queues.setdefault(op.lane % nl, []).append((k, op))
+        chain_pos = {}
+        for k, op in enumerate(region):
+            ck = getattr(op, "chain", None)
+            if ck is not None and not getattr(op, "side", False):
+                chain_pos.setdefault(ck, []).append(k)
+        done = set()
+        while any(queues.values()):
+            progressed = False
+            for s in sorted(queues, reverse=True):
+                q = queues[s]
+                while q:
+                    k, op = q[0]
+                    ck = getattr(op, "chain", None)
+                    if ck is not None and any(p < k and p not in done for p in chain_pos[ck]):
+                        break
+                    assert not getattr(op, "join", False), "a join inside a lane region is not expected"
+                    op(stream)
+                    done.add(k)
+                    q.pop(0)
+                    progressed = True
+                if progressed:
+                    break               # restart from the highest stream
+            assert progressed, "hints deadlock"
+        i = j
+    for d in delayed:
+        d(stream)
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1"])
+def test_lane_and_chain_hints_allow_any_stream_interleaving(variant, monkeypatch):
+    """Plan scheduling hints (graph._Ops): running the branches / heads of a step in the most hostile order the hints
+    allow must give bit-identical losses and parameters to the emission order (CPU emulation is deterministic)."""
+    p = _rand_params(variant)
+    x, y = O.synth_batch(2, 64, 3, N_CLS, seed=11, block=16)
+    res = []
+    for hostile in (False, True):
+        m = build_model((64, 64, 3), N_CLS, True, variant, dtype="fp32")
+        m.net.set_weights(p)
+        m.compile(optimizer=SGD(lr=1e-2, momentum=0.5), loss=_losses("tanimoto")[0], loss_weights=LW)
+        if hostile:
+            monkeypatch.setattr(type(m), "_run_ops", lambda self, ops, stream: _adversarial_run(list(ops), stream))
+        out = [m.train_on_batch(x, y) for _ in range(2)]
+        pl = m.net.plan(2, True, m.loss_spec)
+        lanes = {getattr(op, "lane", None) for op in list(pl.fwd) + list(pl.bwd)}
+        assert {0, 1, 2, 3} <= lanes, "branches and heads carry lanes"
+        assert any(hasattr(op, "chain") for op in pl.fwd) and any(hasattr(op, "chain") for op in pl.bwd)
+        res.append((np.array(out), m.net.params.data.clone()))
+        monkeypatch.undo()
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
