@@ -320,3 +320,42 @@ def test_reused_host_buffers_take_the_registered_zero_copy_path():
     # the weight-gradient atomics are unordered
     np.testing.assert_allclose(res["1"][:, :6], res["0"][:, :6], rtol=1e-4)
     np.testing.assert_allclose(res["1"][:, 6:], res["0"][:, 6:], rtol=1e-4, atol=3)
+
+
+def test_bf16_step_survives_hostile_launch_order(monkeypatch):
+    """Scheduling hints of the tensor-core plan (side / join / lane / chain, graph._Ops): one SGD step whose launches are
+    issued in the most hostile order the hints allow - weight gradients delayed to the next join, the highest stream
+    always first - must produce the same parameter update as the emission order.  Two identical bf16 steps already
+    differ (the order of fp32 atomics moves BatchNorm statistics in the last bit, which re-draws bf16 roundings
+    downstream: about 1 % of the whole update, 10-20 % of a small parameter tensor on this random net), so the hostile
+    run is held against that measured floor per parameter; a missing dependency corrupts whole layers."""
+    from sched_util import adversarial_run
+    hw, n, B = 64, 5, 4
+    p = rand_params("v2", hw, 3, n)
+    x, y = O.synth_batch(B, hw, 3, n, seed=21, block=16)
+    upd = []
+    for mode in ("plain", "plain", "hostile"):
+        m = build_model((hw, hw, 3), n, True, "v2", dtype="bf16")
+        m.use_cuda_graph = False
+        m.net.set_weights(p)
+        m.compile(optimizer=SGD(lr=1.0), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+        if mode == "hostile":
+            monkeypatch.setattr(type(m), "_run_ops", lambda self, ops, stream: adversarial_run(list(ops), stream))
+        before = {k: v.clone() for k, v in m.net.get_weights().items()}
+        m.train_on_batch(x, y)
+        after = m.net.get_weights()
+        pl = m.net.plan(B, True, m.loss_spec)
+        assert sum(getattr(op, "side", False) for op in pl.bwd) > 50, "weight-gradient launches are tagged"
+        assert any(getattr(op, "join", False) for op in pl.bwd)
+        upd.append({k: (after[k] - before[k]).double() for k in before if "/moving_" not in k})
+        monkeypatch.undo()
+    A, Bv, H = upd
+    cat = lambda u: torch.cat([u[k].flatten() for k in A])
+    floor = float((cat(Bv) - cat(A)).norm() / cat(A).norm())
+    whole = float((cat(H) - cat(A)).norm() / cat(A).norm())
+    assert whole <= 2.0 * floor + 1e-3, (whole, floor)
+    for k in A:
+        na = float(A[k].norm())
+        if na > 0:
+            dh, ds = float((H[k] - A[k]).norm()), float((Bv[k] - A[k]).norm())
+            assert dh <= 3.0 * ds + 0.02 * na, (k, dh / na, ds / na)
