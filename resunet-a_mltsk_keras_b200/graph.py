@@ -47,7 +47,7 @@ def psp_levels(img_width):
 class T:
     """Activation tensor handle (NHWC, dense)."""
     __slots__ = ("name", "N", "H", "W", "C", "dtype", "data", "grad", "grad_written", "needs_grad",
-                 "relu_masked", "stats", "count", "bn_src")
+                 "relu_masked", "stats", "count", "bn_src", "grad_writers")
 
     def __init__(self, name, N, H, W, C, dtype):
         self.name, self.N, self.H, self.W, self.C, self.dtype = name, N, H, W, C, dtype
@@ -59,6 +59,7 @@ class T:
         self.stats = None          # double[2C] {sum, sumsq} view, valid after the producer ran
         self.count = 0.0           # elements per channel behind .stats
         self.bn_src = None         # this tensor is [relu](BatchNorm(x)): what a fused backward reduction needs
+        self.grad_writers = 0      # launches that write / accumulate into .grad (Plan.gacc, identity alias)
 
     @property
     def M(self):
@@ -264,6 +265,7 @@ class Plan:
             t.grad = self.alloc(t.shape, t.dtype)
         acc = t.grad_written
         t.grad_written = True
+        t.grad_writers += 1
         if self._side_reads and t.grad.data_ptr() in self._side_reads:
             self._join_next = True     # the next main-stream launch overwrites what a side launch still reads
         if self._lane is not None:
@@ -564,10 +566,14 @@ class Plan:
         import os
         if (b is not None and not acc and mask is None and b["x"].dtype == torch.bfloat16 and b["x"].shape == src.shape
                 and os.environ.get("RSA_BNR", "1") != "0"):
+            # provisional: the BatchNorm's own backward closure (emitted after every writer of d(src)) withdraws the
+            # fusion when another launch accumulates into d(src) as well (two heads read the PSP output) - sums taken in
+            # this epilogue would miss that contribution.  The launch is bound late, so it follows the final decision.
             b["fused"] = True
             return self._late(lambda: lib.conv_tc3_fwd(
                 [dy], [wt], None, [-dil], g, N, H, W, C, stats=b["red"][0],
-                bnr=(b["x"].data, b["xs"][0], b["cnt"], BN_EPS, b["gamma"], b["beta"], b["relu"])))
+                bnr=(b["x"].data, b["xs"][0], b["cnt"], BN_EPS, b["gamma"], b["beta"], b["relu"]))
+                if b["fused"] else lib.conv_tc3_fwd([dy], [wt], None, [-dil], g, N, H, W, C))
         return lib.conv_tc3_fwd([dy], [wt], None, [-dil], g, N, H, W, C, mask=mask, accumulate=acc)
 
     def _late(self, make):
@@ -732,6 +738,9 @@ class Plan:
                     return
                 dys = [outs[k].grad for k in live]
                 gl, bl, rl = [gam[k] for k in live], [bet[k] for k in live], [reds[k] for k in live]
+                for k in live:       # several writers of d(out): the fused sums would be partial (see _thin_dgrad)
+                    if outs[k].bn_src["fused"] and outs[k].grad_writers > 1:
+                        outs[k].bn_src["fused"] = False
                 # branches whose data-gradient kernel already produced {sum g, sum g*xhat} (conv_tc3 epilogue) are skipped
                 unf = [i for i, k in enumerate(live) if not outs[k].bn_src["fused"]]
                 if unf:
@@ -762,6 +771,7 @@ class Plan:
             if x.grad is None:
                 x.grad = out.grad          # alias: branch gradients accumulate on top of d(out)
                 x.grad_written = True
+                x.grad_writers += 1
             else:
                 g, acc = self.gacc(x)
                 self.bwd.append(self.lib.axpy(g, out.grad, x.M * x.C, acc))
