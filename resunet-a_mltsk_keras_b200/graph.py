@@ -1133,8 +1133,8 @@ class Net:
         self.pack_launch = None
         self.shadow_dirty = True
         engine = os.environ.get("RSA_CONV_ENGINE", "tc")
-        if (self.act_dtype != torch.bfloat16 or getattr(self.lib, "is_emulation", False) or engine != "tc"
-                or not hasattr(self.lib, "conv_tc_fwd")):
+        emulated = getattr(self.lib, "is_emulation", False) and not getattr(self.lib, "emulates_tensor_core", False)
+        if self.act_dtype != torch.bfloat16 or emulated or engine != "tc" or not hasattr(self.lib, "conv_tc_fwd"):
             self.conv_engine = "igemm_simt"
             return
         okc = lambda c: c == 32 or (c >= 64 and c % 64 == 0)

@@ -423,3 +423,194 @@ class EmulLib:
 
     def cast(self, src, dst, n):
         return self._wrap(lambda: _store(dst, src), "rsa_cast")
+
+
+# ------------------------------------------------------------------------------------------------------
+# bf16 tensor-core path (conv_tc*.cu, thin.cu head forward) restated on the CPU: the same launch list the GPU runs in
+# bf16 mode - K-concatenated 1x1 convolutions with up-sampled addends, thin-layer kernels with the fused BatchNorm-backward
+# sums, packed weight copies, tensor-core weight gradients - so that the host logic of that mode (fusions, side / join /
+# lane / chain hints) is testable without a GPU.  Math in float64, tensors stored in bf16 exactly like the kernels' outputs.
+# ------------------------------------------------------------------------------------------------------
+def _taps_conv(x, w, taps, dil, s, H, W):
+    """x f64 [N,Hs,Ws,C], w f64 [taps][Co][C] -> [N,H,W,Co]; sample (h*s+dy*dil, w*s+dx*dil), zero outside."""
+    N, Hs, Ws, C = x.shape
+    Co = w.shape[1]
+    out = torch.zeros(N, H, W, Co, dtype=F64)
+    pad = abs(dil) if taps == 9 else 0
+    xp = torch.nn.functional.pad(x, (0, 0, pad, pad, pad, pad))
+    for t in range(taps):
+        dy, dx = (t // 3 - 1, t % 3 - 1) if taps == 9 else (0, 0)
+        h0, w0 = pad + dy * dil, pad + dx * dil
+        win = xp[:, h0:h0 + (H - 1) * s + 1:s, w0:w0 + (W - 1) * s + 1:s, :]
+        out += win @ w[t].T
+    return out
+
+
+def _taps_wgrad(x, dy, dil):
+    """dw[tap][ci][co] = sum_pix x[pix + off(tap)*dil, ci] * dy[pix, co]; x, dy f64 NHWC."""
+    N, H, W, C = x.shape
+    Co = dy.shape[-1]
+    pad = abs(dil)
+    xp = torch.nn.functional.pad(x, (0, 0, pad, pad, pad, pad))
+    g = dy.reshape(-1, Co)
+    dw = torch.zeros(9, C, Co, dtype=F64)
+    for t in range(9):
+        ddy, ddx = t // 3 - 1, t % 3 - 1
+        win = xp[:, pad + ddy * dil:pad + ddy * dil + H, pad + ddx * dil:pad + ddx * dil + W, :]
+        dw[t] = win.reshape(-1, C).T @ g
+    return dw
+
+
+class EmulLibTC(EmulLib):
+    """EmulLib + the tensor-core entry points: Net takes the bf16 tcgen05 path on the CPU (graph.Net gating)."""
+    emulates_tensor_core = True
+
+    @staticmethod
+    def _pow2(v):
+        return v >= 1 and (v & (v - 1)) == 0
+
+    # shapes: conv_tc.cu:300, conv_tc2.cu:355, conv_tc3.cu (rsa_conv_tc3_supported / _wgrad_supported)
+    def conv_tc_supported(self, N, H, W, Cin, Cout):
+        okc = lambda c: c == 32 or (c >= 64 and c % 64 == 0)
+        return okc(Cin) and okc(Cout) and H == W and self._pow2(W) and W >= 4
+
+    def conv_tc2_supported(self, N, H, W, C0, C1, Cout):
+        if not (self._pow2(H) and self._pow2(W)) or N < 1:
+            return False
+        if C0 == 8 and C1 == 0:
+            return Cout >= 1
+        return not (C0 < 16 or C0 % 16 or (C1 and C1 % 16) or Cout < 1)
+
+    def conv_tc3_supported(self, N, H, W, C):
+        return C in (32, 64) and N >= 1 and H >= 16 and H % 16 == 0 and W >= 32 and W % 32 == 0
+
+    def conv_tc3_wgrad_supported(self, N, H, W, C, dil):
+        return self.conv_tc3_supported(N, H, W, C) and dil > 0 and (C == 32 or dil <= 3)
+
+    def pack_weights_tc(self, params, shadow, table, nlayers, max_elems):
+        import struct
+        raw = bytes(table.cpu().numpy().tobytes())
+
+        def run():
+            for l in range(nlayers):
+                src, fwd, bwd, taps, cin, cout, pad = struct.unpack_from("<qqqiiii", raw, l * 40)
+                coutp = pad if pad > 0 else cout
+                w = params[src:src + taps * cin * cout].reshape(taps, cin, cout)
+                shadow[bwd:bwd + taps * cin * cout] = w.reshape(-1).to(torch.bfloat16)
+                f = shadow[fwd:fwd + taps * coutp * cin].view(taps, coutp, cin)
+                f[:, :cout, :] = w.permute(0, 2, 1).to(torch.bfloat16)
+        return self._wrap(run, "rsa_pack_weights_tc")
+
+    @staticmethod
+    def _epilogue(acc, out, Cout, residual, mask, accumulate, relu, stats, os_=1):
+        """acc f64 [N,H,W,Cout] -> store (bf16 or fp32) at stride os_; order: residual, accumulate, relu, mask."""
+        N, H, W, _ = acc.shape
+        ov = out.reshape(N, H * os_, W * os_, Cout)[:, ::os_, ::os_, :]
+        if residual is not None:
+            acc = acc + residual.reshape(N, H * os_, W * os_, Cout)[:, ::os_, ::os_, :].to(F64)
+        if accumulate:
+            acc = acc + ov.to(F64)
+        if relu:
+            acc = acc.clamp_min(0)
+        if mask is not None:
+            acc = acc * (mask.reshape(N, H * os_, W * os_, Cout)[:, ::os_, ::os_, :].to(F64) > 0)
+        ov.copy_(acc.to(out.dtype))
+        if stats is not None:
+            v = ov.to(F64).reshape(-1, Cout)       # statistics of the stored (rounded) values
+            stats[:Cout] += v.sum(0)
+            stats[Cout:2 * Cout] += (v * v).sum(0)
+
+    def conv_tc2_fwd(self, x0, x1, wt, CoutP, bias, out, N, H, W, Cout, taps=1, dil=1, in_stride=1, ups=(),
+                     residual=None, mask=None, stats=None, accumulate=False, relu=False, k_base=0, k_total=0,
+                     out_stride=1, bnr_x=None, bnr_coef=None):
+        assert bnr_x is None, "the conv_tc2 fused-reduction epilogue is not emulated (unused by the graph)"
+        C0 = x0.shape[-1]
+        C1 = x1.shape[-1] if x1 is not None else 0
+        K = C0 + C1
+        kt = k_total if k_total else K
+
+        def run():
+            s = in_stride
+            xs = x0.reshape(N, H * s, W * s, C0).to(F64)
+            if x1 is not None:
+                xs = torch.cat([xs, x1.reshape(N, H * s, W * s, C1).to(F64)], -1)
+            # rows [0, Cout) of every tap's [CoutP][kt] matrix, columns [k_base, k_base + K)
+            w = torch.stack([torch.as_strided(wt, (Cout, K), (kt, 1), wt.storage_offset() + t * CoutP * kt + k_base)
+                             for t in range(taps)]).to(F64)
+            acc = _taps_conv(xs, w, taps, dil, s, H, W)
+            if bias is not None:
+                acc = acc + bias[:Cout].to(F64)
+            for q, sh in ups:
+                qv = q.reshape(N, H >> sh, W >> sh, Cout).to(F64)
+                acc = acc + qv.repeat_interleave(1 << sh, 1).repeat_interleave(1 << sh, 2)
+            self._epilogue(acc, out, Cout, residual, mask, accumulate, relu, stats, out_stride)
+        return self._wrap(run, "rsa_conv_tc2_fwd")
+
+    def conv_tc3_fwd(self, xs, wts, biases, dils, out, N, H, W, C, residual=None, mask=None, stats=None,
+                     accumulate=False, relu=False, bnr=None):
+        assert not (residual is not None and accumulate), "one addend"
+
+        def run():
+            acc = torch.zeros(N, H, W, C, dtype=F64)
+            for b, (x, w, d) in enumerate(zip(xs, wts, dils)):
+                acc += _taps_conv(x.reshape(N, H, W, C).to(F64), w.reshape(9, C, C).to(F64), 9, int(d), 1, H, W)
+                if biases is not None and biases[b] is not None:
+                    acc += biases[b].to(F64)
+            if bnr is None:
+                self._epilogue(acc, out, C, residual, mask, accumulate, relu, stats)
+                return
+            bx, bst, cnt, eps, gam, bet, brelu = bnr
+            assert mask is None and stats is not None
+            if residual is not None:
+                acc = acc + residual.reshape(N, H, W, C).to(F64)
+            if accumulate:
+                acc = acc + out.reshape(N, H, W, C).to(F64)
+            mean, inv = _mean_inv(bst, cnt, C, eps)
+            xh = (bx.reshape(N, H, W, C).to(F64) - mean) * inv
+            if brelu:
+                acc = acc * ((gam.to(F64) * xh + bet.to(F64)) > 0)
+            stats[:C] += acc.reshape(-1, C).sum(0)                   # sums of the fp32 values, before the bf16 store
+            stats[C:2 * C] += (acc * xh).reshape(-1, C).sum(0)
+            out.reshape(N, H, W, C).copy_(acc.to(out.dtype))
+        return self._wrap(run, "rsa_conv_tc3_fwd")
+
+    def conv_tc_wgrad(self, x, dy, dw, N, H, W, Cin, Cout, dil):
+        def run():
+            d = _taps_wgrad(x.reshape(N, H, W, Cin).to(F64), dy.reshape(N, H, W, Cout).to(F64), dil)
+            dw[:9 * Cin * Cout] += d.reshape(-1).to(torch.float32)
+        return self._wrap(run, "rsa_conv_tc_wgrad")
+
+    def conv_tc3_wgrad(self, x, dy, dw, N, H, W, C, dil):
+        op = self.conv_tc_wgrad(x, dy, dw, N, H, W, C, C, dil)
+        op.kernel = "rsa_conv_tc3_wgrad"
+        return op
+
+    def pw_wgrad_tc(self, x, dz, dw, ldw, N, H, W, Cin, Cout, in_stride=1):
+        def run():
+            s = in_stride
+            xv = x.reshape(N, H * s, W * s, Cin)[:, ::s, ::s, :].to(F64).reshape(-1, Cin)
+            d = (xv.T @ dz.reshape(-1, Cout).to(F64)).to(torch.float32)
+            view = torch.as_strided(dw, (Cin, Cout), (ldw, 1), dw.storage_offset())
+            view += d
+        return self._wrap(run, "rsa_pw_wgrad_tc")
+
+    def bias_grad(self, dy, M, C, dbs):
+        def run():
+            g = dy.reshape(M, C).to(F64).sum(0).to(torch.float32)
+            for db in dbs:
+                if db is not None:
+                    db.add_(g)
+        return self._wrap(run, "rsa_bias_grad")
+
+    def head_fwd(self, h, w, b, z, M, n):
+        def run():
+            v = h.reshape(M, 32).to(F64) @ w[:32 * n].reshape(32, n).to(F64)
+            if b is not None:
+                v = v + b.to(F64)
+            _store(z, v)
+        return self._wrap(run, "rsa_head_fwd")
+
+    def conv_tc_fwd(self, x, wt, bias, out, N, H, W, Cin, Cout, taps, dil, residual=None, mask=None, stats=None,
+                    accumulate=False, relu=False):
+        return self.conv_tc2_fwd(x.reshape(N, H, W, Cin), None, wt, Cout, bias, out, N, H, W, Cout, taps=taps, dil=dil,
+                                 residual=residual, mask=mask, stats=stats, accumulate=accumulate, relu=relu)

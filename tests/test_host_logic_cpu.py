@@ -241,3 +241,63 @@ def test_lane_and_chain_hints_allow_any_stream_interleaving(variant, monkeypatch
         monkeypatch.undo()
     np.testing.assert_array_equal(res[0][0], res[1][0])
     assert torch.equal(res[0][1], res[1][1])
+
+
+# ---- bf16 tensor-core mode on the CPU emulation of its entry points (emul_lib.EmulLibTC) ------------------------------
+def _bf16_step(variant, hostile=False, monkeypatch=None, steps=1):
+    from emul_lib import EmulLibTC
+    _capi.set_lib(EmulLibTC())
+    p = _rand_params(variant)
+    x, y = O.synth_batch(2, 64, 3, N_CLS, seed=11, block=16)
+    m = build_model((64, 64, 3), N_CLS, True, variant, dtype="bf16")
+    assert m.net.conv_engine.startswith("tcgen05"), "the emulation must take the tensor-core launch list"
+    m.net.set_weights(p)
+    m.compile(optimizer=SGD(lr=1.0), loss=_losses("tanimoto")[0], loss_weights=LW)
+    if hostile:
+        monkeypatch.setattr(type(m), "_run_ops", lambda self, ops, stream: _adversarial_run(list(ops), stream))
+    before = {k: v.clone() for k, v in m.net.get_weights().items()}
+    out = [m.train_on_batch(x, y) for _ in range(steps)]
+    after = m.net.get_weights()
+    if hostile:
+        monkeypatch.undo()
+    return m, p, x, y, before, after, np.array(out)
+
+
+@pytest.mark.parametrize("variant", ["v2", "v1"])
+def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant):
+    """Host logic of the bf16 mode (K-concatenated 1x1 convolutions with up-sampled addends, packed weights, thin-layer
+    launches with fused BatchNorm-backward sums, pooled adjoints): the launch list the GPU replays, executed by the CPU
+    restatement of its entry points, must give the oracle's gradient up to bf16 storage noise (GPU: 2-3 % / 11 %)."""
+    m, p, x, y, before, after, out = _bf16_step(variant)
+    p64 = {k: v.double() for k, v in p.items()}
+    tot, _, _, grads, _ = O.loss_and_grads(p64, torch.from_numpy(x).double(),
+                                           {k: torch.from_numpy(v).double() for k, v in y.items()},
+                                           {k: O.tanimoto_dual_loss for k in LW}, LW, N_CLS, variant=variant)
+    assert abs(out[0][0] - tot.item()) <= 1e-2 * abs(tot.item())
+    keys = [k for k in grads if k in before and "/moving_" not in k]
+    mine = {k: (before[k] - after[k]).double().flatten() for k in keys}
+    ref = {k: grads[k].double().flatten() for k in keys}
+    gm, gr = torch.cat([mine[k] for k in keys]), torch.cat([ref[k] for k in keys])
+    rel_max, cos_min = (0.08, 0.997) if variant == "v2" else (0.2, 0.985)
+    assert float((gm - gr).norm() / gr.norm()) <= rel_max
+    assert float(gm @ gr / (gm.norm() * gr.norm())) >= cos_min
+    big = [k for k in keys if float(ref[k].norm()) >= 3e-3 * float(gr.norm())]
+    assert len(big) >= 40
+    for k in big:       # a fault in one layer's backward (e.g. partial fused sums) leaves its gradient uncorrelated
+        assert float(mine[k] @ ref[k] / (mine[k].norm() * ref[k].norm())) >= 0.5, k
+    pl = m.net.plan(2, True, m.loss_spec)
+    kernels = {getattr(op, "kernel", "?") for op in list(pl.fwd) + list(pl.bwd)}
+    assert {"rsa_conv_tc2_fwd", "rsa_conv_tc3_fwd", "rsa_conv_tc3_wgrad", "rsa_conv_tc_wgrad", "rsa_pw_wgrad_tc",
+            "rsa_bias_grad", "rsa_head_fwd"} <= kernels
+
+
+def test_bf16_side_join_lane_chain_hints_allow_any_order(monkeypatch):
+    """All four scheduling hints on the tensor-core launch list: weight gradients delayed to the next join, the highest
+    stream first.  The CPU emulation is deterministic, so two steps must agree bit for bit with the emission order."""
+    a = _bf16_step("v2", steps=2)
+    b = _bf16_step("v2", hostile=True, monkeypatch=monkeypatch, steps=2)
+    pl = a[0].net.plan(2, True, a[0].loss_spec)
+    assert sum(getattr(op, "side", False) for op in pl.bwd) > 50 and any(getattr(op, "join", False) for op in pl.bwd)
+    np.testing.assert_array_equal(a[6], b[6])
+    for k in a[5]:
+        assert torch.equal(a[5][k], b[5][k]), k
