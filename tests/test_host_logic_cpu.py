@@ -244,12 +244,12 @@ def test_lane_and_chain_hints_allow_any_stream_interleaving(variant, monkeypatch
 
 
 # ---- bf16 tensor-core mode on the CPU emulation of its entry points (emul_lib.EmulLibTC) ------------------------------
-def _bf16_step(variant, hostile=False, monkeypatch=None, steps=1):
+def _bf16_step(variant, hostile=False, monkeypatch=None, steps=1, hw=64, cin=3, n=N_CLS, B=2):
     from emul_lib import EmulLibTC
     _capi.set_lib(EmulLibTC())
-    p = _rand_params(variant)
-    x, y = O.synth_batch(2, 64, 3, N_CLS, seed=11, block=16)
-    m = build_model((64, 64, 3), N_CLS, True, variant, dtype="bf16")
+    p = O.init_params((hw, hw, cin), n, True, variant, seed=7) if (hw, cin, n) != (64, 3, N_CLS) else _rand_params(variant)
+    x, y = O.synth_batch(B, hw, cin, n, seed=11, block=16)
+    m = build_model((hw, hw, cin), n, True, variant, dtype="bf16")
     assert m.net.conv_engine.startswith("tcgen05"), "the emulation must take the tensor-core launch list"
     m.net.set_weights(p)
     m.compile(optimizer=SGD(lr=1.0), loss=_losses("tanimoto")[0], loss_weights=LW)
@@ -263,16 +263,16 @@ def _bf16_step(variant, hostile=False, monkeypatch=None, steps=1):
     return m, p, x, y, before, after, np.array(out)
 
 
-@pytest.mark.parametrize("variant", ["v2", "v1"])
-def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant):
+@pytest.mark.parametrize("variant,hw,cin,n,B", [("v2", 64, 3, N_CLS, 2), ("v1", 64, 3, N_CLS, 2), ("v2", 128, 14, 3, 1)])
+def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant, hw, cin, n, B):
     """Host logic of the bf16 mode (K-concatenated 1x1 convolutions with up-sampled addends, packed weights, thin-layer
     launches with fused BatchNorm-backward sums, pooled adjoints): the launch list the GPU replays, executed by the CPU
     restatement of its entry points, must give the oracle's gradient up to bf16 storage noise (GPU: 2-3 % / 11 %)."""
-    m, p, x, y, before, after, out = _bf16_step(variant)
+    m, p, x, y, before, after, out = _bf16_step(variant, hw=hw, cin=cin, n=n, B=B)
     p64 = {k: v.double() for k, v in p.items()}
     tot, _, _, grads, _ = O.loss_and_grads(p64, torch.from_numpy(x).double(),
                                            {k: torch.from_numpy(v).double() for k, v in y.items()},
-                                           {k: O.tanimoto_dual_loss for k in LW}, LW, N_CLS, variant=variant)
+                                           {k: O.tanimoto_dual_loss for k in LW}, LW, n, variant=variant)
     assert abs(out[0][0] - tot.item()) <= 1e-2 * abs(tot.item())
     keys = [k for k in grads if k in before and "/moving_" not in k]
     mine = {k: (before[k] - after[k]).double().flatten() for k in keys}
@@ -285,7 +285,7 @@ def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant):
     assert len(big) >= 40
     for k in big:       # a fault in one layer's backward (e.g. partial fused sums) leaves its gradient uncorrelated
         assert float(mine[k] @ ref[k] / (mine[k].norm() * ref[k].norm())) >= 0.5, k
-    pl = m.net.plan(2, True, m.loss_spec)
+    pl = m.net.plan(B, True, m.loss_spec)
     kernels = {getattr(op, "kernel", "?") for op in list(pl.fwd) + list(pl.bwd)}
     assert {"rsa_conv_tc2_fwd", "rsa_conv_tc3_fwd", "rsa_conv_tc3_wgrad", "rsa_conv_tc_wgrad", "rsa_pw_wgrad_tc",
             "rsa_bias_grad", "rsa_head_fwd"} <= kernels
