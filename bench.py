@@ -266,6 +266,9 @@ def run_ours(args):
                     traffic=traffic, traffic_source=traffic_src, kernel="3x3 conv fwd+dgrad+wgrad (ResBlock-a + heads)", launches=nconv,
                     avg_launch_ms=conv_ms / max(nconv, 1), conv_ms_per_step=conv_ms,
                     conv_share_of_step=conv_ms / (ms_total / args.steps), frac_of_burst=achieved / pk["tf_burst"],
+                    share_note="the conv launches are timed on ONE stream (graph with / without them); the step itself overlaps "
+                               "weight gradients with the data-gradient chain, so the share relates single-stream conv time to "
+                               "the concurrent step",
                     peak_source=pk["src"] + " (sustained: timed inside a long step)",
                     algorithmic_flop_per_launch=flops / max(nconv, 1))
 
@@ -285,6 +288,10 @@ def run_ours(args):
                                 global_batch=args.batch * world, parallelism=f"dp{world}",
                                 l2="working set per step (>8 GB of activations) is far larger than the 126 MB L2",
                                 cuda_graph=bool(model.use_cuda_graph),
+                                streams=("weight/bias-gradient launches on a side stream, ResBlock-a branches and heads over "
+                                         f"{os.environ.get('RSA_LANES', '2')} lanes (one stream: RSA_WGRAD_STREAM=0 RSA_LANES=0)"
+                                         if os.environ.get("RSA_WGRAD_STREAM", "1") != "0" or os.environ.get("RSA_LANES", "2") != "0"
+                                         else "one stream"),
                                 dp_mode=("graph replay; gradient all-reduce in two ranges, the parameter-heavy one overlapped with the rest of backward"
                                          if world > 1 and not strat.dp.overlap and os.environ.get("RSA_DP_GRAPH_OVERLAP", "1") != "0"
                                          else "graph fwd+bwd, one all-reduce, graph optimizer" if world > 1 and not strat.dp.overlap
