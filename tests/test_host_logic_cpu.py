@@ -301,3 +301,25 @@ def test_bf16_side_join_lane_chain_hints_allow_any_order(monkeypatch):
     np.testing.assert_array_equal(a[6], b[6])
     for k in a[5]:
         assert torch.equal(a[5][k], b[5][k]), k
+
+
+@pytest.mark.parametrize("variant,hw,cin,n,multi", [("v2", 64, 3, N_CLS, True), ("v1", 64, 3, N_CLS, True),
+                                                    ("v2", 128, 14, 3, True), ("v2", 64, 3, N_CLS, False)])
+def test_bf16_tensor_core_launch_list_predict_matches_oracle(variant, hw, cin, n, multi):
+    """Inference launch list of the bf16 mode (moving statistics, no loss) on the CPU restatement of its entry points:
+    bf16 storage noise only (random weights leave near-tie logits, so the argmax bar is lower than on the trained toy
+    model of the GPU test)."""
+    from emul_lib import EmulLibTC
+    _capi.set_lib(EmulLibTC())
+    p = _rand_params(variant, hw=hw, multitask=multi) if (cin, n) == (3, N_CLS) else O.init_params((hw, hw, cin), n, multi, variant, seed=7)
+    m = build_model((hw, hw, cin), n, multi, variant, dtype="bf16")
+    m.net.set_weights(p)
+    x = np.random.RandomState(1).rand(3, hw, hw, cin).astype(np.float32)
+    out = m.predict(x, batch_size=2)
+    ref = O.forward(p, torch.from_numpy(x), False, n, multi, variant)
+    out = out if isinstance(out, dict) else {"seg": out}
+    ref = ref if isinstance(ref, dict) else {"seg": ref}
+    for k in out:
+        a, b = out[k].astype(np.float64), ref[k].numpy().astype(np.float64)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 2e-2, k
+    assert (out["seg"].argmax(-1) == ref["seg"].numpy().argmax(-1)).mean() >= 0.99
