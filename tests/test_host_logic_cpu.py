@@ -291,13 +291,16 @@ def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant, hw, c
             "rsa_bias_grad", "rsa_head_fwd"} <= kernels
 
 
-def test_bf16_side_join_lane_chain_hints_allow_any_order(monkeypatch):
+@pytest.mark.parametrize("variant,hw,cin,n,B", [("v2", 64, 3, N_CLS, 2), ("v1", 64, 3, N_CLS, 2), ("v2", 128, 14, 3, 1)])
+def test_bf16_side_join_lane_chain_hints_allow_any_order(variant, hw, cin, n, B, monkeypatch):
     """All four scheduling hints on the tensor-core launch list: weight gradients delayed to the next join, the highest
     stream first.  The CPU emulation is deterministic, so two steps must agree bit for bit with the emission order."""
-    a = _bf16_step("v2", steps=2)
-    b = _bf16_step("v2", hostile=True, monkeypatch=monkeypatch, steps=2)
-    pl = a[0].net.plan(2, True, a[0].loss_spec)
-    assert sum(getattr(op, "side", False) for op in pl.bwd) > 50 and any(getattr(op, "join", False) for op in pl.bwd)
+    a = _bf16_step(variant, steps=2, hw=hw, cin=cin, n=n, B=B)
+    b = _bf16_step(variant, hostile=True, monkeypatch=monkeypatch, steps=2, hw=hw, cin=cin, n=n, B=B)
+    pl = a[0].net.plan(B, True, a[0].loss_spec)
+    assert sum(getattr(op, "side", False) for op in pl.bwd) > 50
+    # model2's identity term aliases d(out) as d(x): branch gradients accumulate into a buffer weight gradients still read
+    assert any(getattr(op, "join", False) for op in pl.bwd) == (variant == "v2")
     np.testing.assert_array_equal(a[6], b[6])
     for k in a[5]:
         assert torch.equal(a[5][k], b[5][k]), k
