@@ -326,3 +326,44 @@ def test_bf16_tensor_core_launch_list_predict_matches_oracle(variant, hw, cin, n
         a, b = out[k].astype(np.float64), ref[k].numpy().astype(np.float64)
         assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 2e-2, k
     assert (out["seg"].argmax(-1) == ref["seg"].numpy().argmax(-1)).mean() >= 0.99
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_gradient_readiness_bookkeeping_is_exact(dtype):
+    """Plan.grad_ready drives both data-parallel schedules (distribute.py): a bucket's all-reduce is issued right after the
+    launch that is recorded as completing it.  Replay the backward list launch by launch and check that every range is
+    already FINAL at its recorded index - for the bucket schedule and for the two-range split of the graph-replayed step."""
+    from emul_lib import EmulLib, EmulLibTC
+    from resuneta_b200.distribute import DataParallel
+    _capi.set_lib(EmulLibTC() if dtype == "bf16" else EmulLib())
+    p = _rand_params("v2")
+    x, y = O.synth_batch(2, 64, 3, N_CLS, seed=11, block=16)
+    m = build_model((64, 64, 3), N_CLS, True, "v2", dtype=dtype)
+    m.net.set_weights(p)
+    m.compile(optimizer=SGD(lr=0.0), loss=_losses("tanimoto")[0], loss_weights=LW)
+    m.train_on_batch(x, y)                      # inputs and labels now sit in the plan's buffers; lr 0 keeps the weights
+    pl = m.net.plan(2, True, m.loss_spec)
+    ps = m.net.params
+    dp = DataParallel(n_buckets=7)
+    buckets = dp._schedule(pl, ps)
+    split = dp.two_phase_split(pl, ps, min_frac=0.3)
+    assert split is not None and 0 < split[0] < len(pl.bwd) - 1 and 0 < split[1] < ps.n_train
+    pl.scratch.zero_()
+    ps.grad.zero_()
+    if m.net.pack_launch is not None:
+        m.net.pack_launch(0)
+    for op in pl.fwd:
+        op(0)
+    snaps = {}
+    for i, op in enumerate(pl.bwd):
+        op(0)
+        for (ready, lo, hi) in buckets:
+            if ready == i:
+                snaps[(lo, hi)] = ps.grad[lo:hi].clone()
+        if i == split[0]:
+            snaps["tail"] = ps.grad[split[1]:ps.n_train].clone()
+    assert len(snaps) == len(buckets) + 1
+    assert float(ps.grad[:ps.n_train].abs().max()) > 0
+    for key, snap in snaps.items():
+        lo, hi = (split[1], ps.n_train) if key == "tail" else key
+        assert torch.equal(snap, ps.grad[lo:hi]), key
