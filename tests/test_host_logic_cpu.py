@@ -367,3 +367,35 @@ def test_gradient_readiness_bookkeeping_is_exact(dtype):
     for key, snap in snaps.items():
         lo, hi = (split[1], ps.n_train) if key == "tail" else key
         assert torch.equal(snap, ps.grad[lo:hi]), key
+
+
+def test_bf16_weight_copies_follow_every_parameter_change():
+    """The tensor-core path computes from packed bf16 copies of the fp32 master weights: they must be refreshed after
+    set_weights, after a training step and after load_model before the next inference launch reads them."""
+    from emul_lib import EmulLibTC
+    _capi.set_lib(EmulLibTC())
+    x = np.random.RandomState(2).rand(2, 64, 64, 3).astype(np.float32)
+    xt = torch.from_numpy(x)
+
+    def close(m, p):
+        out = m.predict(x, batch_size=2)
+        ref = O.forward(p, xt, False, N_CLS, True, "v2")
+        return all(np.linalg.norm(out[k] - ref[k].numpy()) / np.linalg.norm(ref[k].numpy()) <= 2e-2 for k in out)
+
+    pa, pb = _rand_params("v2", seed=7), _rand_params("v2", seed=8)
+    m = build_model((64, 64, 3), N_CLS, True, "v2", dtype="bf16")
+    m.net.set_weights(pa)
+    assert close(m, pa)
+    m.net.set_weights(pb)
+    assert close(m, pb) and not close(m, pa)
+    m.compile(optimizer=SGD(lr=0.5), loss=_losses("tanimoto")[0], loss_weights=LW)
+    xb, yb = O.synth_batch(2, 64, 3, N_CLS, seed=5, block=16)
+    for _ in range(2):
+        m.train_on_batch(xb, yb)
+    pc = {k: v.clone() for k, v in m.net.get_weights().items()}
+    assert close(m, pc) and not close(m, pb)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "m.h5")
+        m.save(path)
+        m2 = load_model(path, compile=False)
+    assert close(m2, pc)
