@@ -399,3 +399,91 @@ def test_bf16_weight_copies_follow_every_parameter_change():
         m.save(path)
         m2 = load_model(path, compile=False)
     assert close(m2, pc)
+
+
+def test_executor_enforces_the_hint_semantics_on_streams(monkeypatch):
+    """keras_api._run_ops is the only consumer of the scheduling hints and only ever runs on a GPU; here it issues the
+    real tensor-core backward and forward lists of a plan onto fake streams / events that track happens-before, and the
+    orderings the hints promise (the ones tests/sched_util.adversarial_run relies on) are checked one by one."""
+    from emul_lib import EmulLibTC
+    from resuneta_b200 import keras_api as KA
+    _capi.set_lib(EmulLibTC())
+    m = build_model((64, 64, 3), N_CLS, True, "v2", dtype="bf16")
+    m.compile(optimizer=SGD(lr=0.1), loss=_losses("tanimoto")[0], loss_weights=LW)
+    pl = m.net.plan(2, True, m.loss_spec)
+
+    class FakeStream:
+        n = 0
+
+        def __init__(self):
+            FakeStream.n += 1
+            self.cuda_stream = 1000 + FakeStream.n
+            self.deps = set()
+            streams[self.cuda_stream] = self
+
+        def wait_stream(self, other):
+            self.deps |= other.deps
+
+        def wait_event(self, ev):
+            self.deps |= ev.deps
+
+    class FakeEvent:
+        def record(self, s):
+            self.deps = set(s.deps)
+
+    for nstreams, hints in ((4, list(pl.bwd)), (3, list(pl.fwd))):
+        streams = {}
+        main = FakeStream()
+        hb, where = {}, {}
+
+        def fake(k, src):
+            def op(handle):
+                s = streams[handle]
+                hb[k] = set(s.deps)
+                where[k] = handle
+                s.deps.add(k)
+            for a in ("lane", "side", "join", "chain"):
+                if hasattr(src, a):
+                    setattr(op, a, getattr(src, a))
+            return op
+        ops = [fake(k, src) for k, src in enumerate(hints)]
+        monkeypatch.setattr(torch.cuda, "current_stream", lambda: main)
+        monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+        monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+        holder = type("M", (), {})()
+        holder.net = type("N", (), {"device": type("D", (), {"type": "cuda"})()})()
+        KA.Model._run_ops(holder, ops, main.cuda_stream)
+        monkeypatch.undo()
+        is_side = lambda k: getattr(ops[k], "side", False)
+        lane = lambda k: getattr(ops[k], "lane", None)
+        n = len(ops)
+        assert set(range(n)) <= main.deps, "a range ends with everything joined into the calling stream"
+        assert len({where[k] for k in range(n)}) == nstreams, "main + two lanes (+ the side stream in backward)"
+        last_chain, last_in_ctx, sides, before_barrier = {}, {}, [], []
+        for k in range(n):
+            if is_side(k):
+                ctx = lane(k) % 2 if lane(k) is not None else None
+                prev = last_in_ctx.get(ctx, last_in_ctx.get(None))
+                if prev is not None:
+                    assert prev in hb[k], f"side launch {k} must follow the producer of its input ({prev})"
+                assert where[k] != main.cuda_stream
+                sides.append(k)
+                continue
+            if lane(k) is None:                      # barrier: after every earlier launch of the chain, before every later one
+                assert all(j in hb[k] for j in before_barrier), f"barrier {k}"
+                last_in_ctx = {None: k}
+                before_barrier = [k]
+            else:
+                ctx = lane(k) % 2
+                prev = last_in_ctx.get(ctx, last_in_ctx.get(None))
+                if prev is not None:
+                    assert prev in hb[k], f"lane launch {k} after {prev}"
+                last_in_ctx[ctx] = k
+                before_barrier.append(k)
+            if getattr(ops[k], "join", False):
+                assert all(j in hb[k] for j in sides), f"join {k} waits for every pending weight-gradient launch"
+            ck = getattr(ops[k], "chain", None)
+            if ck is not None:
+                if ck in last_chain:
+                    assert last_chain[ck] in hb[k], f"chain order {last_chain[ck]} -> {k}"
+                last_chain[ck] = k
