@@ -263,7 +263,8 @@ def _bf16_step(variant, hostile=False, monkeypatch=None, steps=1, hw=64, cin=3, 
     return m, p, x, y, before, after, np.array(out)
 
 
-@pytest.mark.parametrize("variant,hw,cin,n,B", [("v2", 64, 3, N_CLS, 2), ("v1", 64, 3, N_CLS, 2), ("v2", 128, 14, 3, 1)])
+@pytest.mark.parametrize("variant,hw,cin,n,B", [("v2", 64, 3, N_CLS, 2), ("v1", 64, 3, N_CLS, 2), ("v2", 128, 14, 3, 1),
+                                                ("v2", 256, 3, 6, 1)])      # the last one is config 2's topology (4 PSP levels)
 def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant, hw, cin, n, B):
     """Host logic of the bf16 mode (K-concatenated 1x1 convolutions with up-sampled addends, packed weights, thin-layer
     launches with fused BatchNorm-backward sums, pooled adjoints): the launch list the GPU replays, executed by the CPU
