@@ -21,6 +21,8 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
+import struct
 from collections import OrderedDict
 
 import torch
@@ -563,7 +565,6 @@ class Plan:
         d(src), the BatchNormalization backward reductions ride in its epilogue (no separate reduction pass)."""
         lib = self.lib
         b = src.bn_src
-        import os
         if (b is not None and not acc and mask is None and b["x"].dtype == torch.bfloat16 and b["x"].shape == src.shape
                 and os.environ.get("RSA_BNR", "1") != "0"):
             # provisional: the BatchNorm's own backward closure (emitted after every writer of d(src)) withdraws the
@@ -1126,8 +1127,6 @@ class Net:
 
     # -- bf16 tensor-core path: bf16 weight copies [tap][Cout][Cin] (fwd) / [tap][Cin][Cout] (dgrad) -------
     def _init_tensor_core_path(self):
-        import os
-        import struct
         self.tc = {}
         self.shadow = None
         self.pack_launch = None
@@ -1179,7 +1178,6 @@ class Net:
 
     def thin_ok(self, N, H, W, cin, cout):
         """conv_tc3 (thin-layer kernel: halo tiles, resident weights) handles this 3x3 convolution."""
-        import os
         return (cin == cout and hasattr(self.lib, "conv_tc3_supported") and os.environ.get("RSA_TC3", "1") != "0"
                 and self.lib.conv_tc3_supported(N, H, W, cin))
 
