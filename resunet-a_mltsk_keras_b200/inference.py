@@ -80,10 +80,21 @@ def compute_metrics(true_labels, predicted_labels):
     return metrics_from_confusion(confusion_matrix(true_labels, predicted_labels))
 
 
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_world_size(), dist.get_rank()
+    return None, 1, 0
+
+
 def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, num_classes=None):
     """Whole-scene inference (test_ISPRS.py:268-333): returns dict with
     ``seg_pred`` [P,ps,ps] int32, ``reconstructed`` (H,W) float64, and — when ``reference`` (H,W)
-    integer labels is given — ``confusion`` (sklearn-shaped int64), ``labels`` and ``metrics``."""
+    integer labels is given — ``confusion`` (sklearn-shaped int64), ``labels`` and ``metrics``.
+
+    Under ``torch.distributed`` (one process per GPU) the patches are independent: every rank predicts a
+    contiguous share of them, the int64 confusion matrices are summed with one all-reduce and the label tiles are
+    all-gathered, so every rank returns the complete result (as ``MirroredStrategy.predict`` does, test_ISPRS.py:276-277)."""
     net = model.net
     lib = net.lib
     K = int(num_classes or net.num_classes)
@@ -93,22 +104,33 @@ def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, n
     if reference is not None:
         ref_p = extract_patches(np.asarray(reference), patch_size).astype(np.int32)
     dev = net.device
-    seg_pred = np.empty((P, patch_size, patch_size), dtype=np.int32)
+    dist, world, rank = _world()
+    share = -(-P // world)                                   # patches per rank (the last ranks may get fewer / none)
+    lo, hi = min(P, rank * share), min(P, (rank + 1) * share)
+    local = torch.zeros((share, patch_size, patch_size), dtype=torch.int32, device=dev)
     cm = torch.zeros(K * K, dtype=torch.int64, device=dev)
-    stream = model._stream()
-    for i in range(0, P, batch_size):
-        xb = patches[i:i + batch_size]
+    for i in range(lo, hi, batch_size):
+        xb = patches[i:min(i + batch_size, hi)]
         n = xb.shape[0]
         pl = net.plan(n, False, None)
         model._load_inputs(pl, xb, None)
         model._execute(pl, False)
         prob = pl.outputs["seg"]
-        lab = torch.empty(prob.M, dtype=torch.int32, device=dev)
+        lab = local[i - lo:i - lo + n].view(-1)
         tl = None
         if ref_p is not None:
             tl = torch.from_numpy(ref_p[i:i + n].reshape(-1)).to(dev)
         lib.argmax_confusion(prob.data, prob.M, prob.C, lab, tl, K, cm if tl is not None else None)(model._stream())
-        seg_pred[i:i + n] = lab.cpu().numpy().reshape(n, patch_size, patch_size)
+    if world > 1:
+        if dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        if ref_p is not None:
+            dist.all_reduce(cm)
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local)
+        seg_pred = torch.cat(parts)[:P].cpu().numpy()
+    else:
+        seg_pred = local[:P].cpu().numpy()
     out = dict(seg_pred=seg_pred)
     h, w = np.asarray(image).shape[:2]
     out["reconstructed"] = pred_recostruction(patch_size, seg_pred, np.zeros((h, w), dtype=np.uint8))

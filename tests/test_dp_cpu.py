@@ -91,3 +91,64 @@ def test_two_rank_data_parallel_step_matches_oracle_average(overlap):
         want = p64[k] - 1e-2 * g / 2
         err = (torch.from_numpy(w1a[k]).double() - want).norm().item()
         assert err <= 1e-2 * (2e-3 * g.norm().item() / 2 + 1e-5 * gmax) + 1e-6 * want.norm().item(), (k, err)
+
+
+def _scene_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(2)
+    import torch.distributed as dist
+    import resuneta_b200  # noqa: F401
+    from emul_lib import EmulLib
+    from resuneta_b200 import _capi, inference
+    from resuneta_b200.builder import build_model
+    _capi.set_lib(EmulLib())
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = build_model((HW, HW, 3), N_CLS, True, "v2", dtype="fp32", seed=3)      # same seed: identical replicas
+    scene, ref = _scene()
+    r = inference.predict_scene(m, scene, ref, patch_size=HW, batch_size=2, num_classes=N_CLS)
+    q.put((rank, r["seg_pred"], r["confusion_full"], r["reconstructed"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _scene():
+    rs = np.random.RandomState(4)
+    return rs.rand(3 * HW + 5, 2 * HW + 9, 3).astype(np.float32), rs.randint(0, N_CLS, (3 * HW + 5, 2 * HW + 9))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 4])
+def test_scene_inference_shards_patches_and_sums_confusion(world):
+    """SURVEY §8e, inference: the 6 patches of the scene are split over the ranks (4 ranks: 2+2+2+0), the int64 confusion
+    matrices are all-reduced and the label tiles all-gathered - every rank must return the single-process result."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import resuneta_b200  # noqa: F401
+    from emul_lib import EmulLib
+    from resuneta_b200 import _capi, inference
+    from resuneta_b200.builder import build_model
+    old = _capi._LIB
+    _capi.set_lib(EmulLib())
+    try:
+        m = build_model((HW, HW, 3), N_CLS, True, "v2", dtype="fp32", seed=3)
+        scene, ref = _scene()
+        want = inference.predict_scene(m, scene, ref, patch_size=HW, batch_size=4, num_classes=N_CLS)
+    finally:
+        _capi.set_lib(old)
+    assert want["seg_pred"].shape == (6, HW, HW) and want["confusion_full"].sum() == 6 * HW * HW
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_scene_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=500) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, seg, cm, rec in out:
+        np.testing.assert_array_equal(seg, want["seg_pred"])
+        np.testing.assert_array_equal(cm, want["confusion_full"])
+        np.testing.assert_array_equal(rec, want["reconstructed"])
