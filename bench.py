@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — train patches/s of the ResUnet-a d6 multitask hot path (BASELINE.json config 2).
+"""bench.py — throughput of the ResUnet-a d6 hot path on B200 (BASELINE.json configs).
 
-    python bench.py --gpus 1 --steps 10 --warmup 3
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # config 2, the headline (train patches/s)
+    python bench.py --config 1|3|5 ...                             # the other BASELINE.json configs
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the CPU restatement of the reference on the host cores
+    python bench.py --impl reference [--config C] ...              # the CPU restatement of the reference on the host cores
 
-A "step" = one fwd + bwd + Adam update of model2 (multitask, Tanimoto dual x4) on a synthetic batch of
-16 patches 256x256x3 per GPU.  Prints ONE JSON line (rank 0).  `value` times the step with inputs
-resident in HBM (CUDA events, max over ranks); `e2e` times Model.train_on_batch with HOST numpy
-buffers (pinned H2D of the batch + D2H of the 10 step results inside the timed region).
+config 2 (default): a "step" = one fwd + bwd + Adam update of model2 (multitask, Tanimoto dual x4) on a synthetic batch
+of 16 patches 256x256x3 per GPU.  config 3: the Amazon shape (128x128x14, 3 classes, weighted CE + BCE + MSE x2).
+config 1: single-task forward of one 256x256x3 patch (latency).  config 5: a 6000x6000 scene through
+inference.predict_scene (529 patches, batch 64, argmax + confusion matrix + reconstruction); the scene is sharded over
+the ranks when N > 1.  Prints ONE JSON line (rank 0).  `value` times the step with inputs resident in HBM (CUDA events,
+max over ranks); `e2e` times the public API call with HOST numpy buffers (H2D of the inputs + D2H of the results inside
+the timed region).
 """
 import argparse
 import json
@@ -25,8 +29,15 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-FLOP_PER_PATCH_CONV = 224.7e9      # ResBlock-a 3x3 convs fwd+bwd, dense 9-tap count
-FLOP_PER_PATCH_ALL = 252.4e9
+# algorithmic FLOPs per patch (dense 9-tap count, padding MACs included)
+FLOP = {
+    1: dict(all=78.02e9, kind="fwd"),                       # single-task forward, 256^2 x 3, n = 6
+    2: dict(all=252.4e9, conv=224.7e9, kind="fwd+bwd"),      # multitask fwd+bwd; conv = ResBlock-a 3x3 only
+    3: dict(all=63.0e9, kind="fwd+bwd"),                     # Amazon 128^2 x 14, n = 3
+    5: dict(all=84.12e9, kind="fwd"),                        # multitask forward, 256^2 x 3, n = 6
+}
+HEADS = ("seg", "bound", "dist", "color")
+AMAZON_WEIGHTS = [1.1, 9.0, 0.0]     # synthetic stand-in for [tot/n0, tot/n1, 0] (amazon_py/main_tcc.py:82-84,190)
 
 
 def peaks():
@@ -73,238 +84,458 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def synth(batch, hw, n, seed):
-    from oracle import resuneta_oracle as O   # data generator shared with the tests (not the product path)
-    return O.synth_batch(batch, hw, 3, n, seed=seed, block=16)
+# ------------------------------------------------------------------------------------------------------
+# synthetic workloads; the generator is shared with the tests, never part of a timed region
+# ------------------------------------------------------------------------------------------------------
+def synth_train(cfg, batch, seed):
+    from oracle import resuneta_oracle as O
+    if cfg == 3:
+        x, y = O.synth_batch(batch, 128, 14, 3, seed=seed, block=16)
+        x = np.random.RandomState(seed).randn(*x.shape).astype(np.float32)      # StandardScaler-like bands
+        return x, y
+    return O.synth_batch(batch, 256, 3, 6, seed=seed, block=16)
+
+
+def workload_name(cfg, batch=None):
+    return {
+        1: "config1: ResUnet-a d6 model2 single-task forward (inference mode), 256x256x3, 6 classes, batch 1",
+        2: f"config2: ResUnet-a d6 model2 multitask fwd+bwd+Adam, Tanimoto dual x4, 256x256x3, 6 classes, batch {batch}/GPU",
+        3: f"config3: Amazon shape, ResUnet-a d6 model2 multitask fwd+bwd+Adam, weighted CE + BCE + MSE x2, 128x128x14, "
+           f"3 classes, batch {batch}/GPU",
+        5: "config5: 6000x6000x3 scene -> 529 patches of 256x256 (batch 64), multitask forward, argmax + int64 confusion "
+           "matrix + reconstruction",
+    }[cfg]
+
+
+METRIC = {
+    1: "forward patches/s (256^2, single-task, batch 1)",
+    2: "train patches/s (256^2, multitask fwd+bwd)",
+    3: "train patches/s (128^2 x14, multitask fwd+bwd, weighted CE)",
+    5: "scene inference patches/s (6000^2, batch 64, argmax + confusion + reconstruction)",
+}
+
+
+def host_threads():
+    """All host cores, whatever OMP_NUM_THREADS says: torchrun exports OMP_NUM_THREADS=1 to every rank, which made the
+    round-1 reference arm at N > 1 a single-thread run."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(steps, warmup, hw, n, batch, threads=None):
-    """patches/s of the CPU restatement of the reference (torch fp32, all host threads): one
-    fwd+bwd+Adam step of model2 multitask + Tanimoto dual on a bounded sample of `batch` patches."""
+# the reference arm / cpu_baseline: oracle port (torch-CPU fp32) on the host cores, bounded samples
+# ------------------------------------------------------------------------------------------------------
+def cpu_rate(cfg, steps, warmup, ref_batch):
+    """(patches/s, seconds per step, threads, sample description) of the CPU restatement on a bounded sample."""
     from oracle import resuneta_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
-    p = O.init_params((hw, hw, 3), n, True, "v2", seed=1234)
-    x, y = O.synth_batch(batch, hw, 3, n, seed=1234, block=16)
-    xt = torch.from_numpy(x)
-    yt = {k: torch.from_numpy(v) for k, v in y.items()}
-    opt = O.Adam(lr=1e-3)
-    losses = {k: O.tanimoto_dual_loss for k in yt}
-    for _ in range(warmup):
-        O.train_on_batch(p, opt, xt, yt, losses, {}, n)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.train_on_batch(p, opt, xt, yt, losses, {}, n)
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads()
+    threads = host_threads()
+    if cfg in (2, 3):
+        hw, cin, n = (256, 3, 6) if cfg == 2 else (128, 14, 3)
+        p = O.init_params((hw, hw, cin), n, True, "v2", seed=1234)
+        x, y = synth_train(cfg, ref_batch, 1234)
+        xt, yt = torch.from_numpy(x), {k: torch.from_numpy(v) for k, v in y.items()}
+        opt = O.Adam(lr=1e-3)
+        if cfg == 2:
+            losses = {k: O.tanimoto_dual_loss for k in yt}
+        else:
+            losses = dict(seg=O.weighted_categorical_crossentropy(AMAZON_WEIGHTS), bound=O.binary_crossentropy,
+                          dist=O.mean_squared_error, color=O.mean_squared_error)
+        step = lambda: O.train_on_batch(p, opt, xt, yt, losses, {}, n)
+        per = ref_batch
+        sample = f"{steps} fwd+bwd+Adam steps of batch {ref_batch} ({hw}x{hw}x{cin}) after {warmup} warm-up"
+    elif cfg == 1:
+        p = O.init_params((256, 256, 3), 6, False, "v2", seed=1234)
+        xt = torch.from_numpy(np.random.RandomState(0).rand(1, 256, 256, 3).astype(np.float32))
+        step = lambda: O.forward(p, xt, False, 6, False, "v2")
+        per = 1
+        sample = f"median of {steps} single-task forwards of one 256x256x3 patch after {warmup} warm-up"
+    else:
+        from sklearn.metrics import confusion_matrix
+        p = O.init_params((256, 256, 3), 6, True, "v2", seed=1234)
+        rs = np.random.RandomState(7)
+        xs = rs.rand(ref_batch, 256, 256, 3).astype(np.float32)
+        ref = rs.randint(0, 6, size=(ref_batch, 256, 256))
+
+        def step():
+            # test_ISPRS.py:26-36 predicts patch by patch (batch_size=1), argmax, sklearn confusion matrix
+            pr = [O.forward(p, torch.from_numpy(xs[i:i + 1]), False, 6, True, "v2")["seg"].numpy().argmax(-1)
+                  for i in range(ref_batch)]
+            confusion_matrix(ref.ravel(), np.concatenate(pr).ravel())
+        per = ref_batch
+        sample = (f"{steps} passes over {ref_batch} of the 529 patches (batch-1 multitask forward, argmax, sklearn "
+                  f"confusion matrix) after {warmup} warm-up")
+    with torch.no_grad() if cfg in (1, 5) else torch.enable_grad():
+        for _ in range(warmup):
+            step()
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            step()
+            ts.append(time.perf_counter() - t0)
+    sec = float(np.median(ts)) if cfg == 1 else float(np.mean(ts))
+    return per / sec, sec, threads, sample + ", torch-CPU fp32 oracle port (stand-in for the reference's TF-CPU path)"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = args.config
     steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
-    rate, sps, threads = cpu_reference_rate(steps, warm, args.hw, args.classes, args.ref_batch)
-    sample = f"{steps} fwd+bwd+Adam steps of batch {args.ref_batch} ({args.hw}x{args.hw}x3), torch-CPU fp32 oracle port"
-    line = dict(impl="reference", metric="train patches/s (256^2, multitask fwd+bwd)", value=rate, unit="patches/s",
-                n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=sps * 1e3, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="config2: ResUnet-a d6 model2 multitask fwd+bwd+Adam, Tanimoto dual x4, "
-                                     f"{args.hw}x{args.hw}x3, {args.classes} classes",
-                            per_step_batch=args.ref_batch, note="TensorFlow is not installable here; this is the "
-                            "CPU restatement (oracle port) of the reference on the host cores"),
+    warm = 1
+    rate, sps, threads, sample = cpu_rate(cfg, steps, warm, args.ref_batch)
+    line = dict(impl="reference", metric=METRIC[cfg], value=rate, unit="patches/s", n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=sps * 1e3, higher_is_better=True, scaling="strong" if cfg == 5 else "weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=workload_name(cfg, args.batch), per_step_batch=args.ref_batch if cfg != 1 else 1,
+                            note="TensorFlow is not installable here; this is the CPU restatement (oracle port) of the "
+                                 "reference on the host cores.  Each step is a BOUNDED sample of the workload "
+                                 f"(batch {args.ref_batch} instead of {args.batch} for the training configs), so that the run "
+                                 "ends within minutes; patches/s is per patch and comparable.",
+                            host_threads=threads, omp_num_threads_env=os.environ.get("OMP_NUM_THREADS")),
                 cpu_baseline=dict(value=rate, unit="patches/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=rate, unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
+# product arm
+# ------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max(self, v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+
+def profile_single_stream(model, pl, pk):
+    """One single-stream pass of the step with CUDA events around EVERY launch.  The stream is first parked behind a
+    ~25 ms spin kernel so that the host is hundreds of launches ahead: the events then time kernels that run back to
+    back on the launching stream (no idle-start latency inside the intervals), like the launches of the replayed graph.
+    Returns (roofline block of the 3x3 convolutions, per-kernel table of the bandwidth-bound launches, summed ms)."""
+    stream = torch.cuda.current_stream().cuda_stream
+    seq = ([model.net.pack_launch] if model.net.pack_launch is not None else []) + list(pl.fwd) + [pl.bn_update] + list(pl.bwd) \
+        + [model._opt_launch]
+    seq = [op for op in seq if op is not None]
+    best = None
+    for _ in range(2):
+        torch.cuda.synchronize()
+        model._push_lr()
+        pl.scratch.zero_()
+        model.net.params.grad.zero_()
+        torch.cuda._sleep(int(50e6))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(seq) + 1)]
+        evs[0].record()
+        for i, op in enumerate(seq):
+            op(stream)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(seq))]
+        if best is None or sum(ms) < sum(best):
+            best = ms
+    ms = best
+    conv = [(op, t) for op, t in zip(seq, ms) if getattr(op, "tag", None)]
+    flops = sum(op.flops for op, _ in conv)
+    conv_ms = sum(t for _, t in conv)
+    by_tag = {}
+    for op, t in conv:
+        k = (op.tag, getattr(op, "kernel", "?"))
+        a = by_tag.setdefault(k, [0, 0.0, 0.0])
+        a[0] += 1; a[1] += t; a[2] += op.flops
+    hbm = {}
+    for op, t in zip(seq, ms):
+        b = getattr(op, "hbm_bytes", None)
+        if b:
+            a = hbm.setdefault(getattr(op, "kernel", "?"), [0, 0.0, 0.0])
+            a[0] += 1; a[1] += t; a[2] += b
+    hbm_tab = {k: dict(launches=n, ms=round(t, 4), algorithmic_gb=round(b / 1e9, 4), gbs=round(b / (t * 1e-3) / 1e9, 1),
+                       frac_of_hbm_peak=round(b / (t * 1e-3) / 1e9 / pk["hbm"], 3)) for k, (n, t, b) in sorted(hbm.items())}
+    roof = None
+    if conv:
+        achieved = flops / (conv_ms / 1e3) / 1e12
+        roof = dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s", frac=achieved / pk["tf_sust"],
+                    frac_of_burst=achieved / pk["tf_burst"],
+                    kernel="3x3 conv fwd+dgrad+wgrad (ResBlock-a + heads)", launches=len(conv),
+                    avg_launch_ms=conv_ms / len(conv), conv_ms_per_step=conv_ms,
+                    algorithmic_flop_per_launch=flops / len(conv),
+                    how="CUDA events around every launch of one single-stream pass of the step, stream pre-loaded behind a spin "
+                        "kernel so the launches run back to back; best of 2 passes",
+                    peak_source=pk["src"] + " (sustained cuBLAS bf16: the kernels are timed inside a long step)",
+                    by_kernel={f"{tag} {kern}": dict(launches=n, ms=round(t, 4), tflops=round(f / (t * 1e-3) / 1e12, 1))
+                               for (tag, kern), (n, t, f) in sorted(by_tag.items())})
+        tpath = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            roof.update(traffic=tj.get("mean_dram_bytes_per_launch"), traffic_source=tj.get("source"),
+                        algorithmic_bytes_per_launch=tj.get("algorithmic_bytes_per_launch"),
+                        l2_to_sm_bytes_per_launch=tj.get("mean_l2_to_sm_bytes_per_launch"),
+                        tensor_pipe_active_pct=tj.get("mean_tensor_pipe_active_pct"))
+        else:
+            roof.update(traffic=None, traffic_source="no ncu capture of this code under profiles/")
+    return roof, hbm_tab, sum(ms)
+
+
+def run_train(args, D):
+    cfg = args.config
     import __graft_entry__ as ge
-    if rank == 0:
+    if D.rank == 0:
         ge.build()
-    from resuneta_b200 import Adam, Tanimoto_dual_loss
+    from resuneta_b200 import (Adam, BinaryCrossentropy, MeanSquaredError, Tanimoto_dual_loss,
+                               weighted_categorical_crossentropy)
     from resuneta_b200.builder import build_model
     from resuneta_b200.distribute import MirroredStrategy
     strat = MirroredStrategy()
-    if world > 1:
-        dist.barrier()
-    heads = ("seg", "bound", "dist", "color")
+    D.barrier()
+    hw, cin, n = (256, 3, 6) if cfg == 2 else (128, 14, 3)
     with strat.scope():
-        model = build_model((args.hw, args.hw, 3), args.classes, True, "v2", dtype=args.dtype, seed=1234)
-        model.compile(optimizer=Adam(lr=1e-3), loss={h: Tanimoto_dual_loss() for h in heads},
-                      loss_weights={h: 1.0 for h in heads})
-    lib = model.net.lib
-    x, y = synth(args.batch, args.hw, args.classes, 1234 + rank)
+        model = build_model((hw, hw, cin), n, True, "v2", dtype=args.dtype, seed=1234)
+        if cfg == 2:
+            losses = {h: Tanimoto_dual_loss() for h in HEADS}
+        else:
+            losses = dict(seg=weighted_categorical_crossentropy(AMAZON_WEIGHTS), bound=BinaryCrossentropy(),
+                          dist=MeanSquaredError(), color=MeanSquaredError())
+        model.compile(optimizer=Adam(lr=1e-3), loss=losses, loss_weights={h: 1.0 for h in HEADS})
+    x, y = synth_train(cfg, args.batch, 1234 + D.rank)
+    warm = max(args.warmup, 3)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- warm-up through the public API (stages inputs, captures the CUDA graph at N=1) ----------------
-    for _ in range(max(args.warmup, 3)):
+    # ---- warm-up through the public API (stages inputs, captures the CUDA graphs) -------------------------------
+    for _ in range(warm):
         last = model.train_on_batch(x, y)
     pl = model.net.plan(args.batch, True, model.loss_spec)
-    ops_per_step = len(pl.fwd) + len(pl.bwd) + 2      # + bn_update_moving + optimizer (memsets not counted)
-    # device-resident warm-up: the first replays on a fresh box run 2-3 ms slower (power state / first-touch effects
-    # measured run to run); these untimed steps are counted in the reported `warmup`
+    ops_per_step = len(pl.fwd) + len(pl.bwd) + 2 + (1 if model.net.pack_launch is not None else 0)
+    # device-resident warm-up: the first replays on a fresh box run 2-3 ms slower (power state / first-touch effects);
+    # reported separately as extra_device_warmup
     extra_warm = 10
     for _ in range(extra_warm):
         model._push_lr()
         model._execute(pl, True)
 
-    # ---- device-resident timed region --------------------------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
+    # ---- device-resident timed region ------------------------------------------------------------------------------
+    sampler = ClockSampler(D.local)
+    if D.rank == 0:
         sampler.start()
-    barrier()
+    D.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         model._push_lr()
         model._execute(pl, True)
     e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = ms.item()
-    clocks = sampler.stop() if rank == 0 else None
-    value = args.batch * world * args.steps / (ms_total / 1e3)
+    D.barrier()
+    ms_total = D.max(e0.elapsed_time(e1))
+    clocks = sampler.stop() if D.rank == 0 else None
+    value = args.batch * D.world * args.steps / (ms_total / 1e3)
 
-    # ---- end-to-end through Model.train_on_batch with host buffers ---------------------------------------------
-    barrier()
+    # ---- end to end through Model.train_on_batch, host buffers ------------------------------------------------------
+    # (a) the reference's pattern: the SAME numpy batch buffers refilled every step (train_ISPRS.py:71-92,121-141); from
+    #     their second sighting they are page-locked in place (keras_api._registered_view) and copied without staging
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         last = model.train_on_batch(x, y)
     torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = args.batch * world * args.steps / t.item()
+    e2e = args.batch * D.world * args.steps / D.max(time.perf_counter() - t0)
     h2d, d2h = model.last_h2d_bytes, model.last_d2h_bytes
+    # (b) a loop that hands over freshly allocated arrays every step: pageable -> pinned staging memcpy -> H2D
+    nfresh = min(args.steps, 6)
+    fresh = [(x.copy(), {k: v.copy() for k, v in y.items()}) for _ in range(nfresh)]
+    D.barrier()
+    t0 = time.perf_counter()
+    for xb, yb in fresh:
+        last = model.train_on_batch(xb, yb)
+    torch.cuda.synchronize()
+    e2e_fresh = args.batch * D.world * nfresh / D.max(time.perf_counter() - t0)
+    del fresh
 
-    # ---- roofline of the dominant kernel family: the ResBlock-a / head 3x3 convolutions ------------------
-    roof = None
-    if rank == 0:
-        pk = peaks()
-        stream = torch.cuda.current_stream().cuda_stream
-        evs, flops, nconv = [], 0.0, 0
-        torch.cuda.synchronize()
-        model._push_lr()
-        pl.scratch.zero_()
-        model.net.params.grad.zero_()
-        seq = list(pl.fwd) + [pl.bn_update] + list(pl.bwd)
-        for op in seq:
-            tag = getattr(op, "tag", None)
-            if tag:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                op(stream)
-                b.record()
-                evs.append((a, b))
-                flops += op.flops
-                nconv += 1
-            else:
-                op(stream)
-        model._opt_launch(stream)
-        torch.cuda.synchronize()
-        conv_ms = sum(a.elapsed_time(b) for a, b in evs)
-        achieved = flops / (conv_ms / 1e3) / 1e12
-        # DRAM bytes per launch of this kernel family from the committed ncu capture (profiles/, per launch like `achieved`)
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1b_conv_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj.get("mean_dram_bytes_per_launch"), tj.get("source")
-        # The per-launch events above run in eager mode: every interval also contains the launch latency of a kernel
-        # that starts on an idle GPU (3-5 us on ~45 us kernels).  In-graph duration of the same 201 launches, still with CUDA
-        # events on the launching stream: replay the forward+backward graph with and without the convolution launches
-        # (no optimizer, so the weights stay put) and take the difference.
-        per_launch = dict(achieved=achieved, conv_ms_per_step=conv_ms, how="CUDA events around each eager launch")
-        try:
-            def replay_ms(ops, reps=10):
-                g = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize()
-                with torch.cuda.graph(g):
-                    st_ = torch.cuda.current_stream().cuda_stream
-                    pl.scratch.zero_()
-                    model.net.params.grad.zero_()
-                    for op in ops:
-                        op(st_)
-                for _ in range(3):
-                    g.replay()
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(reps):
-                    g.replay()
-                b.record()
-                torch.cuda.synchronize()
-                return a.elapsed_time(b) / reps
-            chain = ([model.net.pack_launch] if model.net.pack_launch is not None else []) + list(pl.fwd) + list(pl.bwd)
-            t_all = replay_ms(chain)
-            t_rest = replay_ms([op for op in chain if not getattr(op, "tag", None)])
-            conv_graph_ms = t_all - t_rest
-            if 0.5 * conv_ms < conv_graph_ms <= conv_ms:
-                conv_ms = conv_graph_ms
-                achieved = flops / (conv_ms / 1e3) / 1e12
-                per_launch["in_graph"] = dict(fwd_bwd_ms=t_all, without_conv_launches_ms=t_rest)
-        except Exception as e:      # keep the eager per-launch number
-            per_launch["in_graph_error"] = repr(e)
-        roof = dict(bound="tensor", achieved=achieved, peak=pk["tf_sust"], unit="TFLOP/s", frac=achieved / pk["tf_sust"],
-                    eager_per_launch=per_launch,
-                    traffic=traffic, traffic_source=traffic_src, kernel="3x3 conv fwd+dgrad+wgrad (ResBlock-a + heads)", launches=nconv,
-                    avg_launch_ms=conv_ms / max(nconv, 1), conv_ms_per_step=conv_ms,
-                    conv_share_of_step=conv_ms / (ms_total / args.steps), frac_of_burst=achieved / pk["tf_burst"],
-                    share_note="the conv launches are timed on ONE stream (graph with / without them); the step itself overlaps "
-                               "weight gradients with the data-gradient chain, so the share relates single-stream conv time to "
-                               "the concurrent step",
-                    peak_source=pk["src"] + " (sustained: timed inside a long step)",
-                    algorithmic_flop_per_launch=flops / max(nconv, 1))
+    roof = hbm_tab = None
+    single_ms = None
+    if D.rank == 0:
+        roof, hbm_tab, single_ms = profile_single_stream(model, pl, peaks())
+        if roof is not None:
+            roof["conv_share_of_single_stream_step"] = roof["conv_ms_per_step"] / single_ms
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) ---------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sps, threads = cpu_reference_rate(2, 1, args.hw, args.classes, args.ref_batch)
-        cpu = dict(value=rate, unit="patches/s", cores=threads, kind="port",
-                   sample=f"2 fwd+bwd+Adam steps of batch {args.ref_batch} after 1 warm-up, torch-CPU fp32 oracle "
-                          f"(stand-in for the reference's TF-CPU path)")
-    if rank == 0:
-        line = dict(metric="train patches/s (256^2, multitask fwd+bwd)", value=value, unit="patches/s", n_gpus=world,
-                    steps=args.steps, warmup=max(args.warmup, 3) + extra_warm, ms_per_step=ms_total / args.steps,
+    if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
+        rate, sps, threads, sample = cpu_rate(cfg, 2, 1, args.ref_batch)
+        cpu = dict(value=rate, unit="patches/s", cores=threads, kind="port", sample=sample)
+    if D.rank == 0:
+        streams = ("weight/bias-gradient launches on a side stream, ResBlock-a branches and heads over "
+                   f"{os.environ.get('RSA_LANES', '2')} lanes (one stream: RSA_WGRAD_STREAM=0 RSA_LANES=0)"
+                   if os.environ.get("RSA_WGRAD_STREAM", "1") != "0" or os.environ.get("RSA_LANES", "2") != "0" else "one stream")
+        dp_mode = None
+        if D.world > 1:
+            dp_mode = ("eager, bucketed all-reduce overlapped with backward" if strat.dp.overlap else
+                       "graph replay; gradient all-reduce in ranges overlapped with the rest of backward"
+                       if os.environ.get("RSA_DP_GRAPH_OVERLAP", "1") != "0" else "graph fwd+bwd, one all-reduce, graph optimizer")
+        line = dict(metric=METRIC[cfg], value=value, unit="patches/s", n_gpus=D.world, steps=args.steps, warmup=args.warmup,
+                    extra_device_warmup=extra_warm + (warm - args.warmup), ms_per_step=ms_total / args.steps,
                     higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
-                    config=dict(workload="config2: ResUnet-a d6 model2 multitask fwd+bwd+Adam, Tanimoto dual x4, "
-                                         f"{args.hw}x{args.hw}x3, {args.classes} classes, batch {args.batch}/GPU",
-                                global_batch=args.batch * world, parallelism=f"dp{world}",
-                                l2="working set per step (>8 GB of activations) is far larger than the 126 MB L2",
-                                cuda_graph=bool(model.use_cuda_graph),
-                                streams=("weight/bias-gradient launches on a side stream, ResBlock-a branches and heads over "
-                                         f"{os.environ.get('RSA_LANES', '2')} lanes (one stream: RSA_WGRAD_STREAM=0 RSA_LANES=0)"
-                                         if os.environ.get("RSA_WGRAD_STREAM", "1") != "0" or os.environ.get("RSA_LANES", "2") != "0"
-                                         else "one stream"),
-                                dp_mode=("graph replay; gradient all-reduce in two ranges, the parameter-heavy one overlapped with the rest of backward"
-                                         if world > 1 and not strat.dp.overlap and os.environ.get("RSA_DP_GRAPH_OVERLAP", "1") != "0"
-                                         else "graph fwd+bwd, one all-reduce, graph optimizer" if world > 1 and not strat.dp.overlap
-                                         else ("eager, bucketed all-reduce overlapped with backward" if world > 1 else None)),
+                    config=dict(workload=workload_name(cfg, args.batch), global_batch=args.batch * D.world,
+                                parallelism=f"dp{D.world}",
+                                l2="working set per step (GBs of activations) is far larger than the 126 MB L2",
+                                cuda_graph=bool(model.use_cuda_graph), streams=streams, dp_mode=dp_mode,
                                 conv_engine=getattr(model.net, "conv_engine", "igemm_simt")),
-                    e2e=dict(value=e2e, unit="patches/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    e2e=dict(value=e2e, unit="patches/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             host_buffers="reused numpy buffers (page-locked in place on second sight, no staging copy)",
+                             fresh_buffers=dict(value=e2e_fresh, unit="patches/s", steps=nfresh,
+                                                how="newly allocated pageable arrays every step: staging memcpy into "
+                                                    "pinned memory + H2D inside the timed region")),
                     gpu_launches=ops_per_step * args.steps, launches_per_step=ops_per_step,
-                    clocks=clocks, roofline=roof, cpu_baseline=cpu, last_loss=last[0],
-                    tflops_all_convs=FLOP_PER_PATCH_ALL * value / 1e12)
+                    clocks=clocks, roofline=roof, hbm_kernels=hbm_tab, single_stream_step_ms=single_ms, cpu_baseline=cpu,
+                    last_loss=last[0], tflops_whole_step=FLOP[cfg]["all"] * value / 1e12)
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+
+
+def run_forward_latency(args, D):
+    """config 1: batch-1 single-task forward (test_ISPRS.py:26-36 predicts one patch at a time).  N > 1: replicas only."""
+    import __graft_entry__ as ge
+    if D.rank == 0:
+        ge.build()
+    from resuneta_b200.builder import build_model
+    from resuneta_b200.distribute import MirroredStrategy
+    MirroredStrategy()              # only for the barrier / max-over-ranks under torchrun: the replicas do not communicate
+    D.barrier()
+    model = build_model((256, 256, 3), 6, False, "v2", dtype=args.dtype, seed=1234)
+    # moving statistics that are not the identity (SURVEY 8d): mean N(0, .1), variance U[.5, 1.5]
+    g = torch.Generator().manual_seed(0)
+    w = model.net.get_weights()
+    for k in w:
+        if k.endswith("/moving_mean"):
+            w[k] = 0.1 * torch.randn(w[k].shape, generator=g)
+        if k.endswith("/moving_variance"):
+            w[k] = 0.5 + torch.rand(w[k].shape, generator=g)
+    model.net.set_weights(w)
+    x = np.random.RandomState(0).rand(1, 256, 256, 3).astype(np.float32)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        out = model.predict(x, batch_size=1)
+    pl = model.net.plan(1, False, None)
+    sampler = ClockSampler(D.local)
+    if D.rank == 0:
+        sampler.start()
+    D.barrier()
+    lat = []
+    for _ in range(max(args.steps, 5)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model._execute(pl, False)
+        e1.record()
+        torch.cuda.synchronize()
+        lat.append(e0.elapsed_time(e1))
+    dev_ms = D.max(float(np.median(lat)))
+    clocks = sampler.stop() if D.rank == 0 else None
+    lat2 = []
+    for _ in range(max(args.steps, 5)):
+        t0 = time.perf_counter()
+        out = model.predict(x, batch_size=1)
+        lat2.append(time.perf_counter() - t0)
+    e2e_ms = D.max(float(np.median(lat2)) * 1e3)
+    cpu = None
+    if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
+        rate, sps, threads, sample = cpu_rate(1, 5, 1, 1)
+        cpu = dict(value=rate, unit="patches/s", cores=threads, kind="port", sample=sample, ms_per_patch=sps * 1e3)
+    if D.rank == 0:
+        pk = peaks()
+        tf = FLOP[1]["all"] / (dev_ms * 1e-3) / 1e12
+        line = dict(metric=METRIC[1], value=D.world * 1e3 / dev_ms, unit="patches/s", n_gpus=D.world, steps=max(args.steps, 5),
+                    warmup=args.warmup, extra_device_warmup=warm - args.warmup, ms_per_step=dev_ms, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
+                    config=dict(workload=workload_name(1), parallelism="replicas only" if D.world > 1 else "dp1",
+                                statistic="median latency of one graph-replayed forward", cuda_graph=bool(model.use_cuda_graph)),
+                    e2e=dict(value=D.world * 1e3 / e2e_ms, unit="patches/s", ms=e2e_ms, h2d_bytes_per_step=int(x.nbytes),
+                             d2h_bytes_per_step=int(out.nbytes), how="Model.predict(x, batch_size=1): host numpy in, numpy out"),
+                    gpu_launches=len(pl.fwd) * max(args.steps, 5), launches_per_step=len(pl.fwd), clocks=clocks,
+                    roofline=dict(bound="latency", achieved=tf, peak=pk["tf_sust"], unit="TFLOP/s", frac=tf / pk["tf_sust"],
+                                  traffic=None, note=f"one patch = {len(pl.fwd)} dependent launches on 1-64 CTAs each: a batch-1 "
+                                  "forward is launch/latency bound, the fraction of tensor peak is reported for completeness",
+                                  peak_source=pk["src"]),
+                    cpu_baseline=cpu)
+        print(json.dumps(line))
+
+
+def run_scene(args, D):
+    """config 5: sliding-window inference of a 6000 x 6000 scene (test_ISPRS.py:268-333)."""
+    import __graft_entry__ as ge
+    if D.rank == 0:
+        ge.build()
+    from resuneta_b200 import inference
+    from resuneta_b200.builder import build_model
+    from resuneta_b200.distribute import MirroredStrategy
+    strat = MirroredStrategy()      # initialises torch.distributed under torchrun; predict_scene shards by rank
+    D.barrier()
+    side = args.scene
+    model = build_model((256, 256, 3), 6, True, "v2", dtype=args.dtype, seed=1234)
+    rs = np.random.RandomState(7)
+    scene = rs.rand(side, side, 3).astype(np.float32)
+    ref = rs.randint(0, 6, size=(side, side))
+    npatch = (side // 256) ** 2
+    warm = max(args.warmup, 3)
+    for _ in range(min(warm, 3)):
+        r = inference.predict_scene(model, scene, ref, patch_size=256, batch_size=args.scene_batch, num_classes=6)
+    # ---- device-resident: the patches of this rank already in HBM, forward + argmax + confusion per batch ----------
+    dev = inference.SceneOnDevice(model, scene, ref, 256, args.scene_batch, 6)
+    for _ in range(2):
+        dev.run()
+    sampler = ClockSampler(D.local)
+    if D.rank == 0:
+        sampler.start()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        dev.run()
+    e1.record()
+    D.barrier()
+    ms_total = D.max(e0.elapsed_time(e1))
+    clocks = sampler.stop() if D.rank == 0 else None
+    value = npatch * args.steps / (ms_total / 1e3)
+    # ---- end to end: host scene in, host label map + confusion matrix out ----------------------------------------------
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = inference.predict_scene(model, scene, ref, patch_size=256, batch_size=args.scene_batch, num_classes=6)
+    e2e_s = D.max(time.perf_counter() - t0)
+    cpu = None
+    if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
+        rate, sps, threads, sample = cpu_rate(5, 2, 1, 4)
+        cpu = dict(value=rate, unit="patches/s", cores=threads, kind="port", sample=sample)
+    if D.rank == 0:
+        pk = peaks()
+        tf = FLOP[5]["all"] * value / D.world / 1e12
+        line = dict(metric=METRIC[5], value=value, unit="patches/s", n_gpus=D.world, steps=args.steps, warmup=args.warmup,
+                    extra_device_warmup=2, ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype=args.dtype, data="synthetic",
+                    config=dict(workload=workload_name(5) if side == 6000 else f"config5 at {side}x{side}: {npatch} patches",
+                                patches=npatch, batch=args.scene_batch, parallelism=f"patches sharded over {D.world} rank(s)",
+                                l2="each batch of 64 patches streams >1 GB of activations", cuda_graph=bool(model.use_cuda_graph)),
+                    e2e=dict(value=npatch * args.steps / e2e_s, unit="patches/s", h2d_bytes_per_step=int(npatch * 256 * 256 * 3 * 4 / D.world),
+                             d2h_bytes_per_step=int(npatch * 256 * 256 * 4 / D.world + 36 * 8),
+                             how="inference.predict_scene(model, scene, reference): host chop, H2D per batch, forward, argmax + "
+                                 "confusion on the device, D2H of the label tiles, host reconstruction"),
+                    gpu_launches=dev.launches_per_run * args.steps, launches_per_step=dev.launches_per_run, clocks=clocks,
+                    roofline=dict(bound="tensor", achieved=tf, peak=pk["tf_sust"], unit="TFLOP/s", frac=tf / pk["tf_sust"],
+                                  traffic=None, kernel="whole multitask forward (84.12 GFLOP per patch)", peak_source=pk["src"]),
+                    cpu_baseline=cpu, accuracy=float(r["metrics"][0]))
+        print(json.dumps(line))
 
 
 def main():
@@ -313,19 +544,25 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--hw", type=int, default=256)
-    ap.add_argument("--classes", type=int, default=6)
     ap.add_argument("--ref-batch", type=int, default=2)
+    ap.add_argument("--scene", type=int, default=6000)
+    ap.add_argument("--scene-batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
-        if not torch.cuda.is_available():
-            raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path for the product arm")
-        run_ours(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path for the product arm")
+    D = Dist()
+    torch.cuda.set_device(D.local)
+    {1: run_forward_latency, 2: run_train, 3: run_train, 5: run_scene}[args.config](args, D)
+    if D.world > 1 and D.dist.is_initialized():
+        D.dist.barrier()
+        D.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

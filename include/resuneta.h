@@ -144,6 +144,10 @@ int rsa_pixel_loss_fwd(int kind, const float* pred, const float* label, const fl
                        int C, double* loss_sum, void* stream);
 int rsa_pixel_loss_bwd(int kind, const float* pred, const float* label, const float* weights, int64_t M,
                        int C, float scale, float* dpred, void* stream);
+/* out[M] = un-reduced per-pixel loss: what the loss callables return when called directly,
+ * weighted_categorical_crossentropy(w)(y_true, y_pred) -> [B,H,W] (utils.py:478-491). */
+int rsa_pixel_loss_elem(int kind, const float* pred, const float* label, const float* weights, int64_t M,
+                        int C, float* out, void* stream);
 
 /* seg metrics (train_ISPRS.py:446-449): out[5] (int64, zeroed) += {argmax matches, TP, FP, TN, FN}@0.5 */
 int rsa_seg_metrics(const float* pred, const float* label, int64_t M, int C, int64_t* out, void* stream);

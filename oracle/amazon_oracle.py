@@ -79,7 +79,10 @@ def consider(img_reconstructed, ref_clip, clipping_mask_, area):
 def metrics_aa_recall_one(thr, prob_map, reference, mask_amazon_ts, area):
     """One threshold of utils2.py:312-356: returns (recall, precision, alarm area)."""
     rec = (prob_map >= thr).astype(np.float64)
-    ref_final, pre_final, _ = consider(rec, reference, (mask_amazon_ts == 1).astype(np.float64), area)
+    _, _, mask_no_consider = consider(rec, reference, (mask_amazon_ts == 1).astype(np.float64), area)
+    # utils2.py:332-336: the selection uses mask_amazon_ts alone; masked-out pixels remain as (0, 0) pairs
+    ref_final = (mask_no_consider * reference)[mask_amazon_ts == 1]
+    pre_final = (mask_no_consider * rec)[mask_amazon_ts == 1]
     tp = np.sum((ref_final == 1) & (pre_final == 1))
     fp = np.sum((ref_final == 0) & (pre_final == 1))
     fn = np.sum((ref_final == 1) & (pre_final == 0))

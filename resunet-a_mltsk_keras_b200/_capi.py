@@ -103,6 +103,8 @@ _SIGS = {
                            C.c_void_p],
     "rsa_pixel_loss_bwd": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float,
                            C.c_void_p, C.c_void_p],
+    "rsa_pixel_loss_elem": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                            C.c_void_p],
     "rsa_seg_metrics": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p],
     "rsa_adam_step": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_float,
                       C.c_float, C.c_float, C.c_float, C.c_void_p],
@@ -329,6 +331,10 @@ class Lib:
     def pixel_loss_bwd(self, kind, pred, label, weights, M, C_, scale, dpred):
         return self._bind("rsa_pixel_loss_bwd", kind, _p(pred), _p(label), _p(weights), M, C_, float(scale),
                           _p(dpred), keep=(pred, label, weights, dpred))
+
+    def pixel_loss_elem(self, kind, pred, label, weights, M, C_, out):
+        return self._bind("rsa_pixel_loss_elem", kind, _p(pred), _p(label), _p(weights), M, C_, _p(out),
+                          keep=(pred, label, weights, out))
 
     def seg_metrics(self, pred, label, M, C_, out):
         return self._bind("rsa_seg_metrics", _p(pred), _p(label), M, C_, _p(out), keep=(pred, label, out))

@@ -98,13 +98,16 @@ def prediction(model, image_array, image_ref, final_mask, mask_amazon_ts_, patch
 def matrics_AA_recall(thresholds, prob_map, reference, mask_amazon_ts, area, verbose=False):
     """utils2.matrics_AA_recall (:312-356): rows of (recall, precision, alarm area) per threshold."""
     out = []
+    # utils2.py:335-336 selects with mask_amazon_ts == 1 ONLY: pixels removed by the area filter or the reference borders
+    # stay in ref_final / pre_final as (0, 0) pairs, so they count in the alarm-area denominator (TP, FP, FN are the same)
+    n_sel = int(np.count_nonzero(np.asarray(mask_amazon_ts) == 1))
     for thr in thresholds:
         rec = (np.asarray(prob_map) >= thr).astype(np.float64)
-        ref_final, pre_final, cm3 = consider(rec, reference, np.asarray(mask_amazon_ts) == 1, area)
+        _, _, cm3 = consider(rec, reference, np.asarray(mask_amazon_ts) == 1, area)
         cm = cm3[:2, :2]
         if verbose:
             print(thr, "\n", cm, metrics_from_confusion(cm))
         tp, fp, fn = cm[1, 1], cm[0, 1], cm[1, 0]
         with np.errstate(divide="ignore", invalid="ignore"):
-            out.append(np.hstack((np.float64(tp) / (tp + fn), np.float64(tp) / (tp + fp), (tp + fp) / max(len(ref_final), 1))))
+            out.append(np.hstack((np.float64(tp) / (tp + fn), np.float64(tp) / (tp + fp), (tp + fp) / max(n_sel, 1))))
     return np.asarray(out)

@@ -49,7 +49,7 @@ struct Smem2 {
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING = STAGES * STAGE_BYTES;
-  static constexpr int CS_BYTES = 2 * 1024 * 4;           // per-CTA channel sums (Cout <= 1024)
+  static constexpr int CS_BYTES = 2 * 512 * 8;            // per-CTA channel sums in double (Cout <= 512; wider layers flush per tile)
   static constexpr int BAR_OFF = RING + CS_BYTES;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
@@ -65,8 +65,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
   constexpr int SWZ = KC * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* csum = reinterpret_cast<float*>(smem + L::RING);
-  float* csq = csum + 1024;
+  // double accumulators: the four epilogue warps add in whatever order they arrive, and double sums of fp32 partials
+  // are order-independent far below fp32 resolution, so the statistics are reproducible run to run
+  double* csum = reinterpret_cast<double*>(smem + L::RING);
+  double* csq = csum + 512;
+  const bool cs_smem = p.Cout <= 512;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull = empty_bar + STAGES;     // [2]
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (p.stats && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < 2048; i += 128) csum[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < 1024; i += 128) csum[i] = 0.0;
   }
   pdl_wait();                        // everything above is private to the CTA; global memory is touched only below
   if (threadIdx.x == 0) pdl_launch_dependents();
@@ -299,8 +302,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
           if (lane < nval) {
             float qv = sq[0];
             if (p.bnr_x) qv = __ldg(p.bnr_coef + p.Cout + co + lane) * (qv - __ldg(p.bnr_coef + co + lane) * s[0]);
-            atomicAdd(&csum[co + lane], s[0]);
-            atomicAdd(&csq[co + lane], qv);
+            if (cs_smem) {
+              atomicAdd(&csum[co + lane], (double)s[0]);
+              atomicAdd(&csq[co + lane], (double)qv);
+            } else {
+              atomicAdd(p.stats + co + lane, (double)s[0]);
+              atomicAdd(p.stats + p.Cout + co + lane, (double)qv);
+            }
           }
         }
       }
@@ -309,13 +317,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    if (p.stats) {
+    if (p.stats && cs_smem) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = threadIdx.x - 64; i < p.Cout; i += 128) {
-        const float s = csum[i], sq = csq[i];
-        if (s != 0.f || sq != 0.f) {
-          atomicAdd(p.stats + i, (double)s);
-          atomicAdd(p.stats + p.Cout + i, (double)sq);
+        const double s = csum[i], sq = csq[i];
+        if (s != 0.0 || sq != 0.0) {
+          atomicAdd(p.stats + i, s);
+          atomicAdd(p.stats + p.Cout + i, sq);
         }
       }
     }

@@ -127,8 +127,8 @@ struct Tc3Smem {
     st_off = (nbr * 9 * C * C * 2 + 1023) & ~1023;
     side_off = st_off + nsb * 128 * C * 2;                   // [nsi][nside] tiles of 128 pixels
     ring_off = side_off + nsi * nside * 128 * C * 2;
-    misc_off = ring_off + nstages * slot_bytes;              // bias[C], csum[C], csq[C], BN coefficients [4][C]
-    bar_off = misc_off + 7 * C * 4;
+    misc_off = ring_off + nstages * slot_bytes;              // bias[C], csum[4][C], csq[4][C], BN coefficients [4][C]
+    bar_off = misc_off + 13 * C * 4;
     total = bar_off + (2 * nstages + 4 * T3_MAXSB + 8) * 8 + 16 + 1024;
   }
 };
@@ -149,9 +149,9 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
   uint8_t* sidesm = smem + L.side_off;
   uint8_t* ring = smem + L.ring_off;
   float* bias_s = reinterpret_cast<float*>(smem + L.misc_off);
-  float* csum = bias_s + C;
-  float* csq = csum + C;
-  float* bnc = csq + C;                      // [4][C]: invstd, -mean*invstd, gamma, beta of the fused BatchNorm backward
+  float* csum = bias_s + C;                  // [4][C]: one slot per lane quarter, summed in a fixed order (deterministic)
+  float* csq = csum + 4 * C;
+  float* bnc = csq + 4 * C;                  // [4][C]: invstd, -mean*invstd, gamma, beta of the fused BatchNorm backward
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + p.nstages;
   uint64_t* tfull = empty_bar + p.nstages;   // [2]
@@ -193,8 +193,6 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
     float b = 0.f;
     for (int k = 0; k < p.nbr; ++k) if (p.bias[k]) b += __ldg(p.bias[k] + c);
     bias_s[c] = b;
-    csum[c] = 0.f;
-    csq[c] = 0.f;
     if (p.has_bnx) {
       float mean, inv;
       bn_mean_invstd(p.bnr_stats, p.bnr_count, C, c, p.bnr_eps, nullptr, nullptr, mean, inv);
@@ -491,16 +489,18 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
           acc_s[cc] += __shfl_xor_sync(0xffffffffu, acc_s[cc], off);
           acc_q[cc] += __shfl_xor_sync(0xffffffffu, acc_q[cc], off);
         }
-        if ((lane & (REST - 1)) == 0) {
-          atomicAdd(&csum[hs * NCT + cc + ch], acc_s[cc]);
-          atomicAdd(&csq[hs * NCT + cc + ch], acc_q[cc]);
+        if ((lane & (REST - 1)) == 0) {      // exactly one warp (q, hs) owns slot [q][channel]: no atomics, fixed order below
+          csum[q * C + hs * NCT + cc + ch] = acc_s[cc];
+          csq[q * C + hs * NCT + cc + ch] = acc_q[cc];
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       if (it > 0 && warp < EPI0 + C / 32) {
         const int c = (warp - EPI0) * 32 + lane;
-        atomicAdd(p.stats + c, (double)csum[c]);
-        atomicAdd(p.stats + C + c, (double)csq[c]);
+        const double s4 = (((double)csum[c] + (double)csum[C + c]) + (double)csum[2 * C + c]) + (double)csum[3 * C + c];
+        const double q4 = (((double)csq[c] + (double)csq[C + c]) + (double)csq[2 * C + c]) + (double)csq[3 * C + c];
+        atomicAdd(p.stats + c, s4);
+        atomicAdd(p.stats + C + c, q4);
       }
     }
     tc_fence_before();

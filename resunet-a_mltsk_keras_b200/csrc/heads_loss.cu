@@ -231,36 +231,49 @@ __device__ __forceinline__ float block_sum_to_double_atomic(double v, double* ou
 
 constexpr float KEPS = 1e-7f;   // keras.backend.epsilon()
 
+// loss of one pixel: kind 0 weighted categorical cross-entropy (utils.py:479-490), 1 binary cross-entropy, 2 squared error
+// (keras BinaryCrossentropy / MeanSquaredError: mean over the last axis)
+__device__ __forceinline__ float pixel_loss_one(int kind, const float* __restrict__ p, const float* __restrict__ y,
+                                                const float* __restrict__ weights, int C) {
+  float l = 0.f;
+  if (kind == 0) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += p[c];
+    for (int c = 0; c < C; ++c) {
+      float q = fminf(fmaxf(p[c] / s, KEPS), 1.f - KEPS);
+      float w = weights ? weights[c] : 1.f;
+      l -= y[c] * logf(q) * w;
+    }
+  } else if (kind == 1) {
+    for (int c = 0; c < C; ++c) {
+      float q = fminf(fmaxf(p[c], KEPS), 1.f - KEPS);
+      l -= y[c] * logf(q) + (1.f - y[c]) * logf(1.f - q);
+    }
+    l /= C;
+  } else {
+    for (int c = 0; c < C; ++c) { float d = p[c] - y[c]; l += d * d; }
+    l /= C;
+  }
+  return l;
+}
+
 __global__ void __launch_bounds__(NT) pixel_loss_fwd_kernel(int kind, const float* __restrict__ pred,
                                                             const float* __restrict__ label,
                                                             const float* __restrict__ weights, int64_t M, int C,
                                                             double* __restrict__ loss_sum) {
   double acc = 0;
-  for (int64_t m = (int64_t)blockIdx.x * NT + threadIdx.x; m < M; m += (int64_t)gridDim.x * NT) {
-    const float* p = pred + m * C;
-    const float* y = label + m * C;
-    float l = 0.f;
-    if (kind == 0) {
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) s += p[c];
-      for (int c = 0; c < C; ++c) {
-        float q = fminf(fmaxf(p[c] / s, KEPS), 1.f - KEPS);
-        float w = weights ? weights[c] : 1.f;
-        l -= y[c] * logf(q) * w;
-      }
-    } else if (kind == 1) {
-      for (int c = 0; c < C; ++c) {
-        float q = fminf(fmaxf(p[c], KEPS), 1.f - KEPS);
-        l -= y[c] * logf(q) + (1.f - y[c]) * logf(1.f - q);
-      }
-      l /= C;
-    } else {
-      for (int c = 0; c < C; ++c) { float d = p[c] - y[c]; l += d * d; }
-      l /= C;
-    }
-    acc += (double)l;
-  }
+  for (int64_t m = (int64_t)blockIdx.x * NT + threadIdx.x; m < M; m += (int64_t)gridDim.x * NT)
+    acc += (double)pixel_loss_one(kind, pred + m * C, label + m * C, weights, C);
   block_sum_to_double_atomic(acc, loss_sum);
+}
+
+// the un-reduced loss map a keras loss callable returns ([B,H,W]): standalone use of the loss functions
+__global__ void __launch_bounds__(NT) pixel_loss_elem_kernel(int kind, const float* __restrict__ pred,
+                                                             const float* __restrict__ label,
+                                                             const float* __restrict__ weights, int64_t M, int C,
+                                                             float* __restrict__ out) {
+  for (int64_t m = (int64_t)blockIdx.x * NT + threadIdx.x; m < M; m += (int64_t)gridDim.x * NT)
+    out[m] = pixel_loss_one(kind, pred + m * C, label + m * C, weights, C);
 }
 
 __global__ void __launch_bounds__(NT) pixel_loss_bwd_kernel(int kind, const float* __restrict__ pred,
@@ -443,6 +456,17 @@ extern "C" int rsa_pixel_loss_fwd(int kind, const float* pred, const float* labe
   RSA_REQUIRE(pred && label && loss_sum && M > 0 && C >= 1 && C <= MAXC && kind >= 0 && kind <= 2, RSA_ERR_SHAPE,
               "pixel_loss_fwd: bad args");
   pixel_loss_fwd_kernel<<<grid1d(M, 4), NT, 0, (cudaStream_t)stream>>>(kind, pred, label, weights, M, C, loss_sum);
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+
+/* out[m] = loss of pixel m (no reduction): what weighted_categorical_crossentropy(w)(y, p) (utils.py:466-491) and the
+ * keras BinaryCrossentropy / MeanSquaredError functions return before keras averages them. */
+extern "C" int rsa_pixel_loss_elem(int kind, const float* pred, const float* label, const float* weights,
+                                   int64_t M, int C, float* out, void* stream) {
+  RSA_REQUIRE(pred && label && out && M > 0 && C >= 1 && C <= MAXC && kind >= 0 && kind <= 2, RSA_ERR_SHAPE,
+              "pixel_loss_elem: bad args");
+  pixel_loss_elem_kernel<<<grid1d(M), NT, 0, (cudaStream_t)stream>>>(kind, pred, label, weights, M, C, out);
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }

@@ -46,7 +46,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(NT) igemm_fwd_kernel(const IgemmParams p) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
-  __shared__ float red_s[BN], red_q[BN];
+  __shared__ double red_s[BN], red_q[BN];   // double: order-independent below fp32 resolution (reproducible statistics)
 
   const int tid = threadIdx.x;
   const int64_t M = (int64_t)p.N * p.Ho * p.Wo;
@@ -198,17 +198,17 @@ __global__ void __launch_bounds__(NT) igemm_fwd_kernel(const IgemmParams p) {
     for (int j = 0; j < 4; ++j) { ssum[j] += v[j]; ssq[j] += v[j] * v[j]; }
   }
   if (p.stats) {
-    if (tid < BN) { red_s[tid] = 0.f; red_q[tid] = 0.f; }
+    if (tid < BN) { red_s[tid] = 0.0; red_q[tid] = 0.0; }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&red_s[tx * 4 + j], ssum[j]);
-      atomicAdd(&red_q[tx * 4 + j], ssq[j]);
+      atomicAdd(&red_s[tx * 4 + j], (double)ssum[j]);
+      atomicAdd(&red_q[tx * 4 + j], (double)ssq[j]);
     }
     __syncthreads();
     if (tid < BN && n0 + tid < p.Co) {
-      atomicAdd(p.stats + n0 + tid, (double)red_s[tid]);
-      atomicAdd(p.stats + p.Co + n0 + tid, (double)red_q[tid]);
+      atomicAdd(p.stats + n0 + tid, red_s[tid]);
+      atomicAdd(p.stats + p.Co + n0 + tid, red_q[tid]);
     }
   }
 }

@@ -105,6 +105,8 @@ class PatchBatchLoader:
       a slot is only refilled after the consumer has moved two batches on, by which time the asynchronous H2D copy
       issued by `train_on_batch` for it has completed (the step that follows collects its results on the same stream);
     * world/rank shard the batch list for data-parallel training (one process per GPU): rank r takes batches r, r+world, ...
+      of the first (n // batch_size) // world * world batches, so every rank runs the same number of steps (each step is
+      one gradient all-reduce; a rank with an extra batch would wait for peers that have already left the epoch).
     """
 
     def __init__(self, x_paths, y_paths, batch_size, shuffle=False, seed=0, workers=8, prefetch=3, rank=0, world=1,
@@ -120,8 +122,8 @@ class PatchBatchLoader:
         self.rank, self.world = int(rank), int(world)
         self.pin = torch.cuda.is_available() if pin is None else bool(pin)
         self.epoch = 0
-        if len(self.x_paths) < self.batch_size:
-            raise ValueError("fewer patches than one batch")
+        if len(self.x_paths) < self.batch_size * self.world:
+            raise ValueError("fewer patches than one batch per rank")
         self._shapes = {"x": self._probe(self.x_paths[0])}
         self._shapes.update({h: self._probe(p[0]) for h, p in self.y_paths.items()})
         self._slots = None
@@ -131,9 +133,12 @@ class PatchBatchLoader:
         a = np.load(path, mmap_mode="r")
         return tuple(a.shape)
 
+    def _n_batches(self):
+        """Batches of the whole job per epoch: a multiple of the world size."""
+        return len(self.x_paths) // self.batch_size // self.world * self.world
+
     def __len__(self):
-        nb = len(self.x_paths) // self.batch_size
-        return (nb - self.rank + self.world - 1) // self.world
+        return self._n_batches() // self.world
 
     def _alloc(self):
         if self._slots is None:
@@ -149,8 +154,7 @@ class PatchBatchLoader:
         slots = self._alloc()
         order = self.order(self.epoch)
         self.epoch += 1
-        nb = len(self.x_paths) // self.batch_size
-        mine = list(range(self.rank, nb, self.world))
+        mine = list(range(self.rank, self._n_batches(), self.world))
         free, ready = queue.Queue(), queue.Queue()
         for s in range(len(slots)):
             free.put(s)
@@ -220,7 +224,10 @@ def train_model(net, train_loader, val_loader, epochs, results_path, patience=10
     (train_ISPRS.py:97-189), per-task table, MCC of the segmentation head, early stopping on the validation loss with
     `delta` / `patience` and a checkpoint of the best model (train_ISPRS.py:276-292).  Returns (net, history)."""
     names = list(metrics_names or net.metrics_names)
-    os.makedirs(results_path, exist_ok=True)
+    dp = getattr(net, "dp", None)
+    multi = dp is not None and dp.world_size > 1
+    if not multi or dp.rank == 0:
+        os.makedirs(results_path, exist_ok=True)
     min_loss, cont, history = float("inf"), 0, []
     for epoch in range(epochs):
         tr = np.zeros(len(names))
@@ -235,6 +242,10 @@ def train_model(net, train_loader, val_loader, epochs, results_path, patience=10
             va += np.asarray(net.test_on_batch(x, y), dtype=np.float64)
             nv += 1
         va /= max(nv, 1)
+        if multi:
+            # every rank must take the same early-stop / checkpoint decision (Model.save is a collective): average the
+            # per-rank means; BN moving statistics are per-replica, so the validation losses differ across ranks
+            tr, va = dp.mean_host(tr), dp.mean_host(va)
         trm, vam = dict(zip(names, tr.tolist())), dict(zip(names, va.tolist()))
         pre = "seg_" if "seg_true_positives" in vam else ""
         mcc = None

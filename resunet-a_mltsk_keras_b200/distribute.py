@@ -127,6 +127,17 @@ class DataParallel:
             dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.group)
             tail.div_(self.world_size)
 
+    def mean_host(self, values):
+        """Mean over ranks of a small host vector (epoch metrics): every rank gets the same numbers back."""
+        import numpy as np
+        v = np.asarray(values, dtype=np.float64)
+        if self.world_size <= 1:
+            return v
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.from_numpy(v.copy()).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return (t / self.world_size).cpu().numpy()
+
     def all_reduce_async(self, t):
         """Sum all-reduce on NCCL's stream (ordered after the work already enqueued on the current stream); the returned
         handle's wait() makes the current stream wait for it."""

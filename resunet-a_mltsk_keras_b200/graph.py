@@ -291,9 +291,19 @@ class Plan:
         return op
 
     @staticmethod
-    def _tag(op, tag, flops):
+    def _tag(op, tag, flops, nbytes=None):
+        """3x3 convolution launch: algorithmic FLOPs (dense 9-tap count) and minimal HBM bytes (one operand tensor read, one
+        result tensor written / second operand read; side inputs and weights not counted)."""
         op.tag = tag
         op.flops = flops
+        op.conv_bytes = nbytes
+        return op
+
+    @staticmethod
+    def _hb(op, nbytes):
+        """Algorithmic HBM bytes of a bandwidth-bound launch (what it must read + write once): bench.py and
+        scripts/hbm_kernels.py divide them by the measured duration (roofline of the PSP / BN / head / loss kernels)."""
+        op.hbm_bytes = float(nbytes)
         return op
 
     def _ready(self, *names):
@@ -387,14 +397,16 @@ class Plan:
         lib, M, n = self.lib, out.M, t.C
         W_, b_ = self.P(name + "/kernel"), self.P(name + "/bias")
         st = out.stats
-        self.fwd.append(self._late(lambda: lib.stem_fwd(t.data, W_, b_, out.data, M, n, st[0] if st else None)))
+        esz = out.data.element_size()
+        self.fwd.append(self._hb(self._late(lambda: lib.stem_fwd(t.data, W_, b_, out.data, M, n, st[0] if st else None)),
+                                 M * (n + 32) * esz))
         if self.training:
             def bwd():
                 if out.grad is None:
                     return
                 assert not t.needs_grad, "the stem input carries no gradient"
-                self.bwd.append(lib.stem_wgrad(t.data, out.grad, M, n, self.G(name + "/kernel"),
-                                               self.G(name + "/bias") if bias_grad else None))
+                self.bwd.append(self._hb(lib.stem_wgrad(t.data, out.grad, M, n, self.G(name + "/kernel"),
+                                                        self.G(name + "/bias") if bias_grad else None), M * (n + 32) * esz))
                 self._ready(name + "/kernel", name + "/bias")
             self.tape.append(bwd)
         return True
@@ -407,7 +419,7 @@ class Plan:
         if mode != "plain" or relu_in or t.C != 32 or t.dtype != torch.bfloat16:
             return False
         W_, b_ = self.P(name + "/kernel"), self.P(name + "/bias")
-        self.fwd.append(self.lib.head_fwd(t.data, W_, b_, out.data, out.M, cout))
+        self.fwd.append(self._hb(self.lib.head_fwd(t.data, W_, b_, out.data, out.M, cout), out.M * (64 + 4 * cout)))
         if self.training:
             def bwd():
                 if out.grad is None:
@@ -425,9 +437,10 @@ class Plan:
         if mode != "plain" or relu_in or t.C != 32:
             return False
         g, acc = self.gacc(t) if t.needs_grad else (None, False)
-        self.bwd.append(self.lib.head_bwd(t.data, out.grad, self.P(name + "/kernel"), out.M, cout, g, acc,
-                                          t.relu_masked, self.G(name + "/kernel"),
-                                          self.G(name + "/bias") if bias_grad else None))
+        self.bwd.append(self._hb(self.lib.head_bwd(t.data, out.grad, self.P(name + "/kernel"), out.M, cout, g, acc,
+                                                   t.relu_masked, self.G(name + "/kernel"),
+                                                   self.G(name + "/bias") if bias_grad else None),
+                                 out.M * (64 + 4 * cout + (64 * (2 if acc else 1) if g is not None else 0))))
         self._ready(name + "/kernel", name + "/bias")
         return True
 
@@ -515,7 +528,8 @@ class Plan:
             db_simt = [None]
             if bias_grad:
                 if cout % 8 == 0 and bf:
-                    self.bwd.append(self._side(lib.bias_grad(dz, out.M, cout, [self.G(name + "/bias")]), dz))
+                    self.bwd.append(self._side(self._hb(lib.bias_grad(dz, out.M, cout, [self.G(name + "/bias")]),
+                                                        out.M * cout * dz.element_size()), dz))
                 else:   # fp32 head logits / odd channel counts: folded into the CUDA-core wgrad of the first main
                     db_simt[0] = self.G(name + "/bias")
             sp = {}
@@ -553,7 +567,8 @@ class Plan:
             need = sorted({sh for _, sh, _, _ in qs if sh > 0})
             if need:   # adjoint of nearest up-sampling: window sums of dz, all levels in one pass
                 sp = {sh: self.alloc((N, out.H >> sh, out.W >> sh, cout), dz.dtype) for sh in need}
-                self.bwd.append(lib.sumpool_pyr(dz, N, out.H, out.W, cout, sp.get(1), sp.get(2), sp.get(3)))
+                self.bwd.append(self._hb(lib.sumpool_pyr(dz, N, out.H, out.W, cout, sp.get(1), sp.get(2), sp.get(3)),
+                                         out.M * cout * dz.element_size() * (1 + sum(0.25 ** sh for sh in need))))
             for t, sh, koff, q in qs:
                 one_source(t, koff, dz if sh == 0 else sp[sh], t.H, t.W, 1)
             assert db_simt[0] is None, "bias gradient was not emitted"
@@ -619,7 +634,8 @@ class Plan:
                     if not pyr:   # adjoint of nearest up-sampling = window sums of dy, one pass for all levels
                         need = sorted({m[1] for _, m, _ in inputs if isinstance(m, tuple) and m[1] > 1})
                         lv = {s: self.alloc((N, out.H >> s, out.W >> s, cout), dy.dtype) for s in need}
-                        self.bwd.append(lib.sumpool_pyr(dy, N, out.H, out.W, cout, lv.get(1), lv.get(2), lv.get(3)))
+                        self.bwd.append(self._hb(lib.sumpool_pyr(dy, N, out.H, out.W, cout, lv.get(1), lv.get(2), lv.get(3)),
+                                                 out.M * cout * dy.element_size() * (1 + sum(0.25 ** sh for sh in need))))
                         pyr.update(lv)
                     sg = [Seg(pyr[mode[1]], cout, t.H, t.W, w_off=woff)]
                 self.bwd.append(lib.igemm_fwd(sg, W_, cout, True, None, g, N, t.H, t.W, t.C, mask=mask,
@@ -647,20 +663,21 @@ class Plan:
         st = out.stats
         res = residual.data if residual is not None else None
         flops = 2.0 * N * H * W * 9 * C * cout
+        nb = 2.0 * N * H * W * (C + cout)        # bf16 operand in + result out (fwd / dgrad) or two operands (wgrad)
         tcw = self.net.tc_weights(name, N, H, W)
         thin = tcw is not None and self.net.thin_ok(N, H, W, C, cout)
         if thin:
             self.fwd.append(self._tag(self._late(lambda: lib.conv_tc3_fwd(
                 [x.data], [tcw[0]], [b_], [dil], out.data, N, H, W, C, residual=res,
-                stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
+                stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops, nb))
         elif tcw is not None:
             self.fwd.append(self._tag(self._late(lambda: lib.conv_tc2_fwd(
                 x.data, None, tcw[0], cout, b_, out.data, N, H, W, cout, taps=9, dil=dil, residual=res,
-                stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
+                stats=st[0] if st else None, accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops, nb))
         else:
             self.fwd.append(self._tag(self._late(lambda: lib.igemm_fwd(
                 segs, W_, cout, False, b_, out.data, N, H, W, cout, residual=res, stats=st[0] if st else None,
-                accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops))
+                accumulate=accumulate, relu=relu)), "conv3x3_fwd", flops, nb))
         if self.training:
             def bwd():
                 if out.grad is None:
@@ -671,15 +688,16 @@ class Plan:
                 if tcw is not None and C == cout:
                     if thin and lib.conv_tc3_wgrad_supported(N, H, W, C, dil):
                         self.bwd.append(self._side(self._tag(lib.conv_tc3_wgrad(x.data, dy, dW, N, H, W, C, dil),
-                                                             "conv3x3_wgrad", flops), x.data, dy))
+                                                             "conv3x3_wgrad", flops, nb), x.data, dy))
                     else:
                         self.bwd.append(self._side(self._tag(lib.conv_tc_wgrad(x.data, dy, dW, N, H, W, C, cout, dil),
-                                                             "conv3x3_wgrad", flops), x.data, dy))
+                                                             "conv3x3_wgrad", flops, nb), x.data, dy))
                     if db is not None:
-                        self.bwd.append(self._side(lib.bias_grad(dy, N * H * W, cout, [db]), dy))
+                        self.bwd.append(self._side(self._hb(lib.bias_grad(dy, N * H * W, cout, [db]),
+                                                            N * H * W * cout * dy.element_size()), dy))
                 else:
                     self.bwd.append(self._tag(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout),
-                                              "conv3x3_wgrad", flops))
+                                              "conv3x3_wgrad", flops, nb))
                 self._ready(name + "/kernel", name + "/bias")
                 if x.needs_grad:
                     g, acc = self.gacc(x)
@@ -688,14 +706,14 @@ class Plan:
                     mask = x.data if x.relu_masked else None
                     if thin:
                         self.bwd.append(self._tag(self._thin_dgrad(x, dy, tcw[1], g, acc, mask, dil, N, H, W, C),
-                                                  "conv3x3_dgrad", flops))
+                                                  "conv3x3_dgrad", flops, nb))
                     elif tcw is not None:
                         self.bwd.append(self._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9,
                                                                    dil=-dil, mask=mask, accumulate=acc),
-                                                  "conv3x3_dgrad", flops))
+                                                  "conv3x3_dgrad", flops, nb))
                     else:
                         self.bwd.append(self._tag(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask,
-                                                                accumulate=acc), "conv3x3_dgrad", flops))
+                                                                accumulate=acc), "conv3x3_dgrad", flops, nb))
             self.tape.append(bwd)
         return out
 
@@ -721,8 +739,10 @@ class Plan:
             xs, cnt = x.stats, x.count
             for n in names:
                 self.bn_table.append((xs, C, n + "/moving_mean", n + "/moving_variance", cnt, cnt * full_mult))
-            self.fwd.append(self._late(lambda: lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, xs[0],
-                                                             cnt, None, None, BN_EPS, relu)))
+            esz = x.data.element_size()
+            self.fwd.append(self._hb(self._late(lambda: lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, xs[0],
+                                                                      cnt, None, None, BN_EPS, relu)),
+                                     (1 + len(outs)) * M * C * esz))
             if derive:   # statistics of y = gamma*xhat+beta are known in closed form
                 o = outs[0]
                 self._new_stats(o, o.M)
@@ -745,19 +765,20 @@ class Plan:
                 # branches whose data-gradient kernel already produced {sum g, sum g*xhat} (conv_tc3 epilogue) are skipped
                 unf = [i for i, k in enumerate(live) if not outs[k].bn_src["fused"]]
                 if unf:
-                    self.bwd.append(self._late(lambda: lib.bn_bwd_reduce_multi(
+                    self.bwd.append(self._hb(self._late(lambda: lib.bn_bwd_reduce_multi(
                         [dys[i] for i in unf], x.data, M, C, xs[0], cnt, BN_EPS, [gl[i] for i in unf], [bl[i] for i in unf],
-                        relu, [rl[i][0] for i in unf])))
+                        relu, [rl[i][0] for i in unf])), (len(unf) + 1) * M * C * esz))
                 if x.needs_grad:
                     g, acc = self.gacc(x)
-                    self.bwd.append(self._late(lambda: lib.bn_bwd_apply_multi(
+                    self.bwd.append(self._hb(self._late(lambda: lib.bn_bwd_apply_multi(
                         dys, x.data, M, C, xs[0], cnt, BN_EPS, gl, bl, relu, [r[0] for r in rl], g, acc,
-                        [self.G(names[k] + "/gamma") for k in live], [self.G(names[k] + "/beta") for k in live])))
+                        [self.G(names[k] + "/gamma") for k in live], [self.G(names[k] + "/beta") for k in live])),
+                        (len(live) + 2 + (1 if acc else 0)) * M * C * esz))
                     self._ready(*[names[k] + sfx for k in live for sfx in ("/gamma", "/beta")])
             self.tape.append(bwd)
         else:
-            self.fwd.append(lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, None, 1.0, mm, mv, BN_EPS,
-                                         relu))
+            self.fwd.append(self._hb(lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, None, 1.0, mm, mv, BN_EPS,
+                                                  relu), (1 + len(outs)) * M * C * x.data.element_size()))
         return outs
 
     # ---------------------------------------------------------------------------------------------
@@ -775,7 +796,8 @@ class Plan:
                 x.grad_writers += 1
             else:
                 g, acc = self.gacc(x)
-                self.bwd.append(self.lib.axpy(g, out.grad, x.M * x.C, acc))
+                self.bwd.append(self._hb(self.lib.axpy(g, out.grad, x.M * x.C, acc),
+                                         (3 if acc else 2) * x.M * x.C * g.element_size()))
         self.tape.append(bwd)
 
     def block_bias_grad(self, out, conv_names, f):
@@ -790,7 +812,8 @@ class Plan:
             if out.grad is None:
                 return
             dbs = [self.G(n + "/bias") for n in conv_names]
-            self.bwd.append(self._side(self.lib.bias_grad(out.grad, out.M, out.C, dbs), out.grad))
+            self.bwd.append(self._side(self._hb(self.lib.bias_grad(out.grad, out.M, out.C, dbs),
+                                                out.M * out.C * out.grad.element_size()), out.grad))
             self._ready(*[n + "/bias" for n in conv_names])
         self.tape.append(bwd)
 
@@ -801,14 +824,17 @@ class Plan:
             return outs
         lib, N = self.lib, self.N
         d = lambda k: outs[k].data if k in outs else None
-        self.fwd.append(lib.maxpool_pyr_fwd(x.data, N, x.H, x.W, x.C, d(2), d(4), d(8)))
+        esz = 2 if x.dtype == torch.bfloat16 else 4
+        frac = sum(1.0 / (k * k) for k in levels)
+        self.fwd.append(self._hb(lib.maxpool_pyr_fwd(x.data, N, x.H, x.W, x.C, d(2), d(4), d(8)), x.M * x.C * esz * (1 + frac)))
         if self.training:
             def bwd():
                 gr = lambda k: outs[k].grad if k in outs else None
                 if all(gr(k) is None for k in (2, 4, 8)) or not x.needs_grad:
                     return
                 g, acc = self.gacc(x)
-                self.bwd.append(lib.maxpool_pyr_bwd(x.data, N, x.H, x.W, x.C, gr(2), gr(4), gr(8), g, acc))
+                self.bwd.append(self._hb(lib.maxpool_pyr_bwd(x.data, N, x.H, x.W, x.C, gr(2), gr(4), gr(8), g, acc),
+                                         x.M * x.C * esz * (2 + frac + (1 if acc else 0))))
             self.tape.append(bwd)
         return outs
 
@@ -820,9 +846,9 @@ class Plan:
             return p
         lib = self.lib
         if kind == "softmax":
-            self.fwd.append(lib.softmax_fwd(z.data, p.data, z.M, z.C))
+            self.fwd.append(self._hb(lib.softmax_fwd(z.data, p.data, z.M, z.C), 8 * z.M * z.C))
         else:
-            self.fwd.append(lib.sigmoid_fwd(z.data, p.data, z.M * z.C))
+            self.fwd.append(self._hb(lib.sigmoid_fwd(z.data, p.data, z.M * z.C), 8 * z.M * z.C))
         if self.training:
             def bwd():
                 if p.grad is None:
@@ -830,9 +856,9 @@ class Plan:
                 z.grad = p.grad
                 z.grad_written = True
                 if kind == "softmax":
-                    self.bwd.append(lib.softmax_bwd(p.data, p.grad, z.grad, z.M, z.C))
+                    self.bwd.append(self._hb(lib.softmax_bwd(p.data, p.grad, z.grad, z.M, z.C), 12 * z.M * z.C))
                 else:
-                    self.bwd.append(lib.sigmoid_bwd(p.data, p.grad, z.grad, z.M * z.C))
+                    self.bwd.append(self._hb(lib.sigmoid_bwd(p.data, p.grad, z.grad, z.M * z.C), 12 * z.M * z.C))
             self.tape.append(bwd)
         return p
 
@@ -855,14 +881,14 @@ class Plan:
             sums = self.zeroed(B * C * 5)
             res = self.res_f32[slot:slot + 1]
             coef = self.alloc((B * C * 3,), torch.float32)
-            self.fwd.append(self._late(lambda: lib.tanimoto_sums(p.data, y.data, B, HW, C, sums[0])))
+            self.fwd.append(self._hb(self._late(lambda: lib.tanimoto_sums(p.data, y.data, B, HW, C, sums[0])), 8 * B * HW * C))
             self.fwd.append(self._late(lambda: lib.tanimoto_finalize(sums[0], B, HW, C, weight, None, res, coef)))
             self.loss_out[head] = ("mean", slot)
             if self.training:
                 def bwd():
                     g, acc = self.gacc(p)
                     assert not acc
-                    self.bwd.append(lib.tanimoto_bwd(p.data, y.data, coef, B, HW, C, g))
+                    self.bwd.append(self._hb(lib.tanimoto_bwd(p.data, y.data, coef, B, HW, C, g), 12 * B * HW * C))
                 self.tape.append(bwd)
         else:
             code = {"cce": 0, "bce": 1, "mse": 2}[kind]
@@ -870,22 +896,23 @@ class Plan:
             if class_weights is not None:
                 cw = torch.tensor(list(class_weights), dtype=torch.float32).to(self.device)
                 assert cw.numel() == C
-            self.fwd.append(self._late(lambda: lib.pixel_loss_fwd(code, p.data, y.data, cw, B * HW, C,
-                                                                  rz[0][slot:slot + 1])))
+            self.fwd.append(self._hb(self._late(lambda: lib.pixel_loss_fwd(code, p.data, y.data, cw, B * HW, C,
+                                                                           rz[0][slot:slot + 1])), 8 * B * HW * C))
             self.loss_out[head] = ("sum", slot, float(B * HW))
             if self.training:
                 def bwd():
                     g, acc = self.gacc(p)
                     assert not acc
-                    self.bwd.append(lib.pixel_loss_bwd(code, p.data, y.data, cw, B * HW, C, weight / (B * HW), g))
+                    self.bwd.append(self._hb(lib.pixel_loss_bwd(code, p.data, y.data, cw, B * HW, C, weight / (B * HW), g),
+                                             12 * B * HW * C))
                 self.tape.append(bwd)
 
     def attach_seg_metrics(self, p):
         y = self.labels["seg"]
         rz = self.res_z
         self.metrics = True
-        self.fwd.append(self._late(lambda: self.lib.seg_metrics(p.data, y.data, p.M, p.C,
-                                                                 rz[0][8:13].view(torch.int64))))
+        self.fwd.append(self._hb(self._late(lambda: self.lib.seg_metrics(p.data, y.data, p.M, p.C,
+                                                                          rz[0][8:13].view(torch.int64))), 8 * p.M * p.C))
 
     # ---------------------------------------------------------------------------------------------
     def finish(self):
@@ -963,17 +990,18 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
             for ky in range(3) for kx in range(3)]
     res = residual.data if (first and residual is not None) else None
     flops = 2.0 * N * H * W * 9 * C * f
+    nb = 2.0 * N * H * W * (C + f)
     tcw = pl.net.tc_weights(name, N, H, W)
     thin = tcw is not None and pl.net.thin_ok(N, H, W, C, f)
     if thin:
         pl.fwd.append(pl._tag(lib.conv_tc3_fwd([a.data], [tcw[0]], [b_], [d], out.data, N, H, W, C, residual=res,
-                                               accumulate=not first, relu=relu), "conv3x3_fwd", flops))
+                                               accumulate=not first, relu=relu), "conv3x3_fwd", flops, nb))
     elif tcw is not None:
         pl.fwd.append(pl._tag(lib.conv_tc2_fwd(a.data, None, tcw[0], f, b_, out.data, N, H, W, f, taps=9, dil=d,
-                                               residual=res, accumulate=not first, relu=relu), "conv3x3_fwd", flops))
+                                               residual=res, accumulate=not first, relu=relu), "conv3x3_fwd", flops, nb))
     else:
         pl.fwd.append(pl._tag(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res,
-                                            accumulate=not first, relu=relu), "conv3x3_fwd", flops))
+                                            accumulate=not first, relu=relu), "conv3x3_fwd", flops, nb))
     pl.fwd[-1].chain = out.data.data_ptr()     # the branch sum is a read-modify-write sequence on `out`
     if pl.training:
         def bwd():
@@ -984,25 +1012,25 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
                 # bias gradient: one column-sum of d(out) per block (block_bias_grad)
                 if thin and lib.conv_tc3_wgrad_supported(N, H, W, C, d):
                     pl.bwd.append(pl._side(pl._tag(lib.conv_tc3_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, d),
-                                                   "conv3x3_wgrad", flops), a.data, dy))
+                                                   "conv3x3_wgrad", flops, nb), a.data, dy))
                 else:
                     pl.bwd.append(pl._side(pl._tag(lib.conv_tc_wgrad(a.data, dy, pl.G(name + "/kernel"), N, H, W, C, f, d),
-                                                   "conv3x3_wgrad", flops), a.data, dy))
+                                                   "conv3x3_wgrad", flops, nb), a.data, dy))
             else:
                 pl.bwd.append(pl._tag(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N,
-                                                      H, W, f), "conv3x3_wgrad", flops))
+                                                      H, W, f), "conv3x3_wgrad", flops, nb))
             pl._ready(name + "/kernel", name + "/bias")
             g, acc = pl.gacc(a)
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
                   for ky in range(3) for kx in range(3)]
             if thin:
-                pl.bwd.append(pl._tag(pl._thin_dgrad(a, dy, tcw[1], g, acc, None, d, N, H, W, C), "conv3x3_dgrad", flops))
+                pl.bwd.append(pl._tag(pl._thin_dgrad(a, dy, tcw[1], g, acc, None, d, N, H, W, C), "conv3x3_dgrad", flops, nb))
             elif tcw is not None:
                 pl.bwd.append(pl._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9, dil=-d,
-                                                       accumulate=acc), "conv3x3_dgrad", flops))
+                                                       accumulate=acc), "conv3x3_dgrad", flops, nb))
             else:
                 pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
-                                      "conv3x3_dgrad", flops))
+                                      "conv3x3_dgrad", flops, nb))
         pl.tape.append(bwd)
 
 
@@ -1166,6 +1194,7 @@ class Net:
         self._pack_table = torch.frombuffer(bytearray(table), dtype=torch.uint8).to(self.device)
         self.pack_launch = self.lib.pack_weights_tc(self.params.data, self.shadow, self._pack_table, len(self.tc),
                                                     max_elems)
+        self.pack_launch.hbm_bytes = 8.0 * sum(e["taps"] * e["cin"] * e["cout"] for e in self.tc.values())
         self.conv_engine = "tcgen05 (3x3 fwd/dgrad/wgrad persistent TMA kernels; 1x1 on tensor cores where K,N % 16 == 0)"
 
     def tc_weights(self, name, N, H, W):

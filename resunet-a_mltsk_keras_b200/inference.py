@@ -87,44 +87,125 @@ def _world():
     return None, 1, 0
 
 
+def _patch_rows(image, patch_size):
+    """(nh, nw, [nh, ps, nw, ps, ...] strided view of the covered part of the scene): patch i = view[i // nw, :, i % nw]."""
+    img = np.asarray(image)
+    h, w = img.shape[:2]
+    nh, nw = h // patch_size, w // patch_size
+    v = img[:nh * patch_size, :nw * patch_size].reshape((nh, patch_size, nw, patch_size) + img.shape[2:])
+    return nh, nw, v
+
+
+def _gather_patches(view, nw, lo, hi, dst):
+    """dst[k] = patch lo + k of the scene, written straight into (pinned) memory: one host copy, spread over the copy pool
+    (numpy releases the GIL while it copies)."""
+    from . import keras_api as KA
+    pool = KA._copy_pool()
+    futs = [pool.submit(np.copyto, dst[k], view[(lo + k) // nw, :, (lo + k) % nw]) for k in range(hi - lo)]
+    for f in futs:
+        f.result()
+
+
+class SceneOnDevice:
+    """The device part of scene inference with this rank's patches and reference labels resident in HBM: per batch one
+    forward (graph-replayed), argmax + int64 confusion counts right behind it.  bench.py times `run()` for the
+    device-resident figure of BASELINE config 5; predict_scene is the end-to-end path."""
+
+    def __init__(self, model, image, reference, patch_size, batch_size, num_classes):
+        net = model.net
+        self.model, self.net, self.K, self.bs = model, net, int(num_classes or net.num_classes), int(batch_size)
+        dist, world, rank = _world()
+        nh, nw, view = _patch_rows(image, patch_size)
+        P = nh * nw
+        share = -(-P // world)
+        lo, hi = min(P, rank * share), min(P, (rank + 1) * share)
+        self.n = hi - lo
+        dev = net.device
+        host = np.empty((max(self.n, 1), patch_size, patch_size) + view.shape[4:], dtype=np.float32)
+        if self.n:
+            _gather_patches(view, nw, lo, hi, host)
+        self.x = torch.from_numpy(host[:self.n]).to(dev)
+        self.ref = None
+        if reference is not None:
+            rp = extract_patches(np.asarray(reference), patch_size)[lo:hi].astype(np.int32)
+            self.ref = torch.from_numpy(rp.reshape(self.n, -1)).to(dev)
+        self.labels = torch.zeros((max(self.n, 1), patch_size * patch_size), dtype=torch.int32, device=dev)
+        self.cm = torch.zeros(self.K * self.K, dtype=torch.int64, device=dev)
+        self.launches_per_run = 0
+        for i in range(0, self.n, self.bs):
+            pl = net.plan(min(self.bs, self.n - i), False, None)
+            self.launches_per_run += len(pl.fwd) + 2      # + input cast + argmax/confusion
+
+    def run(self):
+        model, net, lib = self.model, self.net, self.net.lib
+        self.cm.zero_()
+        for i in range(0, self.n, self.bs):
+            n = min(self.bs, self.n - i)
+            pl = net.plan(n, False, None)
+            model._load_x(pl, self.x[i:i + n])
+            model._execute(pl, False)
+            prob = pl.outputs["seg"]
+            tl = self.ref[i:i + n].reshape(-1) if self.ref is not None else None
+            lib.argmax_confusion(prob.data, prob.M, prob.C, self.labels[i:i + n].view(-1), tl, self.K,
+                                 self.cm if tl is not None else None)(model._stream())
+        return self.labels, self.cm
+
+
 def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, num_classes=None):
     """Whole-scene inference (test_ISPRS.py:268-333): returns dict with
     ``seg_pred`` [P,ps,ps] int32, ``reconstructed`` (H,W) float64, and — when ``reference`` (H,W)
     integer labels is given — ``confusion`` (sklearn-shaped int64), ``labels`` and ``metrics``.
 
-    Under ``torch.distributed`` (one process per GPU) the patches are independent: every rank predicts a
-    contiguous share of them, the int64 confusion matrices are summed with one all-reduce and the label tiles are
-    all-gathered, so every rank returns the complete result (as ``MirroredStrategy.predict`` does, test_ISPRS.py:276-277)."""
+    Host side: every batch is gathered from the scene straight into one of two pinned buffers (one multi-threaded copy, no
+    intermediate patch array) while the previous batch is still on the GPU; the reference labels go up once; the label
+    tiles come back in one copy at the end.  Under ``torch.distributed`` (one process per GPU) the patches are
+    independent: every rank predicts a contiguous share of them, the int64 confusion matrices are summed with one
+    all-reduce and the label tiles are all-gathered, so every rank returns the complete result (as
+    ``MirroredStrategy.predict`` does, test_ISPRS.py:276-277)."""
     net = model.net
     lib = net.lib
     K = int(num_classes or net.num_classes)
-    patches = extract_patches(image, patch_size)
-    P = patches.shape[0]
-    ref_p = None
-    if reference is not None:
-        ref_p = extract_patches(np.asarray(reference), patch_size).astype(np.int32)
+    nh, nw, view = _patch_rows(image, patch_size)
+    P = nh * nw
     dev = net.device
+    on_gpu = dev.type == "cuda"
     dist, world, rank = _world()
     share = -(-P // world)                                   # patches per rank (the last ranks may get fewer / none)
     lo, hi = min(P, rank * share), min(P, (rank + 1) * share)
+    ref_dev = None
+    if reference is not None and hi > lo:
+        rp = extract_patches(np.asarray(reference), patch_size)[lo:hi]
+        ref_dev = torch.from_numpy(np.ascontiguousarray(rp, dtype=np.int32).reshape(hi - lo, -1)).to(dev)
     local = torch.zeros((share, patch_size, patch_size), dtype=torch.int32, device=dev)
     cm = torch.zeros(K * K, dtype=torch.int64, device=dev)
-    for i in range(lo, hi, batch_size):
-        xb = patches[i:min(i + batch_size, hi)]
-        n = xb.shape[0]
+    shape = (batch_size, patch_size, patch_size) + view.shape[4:]
+    key = ("scene", shape)
+    ring = getattr(model, "_scene_ring", {}).get(key)
+    if ring is None:
+        ring = [[torch.empty(shape, dtype=torch.float32, pin_memory=on_gpu), None] for _ in range(2)]
+        if not hasattr(model, "_scene_ring"):
+            model._scene_ring = {}
+        model._scene_ring[key] = ring
+    for bi, i in enumerate(range(lo, hi, batch_size)):
+        n = min(batch_size, hi - i)
+        buf = ring[bi & 1]
+        if buf[1] is not None:
+            buf[1].synchronize()                              # the H2D copy that last read this buffer has finished
+        _gather_patches(view, nw, i, i + n, buf[0].numpy())     # np.copyto casts other dtypes to float32 on the way
         pl = net.plan(n, False, None)
-        model._load_inputs(pl, xb, None)
+        model._load_x(pl, buf[0][:n])                         # pinned tensor: asynchronous copy, no staging
+        if on_gpu:
+            buf[1] = torch.cuda.Event()
+            buf[1].record(torch.cuda.current_stream())
         model._execute(pl, False)
         prob = pl.outputs["seg"]
         lab = local[i - lo:i - lo + n].view(-1)
-        tl = None
-        if ref_p is not None:
-            tl = torch.from_numpy(ref_p[i:i + n].reshape(-1)).to(dev)
+        tl = ref_dev[i - lo:i - lo + n].reshape(-1) if ref_dev is not None else None
         lib.argmax_confusion(prob.data, prob.M, prob.C, lab, tl, K, cm if tl is not None else None)(model._stream())
     if world > 1:
-        if dev.type == "cuda":
+        if on_gpu:
             torch.cuda.current_stream().synchronize()
-        if ref_p is not None:
+        if reference is not None:
             dist.all_reduce(cm)
         parts = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(parts, local)
@@ -134,7 +215,7 @@ def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, n
     out = dict(seg_pred=seg_pred)
     h, w = np.asarray(image).shape[:2]
     out["reconstructed"] = pred_recostruction(patch_size, seg_pred, np.zeros((h, w), dtype=np.uint8))
-    if ref_p is not None:
+    if reference is not None:
         full = cm.cpu().numpy().reshape(K, K)
         out["confusion_full"] = full
         out["confusion"], out["labels"] = compact_confusion(full)

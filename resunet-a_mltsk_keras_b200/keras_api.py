@@ -68,22 +68,27 @@ def _registered_view(a):
     return t if t.is_pinned() else None
 
 
+def _copy_pool():
+    global _COPY_POOL
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max(1, int(os.environ.get("RSA_COPY_THREADS", "8"))))
+    return _COPY_POOL
+
+
 def _host_copy(dst_np, src_np, min_chunk=4 << 20):
     """Parallel memcpy of a host batch into its pinned staging buffer.  Own thread pool (numpy releases the GIL while it
     copies): torch's intra-op threads are not usable for this under torchrun, which sets OMP_NUM_THREADS=1 per rank and
     turned the 100 MB/step staging copy into a 20+ ms single-thread memcpy at N > 1."""
-    global _COPY_POOL
     n = dst_np.size
     nthreads = int(os.environ.get("RSA_COPY_THREADS", "8"))
     if nthreads <= 1 or n * dst_np.itemsize < 2 * min_chunk:
         np.copyto(dst_np, src_np)
         return
-    if _COPY_POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _COPY_POOL = ThreadPoolExecutor(nthreads)
+    pool = _copy_pool()
     d, s_ = dst_np.reshape(-1), src_np.reshape(-1)
     step = max(min_chunk // dst_np.itemsize, (n + nthreads - 1) // nthreads)
-    futs = [_COPY_POOL.submit(np.copyto, d[i:i + step], s_[i:i + step]) for i in range(0, n, step)]
+    futs = [pool.submit(np.copyto, d[i:i + step], s_[i:i + step]) for i in range(0, n, step)]
     for f in futs:
         f.result()
 
@@ -131,12 +136,17 @@ class SGD(Optimizer):
 # losses: factories return callables tagged with the kernel that implements them
 # ------------------------------------------------------------------------------------------------------
 def _run_loss_standalone(kind, y_true, y_pred, class_weights=None):
-    """Evaluate a loss on the device outside a model (what calling the keras loss fn directly does)."""
+    """Evaluate a loss on the device outside a model (what calling the keras loss fn directly does).
+    tanimoto -> [B] (multitasking_utils.py:71-85); cce -> [B,H,W] (utils.py:466-491); bce / mse -> [B,H,W] (mean over the
+    last axis, keras BinaryCrossentropy / MeanSquaredError).  Same kernels as inside a model: rsa_tanimoto_* and
+    rsa_pixel_loss_elem."""
     from . import _capi
     lib = _capi.get_lib()
     dev = torch.device("cpu") if getattr(lib, "is_emulation", False) else torch.device("cuda")
     p = torch.as_tensor(np.asarray(y_pred), dtype=torch.float32).to(dev).contiguous()
     y = torch.as_tensor(np.asarray(y_true), dtype=torch.float32).to(dev).contiguous()
+    if p.shape != y.shape or p.dim() != 4:
+        raise ValueError(f"loss: y_true {tuple(y.shape)} and y_pred {tuple(p.shape)} must be equal [B,H,W,C] tensors")
     B, H, W, C = p.shape
     stream = 0 if dev.type == "cpu" else torch.cuda.current_stream().cuda_stream
     if kind == "tanimoto":
@@ -145,8 +155,15 @@ def _run_loss_standalone(kind, y_true, y_pred, class_weights=None):
         lib.tanimoto_sums(p, y, B, H * W, C, sums)(stream)
         lib.tanimoto_finalize(sums, B, H * W, C, 1.0, lb, None, None)(stream)
         return lb.cpu().numpy()
-    raise NotImplementedError("element-wise losses are evaluated inside the model (loss value returned by "
-                              "train_on_batch/test_on_batch)")
+    code = {"cce": 0, "bce": 1, "mse": 2}[kind]
+    cw = None
+    if class_weights is not None:
+        cw = torch.tensor(list(class_weights), dtype=torch.float32).to(dev)
+        if cw.numel() != C:
+            raise ValueError(f"loss: {cw.numel()} class weights for {C} classes")
+    out = torch.empty(B * H * W, dtype=torch.float32, device=dev)
+    lib.pixel_loss_elem(code, p, y, cw, B * H * W, C, out)(stream)
+    return out.view(B, H, W).cpu().numpy()
 
 
 def Tanimoto_dual_loss():
@@ -163,10 +180,7 @@ def weighted_categorical_crossentropy(weights):
     w = [float(v) for v in np.asarray(weights).ravel()]
 
     def loss(y_true, y_pred):
-        p = np.asarray(y_pred, dtype=np.float64)
-        p = p / p.sum(-1, keepdims=True)
-        p = np.clip(p, 1e-7, 1 - 1e-7)
-        return -(np.asarray(y_true) * np.log(p) * np.asarray(w)).sum(-1)
+        return _run_loss_standalone("cce", y_true, y_pred, w)
     loss.rsa_kind = "cce"
     loss.rsa_class_weights = tuple(w)
     return loss
@@ -174,6 +188,10 @@ def weighted_categorical_crossentropy(weights):
 
 class _KerasLoss:
     rsa_class_weights = None
+
+    def __call__(self, y_true, y_pred):
+        """keras loss objects reduce with SUM_OVER_BATCH_SIZE: the mean over every element the function returns."""
+        return float(_run_loss_standalone(self.rsa_kind, y_true, y_pred).mean())
 
 
 class CategoricalCrossentropy(_KerasLoss):
@@ -206,17 +224,69 @@ def _resolve_loss(l):
 
 
 # ------------------------------------------------------------------------------------------------------
+# metrics accepted by compile(metrics=...) (train_ISPRS.py:446-452): all are computed by rsa_seg_metrics
+# ------------------------------------------------------------------------------------------------------
+class _Metric:
+    def __init__(self, name=None):
+        self.name = name or self.rsa_metric
+
+
+class TruePositives(_Metric):
+    rsa_metric = "true_positives"
+
+
+class FalsePositives(_Metric):
+    rsa_metric = "false_positives"
+
+
+class TrueNegatives(_Metric):
+    rsa_metric = "true_negatives"
+
+
+class FalseNegatives(_Metric):
+    rsa_metric = "false_negatives"
+
+
+_METRIC_SLOTS = {"accuracy": 0, "acc": 0, "categorical_accuracy": 0, "true_positives": 1, "false_positives": 2,
+                 "true_negatives": 3, "false_negatives": 4}
+
+
+def _resolve_metric(m):
+    """-> (reported name, slot in the rsa_seg_metrics result)."""
+    if isinstance(m, str):
+        if m not in _METRIC_SLOTS:
+            raise ValueError(f"unsupported metric '{m}' (have: accuracy, TruePositives, FalsePositives, TrueNegatives, "
+                             "FalseNegatives)")
+        return ("accuracy" if _METRIC_SLOTS[m] == 0 else m), _METRIC_SLOTS[m]
+    kind = getattr(m, "rsa_metric", None)
+    if kind is None:
+        raise ValueError(f"unsupported metric object {m!r}")
+    return m.name, _METRIC_SLOTS[kind]
+
+
+# ------------------------------------------------------------------------------------------------------
 # callbacks used by the reference's fit() call (amazon_py/main_tcc.py:212-218)
 # ------------------------------------------------------------------------------------------------------
+def _monitor_sign(monitor, mode):
+    """+1 when smaller is better, -1 when larger is better (keras 'auto': accuracy-like monitors maximise)."""
+    if mode not in ("min", "max", "auto"):
+        raise ValueError(f"mode must be 'min', 'max' or 'auto', got {mode!r}")
+    if mode == "auto":
+        mode = "max" if ("acc" in monitor or monitor.startswith("fmeasure")) else "min"
+    return 1.0 if mode == "min" else -1.0
+
+
 class EarlyStopping:
-    def __init__(self, monitor="val_loss", min_delta=0.0, patience=0, verbose=0, mode="min"):
-        self.monitor, self.min_delta, self.patience = monitor, min_delta, patience
+    def __init__(self, monitor="val_loss", min_delta=0.0, patience=0, verbose=0, mode="auto"):
+        self.monitor, self.min_delta, self.patience = monitor, abs(min_delta), patience
+        self.sign = _monitor_sign(monitor, mode)
         self.best, self.wait = math.inf, 0
 
     def on_epoch_end(self, model, epoch, logs):
         cur = logs.get(self.monitor)
         if cur is None:
             return False
+        cur = self.sign * cur
         if cur < self.best - self.min_delta:
             self.best, self.wait = cur, 0
             return False
@@ -225,12 +295,14 @@ class EarlyStopping:
 
 
 class ModelCheckpoint:
-    def __init__(self, filepath, monitor="val_loss", verbose=0, save_best_only=False, mode="min"):
+    def __init__(self, filepath, monitor="val_loss", verbose=0, save_best_only=False, mode="auto"):
         self.filepath, self.monitor, self.save_best_only = filepath, monitor, save_best_only
+        self.sign = _monitor_sign(monitor, mode)
         self.best = math.inf
 
     def on_epoch_end(self, model, epoch, logs):
         cur = logs.get(self.monitor)
+        cur = None if cur is None else self.sign * cur
         if not self.save_best_only or (cur is not None and cur < self.best):
             if cur is not None:
                 self.best = min(self.best, cur)
@@ -259,7 +331,11 @@ class Model:
         self.loss_spec = None
         self.loss_weights = {}
         self.metrics_names = []
+        self._metric_sel = []
+        self._metrics_cfg = None
         self._opt_state = None
+        self._opt_launch = None
+        self._saved_opt_state = None
         self._graphs = {}
         self.use_cuda_graph = os.environ.get("RSA_CUDA_GRAPH", "1") != "0"
         self._staging = {}
@@ -283,9 +359,18 @@ class Model:
 
     # -- compile ---------------------------------------------------------------------------------------------
     def compile(self, optimizer=None, loss=None, loss_weights=None, metrics=None):
+        """keras Model.compile (train_ISPRS.py:446-461).  optimizer=None keeps the optimizer (and its restored slots) of a
+        model that came from load_model(); a different optimizer object drops the previous optimizer's state.  metrics:
+        list (single output) or dict keyed by output name of 'accuracy' / TruePositives() / FalsePositives() /
+        TrueNegatives() / FalseNegatives() on the segmentation output, reported in the order given; None reports all
+        five (the list the reference trains with)."""
         if isinstance(optimizer, str):
             optimizer = {"adam": Adam, "sgd": SGD}[optimizer.lower()]()
-        self.optimizer = optimizer
+        if optimizer is not None and optimizer is not self.optimizer:
+            self.optimizer = optimizer
+            self._opt_state = None
+            self._opt_launch = None
+            self._saved_opt_state = None
         heads = self.output_names
         if isinstance(loss, dict):
             missing = [h for h in heads if h not in loss]
@@ -299,15 +384,7 @@ class Model:
         for h in heads:
             kind, cw = _resolve_loss(per[h])
             spec.append((h, kind, float(lw.get(h, 1.0)), cw))
-        self.loss_spec = tuple(spec)
-        self.loss_weights = {h: float(lw.get(h, 1.0)) for h in heads}
-        if self.net.multitask:
-            self.metrics_names = ["loss"] + [f"{h}_loss" for h in heads] + [
-                "seg_accuracy", "seg_true_positives", "seg_false_positives", "seg_true_negatives",
-                "seg_false_negatives"]
-        else:
-            self.metrics_names = ["loss", "accuracy", "true_positives", "false_positives", "true_negatives",
-                                  "false_negatives"]
+        self._set_loss_spec(spec, metrics)
         self._graphs.clear()
         from . import distribute
         strat = distribute.current_strategy()
@@ -315,6 +392,26 @@ class Model:
             self.dp = strat.dp
             self.dp.broadcast_parameters(self.net.params)
             self._opt_state = None
+
+    def _set_loss_spec(self, spec, metrics=None):
+        heads = self.output_names
+        self.loss_spec = tuple((h, k, float(w), None if cw is None else tuple(cw)) for h, k, w, cw in spec)
+        self.loss_weights = {h: w for h, _, w, _ in self.loss_spec}
+        if metrics is None:
+            sel = [(n, i) for i, n in enumerate(("accuracy", "true_positives", "false_positives", "true_negatives",
+                                                 "false_negatives"))]
+        else:
+            if isinstance(metrics, dict):
+                extra = [h for h in metrics if h != "seg"]
+                if extra:
+                    raise ValueError(f"metrics are computed on the 'seg' output only, got {extra}")
+                metrics = metrics.get("seg", [])
+            sel = [_resolve_metric(m) for m in (metrics if isinstance(metrics, (list, tuple)) else [metrics])]
+        self._metric_sel = sel
+        self._metrics_cfg = [n for n, _ in sel] if metrics is not None else None
+        pre = "seg_" if self.net.multitask else ""
+        self.metrics_names = ["loss"] + ([f"{h}_loss" for h in heads] if self.net.multitask else []) + [
+            pre + n for n, _ in sel]
 
     # -- data movement -------------------------------------------------------------------------------------
     def _stream(self):
@@ -324,6 +421,9 @@ class Model:
         """host numpy (any float) -> pinned fp32 staging -> device tensor `dst` (fp32) asynchronously.  A float32 torch
         tensor that already lives in pinned memory (data.PatchBatchLoader) is copied from directly."""
         if isinstance(arr, torch.Tensor):
+            if arr.device == dst.device and tuple(arr.shape) == tuple(dst.shape) and arr.device.type != "cpu":
+                dst.copy_(arr)                    # already resident on this device (inference.SceneOnDevice)
+                return 0
             if (arr.dtype == torch.float32 and arr.is_contiguous() and tuple(arr.shape) == tuple(dst.shape)
                     and arr.device.type == "cpu" and self.net.device.type != "cpu" and arr.is_pinned()):
                 dst.copy_(arr, non_blocking=True)
@@ -340,12 +440,16 @@ class Model:
             if rv is not None:
                 dst.copy_(rv, non_blocking=True)
                 return a.nbytes
-        st = self._staging.get((key, a.shape))
-        if st is None:
-            st = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
-            self._staging[(key, a.shape)] = st
+        ent = self._staging.get((key, a.shape))
+        if ent is None:
+            ent = self._staging[(key, a.shape)] = [torch.empty(a.shape, dtype=torch.float32, pin_memory=True), None]
+        st, ev = ent
+        if ev is not None:
+            ev.synchronize()                   # the previous asynchronous copy out of this buffer may still be queued
         _host_copy(st.numpy(), a)              # multi-threaded host copy into the pinned staging buffer
         dst.copy_(st, non_blocking=True)
+        ent[1] = torch.cuda.Event()
+        ent[1].record(torch.cuda.current_stream())
         return a.nbytes
 
     def _load_inputs(self, pl, x, y):
@@ -399,6 +503,8 @@ class Model:
             else:
                 self._opt_launch = lib.sgd_step(ps.data, ps.grad, self._opt_state["vel"], n, self._lr_dev,
                                                 opt.momentum, gs)
+            # algorithmic HBM bytes per parameter: Adam reads p, g, m, v and writes p, m, v; SGD reads p, g, vel, writes p, vel
+            self._opt_launch.hbm_bytes = float(n) * (28 if isinstance(opt, Adam) else 20)
 
     def _push_lr(self):
         opt = self.optimizer
@@ -622,8 +728,8 @@ class Model:
             per.append(float(rf[rec[1]]) if rec[0] == "mean" else float(sums[rec[1]] / rec[2]))
         total = sum(self.loss_weights[h] * v for h, v in zip(pl.loss_out, per))
         seg = pl.outputs["seg"]
-        acc = float(met[0]) / float(seg.M)
-        tail = [acc, float(met[1]), float(met[2]), float(met[3]), float(met[4])]
+        vals = [float(met[0]) / float(seg.M), float(met[1]), float(met[2]), float(met[3]), float(met[4])]
+        tail = [vals[i] for _, i in self._metric_sel]
         if self.net.multitask:
             return [total] + per + tail
         return [total] + tail
@@ -685,16 +791,28 @@ class Model:
     def __call__(self, x, training=False):
         return self.predict(x, batch_size=int(np.shape(x)[0]))
 
+    def _count_mask(self):
+        """True for the entries of a metrics vector that keras accumulates as totals (TP / FP / TN / FN counters); losses
+        and accuracy are sample-weighted means."""
+        nloss = len(self.metrics_names) - len(self._metric_sel)
+        return np.array([False] * nloss + [slot != 0 for _, slot in self._metric_sel])
+
+    def _reduce_batches(self, rows, sizes):
+        rows, sizes = np.asarray(rows, dtype=np.float64), np.asarray(sizes, dtype=np.float64)
+        mean = (rows * sizes[:, None]).sum(0) / sizes.sum()
+        return np.where(self._count_mask(), rows.sum(0), mean)
+
     def evaluate(self, x, y, batch_size=32, verbose=0):
-        n = np.shape(x)[0]
-        acc = None
-        nb = 0
-        for i in range(0, n - batch_size + 1, batch_size):
+        """keras evaluate: losses and accuracy are sample-weighted means over all batches (the short last batch
+        included), the confusion counters are totals."""
+        n = int(np.shape(x)[0])
+        batch_size = max(1, min(int(batch_size), n))
+        rows, sizes = [], []
+        for i in range(0, n, batch_size):
             yb = {k: v[i:i + batch_size] for k, v in y.items()} if isinstance(y, dict) else y[i:i + batch_size]
-            r = np.array(self.test_on_batch(x[i:i + batch_size], yb))
-            acc = r if acc is None else acc + r
-            nb += 1
-        return (acc / max(nb, 1)).tolist()
+            rows.append(self.test_on_batch(x[i:i + batch_size], yb))
+            sizes.append(min(batch_size, n - i))
+        return self._reduce_batches(rows, sizes).tolist()
 
     def fit(self, x, y, batch_size=32, epochs=1, verbose=1, callbacks=None, validation_data=None, shuffle=True):
         """Epoch loop with the semantics the reference relies on (amazon_py/main_tcc.py:218):
@@ -703,16 +821,16 @@ class Model:
         hist = History()
         n = np.shape(x)[0]
         rng = np.random.RandomState(0)
-        nb = max(n // batch_size, 1)
+        batch_size = max(1, min(int(batch_size), n))
         take = lambda a, idx: ({k: v[idx] for k, v in a.items()} if isinstance(a, dict) else a[idx])
         for ep in range(epochs):
             order = rng.permutation(n) if shuffle else np.arange(n)
-            tot = None
-            for b in range(nb):
-                idx = order[b * batch_size:(b + 1) * batch_size]
-                r = np.array(self.train_on_batch(x[idx], take(y, idx)))
-                tot = r if tot is None else tot + r
-            logs = dict(zip(self.metrics_names, (tot / nb).tolist()))
+            rows, sizes = [], []
+            for b0 in range(0, n, batch_size):     # keras trains on the short last batch too
+                idx = order[b0:b0 + batch_size]
+                rows.append(self.train_on_batch(x[idx], take(y, idx)))
+                sizes.append(len(idx))
+            logs = dict(zip(self.metrics_names, self._reduce_batches(rows, sizes).tolist()))
             if validation_data is not None:
                 xv, yv = validation_data[0], validation_data[1]
                 bs = min(batch_size, np.shape(xv)[0])
@@ -739,6 +857,9 @@ class Model:
             self.dp.sync_moving_statistics(self.net.params)
         w = {k: v.numpy() for k, v in self.net.get_weights().items()}
         cfg = dict(self.config)
+        if self.loss_spec is not None:
+            cfg["loss_spec"] = [[h, k, lw_, None if cw is None else list(cw)] for h, k, lw_, cw in self.loss_spec]
+            cfg["metrics"] = self._metrics_cfg
         if self.optimizer is not None:
             cfg["optimizer"] = self.optimizer.config()
             cfg["iterations"] = self.optimizer.iterations
@@ -746,6 +867,8 @@ class Model:
         if self._opt_state is not None:
             for k, v in self._opt_state.items():
                 w["__opt__/" + k] = v.cpu().numpy()
+        if self.dp is not None and self.dp.world_size > 1 and self.dp.rank != 0:
+            return                    # replicas are identical after the statistics sync: rank 0 writes the file
         with open(path, "wb") as f:   # keep the caller's file name (the reference saves 'best_model.h5')
             np.savez(f, **w)
 
@@ -765,4 +888,12 @@ def load_model(path, compile=True, custom_objects=None):
         model.optimizer = Adam(**oc) if kind == "adam" else SGD(**oc)
         model.optimizer.iterations = cfg.get("iterations", 0)
         model._saved_opt_state = {k[len("__opt__/"):]: z[k] for k in z.files if k.startswith("__opt__/")}
+        if cfg.get("loss_spec"):
+            # a compiled checkpoint resumes training without a new compile() (train_ISPRS.py:471-480)
+            model._set_loss_spec([(h, k, w, cw) for h, k, w, cw in cfg["loss_spec"]], cfg.get("metrics"))
+            from . import distribute
+            strat = distribute.current_strategy()
+            if strat is not None and strat.dp.world_size > 1:
+                model.dp = strat.dp
+                model.dp.broadcast_parameters(model.net.params)
     return model

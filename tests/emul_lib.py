@@ -332,6 +332,11 @@ class EmulLib:
             loss_sum.add_(l.sum())
         return self._wrap(run, "rsa_pixel_loss_fwd")
 
+    def pixel_loss_elem(self, kind, pred, label, weights, M, C, out):
+        def run():
+            _store(out, self._pixel_loss(kind, pred.reshape(M, C).to(F64), label.reshape(M, C).to(F64), weights))
+        return self._wrap(run, "rsa_pixel_loss_elem")
+
     def pixel_loss_bwd(self, kind, pred, label, weights, M, C, scale, dpred):
         def run():
             p = pred.reshape(M, C).to(F64).clone().requires_grad_(True)

@@ -37,3 +37,14 @@ def test_consider_pipeline_small_case():
     assert m[0, 0] == 0 and m[5, 0] == 0 and m[3, 3] == 1
     assert len(ref_f) == 6 * 8 - 1 - 8 - 5                         # minus the small blob, the past-deforestation row, column 7 (5 rows left)
     assert pre_f.sum() == 12 and ref_f.sum() == 8
+
+
+def test_alarm_area_counts_masked_pixels_in_the_denominator():
+    """utils2.py:335-336,352: ref_final = ref_consider[mask_amazon_ts == 1] keeps the pixels the area filter / the border
+    mask zeroed, so the alarm area divides by the number of mask_amazon_ts == 1 pixels."""
+    prob = np.zeros((6, 8)); prob[0, 0] = 0.9; prob[2:5, 2:6] = 0.8
+    ref = np.zeros((6, 8)); ref[2:4, 2:6] = 1; ref[5, :] = 2
+    mask = np.ones((6, 8)); mask[:, 7] = 0
+    rec, prec, aa = AO.metrics_aa_recall_one(0.5, prob, ref, mask, 4)
+    assert rec == 1.0 and prec == pytest.approx(8 / 12)
+    assert aa == pytest.approx(12 / (6 * 7))          # 42 selected pixels, not the 34 that survive the masks

@@ -209,6 +209,105 @@ def test_tanimoto_loss_callable_standalone():
     np.testing.assert_allclose(got, want, rtol=1e-5)
 
 
+def test_compiled_checkpoint_resumes_training_without_recompiling():
+    """train_ISPRS.py:471-480: load_model(checkpoint) -> set lr -> train_on_batch.  The checkpoint carries the loss
+    specification, loss weights, metric selection, optimizer slots and the iteration count."""
+    w = [1.1, 2.0, 0.5, 3.0, 0.0]
+    mk = lambda: dict(seg=weighted_categorical_crossentropy(w), bound=BinaryCrossentropy(), dist=MeanSquaredError(),
+                      color=Tanimoto_dual_loss())
+    x, y = O.synth_batch(1, 64, 3, N_CLS, seed=4, block=8)
+    m = build_model((64, 64, 3), N_CLS, True, "v2", dtype="fp32", seed=3)
+    m.compile(optimizer=Adam(lr=1e-3), loss=mk(), loss_weights=LW)
+    m.train_on_batch(x, y)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ckpt.h5")
+        m.save(path)
+        m2 = load_model(path)
+    assert m2.loss_spec == m.loss_spec and m2.metrics_names == m.metrics_names
+    assert m2.optimizer.iterations == 1 and isinstance(m2.optimizer, Adam)
+    m2.optimizer.lr = 1e-3
+    a = m.train_on_batch(x, y)
+    b = m2.train_on_batch(x, y)                      # second Adam step on both: same slots, same bias correction
+    np.testing.assert_allclose(a, b, rtol=1e-6)
+    for k, v in m.net.get_weights().items():
+        np.testing.assert_allclose(m2.net.get_weights()[k].numpy(), v.numpy(), rtol=1e-6, atol=1e-7, err_msg=k)
+    # compile(optimizer=None) keeps the restored optimizer and its state
+    m2.compile(loss=mk(), loss_weights=LW)
+    assert m2.optimizer.iterations == 2
+    # a different optimizer object drops the old slots (Adam -> SGD must not keep running the Adam kernel)
+    m2.compile(optimizer=SGD(lr=1e-2, momentum=0.8), loss=mk(), loss_weights=LW)
+    assert m2._opt_state is None and m2._opt_launch is None
+    m2.train_on_batch(x, y)
+    assert set(m2._opt_state) == {"vel"}
+
+
+def test_compile_metrics_selection_is_honoured():
+    from resuneta_b200.keras_api import FalseNegatives, TruePositives
+    m = build_model((64, 64, 3), N_CLS, True, "v2", dtype="fp32")
+    x, y = O.synth_batch(1, 64, 3, N_CLS, seed=1, block=8)
+    m.compile(optimizer=SGD(lr=0.0), loss={k: Tanimoto_dual_loss() for k in LW})
+    full = m.train_on_batch(x, y)
+    assert len(full) == 10
+    m.compile(optimizer=SGD(lr=0.0), loss={k: Tanimoto_dual_loss() for k in LW},
+              metrics={"seg": [FalseNegatives(), "accuracy", TruePositives()]})
+    assert m.metrics_names[5:] == ["seg_false_negatives", "seg_accuracy", "seg_true_positives"]
+    sub = m.train_on_batch(x, y)
+    assert len(sub) == 8 and sub[5:] == [full[9], full[5], full[6]]
+    with pytest.raises(ValueError):
+        m.compile(optimizer=SGD(), loss={k: Tanimoto_dual_loss() for k in LW}, metrics={"seg": ["auc"]})
+    with pytest.raises(ValueError):
+        m.compile(optimizer=SGD(), loss={k: Tanimoto_dual_loss() for k in LW}, metrics={"bound": ["accuracy"]})
+
+
+def test_element_wise_loss_callables_standalone():
+    """utils.py:466-491 returns [B,H,W]; the keras loss objects return their SUM_OVER_BATCH_SIZE mean."""
+    rng = np.random.RandomState(3)
+    y = np.eye(3, dtype=np.float32)[rng.randint(0, 3, (2, 8, 8))]
+    p = rng.rand(2, 8, 8, 3).astype(np.float32) + 0.05
+    w = [1.1, 9.0, 0.0]
+    got = weighted_categorical_crossentropy(w)(y, p)
+    want = O.weighted_categorical_crossentropy(w)(torch.from_numpy(y).double(), torch.from_numpy(p).double()).numpy()
+    assert got.shape == (2, 8, 8)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+    ps = p / p.sum(-1, keepdims=True)
+    np.testing.assert_allclose(BinaryCrossentropy()(y, ps),
+                               O.binary_crossentropy(torch.from_numpy(y).double(), torch.from_numpy(ps).double()).mean().item(),
+                               rtol=1e-5)
+    np.testing.assert_allclose(MeanSquaredError()(y, ps),
+                               O.mean_squared_error(torch.from_numpy(y).double(), torch.from_numpy(ps).double()).mean().item(),
+                               rtol=1e-5)
+    with pytest.raises(ValueError):
+        weighted_categorical_crossentropy(w)(y, p[:1])
+
+
+def test_evaluate_and_fit_use_the_short_last_batch_and_callback_modes():
+    from resuneta_b200 import EarlyStopping, ModelCheckpoint
+    m = build_model((64, 64, 3), 3, False, "v1", dtype="fp32")
+    m.compile(optimizer=SGD(lr=0.0), loss=weighted_categorical_crossentropy([1.0, 2.0, 0.0]))
+    x, y = O.synth_batch(3, 64, 3, 3, seed=1, block=16)
+    per = [np.array(m.test_on_batch(x[i:i + 1], y["seg"][i:i + 1])) for i in range(3)]
+    ev = m.evaluate(x, y["seg"], batch_size=2)                      # batches of 2 and 1: sample-weighted mean
+    want = np.concatenate([np.mean(per, axis=0)[:2], np.sum(per, axis=0)[2:]])     # loss, accuracy: means; counters: totals
+    np.testing.assert_allclose(ev, want, rtol=1e-5)
+    np.testing.assert_allclose(m.evaluate(x[:1], y["seg"][:1], batch_size=8), per[0], rtol=1e-6)   # n < batch_size
+    calls = []
+    orig = m.train_on_batch
+    m.train_on_batch = lambda xb, yb, **k: (calls.append(len(xb)), orig(xb, yb, **k))[1]
+    m.fit(x, y["seg"], batch_size=2, epochs=1, verbose=0, shuffle=False)
+    assert calls == [2, 1]
+    # mode='max' / accuracy-like monitors maximise
+    es = EarlyStopping(monitor="val_accuracy", patience=2)
+    assert [es.on_epoch_end(m, i, {"val_accuracy": v}) for i, v in enumerate([0.5, 0.6, 0.55, 0.58])] == [False, False, False, True]
+    saved = []
+    ck = ModelCheckpoint("unused", monitor="val_accuracy", save_best_only=True, mode="max")
+    m.save = lambda path: saved.append(path)
+    for v in (0.5, 0.4, 0.7):
+        ck.on_epoch_end(m, 0, {"val_accuracy": v})
+    assert len(saved) == 2
+    with pytest.raises(ValueError):
+        EarlyStopping(mode="best")
+
+
 def test_fit_with_callbacks_runs():
     from resuneta_b200 import EarlyStopping
     m = build_model((64, 64, 3), 3, False, "v1", dtype="fp32")

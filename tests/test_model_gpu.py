@@ -258,6 +258,20 @@ def test_scene_inference_config5_reduced():
     assert acc == a2 and np.array_equal(f1, f2)
 
 
+def test_scene_inference_many_batches_without_reference_labels():
+    """without `reference` nothing in predict_scene synchronises between batches, so the pinned staging
+    buffer of batch k+1 must not be refilled while the asynchronous copy of batch k is still queued.  Eleven batches of
+    distinct patches, compared with predict() (which synchronises per batch)."""
+    n = 5
+    m = build_model((64, 64, 3), n, True, "v2", dtype="bf16", seed=3)
+    rng = np.random.RandomState(11)
+    scene = rng.rand(64 * 5, 64 * 9, 3).astype(np.float32)          # 45 patches -> 11 batches of 4 + 1
+    for _ in range(3):                                              # repeat: a race would not hit every time
+        r = inference.predict_scene(m, scene, None, patch_size=64, batch_size=4, num_classes=n)
+        want = m.predict(inference.extract_patches(scene, 64), batch_size=4)["seg"].argmax(-1)
+        np.testing.assert_array_equal(r["seg_pred"], want)
+
+
 def test_patch_loader_feeds_train_on_batch_from_pinned_memory(tmp_path):
     """§8f rank 1: batches read by data.PatchBatchLoader (pinned tensors, no staging copy) give exactly the step results
     of the reference-style loop that np.load()s every file into numpy batch buffers (train_ISPRS.py:115-148)."""
@@ -334,7 +348,7 @@ def test_bf16_step_survives_hostile_launch_order(monkeypatch):
     p = rand_params("v2", hw, 3, n)
     x, y = O.synth_batch(B, hw, 3, n, seed=21, block=16)
     upd = []
-    for mode in ("plain", "plain", "hostile"):
+    for mode in ("plain", "plain", "plain", "hostile"):
         m = build_model((hw, hw, 3), n, True, "v2", dtype="bf16")
         m.use_cuda_graph = False
         m.net.set_weights(p)
@@ -349,16 +363,27 @@ def test_bf16_step_survives_hostile_launch_order(monkeypatch):
         assert any(getattr(op, "join", False) for op in pl.bwd)
         upd.append({k: (after[k] - before[k]).double() for k in before if "/moving_" not in k})
         monkeypatch.undo()
-    A, Bv, H = upd
+    *plain, H = upd
+    A = plain[0]
     cat = lambda u: torch.cat([u[k].flatten() for k in A])
-    floor = float((cat(Bv) - cat(A)).norm() / cat(A).norm())
-    whole = float((cat(H) - cat(A)).norm() / cat(A).norm())
+    dist = lambda u, v: float((cat(u) - cat(v)).norm())
+    total = float(cat(A).norm())
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    floor = max(dist(plain[i], plain[j]) for i, j in pairs) / total
+    whole = min(dist(H, q) for q in plain) / total
     assert whole <= 2.0 * floor + 1e-3, (whole, floor)
+    checked = 0
     for k in A:
         na = float(A[k].norm())
-        if na > 0:
-            dh, ds = float((H[k] - A[k]).norm()), float((Bv[k] - A[k]).norm())
-            assert dh <= 3.0 * ds + 0.02 * na, (k, dh / na, ds / na)
+        # a parameter whose true gradient is zero (a bias in front of a BatchNormalization) or
+        # rounding-sized carries no signal: two identical runs already differ by 100 % there
+        if na < 1e-3 * total:
+            continue
+        checked += 1
+        ds = max(float((plain[i][k] - plain[j][k]).norm()) for i, j in pairs)     # run-to-run floor, three plain runs
+        dh = min(float((H[k] - q[k]).norm()) for q in plain)
+        assert dh <= 3.0 * ds + 0.02 * na, (k, dh / na, ds / na)
+    assert checked >= 40, checked
 
 
 @pytest.mark.parametrize("variant", ["v2", "v1"])
@@ -394,3 +419,65 @@ def test_bf16_gradients_point_where_the_fp64_oracle_points(variant):
     for k in big:
         cos = float(mine[k] @ ref[k] / (mine[k].norm() * ref[k].norm()))
         assert cos >= 0.5, (k, cos)      # the earliest layers (longest bf16 chain) measure 0.8; a wrong layer measures ~0
+
+
+def test_bf16_train_step_at_the_benchmarked_shape_matches_fp64_oracle(capsys):
+    """BASELINE config 2's network (256 x 256 x 3, 6 classes, model2, multitask, bf16 tensor-core path: thin layers at
+    H = 256 in halo and box mode, the 1024-channel 8 x 8 level, four-level PSPPooling) for one Tanimoto x 4 SGD step at
+    batch 2 against the oracle in float64: loss and per-head losses within north_star's 1e-2, whole gradient and
+    per-layer cosines reported."""
+    n, hw, B = 6, 256, 2
+    p = rand_params("v2", hw, 3, n)
+    x, y = O.synth_batch(B, hw, 3, n, seed=33, block=16)
+    lw = dict(seg=1.0, bound=1.0, dist=1.0, color=1.0)
+    p64 = {k: v.double() for k, v in p.items()}
+    tot, per, out, grads, _ = O.loss_and_grads(p64, torch.from_numpy(x).double(),
+                                               {k: torch.from_numpy(v).double() for k, v in y.items()},
+                                               {k: O.tanimoto_dual_loss for k in lw}, lw, n)
+    m = build_model((hw, hw, 3), n, True, "v2", dtype="bf16")
+    m.net.set_weights(p)
+    # forward in inference mode (moving statistics) at the same shape: probabilities within 1e-2
+    outp = m.predict(x, batch_size=B)
+    refp = O.forward(p64, torch.from_numpy(x).double(), False, n, True, "v2")
+    for k in outp:
+        assert rel_l2(outp[k], refp[k].numpy()) <= 1e-2, (k, rel_l2(outp[k], refp[k].numpy()))
+    m.compile(optimizer=SGD(lr=1.0), loss={k: Tanimoto_dual_loss() for k in lw}, loss_weights=lw)
+    before = {k: v.clone() for k, v in m.net.get_weights().items()}
+    res = m.train_on_batch(x, y)
+    after = m.net.get_weights()
+    assert abs(res[0] - tot.item()) <= 1e-2 * abs(tot.item()), (res[0], tot.item())
+    for a, b in zip(res[1:5], per):
+        assert abs(a - b.item()) <= 1e-2 * max(abs(b.item()), 1e-3)
+    keys = [k for k in grads if k in before and "/moving_" not in k]
+    mine = {k: (before[k] - after[k]).double().flatten() for k in keys}
+    ref = {k: grads[k].double().flatten() for k in keys}
+    gm, gr = torch.cat([mine[k] for k in keys]), torch.cat([ref[k] for k in keys])
+    rel, cos = float((gm - gr).norm() / gr.norm()), float(gm @ gr / (gm.norm() * gr.norm()))
+    big = [k for k in keys if float(ref[k].norm()) >= 3e-3 * float(gr.norm())]
+    cosk = {k: float(mine[k] @ ref[k] / (mine[k].norm() * ref[k].norm())) for k in big}
+    worst = sorted(cosk.items(), key=lambda kv: kv[1])[:8]
+    with capsys.disabled():
+        print(f"\n[256^2 bf16 step vs fp64 oracle] loss {res[0]:.6f} vs {tot.item():.6f}; whole gradient rel-L2 {rel:.4f} "
+              f"cosine {cos:.5f}; {len(big)} layers checked, lowest cosines: "
+              + ", ".join(f"{k} {c:.3f}" for k, c in worst))
+    assert rel <= 0.06 and cos >= 0.998, (rel, cos)
+    assert len(big) >= 40
+    for k, c in cosk.items():
+        assert c >= 0.9, (k, c)
+
+
+def test_bf16_training_converges_like_fp32_on_the_toy_task():
+    """30 Adam steps of the bf16 tensor-core step on the learnable toy task: the loss falls and tracks the fp32
+    validation mode (same initial weights, same batches) within 10 % of the loss at every fifth step."""
+    n, hw = 4, 64
+    hist = {}
+    for dtype in ("fp32", "bf16"):
+        m = build_model((hw, hw, 3), n, True, "v2", dtype=dtype, seed=5)
+        m.compile(optimizer=Adam(lr=2e-3), loss={k: Tanimoto_dual_loss() for k in LW}, loss_weights=LW)
+        losses = []
+        for step in range(6):
+            _, _, last = _train_toy(m, n, hw, 5, seed=100 + step)
+            losses.append(last[0])
+        hist[dtype] = np.array(losses)
+    assert hist["bf16"][-1] < 0.8 * hist["bf16"][0], hist
+    np.testing.assert_allclose(hist["bf16"], hist["fp32"], rtol=0.10)
