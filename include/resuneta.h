@@ -73,11 +73,12 @@ int rsa_igemm_wgrad(const rsa_seg_t* segs, int nseg, int in_dtype, const void* d
  * stats==NULL selects inference mode (moving statistics). */
 int rsa_bn_stats(const void* x, int dtype, int64_t M, int C, double* stats, void* stream);
 /* nout outputs y_k = act(gamma_k * xhat + beta_k), all sharing the statistics of x
- * (the ResBlock-a branches normalise the same input, model2.py:17). */
+ * (the ResBlock-a branches normalise the same input, model2.py:17).  meaninv_out (optional, fp32 [2][C]) receives
+ * {mean, invstd} of x: the table the fused BatchNorm-backward epilogue of rsa_conv_tc2_fwd reads. */
 int rsa_bn_apply(const void* x, int dtype, int64_t M, int C, int nout, void* const* outs,
                  const float* const* gammas, const float* const* betas, const double* stats, double count,
                  const float* const* moving_means, const float* const* moving_vars, float eps, int relu,
-                 void* stream);
+                 float* meaninv_out, void* stream);
 /* red[2*C] (double, zeroed by caller) += { sum g, sum g*xhat },  g = dy * (act>0 if act) */
 int rsa_bn_bwd_reduce(const void* dy, const void* x, const void* act, int dtype, int64_t M, int C,
                       const double* stats, double count, float eps, double* red, void* stream);
@@ -166,16 +167,12 @@ int rsa_sgd_step(float* param, const float* grad, float* vel, int64_t n, float l
 int rsa_argmax_confusion(const float* prob, int64_t M, int C, int32_t* pred_label, const int32_t* true_label,
                          int K, int64_t* cm, void* stream);
 
-/* ---- tensor-core (tcgen05 + TMA) convolution, bf16 mode ------------------------------------------------
- * out[n,h,w,:] = epi( sum_tap sum_ci x[n, h+dy*dil, w+dx*dil, ci] * wt[tap][co][ci] + bias ), taps = 9 (3x3)
- * or 1; x/out/residual/mask bf16 NHWC, wt bf16 [taps][Cout][Cin]; dil < 0 gives the data gradient when wt
- * is the [tap][Cin_fwd][Cout_fwd] copy.  Epilogue flags as rsa_igemm_fwd.  Replaces cuDNN's dilated
- * Conv2D forward / backward-data that keras calls at model2.py:19-24,153-178. */
+/* ---- tensor-core (tcgen05 + TMA) convolutions, bf16 mode --------------------------------------------------
+ * 1 if the 3x3 layer (Cin, Cout at N x H x W) is taken by the tensor-core kernels (rsa_conv_tc2_fwd / rsa_conv_tc3_fwd
+ * forward and data gradient, rsa_conv_tc_wgrad / rsa_conv_tc3_wgrad weight gradient) that replace cuDNN's dilated Conv2D
+ * behind keras at model2.py:19-24,153-178. */
 int rsa_conv_tc_supported(int N, int H, int W, int Cin, int Cout);
-int rsa_conv_tc_fwd(const void* x, const void* wt, const float* bias, void* out, const void* residual,
-                    const void* mask, double* stats, int N, int H, int W, int Cin, int Cout, int taps, int dil,
-                    int accumulate, int relu, void* stream);
-/* Persistent generalisation of rsa_conv_tc_fwd (conv_tc2.cu):
+/* Persistent tcgen05 / TMA implicit-GEMM convolution (conv_tc2.cu): the 3x3 layers with C >= 128 and every 1x1 layer:
  * out[n,h,w,:Cout] = epi( sum_tap sum_src sum_c x_src[n, h*s+dy*dil, w*s+dx*dil, c] * wt[tap][co][koff_src+c]
  *                        + bias + sum_u up_{shift_u}(q_u) )
  * x0 / optional x1: bf16 NHWC sources, K-concatenated (taps = 1; Concatenate model2.py:83) or the single 3x3 source
@@ -202,8 +199,6 @@ int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void*
  *   out = d(a) * relu-mask recomputed from bnr_x, stats += {sum g, sum g*xhat} (residual/accumulate still allowed, no mask).
  * Replaces cuDNN's Conv2D forward / backward-data behind model2.py:19-24,153-178 for the C = 32 layers. */
 int rsa_conv_tc3_supported(int N, int H, int W, int C);
-/* diagnostic: per-CTA barrier-wait cycle counters of the following rsa_conv_tc3_fwd launches (NULL switches it off) */
-int rsa_conv_tc3_set_trace(long long* buf);
 int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, const float* const* biases, const int* dils, int nbr,
                      void* out, const void* residual, const void* mask, double* stats, int N, int H, int W, int C,
                      int accumulate, int relu, const void* bnr_x, const double* bnr_stats, double bnr_count, float bnr_eps,

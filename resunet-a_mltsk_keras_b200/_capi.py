@@ -68,7 +68,7 @@ _SIGS = {
     "rsa_bn_stats": [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p],
     "rsa_bn_apply": [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_double,
-                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_float, C.c_int, C.c_void_p],
+                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_float, C.c_int, C.c_void_p, C.c_void_p],
     "rsa_bn_bwd_reduce": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_double,
                           C.c_float, C.c_void_p, C.c_void_p],
     "rsa_bn_bwd_apply": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_double,
@@ -125,8 +125,6 @@ _SIGS = {
     "rsa_label_hsv": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
     "rsa_head_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p],
     "rsa_axpy": [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p],
-    "rsa_conv_tc_fwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "rsa_conv_tc2_fwd": [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                          C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p,
@@ -147,7 +145,7 @@ _SIGS = {
 
 EXPORTS = sorted(list(_SIGS) + ["rsa_version", "rsa_last_error", "rsa_device_check", "rsa_conv_tc_supported",
                                 "rsa_conv_tc2_supported", "rsa_conv_tc3_supported", "rsa_conv_tc3_wgrad_supported",
-                                "rsa_label_workspace_bytes", "rsa_conv_tc3_set_trace"])
+                                "rsa_label_workspace_bytes"])
 
 
 def load_cdll(path=LIB_PATH):
@@ -171,8 +169,6 @@ def load_cdll(path=LIB_PATH):
     dll.rsa_conv_tc3_supported.restype = C.c_int
     dll.rsa_conv_tc3_wgrad_supported.argtypes = [C.c_int] * 5
     dll.rsa_conv_tc3_wgrad_supported.restype = C.c_int
-    dll.rsa_conv_tc3_set_trace.argtypes = [C.c_void_p]
-    dll.rsa_conv_tc3_set_trace.restype = C.c_int
     dll.rsa_label_workspace_bytes.argtypes = [C.c_int] * 4
     dll.rsa_label_workspace_bytes.restype = C.c_int64
     return dll
@@ -249,11 +245,11 @@ class Lib:
             arr[i] = t.data_ptr()
         return arr
 
-    def bn_apply(self, x, M, C_, outs, gammas, betas, stats, count, mmeans, mvars, eps, relu):
+    def bn_apply(self, x, M, C_, outs, gammas, betas, stats, count, mmeans, mvars, eps, relu, meaninv=None):
         return self._bind("rsa_bn_apply", _p(x), dtype_code(x), M, C_, len(outs), self._ptr_array(outs),
                           self._ptr_array(gammas), self._ptr_array(betas), _p(stats), float(count),
-                          self._ptr_array(mmeans), self._ptr_array(mvars), float(eps), int(relu),
-                          keep=(x, outs, gammas, betas, stats, mmeans, mvars))
+                          self._ptr_array(mmeans), self._ptr_array(mvars), float(eps), int(relu), _p(meaninv),
+                          keep=(x, outs, gammas, betas, stats, mmeans, mvars, meaninv))
 
     def bn_bwd_reduce(self, dy, x, act, M, C_, stats, count, eps, red):
         return self._bind("rsa_bn_bwd_reduce", _p(dy), _p(x), _p(act), dtype_code(x), M, C_, _p(stats),
@@ -346,13 +342,6 @@ class Lib:
     # -- tensor-core convolution (bf16) ------------------------------------------------------------
     def conv_tc_supported(self, N, H, W, Cin, Cout):
         return bool(self.dll.rsa_conv_tc_supported(N, H, W, Cin, Cout))
-
-    def conv_tc_fwd(self, x, wt, bias, out, N, H, W, Cin, Cout, taps, dil, residual=None, mask=None, stats=None,
-                    accumulate=False, relu=False):
-        assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
-        return self._bind("rsa_conv_tc_fwd", _p(x), _p(wt), _p(bias), _p(out), _p(residual), _p(mask), _p(stats),
-                          N, H, W, Cin, Cout, taps, dil, int(accumulate), int(relu),
-                          keep=(x, wt, bias, out, residual, mask, stats))
 
     def conv_tc2_supported(self, N, H, W, C0, C1, Cout):
         return bool(self.dll.rsa_conv_tc2_supported(N, H, W, C0, C1, Cout))

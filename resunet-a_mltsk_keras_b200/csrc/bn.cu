@@ -59,6 +59,8 @@ struct ApplyParams {
   const float* mmean[MAX_OUT];
   const float* mvar[MAX_OUT];
   int nout;
+  float* meaninv;     // optional [2][C] {mean, invstd} table written by block 0 (read by the fused BatchNorm-backward
+                      // epilogue of rsa_conv_tc2_fwd)
 };
 
 template <typename T, int NOUT>
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const T* __restrict__ x, i
     const float scv = ap.gamma[k][c] * invstd;
     tab[(2 * k) * C + c] = scv;
     tab[(2 * k + 1) * C + c] = ap.beta[k][c] - mean * scv;
+    if (ap.meaninv && blockIdx.x == 0 && k == 0) { ap.meaninv[c] = mean; ap.meaninv[C + c] = invstd; }
   }
   __syncthreads();
   const int tpr = C / V, rpi = NT / tpr, tid = threadIdx.x;
@@ -516,12 +519,13 @@ extern "C" int rsa_bn_stats(const void* x, int dtype, int64_t M, int C, double* 
 extern "C" int rsa_bn_apply(const void* x, int dtype, int64_t M, int C, int nout, void* const* outs,
                             const float* const* gammas, const float* const* betas, const double* stats,
                             double count, const float* const* moving_means, const float* const* moving_vars,
-                            float eps, int relu, void* stream) {
+                            float eps, int relu, float* meaninv_out, void* stream) {
   RSA_REQUIRE(x && outs && gammas && betas && M > 0 && nout >= 1 && nout <= MAX_OUT, RSA_ERR_SHAPE,
               "bn_apply: bad args");
   RSA_REQUIRE(stats || (moving_means && moving_vars), RSA_ERR_SHAPE, "bn_apply: no statistics given");
   ApplyParams ap;
   ap.nout = nout;
+  ap.meaninv = meaninv_out;
   for (int k = 0; k < MAX_OUT; ++k) {
     int kk = k < nout ? k : 0;
     ap.out[k] = outs[kk]; ap.gamma[k] = gammas[kk]; ap.beta[k] = betas[kk];

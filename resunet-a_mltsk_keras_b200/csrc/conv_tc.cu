@@ -1,24 +1,11 @@
-// conv_tc.cu — dilated 3x3 (and 1x1) convolution as an implicit GEMM on the 5th-gen tensor cores.
-//
-// The performance path of the ResBlock-a branches (model2.py:19-24) and the head 3x3 convolutions
-// (model2.py:153-178) in bf16 mode, forward and data-gradient (same kernel: negated dilation and the
-// [tap][Cin][Cout] weight copy).  B200-native structure:
-//
-//   * operands: NHWC bf16 activations (already normalised + ReLU'd by bn.cu, so 'same' zero padding is
-//     exactly TMA's out-of-bounds zero fill) and a bf16 weight copy laid out [tap][N][K] (K-major).
-//   * one CTA = one 128-pixel spatial tile (TN images x TH rows x TW cols) x BN output channels.
-//     A-tiles are fetched by 4-D TMA boxes {KC channels, TW, TH, TN} at the *shifted* coordinate
-//     (w0+dx*d, h0+dy*d): the dilation-31 halo never exists in shared memory, and a tap whose box lies
-//     completely outside the image is skipped by producer and MMA issuer alike.
-//   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) issued by one elected thread, fp32
-//     accumulators in TMEM; smem ring of STAGES {A,B} tiles with full/empty mbarriers; tcgen05.commit
-//     releases a stage / publishes the accumulator.
-//   * epilogue warps: tcgen05.ld 32x32b -> +bias (+identity / +running branch sum) (ReLU) (mask) ->
-//     bf16 NHWC stores, and the per-channel sum / sum-of-squares the next BatchNormalization needs
-//     (warp transpose through smem, one double atomic per channel per CTA).
-//
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue
-// (TMEM lane quarter = warp_id % 4).
+// conv_tc.cu — tensor-core helpers of the bf16 path that are not convolutions forward:
+//   * conv_tc_wgrad_kernel: weight gradient of the dilated 3x3 convolutions with C >= 128 (and the large dilations at
+//     C = 64), MN-major operands, K = pixels split across CTAs (Conv2D backward-filter, model2.py:19-24);
+//   * pw_wgrad_kernel: weight gradient of the 1x1 convolutions (model2.py:37,84,92,103-111);
+//   * bias_grad_kernel, pack_weights_kernel (fp32 HWIO master weights -> bf16 [tap][Cout][Cin] / [tap][Cin][Cout] copies);
+//   * rsa_conv_tc_supported: which 3x3 layers the tensor-core path takes.
+// The forward / data-gradient kernels live in conv_tc2.cu (C >= 128 and every 1x1) and conv_tc3.cu (C = 32 / 64); the
+// first-generation forward kernel that used to be here was retired in round 2 (nothing issued it any more).
 #include "tc_common.cuh"
 
 namespace {
@@ -26,202 +13,6 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NTHREADS = 192;
 
-struct ConvTcParams {
-  int N, H, W, Cin, Cout;
-  int dil;            // signed: forward +d, data-gradient -d
-  int taps;           // 9 or 1
-  int TW, TH, TN, tiles_w, tiles_h;
-  const float* bias;
-  bf16* out;
-  const bf16* residual;
-  const bf16* mask;
-  double* stats;
-  int accumulate, relu;
-};
-
-template <int BN, int KC, int STAGES>
-struct SmemLayout {
-  static constexpr int A_BYTES = TILE_M * KC * 2;
-  static constexpr int B_BYTES = BN * KC * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RING = STAGES * STAGE_BYTES;
-  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4 + 2 * BN * 4;   // per-warp transpose + channel sums
-  static constexpr int BAR_OFF = RING > EPI_BYTES ? RING : EPI_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
-};
-
-template <int BN, int KC, int STAGES>
-__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB,
-                                                           const ConvTcParams p) {
-  using L = SmemLayout<BN, KC, STAGES>;
-  constexpr int SWZ = KC * 2;                         // swizzle span in bytes (128 or 64)
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;   // power of two >= 32
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile coordinates
-  int mt = blockIdx.x;
-  const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-  const int th = mt % p.tiles_h; mt /= p.tiles_h;
-  const int n0 = mt * p.TN, h0 = th * p.TH, w0 = tw * p.TW;
-  const int nb = blockIdx.y;      // output-channel block
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int kchunks = p.Cin / KC;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0, phase = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
-        const int ch = h0 + dy * p.dil, cw = w0 + dx * p.dil;
-        if (ch + p.TH <= 0 || ch >= p.H || cw + p.TW <= 0 || cw >= p.W) continue;   // tap entirely in padding
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_4d(sa, &tmA, &full_bar[stage], kc * KC, cw, ch, n0);
-          tma_load_3d(sb, &tmB, &full_bar[stage], kc * KC, nb * BN, tap);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, BN);
-      int stage = 0, phase = 0;
-      uint32_t accum = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
-        const int ch = h0 + dy * p.dil, cw = w0 + dx * p.dil;
-        if (ch + p.TH <= 0 || ch >= p.H || cw + p.TW <= 0 || cw >= p.W) continue;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
-          const uint64_t adesc = make_kmajor_desc(sa, SWZ);
-          const uint64_t bdesc = make_kmajor_desc(sb, SWZ);
-#pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the (addr>>4) field
-            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
-            accum = 1;
-          }
-          umma_commit(&empty_bar[stage]);     // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-      umma_commit(tmem_full);                 // accumulator complete
-    }
-  } else {
-    // ===== epilogue (warps 2..5) =====
-    const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int ew = warp - 2;                  // 0..3 private smem slice
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    float* tr = reinterpret_cast<float*>(smem) + ew * 32 * 33;
-    float* csum = reinterpret_cast<float*>(smem) + 4 * 32 * 33;
-    float* csq = csum + BN;
-    if (p.stats) {
-      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) csum[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    const int r = q * 32 + lane;              // row of the 128-pixel tile
-    const int pw = w0 + r % p.TW;
-    const int ph = h0 + (r / p.TW) % p.TH;
-    const int pn = n0 + r / (p.TW * p.TH);
-    const bool valid = pn < p.N && ph < p.H && pw < p.W;
-    const size_t pix = ((size_t)pn * p.H + ph) * p.W + pw;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      const int co = nb * BN + c0;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + co + j) : 0.f);
-      const size_t o = pix * p.Cout + co;
-      if (valid) {
-        if (p.residual) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) { float t[8]; ldv<bf16>(p.residual + o + j, t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[j + i] += t[i]; }
-        }
-        if (p.accumulate) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) { float t[8]; ldv<bf16>(p.out + o + j, t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[j + i] += t[i]; }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.mask) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) { float t[8]; ldv<bf16>(p.mask + o + j, t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[j + i] = t[i] > 0.f ? f[j + i] : 0.f; }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) stv<bf16>(p.out + o + j, f + j);
-      }
-      if (p.stats) {
-        // transpose through smem: lane c sums channel c over this warp's 32 pixels
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = valid ? f[j] : 0.f;
-        __syncwarp();
-        float s = 0.f, sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { float t = tr[i * 33 + lane]; s += t; sq += t * t; }
-        atomicAdd(&csum[c0 + lane], s);
-        atomicAdd(&csq[c0 + lane], sq);
-        __syncwarp();
-      }
-    }
-    if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < BN; i += 128) {
-        atomicAdd(p.stats + nb * BN + i, (double)csum[i]);
-        atomicAdd(p.stats + p.Cout + nb * BN + i, (double)csq[i]);
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
-  }
-}
-
-// ---- weight packing: fp32 HWIO master -> bf16 [tap][Cout][Cin] (forward) and [tap][Cin][Cout] (dgrad) ----
 struct PackEntry { long long src_off, fwd_off, bwd_off; int taps, Cin, Cout, pad; };
 
 constexpr int PACK_MAXL = 512;
@@ -278,21 +69,6 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   }
 }
 
-// ---- host side -----------------------------------------------------------------------------------------------
-template <int BN, int KC, int STAGES>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, dim3 grid, cudaStream_t st) {
-  using L = SmemLayout<BN, KC, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-    if (e != cudaSuccess) { rsa_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
-    configured = true;
-  }
-  conv_tc_kernel<BN, KC, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(tmA, tmB, p);
-  RSA_CHECK_LAUNCH();
-  return RSA_OK;
-}
-
 }  // namespace
 
 /* 1 if the tcgen05 path handles this shape: channels multiples of 32 (64 above 32), spatial side a
@@ -304,59 +80,6 @@ extern "C" int rsa_conv_tc_supported(int N, int H, int W, int Cin, int Cout) {
   return 1;
 }
 
-/* out[n,h,w,:] = epi( sum_tap sum_ci x[n, h+dy*dil, w+dx*dil, ci] * wt[tap][co][ci] + bias )
- * x, out, residual, mask: bf16 NHWC; wt: bf16 [taps][Cout][Cin]; dil may be negative (data gradient).
- * Replaces cuDNN's Conv2D 3x3 dilated 'same' forward and backward-data called by keras at
- * model2.py:19-24,153-178.  Epilogue flags as rsa_igemm_fwd. */
-extern "C" int rsa_conv_tc_fwd(const void* x, const void* wt, const float* bias, void* out, const void* residual,
-                               const void* mask, double* stats, int N, int H, int W, int Cin, int Cout, int taps,
-                               int dil, int accumulate, int relu, void* stream) {
-  RSA_REQUIRE(x && wt && out, RSA_ERR_SHAPE, "conv_tc_fwd: null pointer");
-  RSA_REQUIRE(taps == 9 || taps == 1, RSA_ERR_SHAPE, "conv_tc_fwd: taps must be 1 or 9");
-  RSA_REQUIRE(rsa_conv_tc_supported(N, H, W, Cin, Cout), RSA_ERR_SHAPE,
-              "conv_tc_fwd: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d", N, H, W, Cin, Cout);
-  EncodeTiledFn enc = get_encode();
-  RSA_REQUIRE(enc, RSA_ERR_CUDA, "conv_tc_fwd: cuTensorMapEncodeTiled not available from the driver");
-  ConvTcParams p;
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.dil = dil; p.taps = taps;
-  p.TW = W < 16 ? W : 16;
-  p.TH = H < TILE_M / p.TW ? H : TILE_M / p.TW;
-  p.TN = TILE_M / (p.TW * p.TH);
-  p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
-  const int tiles_n = (N + p.TN - 1) / p.TN;
-  p.bias = bias; p.out = (bf16*)out; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask; p.stats = stats;
-  p.accumulate = accumulate; p.relu = relu;
-  const int KC = Cin >= 64 ? 64 : 32;
-  const int mtiles = p.tiles_w * p.tiles_h * tiles_n;
-  int BN = Cout >= 128 ? 128 : Cout;
-  if (BN == 128 && mtiles * (Cout / 128) < 120) BN = 64;   // deep levels: more CTAs to fill 148 SMs
-  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUtensorMap tmA, tmB;
-  {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc_fwd: cuTensorMapEncodeTiled(A) failed (%d)", (int)r);
-  }
-  {
-    cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
-    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wt), gdim, gstr, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc_fwd: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
-  }
-  dim3 grid((unsigned)mtiles, (unsigned)(Cout / BN));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (KC == 32) return launch<32, 32, 6>(tmA, tmB, p, grid, st);          // Cin = 32 (=> Cout = 32 in this net)
-  if (BN == 128) return launch<128, 64, 3>(tmA, tmB, p, grid, st);
-  if (BN == 64) return launch<64, 64, 4>(tmA, tmB, p, grid, st);
-  RSA_REQUIRE(false, RSA_ERR_SHAPE, "conv_tc_fwd: no kernel for BN=%d KC=%d", BN, KC);
-}
 
 namespace {
 // =====================================================================================================

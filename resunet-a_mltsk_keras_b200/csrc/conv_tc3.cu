@@ -1,35 +1,37 @@
-// conv_tc3.cu — thin-layer (C = 32) dilated 3x3 'same' convolution on tcgen05, built around what the ncu captures
-// of conv_tc2 showed for these layers (profiles/r1b_*): the tensor pipe sat at 7 % because every 128-pixel tile paid
-// nine TMA round trips and a ~5.7k-cycle register epilogue on 4 warps; a first version of this kernel then showed
-// the single MMA-issuing thread (~100 cycles per 16-cycle N=32 MMA) and shared-memory operand bandwidth as the next
-// limits.  Hence:
+// conv_tc3.cu — thin-layer (C = 32 / 64) dilated 3x3 'same' convolution on tcgen05.
+//
+// History of what bounds these layers (profiles/r1b_*, scripts/exp_mma_rate.cu, scripts/iso_tc3.py):
+//   * conv_tc2 on them sat at 7 % of the tensor pipe: nine TMA round trips and a ~5.7k-cycle register epilogue on 4 warps per
+//     128-pixel tile.  Hence resident weights, halo tiles whose nine taps are shifted UMMA descriptors into ONE box (measured:
+//     with base_offset = 0 any row shift and any stride-byte-offset address a TMA-swizzled tile correctly), KT MMA-issuing
+//     warps (a single thread sustains one N=32 MMA per ~95 cycles, four reach the shared-memory operand limit of 40);
+//   * round 2 switched parts of the kernel off one at a time (RSA_TC3_DEBUG, scripts/iso_tc3.py; C = 32, d = 1, batch 16):
+//     whole kernel 50 us, MMA + loads without the epilogue 35 us, epilogue + stores without any MMA 44 us, and the bare
+//     barrier protocol with no data moved at all 23 us.  The epilogue PIPELINE - eight warps meeting at a staging buffer per
+//     128-pixel sub-tile, a ninth thread storing it and handing the buffer back, a side ring fed by that same thread - was
+//     the bottleneck, not the tensor core and not memory.
+// So the epilogue is now eight independent pipelines: every epilogue warp owns 32 pixels x 32 channels slices (one
+// tcgen05.ld.32x32b.x32, the TMEM lane quarter it may read), its own two staging buffers, its own TMA stores (box 8 x 4
+// pixels x 32 channels) and its own TMA side-input loads with a private mbarrier - no barrier is shared between epilogue
+// warps, the only hand-offs left are accumulator full / empty with the MMA warps.
 //
 //   * weights of all branches stay resident in shared memory for the life of the (persistent) CTA;
-//   * an item is 16 x (8*KT) pixels = KT accumulators; small dilations (|d| <= 3) load ONE halo box per item and
-//     form the nine taps as shifted UMMA descriptors into it (measured in scripts/exp_desc.cu: with base_offset = 0
-//     any row shift and any stride-byte-offset address a TMA-swizzled tile correctly); large dilations load one
-//     16 x (8*KT) box per tap.  Either way one stage feeds all KT sub-tiles;
-//   * KT warps issue the MMAs, one per sub-tile (independent accumulators), so the issue rate scales;
+//   * an item is 16 x (8*KT) pixels = KT accumulators; |d| <= 3: one halo box per item, larger dilations one box per tap;
 //   * up to four branches (ResBlock-a: dilations 1/3/15/31, model2.py:23-31) accumulate into the same TMEM tiles,
 //     so the branch sum and the identity add happen once, in the epilogue;
-//   * the epilogue is spread over 8 warps, prefetches its bf16 side inputs one sub-tile ahead, stages the bf16
-//     tile in shared memory (swizzled, conflict free) and leaves the global write to a TMA store issued by a
-//     dedicated warp; BatchNorm statistics of the stored values are reduced with a 16-wide shuffle butterfly.
+//   * BatchNorm statistics of the stored values: per-thread partial sums over all the slices of a warp, one 32-wide shuffle
+//     butterfly per warp at the end, per-warp shared-memory slots summed in a fixed order (reproducible), one double atomic
+//     per channel per CTA.
 //
-// What bounds it now (scripts/exp_mma_rate.cu, scripts/trace_tc3.py): an SS-mode tcgen05.mma reads its operands from
-// shared memory at 128 B/clk, i.e. 32 cycles for the 128x16 A slice + N/4 for B: 40 cycles per N=32 MMA against a 16-cycle
-// tensor floor, whatever the swizzle.  A C=32 sub-tile (18 MMAs, 90 KB of operand reads) therefore cannot take less than
-// ~700 cycles = 19.7 us per launch at batch 16; an experiment with the stores / TMEM loads removed runs at 35 us, the
-// full kernel at 42-46 us.  (Direct global stores from the epilogue instead of the staged TMA store were measured slower.)
-//
-// Replaces cuDNN's Conv2D forward / backward-data behind keras Conv2D(32, 3, dilation_rate=d, padding='same') at
-// model2.py:19-24,153-178 for the C = 32 layers (enc1, dec1, heads).
+// Replaces cuDNN's Conv2D forward / backward-data behind keras Conv2D(C, 3, dilation_rate=d, padding='same') at
+// model2.py:19-24,153-178 for the C = 32 / 64 layers (enc1/2, dec1/2, heads).
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int T3_MAXBR = 4;
-constexpr int T3_MAXSB = 4;
+constexpr int T3_EW = 8;              // epilogue warps
+constexpr int T3_SLICE = 32 * 64;     // bytes of one epilogue slice: 32 pixels x 32 bf16 channels
 
 // compile-time geometry of one channel class (C = 32: SWIZZLE_64B rows, C = 64: SWIZZLE_128B rows)
 template <int C>
@@ -39,13 +41,21 @@ struct T3 {
   static constexpr int WBYTES = 9 * C * PITCH;      // one branch's weights
   static constexpr uint32_t LAYOUT = C == 32 ? 4u : 2u;   // UMMA layout code: SWIZZLE_64B / SWIZZLE_128B
 };
-// warp roles: 0 TMA producer, 1..KT MMA issuers (one per sub-tile), KT+1 TMA store + side loads, EPI0..EPI0+EW-1 epilogue.
-// The epilogue is a chain of dependent latencies per warp (tcgen05.ld, shared loads, proxy fence), so it is spread over
-// EW = 8 or 16 warps: lane quarter q = warp % 4 (the TMEM lanes a warp may read), column group (warp - EPI0) / 4.
-template <int KT, int EW> struct T3Warps {
-  static constexpr int STORE = KT + 1;
-  static constexpr int EPI0 = (KT + 2 + 3) / 4 * 4;
-  static constexpr int THREADS = (EPI0 + EW) * 32;
+// warp roles: 0..7 epilogue (the TMEM lane quarter a warp may read is warp % 4), 8 TMA producer + TMEM allocation,
+// 9..10 MMA issuers.  scripts/exp_mma_align.cu (profiles/r2_exp_mma_align.txt): ONE thread issues at most one tcgen05.mma per
+// ~100 cycles, however many independent accumulator chains it interleaves (1 thread x 4 chains 96-100 cycles per MMA,
+// 2 threads x 2 chains 54-60, 4 threads 40 = the shared-memory operand limit of an N=32 MMA), but the limit is per THREAD,
+// not per warp: two warps with two issuing lanes each also reach 40.  So every sub-tile (accumulator chain) of an item gets
+// its own issuing lane, KT / 2 lanes in each of the two MMA warps, and the CTA stays at 11 warps = 3 per scheduler = 168
+// registers per thread, which the epilogue (32 accumulator values + 64 statistics partial sums) needs; a fourth warp per
+// scheduler would cap every thread at 128 registers and spill the epilogue.
+template <int KT> struct T3Warps {
+  static constexpr int EPI0 = 0;
+  static constexpr int PROD = T3_EW;
+  static constexpr int MMA0 = T3_EW + 1;
+  static constexpr int NMW = 2;                                  // MMA warps
+  static constexpr int LPW = KT >= 2 ? KT / 2 : 1;               // issuing lanes per MMA warp (KT = 1: warp MMA0 lane 0 only)
+  static constexpr int THREADS = (T3_EW + 1 + NMW) * 32;
 };
 
 struct Tc3Params {
@@ -54,10 +64,11 @@ struct Tc3Params {
   int dil[T3_MAXBR];      // signed: negative = data gradient (taps mirrored)
   int halo[T3_MAXBR];     // 1: one halo box per item, 0: one box per tap
   int items, tiles_w, tiles_h;
-  int nstages, slot_bytes, nsb;
-  int nsb_log, nsi_log;         // nsb, nsi are powers of two
-  int nsi, has_add, has_mask;   // side-input ring: slots, addend present (residual or previous out), ReLU mask present
-  int has_bnx, bnr_relu;        // fused BatchNorm backward: BN input tile in the side ring; the BN was followed by ReLU
+  int nstages, slot_bytes;
+  int alt;                      // 1: the two MMA warps take alternate items (every branch in halo mode, nstages even)
+  int sdepth;                   // side-input buffers per epilogue warp: sdepth - 1 slices are in flight ahead of the one in use
+  int has_add, has_mask;        // addend present (residual or previous out), ReLU mask present
+  int has_bnx, bnr_relu;        // fused BatchNorm backward: BN input slices; the BN was followed by ReLU
   const double* bnr_stats;      // {sum, sumsq} of the BN input (forward statistics)
   double bnr_count;
   float bnr_eps;
@@ -66,34 +77,12 @@ struct Tc3Params {
   const float* bias[T3_MAXBR];
   double* stats;
   int relu;
-  long long* trace;       // diagnostic: per-CTA cycles spent waiting on each barrier family (rsa_conv_tc3_set_trace)
+  int debug;              // diagnostic (RSA_TC3_DEBUG, results are wrong): 1 no MMAs, 2 no epilogue data movement, 4 no TMA
+                          // operand loads, 8 no TMA stores, 16 no tcgen05.ld, 32 no proxy fence, 64 no staging stores -
+                          // isolates which pipeline bounds the kernel (scripts/iso_tc3.py)
 };
 
-// timed mbarrier wait for the diagnostic trace (plain wait when tracing is off)
-__device__ __forceinline__ void twait(uint64_t* bar, uint32_t parity, long long* tr, int slot) {
-  if (!tr) { mbar_wait(bar, parity); return; }
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  tr[slot] += clock64() - t0;
-}
-
-template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[N]);
-template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -117,55 +106,56 @@ __device__ __forceinline__ uint64_t t3_desc(uint32_t hi, uint32_t saddr) {
   return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFF) | (1u << 16));
 }
 
+// a: operand boxes per branch; w: weights per branch; out / add / mask / bnx: 8 x 4 pixel x 32 channel slices (SWIZZLE_64B)
 struct Tc3Maps { CUtensorMap a[T3_MAXBR]; CUtensorMap w[T3_MAXBR]; CUtensorMap out; CUtensorMap add; CUtensorMap mask; CUtensorMap bnx; };
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
 struct Tc3Smem {
   int w_off, st_off, side_off, ring_off, misc_off, bar_off, total;
-  __host__ __device__ Tc3Smem(int C, int nbr, int nsb, int nside, int nsi, int nstages, int slot_bytes) {
+  __host__ __device__ Tc3Smem(int C, int nbr, int nside, int sdepth, int nstages, int slot_bytes) {
     w_off = 0;
     st_off = (nbr * 9 * C * C * 2 + 1023) & ~1023;
-    side_off = st_off + nsb * 128 * C * 2;                   // [nsi][nside] tiles of 128 pixels
-    ring_off = side_off + nsi * nside * 128 * C * 2;
-    misc_off = ring_off + nstages * slot_bytes;              // bias[C], csum[4][C], csq[4][C], BN coefficients [4][C]
-    bar_off = misc_off + 13 * C * 4;
-    total = bar_off + (2 * nstages + 4 * T3_MAXSB + 8) * 8 + 16 + 1024;
+    side_off = st_off + T3_EW * 2 * T3_SLICE;                 // [warp][2] staging slices
+    ring_off = side_off + T3_EW * sdepth * nside * T3_SLICE;  // [warp][sdepth][nside] side slices
+    misc_off = ring_off + nstages * slot_bytes;               // bias[C], csum[8][32], csq[8][32], BN coefficients [4][C]
+    bar_off = misc_off + (5 * C + 2 * T3_EW * 32) * 4;
+    total = bar_off + (2 * nstages + 8 + 4 * T3_EW + 1) * 8 + 16 + 1024;
   }
 };
 
-template <int C, int KT, int EW>
-__global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
+template <int C, int KT>
+__global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
   constexpr int PITCH = T3<C>::PITCH, BOXB = T3<C>::BOXB, WBYTES = T3<C>::WBYTES;
-  constexpr int EPI0 = T3Warps<KT, EW>::EPI0;
-  constexpr int NCT = C / (EW / 4);     // accumulator columns per epilogue thread
-  constexpr int CHK = NCT < 16 ? NCT : 16;   // columns per tcgen05.ld
-  static_assert(CHK == 8 || CHK == 16, "epilogue chunk");
+  constexpr int EPI0 = T3Warps<KT>::EPI0, PROD = T3Warps<KT>::PROD, MMA0 = T3Warps<KT>::MMA0;
+  constexpr int LPW = T3Warps<KT>::LPW;
+  constexpr int ALT_L = KT >= 2 ? 2 : 1, ALT_CH = KT / ALT_L;     // alternating mode: issuing lanes per warp, chains per lane
+  constexpr int NACC = 4;                                  // accumulator stages (power of two)
+  constexpr int SPI = C == 32 ? KT / 2 : KT;        // slices an epilogue warp handles per item
+  static_assert(C == 64 || KT % 2 == 0, "C = 32: the two epilogue warp groups alternate over the sub-tiles of an item");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nside = p.has_add + p.has_mask + p.has_bnx;
-  const Tc3Smem L(C, p.nbr, p.nsb, nside, p.nsi, p.nstages, p.slot_bytes);
+  const Tc3Smem L(C, p.nbr, nside, p.sdepth, p.nstages, p.slot_bytes);
   uint8_t* wsm = smem + L.w_off;
-  uint8_t* ysm = smem + L.st_off;
-  uint8_t* sidesm = smem + L.side_off;
   uint8_t* ring = smem + L.ring_off;
   float* bias_s = reinterpret_cast<float*>(smem + L.misc_off);
-  float* csum = bias_s + C;                  // [4][C]: one slot per lane quarter, summed in a fixed order (deterministic)
-  float* csq = csum + 4 * C;
-  float* bnc = csq + 4 * C;                  // [4][C]: invstd, -mean*invstd, gamma, beta of the fused BatchNorm backward
+  float* bnc = bias_s + C;                   // [4][C]: invstd, -mean*invstd, gamma, beta of the fused BatchNorm backward
+  float* csum = bnc + 4 * C;                 // [8 warps][32]: one slot per epilogue warp, summed in a fixed order
+  float* csq = csum + T3_EW * 32;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + p.nstages;
-  uint64_t* tfull = empty_bar + p.nstages;   // [2]
-  uint64_t* tempty = tfull + 2;              // [2]
-  uint64_t* sready = tempty + 2;             // [nsb] staged tile written by the 8 epilogue warps
-  uint64_t* sfree = sready + T3_MAXSB;       // [nsb] staged tile read by its TMA store
-  uint64_t* ifull = sfree + T3_MAXSB;        // [nsi] side-input tiles landed
-  uint64_t* wbar = ifull + T3_MAXSB;
+  uint64_t* tfull = empty_bar + p.nstages;   // [NACC]
+  uint64_t* tempty = tfull + NACC;           // [NACC]
+  uint64_t* sbar = tempty + NACC;            // [warp][4] side slices landed (private to one epilogue warp)
+  uint64_t* wbar = sbar + 4 * T3_EW;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool has_stats = p.stats != nullptr;
-  long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
-  constexpr uint32_t TMEM_COLS = 2 * KT * C <= 64 ? 64 : (2 * KT * C <= 128 ? 128 : 256);
-  static_assert(2 * KT * C <= 256, "accumulator ring exceeds the TMEM allocation");
+  // NACC accumulator stages of KT sub-tiles each.  The MMA warps may run NACC items ahead of the epilogue; with two stages
+  // the loop MMA(it) -> commit -> epilogue sees it (~1.7k cycles later, scripts/iso_tc3.py) -> epilogue has read the item ->
+  // MMA(it + 2) bounded an item at (commit latency + epilogue latency + MMA time) / 2 = ~4.5k cycles against 2.9k of MMAs.
+  constexpr uint32_t TMEM_COLS = NACC * KT * C <= 128 ? 128 : (NACC * KT * C <= 256 ? 256 : 512);
+  static_assert(NACC * KT * C <= 512, "accumulator ring exceeds TMEM");
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < p.nbr; ++b) { prefetch_tmap(&maps.a[b]); prefetch_tmap(&maps.w[b]); }
@@ -173,16 +163,14 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
     if (p.has_add) prefetch_tmap(&maps.add);
     if (p.has_mask) prefetch_tmap(&maps.mask);
     if (p.has_bnx) prefetch_tmap(&maps.bnx);
-    for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], KT); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], KT); mbar_init(&tempty[s], EW); }
-    for (int s = 0; s < T3_MAXSB; ++s) {
-      mbar_init(&sready[s], EW); mbar_init(&sfree[s], 1);
-      mbar_init(&ifull[s], 1);
-    }
+    const int nissue = p.alt ? ALT_L : KT;          // threads that commit a stage / an accumulator
+    for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nissue); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&tfull[s], nissue); mbar_init(&tempty[s], T3_EW); }
+    for (int s = 0; s < 4 * T3_EW; ++s) mbar_init(&sbar[s], 1);
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == PROD) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -196,7 +184,9 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
     if (p.has_bnx) {
       float mean, inv;
       bn_mean_invstd(p.bnr_stats, p.bnr_count, C, c, p.bnr_eps, nullptr, nullptr, mean, inv);
-      bnc[c] = inv; bnc[C + c] = -mean * inv; bnc[2 * C + c] = p.bnr_gamma[c]; bnc[3 * C + c] = p.bnr_beta[c];
+      // ReLU mask: gamma * xhat + beta > 0  <=>  x * A + B > 0;  sum g * xhat = inv * (sum g * x) - mean * inv * (sum g)
+      const float ga = p.bnr_gamma[c];
+      bnc[c] = ga * inv; bnc[C + c] = p.bnr_beta[c] - ga * mean * inv; bnc[2 * C + c] = inv; bnc[3 * C + c] = -mean * inv;
     }
   }
   tc_fence_before();
@@ -204,7 +194,7 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == PROD) {
     // ===== TMA producer =====
     if (lane == 0) {
       mbar_expect_tx(wbar, p.nbr * WBYTES);
@@ -219,41 +209,102 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
         for (int b = 0; b < p.nbr; ++b) {
           const int d = p.dil[b], ad = d < 0 ? -d : d;
           if (p.halo[b]) {
-            twait(&empty_bar[stage], phase ^ 1, tr, 0);
-            mbar_expect_tx(&full_bar[stage], (16 + 2 * ad) * (8 * KT + 2 * ad) * PITCH);
-            tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, w0 - ad, h0 - ad, n);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (p.debug & 4) mbar_expect_tx(&full_bar[stage], 0);
+            else {
+              mbar_expect_tx(&full_bar[stage], (16 + 2 * ad) * (8 * KT + 2 * ad) * PITCH);
+              tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, w0 - ad, h0 - ad, n);
+            }
             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           } else {
             for (int tap = 0; tap < 9; ++tap) {
               const int ch = h0 + (tap / 3 - 1) * d, cw = w0 + (tap % 3 - 1) * d;
               if (ch + 16 <= 0 || ch >= p.H || cw + 8 * KT <= 0 || cw >= p.W) continue;
-              twait(&empty_bar[stage], phase ^ 1, tr, 0);
-              mbar_expect_tx(&full_bar[stage], KT * BOXB);
-              tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, cw, ch, n);
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (p.debug & 4) mbar_expect_tx(&full_bar[stage], 0);
+              else {
+                mbar_expect_tx(&full_bar[stage], KT * BOXB);
+                tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, cw, ch, n);
+              }
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp <= KT) {
-    // ===== MMA issuers: warp 1+s owns sub-tile s of every item =====
-    if (lane == 0) {
+  } else if (warp >= MMA0) {
+    // ===== MMA issuers =====
+    // A tcgen05.commit holds its thread until the MMAs it issued have drained (~1.1k cycles between two items during which
+    // that thread issues nothing; with all issuing threads on the same item the tensor pipe idles with them, scripts/iso_tc3.py:
+    // 4.0k cycles per 512-pixel item against 2.9k of MMAs).  Halo-only launches therefore give the two MMA warps ALTERNATE
+    // items: while one warp commits and waits, the other one's MMAs keep the pipe busy.  Each warp has ALT_L issuing lanes
+    // (one thread issues at most one MMA per ~100 cycles) that interleave ALT_CH accumulator chains each.  The operand ring is
+    // walked by position (item * branches + branch); an even number of stages keeps every stage with one warp, so a warp
+    // never waits for a barrier phase whose predecessor it has not seen complete.
+    if (p.alt) {
+      if (lane < ALT_L) {
+        constexpr uint32_t idesc = make_idesc(128, C);
+        const int gsel = warp - MMA0, s0 = lane * ALT_CH;
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        const uint32_t wbase = smem_u32(wsm);
+        const uint32_t bhi = t3_desc_hi<C>(8 * PITCH);
+        for (int it = gsel; (long long)blockIdx.x + (long long)it * gridDim.x < p.items; it += 2) {
+          const int as = it & (NACC - 1);
+          mbar_wait(&tempty[as], ((it / NACC) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + (uint32_t)((as * KT + s0) * C);
+          uint32_t started = 0;
+          for (int b = 0; b < p.nbr; ++b) {
+            const int d = p.dil[b], ad = d < 0 ? -d : d;
+            const uint32_t wb = wbase + b * WBYTES;
+            const int Wh = 8 * KT + 2 * ad;
+            const uint32_t ahi = t3_desc_hi<C>(Wh * PITCH);
+            const int pos = it * p.nbr + b, stage = pos % p.nstages, phase = (pos / p.nstages) & 1;
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(ring + stage * p.slot_bytes) + (uint32_t)((ad * Wh + ad + 8 * s0) * PITCH);
+            const int rowb = d * Wh * PITCH, colb = d * PITCH;
+            if (!(p.debug & 1)) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t at = sa + (tap / 3 - 1) * rowb + (tap % 3 - 1) * colb;
+                const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
+#pragma unroll
+                for (int k = 0; k < C / 16; ++k)
+#pragma unroll
+                  for (int u = 0; u < ALT_CH; ++u)
+                    umma_bf16(acc + (uint32_t)(u * C), t3_desc(ahi, at + 8 * u * PITCH) + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                              idesc, started | (tap > 0) | (k > 0));
+              }
+            }
+            started = 1;
+            umma_commit(&empty_bar[stage]);
+          }
+          umma_commit(&tfull[as]);
+        }
+      }
+      // fall through to the common tail
+    } else
+    // same-item mode (a branch with one box per tap): lane l of warp MMA0+m owns sub-tile s = m * LPW + l of every item
+    if (const int s = (warp - MMA0) * LPW + lane; lane < LPW && s < KT) {
       constexpr uint32_t idesc = make_idesc(128, C);
-      const int s = warp - 1;
       mbar_wait(wbar, 0);
       tc_fence_after();
       const uint32_t wbase = smem_u32(wsm);
       const uint32_t bhi = t3_desc_hi<C>(8 * PITCH);
       int stage = 0, phase = 0, it = 0;
+      int tw = (int)blockIdx.x % p.tiles_w, th = ((int)blockIdx.x / p.tiles_w) % p.tiles_h;
+      const int dtw = (int)gridDim.x % p.tiles_w, dth = ((int)gridDim.x / p.tiles_w) % p.tiles_h;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        int r = item;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h;
         const int h0 = th * 16, w0 = tw * 8 * KT;
-        twait(&tempty[it & 1], ((it >> 1) & 1) ^ 1, s == 0 ? tr : nullptr, 2);
+        tw += dtw; th += dth;                       // next item's tile coordinates without a division
+        if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
+        if (th >= p.tiles_h) th -= p.tiles_h;
+        const int as = it & (NACC - 1);
+        mbar_wait(&tempty[as], ((it / NACC) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(((it & 1) * KT + s) * C);
+        const uint32_t acc = tmem_base + (uint32_t)((as * KT + s) * C);
         uint32_t started = 0;
         for (int b = 0; b < p.nbr; ++b) {
           const int d = p.dil[b], ad = d < 0 ? -d : d;
@@ -261,17 +312,19 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
           if (p.halo[b]) {
             const int Wh = 8 * KT + 2 * ad;
             const uint32_t ahi = t3_desc_hi<C>(Wh * PITCH);
-            twait(&full_bar[stage], phase, s == 0 ? tr : nullptr, 3);
+            mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(ring + stage * p.slot_bytes) + (uint32_t)((ad * Wh + ad + 8 * s) * PITCH);
             const int rowb = d * Wh * PITCH, colb = d * PITCH;
+            if (!(p.debug & 1)) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint64_t adesc = t3_desc(ahi, sa + (tap / 3 - 1) * rowb + (tap % 3 - 1) * colb);
-              const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t adesc = t3_desc(ahi, sa + (tap / 3 - 1) * rowb + (tap % 3 - 1) * colb);
+                const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
 #pragma unroll
-              for (int k = 0; k < C / 16; ++k)
-                umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started | (tap > 0) | (k > 0));
+                for (int k = 0; k < C / 16; ++k)
+                  umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started | (tap > 0) | (k > 0));
+              }
             }
             started = 1;
             umma_commit(&empty_bar[stage]);
@@ -281,261 +334,253 @@ __global__ void __launch_bounds__(T3Warps<KT, EW>::THREADS, 1) conv_tc3_kernel(c
             for (int tap = 0; tap < 9; ++tap) {
               const int ch = h0 + (tap / 3 - 1) * d, cw = w0 + (tap % 3 - 1) * d;
               if (ch + 16 <= 0 || ch >= p.H || cw + 8 * KT <= 0 || cw >= p.W) continue;
-              twait(&full_bar[stage], phase, s == 0 ? tr : nullptr, 3);
+              mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
               const uint64_t adesc = t3_desc(ahi, smem_u32(ring + stage * p.slot_bytes) + 8 * s * PITCH);
               const uint64_t bdesc = t3_desc(bhi, wb + tap * C * PITCH);
+              if (!(p.debug & 1)) {
 #pragma unroll
-              for (int k = 0; k < C / 16; ++k)
-                umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started | (k > 0));
+                for (int k = 0; k < C / 16; ++k)
+                  umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started | (k > 0));
+              }
               started = 1;
               umma_commit(&empty_bar[stage]);
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
           }
         }
-        umma_commit(&tfull[it & 1]);
+        umma_commit(&tfull[as]);
       }
     }
-  } else if (warp == T3Warps<KT, EW>::STORE) {
-    // ===== TMA store of the staged tiles; the same thread keeps the side-input ring (addend, ReLU mask, BatchNorm
-    // input: 16x8 boxes like the output tiles) nsi sub-tiles ahead of the epilogue.  sready[j] completing for sub-tile
-    // `seq` also means the eight epilogue warps are done with that sub-tile's side slot, so the slot is refilled right
-    // there - the main operand pipeline (warp 0) never waits for the epilogue =====
-    if (lane == 0) {
-      auto issue_side = [&](int sq) {
-        const int item = blockIdx.x + (sq / KT) * (int)gridDim.x;
-        if (item >= p.items) return;
-        int r = item;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h; r /= p.tiles_h;
-        const int n = r, h0 = th * 16, w0 = tw * 8 * KT + 8 * (sq % KT);
-        const int k = sq & (p.nsi - 1);
-        mbar_expect_tx(&ifull[k], nside * BOXB);
-        uint8_t* dst = sidesm + k * nside * BOXB;
-        if (p.has_add) tma_load_4d(dst, &maps.add, &ifull[k], 0, w0, h0, n);
-        if (p.has_mask) tma_load_4d(dst + p.has_add * BOXB, &maps.mask, &ifull[k], 0, w0, h0, n);
-        if (p.has_bnx) tma_load_4d(dst + (p.has_add + p.has_mask) * BOXB, &maps.bnx, &ifull[k], 0, w0, h0, n);
-      };
-      if (nside)
-        for (int sq = 0; sq < p.nsi; ++sq) issue_side(sq);
-      int seq = 0;
-      const int lag = p.nsb >> 1;          // stores allowed in flight before a buffer is handed back
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int r = item;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h; r /= p.tiles_h;
-        const int n = r, h0 = th * 16, w0 = tw * 8 * KT;
-        for (int s = 0; s < KT; ++s, ++seq) {
-          const int j = seq & (p.nsb - 1);
-          twait(&sready[j], (seq >> p.nsb_log) & 1, tr, 5);
-          if (nside) issue_side(seq + p.nsi);
-          tma_store_4d(&maps.out, ysm + j * BOXB, 0, w0 + 8 * s, h0, n);
-          // the store issued `lag` tiles ago has finished reading its buffer: hand that buffer back
-          if (lag == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          if (seq >= lag) mbar_arrive(&sfree[(seq - lag) & (p.nsb - 1)]);
-        }
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-  } else if (warp >= EPI0) {
-    // ===== epilogue warps: lane quarter q, column group hs =====
-    const int q = warp & 3, hs = (warp - EPI0) >> 2;
-    const int rrow = q * 32 + lane;                 // accumulator row = pixel of the 16x8 sub-tile
-    const uint32_t srow = (uint32_t)rrow * PITCH;
-    const uint32_t sw = C == 32 ? (uint32_t)((rrow >> 1) & 3) : (uint32_t)(rrow & 7);   // swizzle phase of this row
-    float acc_s[NCT], acc_q[NCT];                   // BatchNorm statistics of this thread's pixels (all its sub-tiles)
+  } else {
+    // ===== epilogue: eight independent warp pipelines.  Warp e = warp - EPI0 reads TMEM lane quarter q = e % 4 (pixels
+    // 32q .. 32q+31 of a sub-tile = image rows 4q .. 4q+3, 8 pixels each) and channel block c0 .. c0+31.  C = 32: the two
+    // groups of four warps alternate over the sub-tiles of an item; C = 64: group g takes channel half g of every sub-tile.
+    const int e = warp - EPI0, q = e & 3, g = e >> 2;
+    const int c0 = C == 32 ? 0 : 32 * g;
+    uint8_t* ybuf = smem + L.st_off + e * 2 * T3_SLICE;
+    uint8_t* sbuf = smem + L.side_off + e * p.sdepth * nside * T3_SLICE;
+    uint64_t* mybar = sbar + 4 * e;
+    const uint32_t srow = (uint32_t)lane * 64u;                 // this thread's pixel row inside a slice
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);            // SWIZZLE_64B phase of that row
+    uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < NCT; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
-    float bias_r[C == 32 ? NCT : 1];                // 32 channels: the thread's biases live in registers
-    if constexpr (C == 32) {
+    for (int k = 0; k < 4; ++k) o[k] = srow + (((uint32_t)k ^ sw) << 4);
+    float acc_s[32], acc_q[32];                                 // BatchNorm statistics of this thread's pixels (all its slices)
 #pragma unroll
-      for (int j = 0; j < NCT; ++j) bias_r[j] = bias_s[hs * NCT + j];
-    }
-    int it = 0, seq = 0;
-    long long* etr = (warp == EPI0) ? tr : nullptr;
-    const long long e_t0 = clock64();
+    for (int j = 0; j < 32; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+    // coordinates of the slices of this warp are walked incrementally (no divisions in the loop): the "current" cursor for
+    // the slice being processed, a second cursor `pf` that runs sdepth - 1 slices ahead for the side-input prefetch
+    struct Cur { int item, j, n, h0, w0; };
+    auto cur_init = [&](Cur& c) {
+      c.item = blockIdx.x; c.j = 0;
+      int r = c.item;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      c.n = r; c.h0 = th * 16; c.w0 = tw * 8 * KT;
+    };
+    auto cur_next = [&](Cur& c) {
+      if (++c.j < SPI) return;
+      c.j = 0; c.item += gridDim.x;
+      int r = c.item;                                        // once per item
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; r /= p.tiles_h;
+      c.n = r; c.h0 = th * 16; c.w0 = tw * 8 * KT;
+    };
+    auto sub_of = [&](int j) { return C == 32 ? 2 * j + g : j; };
+    auto issue_side = [&](const Cur& c, int idx) {       // lane 0: TMA loads of the side slices of slice idx into buffer idx % sdepth
+      if (c.item >= p.items) return;
+      const int b = idx % p.sdepth;
+      const int hh = c.h0 + 4 * q, ww = c.w0 + 8 * sub_of(c.j);
+      uint8_t* dst = sbuf + b * nside * T3_SLICE;
+      mbar_expect_tx(&mybar[b], nside * T3_SLICE);
+      if (p.has_add) tma_load_4d(dst, &maps.add, &mybar[b], c0, ww, hh, c.n);
+      if (p.has_mask) tma_load_4d(dst + p.has_add * T3_SLICE, &maps.mask, &mybar[b], c0, ww, hh, c.n);
+      if (p.has_bnx) tma_load_4d(dst + (p.has_add + p.has_mask) * T3_SLICE, &maps.bnx, &mybar[b], c0, ww, hh, c.n);
+    };
+    Cur cur, pf;
+    cur_init(cur);
+    cur_init(pf);
+    int pf_idx = 0;
+    if (nside && lane == 0)
+      for (int k = 0; k < (p.sdepth > 1 ? p.sdepth - 1 : 1); ++k) { issue_side(pf, pf_idx); cur_next(pf); ++pf_idx; }
+    int it = 0, idx = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      if (lane == 0) twait(&tfull[it & 1], (it >> 1) & 1, etr, 6); else mbar_wait(&tfull[it & 1], (it >> 1) & 1);
+      const int as = it & (NACC - 1);
+      mbar_wait(&tfull[as], (it / NACC) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int s = 0; s < KT; ++s, ++seq) {
-        const int j = seq & (p.nsb - 1);
-        uint8_t* yb = ysm + j * BOXB + srow;
-        const int ks = nside ? (seq & (p.nsi - 1)) : 0;
-        const uint8_t* ib = sidesm + ks * nside * BOXB + srow;
+      for (int j = 0; j < SPI; ++j, ++idx) {
+        const int s = sub_of(j);
+        const int n = cur.n, hh = cur.h0 + 4 * q, ww = cur.w0 + 8 * s;
+        cur_next(cur);
+        const int sb = nside ? idx % p.sdepth : 0;
+        const uint8_t* ib = sbuf + sb * nside * T3_SLICE;
         if (nside) {
-          if (lane == 0) twait(&ifull[ks], (seq >> p.nsi_log) & 1, etr, 8);
+          // keep sdepth - 1 slices of side data in flight: the buffer refilled here was read during the previous slice
+          if (p.sdepth > 1 && lane == 0) { issue_side(pf, pf_idx); cur_next(pf); ++pf_idx; }
+          mbar_wait(&mybar[sb], (idx / p.sdepth) & 1);
+        }
+        uint32_t v[32];
+        if (!(p.debug & (2 | 16))) tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * KT + s) * C + c0), v);
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0;
+        }
+        if (j == SPI - 1) {             // this warp's last read of the accumulator stage
+          tc_fence_before();
           __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
         }
+        if (p.debug & 2) {
+          if (nside && p.sdepth == 1) { __syncwarp(); if (lane == 0) { issue_side(pf, pf_idx); cur_next(pf); ++pf_idx; } }
+          continue;
+        }
+        float f[32];
 #pragma unroll
-        for (int cc = 0; cc < NCT; cc += CHK) {
-          uint32_t v[CHK];
-          const long long tl0 = etr ? clock64() : 0;
-          tmem_ld<CHK>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((it & 1) * KT + s) * C + hs * NCT + cc), v);
-          if (etr && lane == 0) etr[11] += clock64() - tl0;
-          if (s == KT - 1 && cc + CHK >= NCT) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[it & 1]);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+          f[i] = __uint_as_float(v[i]) + bv.x; f[i + 1] = __uint_as_float(v[i + 1]) + bv.y;
+          f[i + 2] = __uint_as_float(v[i + 2]) + bv.z; f[i + 3] = __uint_as_float(v[i + 3]) + bv.w;
+        }
+        if (p.has_add) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float t[8];
+            unpack8(*reinterpret_cast<const uint4*>(ib + o[k]), t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[8 * k + i] += t[i];
           }
-          float f[CHK];
-          if constexpr (C == 32) {
+        }
+        if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < CHK; ++i) f[i] = __uint_as_float(v[i]) + bias_r[cc + i];
-          } else {
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.has_mask) {
 #pragma unroll
-            for (int i = 0; i < CHK; i += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias_s + hs * NCT + cc + i);
-              f[i] = __uint_as_float(v[i]) + bv.x; f[i + 1] = __uint_as_float(v[i + 1]) + bv.y;
-              f[i + 2] = __uint_as_float(v[i + 2]) + bv.z; f[i + 3] = __uint_as_float(v[i + 3]) + bv.w;
-            }
+          for (int k = 0; k < 4; ++k) {
+            float t[8];
+            unpack8(*reinterpret_cast<const uint4*>(ib + p.has_add * T3_SLICE + o[k]), t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[8 * k + i] = t[i] > 0.f ? f[8 * k + i] : 0.f;
           }
-          const uint32_t c16 = (uint32_t)((hs * NCT + cc) >> 3);        // first 16-byte chunk of this group inside the row
-          uint32_t o[CHK / 8];
+        }
+        if (p.has_bnx) {
+          // fused BatchNorm(+ReLU) backward reductions: f is d(relu(bn(x))); recompute the ReLU mask from x like the
+          // forward did, keep g = f * mask as the stored value and accumulate {sum g, sum g * x}; the affine step from
+          // sum g * x to sum g * xhat is applied once per channel at the end
+          const float* cf = bnc + c0;
 #pragma unroll
-          for (int k = 0; k < CHK / 8; ++k) o[k] = ((c16 + k) ^ sw) << 4;
-          auto ld_side = [&](const uint8_t* base, float* t) {
+          for (int k = 0; k < 4; ++k) {
+            float xv[8];
+            unpack8(*reinterpret_cast<const uint4*>(ib + (p.has_add + p.has_mask) * T3_SLICE + o[k]), xv);
+            if (p.bnr_relu) {
 #pragma unroll
-            for (int k = 0; k < CHK / 8; ++k) unpack8(*reinterpret_cast<const uint4*>(base + o[k]), t + 8 * k);
-          };
-          if (p.has_add) {
-            float t[CHK];
-            ld_side(ib, t);
-#pragma unroll
-            for (int i = 0; i < CHK; ++i) f[i] += t[i];
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < CHK; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          if (p.has_mask) {
-            float t[CHK];
-            ld_side(ib + p.has_add * BOXB, t);
-#pragma unroll
-            for (int i = 0; i < CHK; ++i) f[i] = t[i] > 0.f ? f[i] : 0.f;
-          }
-          if (p.has_bnx) {
-            // fused BatchNorm(+ReLU) backward reductions: f is d(relu(bn(x))); recompute the ReLU mask from x like the
-            // forward did, keep g = f * mask as the stored value and accumulate {sum g, sum g*xhat} below
-            float xv[CHK], xh[4];
-            ld_side(ib + (p.has_add + p.has_mask) * BOXB, xv);
-            const float* cf = bnc + hs * NCT + cc;
-#pragma unroll
-            for (int i = 0; i < CHK; i += 4) {
-              const float4 ca = *reinterpret_cast<const float4*>(cf + i), cb = *reinterpret_cast<const float4*>(cf + C + i);
-              const float4 cg = *reinterpret_cast<const float4*>(cf + 2 * C + i), ct = *reinterpret_cast<const float4*>(cf + 3 * C + i);
-              xh[0] = fmaf(xv[i], ca.x, cb.x); xh[1] = fmaf(xv[i + 1], ca.y, cb.y);
-              xh[2] = fmaf(xv[i + 2], ca.z, cb.z); xh[3] = fmaf(xv[i + 3], ca.w, cb.w);
-              if (p.bnr_relu) {
-                f[i] = fmaf(cg.x, xh[0], ct.x) > 0.f ? f[i] : 0.f; f[i + 1] = fmaf(cg.y, xh[1], ct.y) > 0.f ? f[i + 1] : 0.f;
-                f[i + 2] = fmaf(cg.z, xh[2], ct.z) > 0.f ? f[i + 2] : 0.f; f[i + 3] = fmaf(cg.w, xh[3], ct.w) > 0.f ? f[i + 3] : 0.f;
+              for (int i = 0; i < 8; i += 4) {
+                const int c = 8 * k + i;
+                const float4 ca = *reinterpret_cast<const float4*>(cf + c), cb = *reinterpret_cast<const float4*>(cf + C + c);
+                f[c] = fmaf(xv[i], ca.x, cb.x) > 0.f ? f[c] : 0.f; f[c + 1] = fmaf(xv[i + 1], ca.y, cb.y) > 0.f ? f[c + 1] : 0.f;
+                f[c + 2] = fmaf(xv[i + 2], ca.z, cb.z) > 0.f ? f[c + 2] : 0.f; f[c + 3] = fmaf(xv[i + 3], ca.w, cb.w) > 0.f ? f[c + 3] : 0.f;
               }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { acc_s[cc + i + e] += f[i + e]; acc_q[cc + i + e] = fmaf(f[i + e], xh[e], acc_q[cc + i + e]); }
             }
-          }
-          uint4 pk[CHK / 8];
 #pragma unroll
-          for (int k = 0; k < CHK / 8; ++k) {
-            pk[k].x = pack_bf16x2(f[8 * k], f[8 * k + 1]); pk[k].y = pack_bf16x2(f[8 * k + 2], f[8 * k + 3]);
-            pk[k].z = pack_bf16x2(f[8 * k + 4], f[8 * k + 5]); pk[k].w = pack_bf16x2(f[8 * k + 6], f[8 * k + 7]);
-          }
-          if (cc == 0) {
-            if (lane == 0) twait(&sfree[j], ((seq >> p.nsb_log) & 1) ^ 1, etr, 7);
-            __syncwarp();
-          }
-#pragma unroll
-          for (int k = 0; k < CHK / 8; ++k) *reinterpret_cast<uint4*>(yb + o[k]) = pk[k];
-          if (has_stats && !p.has_bnx) {
-            // per-thread partial sums of the stored (bf16-rounded) values; reduced across lanes once per CTA
-            float t[CHK];
-#pragma unroll
-            for (int k = 0; k < CHK / 8; ++k) unpack8(pk[k], t + 8 * k);
-#pragma unroll
-            for (int i = 0; i < CHK; ++i) { acc_s[cc + i] += t[i]; acc_q[cc + i] = fmaf(t[i], t[i], acc_q[cc + i]); }
+            for (int i = 0; i < 8; ++i) { acc_s[8 * k + i] += f[8 * k + i]; acc_q[8 * k + i] = fmaf(f[8 * k + i], xv[i], acc_q[8 * k + i]); }
           }
         }
-        const long long tf0 = etr ? clock64() : 0;
-        fence_proxy_async();
+        if (nside && p.sdepth == 1) {       // single side buffer: refill it as soon as every lane has read it
+          __syncwarp();
+          if (lane == 0) { issue_side(pf, pf_idx); cur_next(pf); ++pf_idx; }
+        }
+        uint4 pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          pk[k].x = pack_bf16x2(f[8 * k], f[8 * k + 1]); pk[k].y = pack_bf16x2(f[8 * k + 2], f[8 * k + 3]);
+          pk[k].z = pack_bf16x2(f[8 * k + 4], f[8 * k + 5]); pk[k].w = pack_bf16x2(f[8 * k + 6], f[8 * k + 7]);
+        }
+        if (has_stats && !p.has_bnx) {
+          // statistics of the stored (bf16-rounded) values
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float t[8];
+            unpack8(pk[k], t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc_s[8 * k + i] += t[i]; acc_q[8 * k + i] = fmaf(t[i], t[i], acc_q[8 * k + i]); }
+          }
+        }
+        // staging buffer idx & 1 was last read by this warp's store of slice idx - 2: at most one younger store may be open
+        uint8_t* yb = ybuf + (idx & 1) * T3_SLICE;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
-        if (etr && lane == 0) etr[12] += clock64() - tf0;
-        if (lane == 0) mbar_arrive(&sready[j]);
+        if (!(p.debug & 64)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + o[k]) = pk[k];
+        }
+        if (!(p.debug & 32)) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(p.debug & 8)) tma_store_4d(&maps.out, yb, c0, ww, hh, n);
       }
     }
-    if (etr && lane == 0) { etr[9] += clock64() - e_t0; etr[10] += seq; }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (has_stats) {
-      // CHK-wide butterfly reduce-scatter over the warp's 32 pixels: after log2(CHK) halving exchanges every lane holds one
-      // channel's partial sum; the remaining xor steps finish the sum over the lanes that share that channel
+      // 32-wide butterfly reduce-scatter over the warp's 32 pixel rows: lane l ends with channel c0 + l
 #pragma unroll
-      for (int cc = 0; cc < NCT; cc += CHK) {
-        int ch = 0;
+      for (int off = 16, nn = 16; nn >= 1; off >>= 1, nn >>= 1) {
+        const bool upper = (lane & off) != 0;
 #pragma unroll
-        for (int off = 16, n = CHK / 2; n >= 1; off >>= 1, n >>= 1) {
-          const bool upper = (lane & off) != 0;
-          if (upper) ch += n;
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            const float send_s = upper ? acc_s[cc + i] : acc_s[cc + i + n], keep_s = upper ? acc_s[cc + i + n] : acc_s[cc + i];
-            const float send_q = upper ? acc_q[cc + i] : acc_q[cc + i + n], keep_q = upper ? acc_q[cc + i + n] : acc_q[cc + i];
-            acc_s[cc + i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-            acc_q[cc + i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-          }
-        }
-        constexpr int REST = 32 / CHK;            // lanes sharing one channel: 2 (CHK 16) or 4 (CHK 8)
-#pragma unroll
-        for (int off = REST / 2; off >= 1; off >>= 1) {
-          acc_s[cc] += __shfl_xor_sync(0xffffffffu, acc_s[cc], off);
-          acc_q[cc] += __shfl_xor_sync(0xffffffffu, acc_q[cc], off);
-        }
-        if ((lane & (REST - 1)) == 0) {      // exactly one warp (q, hs) owns slot [q][channel]: no atomics, fixed order below
-          csum[q * C + hs * NCT + cc + ch] = acc_s[cc];
-          csq[q * C + hs * NCT + cc + ch] = acc_q[cc];
+        for (int i = 0; i < nn; ++i) {
+          const float send_s = upper ? acc_s[i] : acc_s[i + nn], keep_s = upper ? acc_s[i + nn] : acc_s[i];
+          const float send_q = upper ? acc_q[i] : acc_q[i + nn], keep_q = upper ? acc_q[i + nn] : acc_q[i];
+          acc_s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+          acc_q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-      if (it > 0 && warp < EPI0 + C / 32) {
-        const int c = (warp - EPI0) * 32 + lane;
-        const double s4 = (((double)csum[c] + (double)csum[C + c]) + (double)csum[2 * C + c]) + (double)csum[3 * C + c];
-        const double q4 = (((double)csq[c] + (double)csq[C + c]) + (double)csq[2 * C + c]) + (double)csq[3 * C + c];
-        atomicAdd(p.stats + c, s4);
-        atomicAdd(p.stats + C + c, q4);
+      // after the halving exchanges lane l holds channel bitrev-free index: upper halves were taken when the lane bit was set
+      int ch = 0;
+#pragma unroll
+      for (int off = 16, nn = 16; nn >= 1; off >>= 1, nn >>= 1) if (lane & off) ch += nn;
+      if (p.has_bnx) acc_q[0] = fmaf(bnc[2 * C + c0 + ch], acc_q[0], bnc[3 * C + c0 + ch] * acc_s[0]);   // sum g*x -> sum g*xhat
+      csum[e * 32 + ch] = acc_s[0];             // exactly one lane of one warp owns a slot: no atomics, fixed order below
+      csq[e * 32 + ch] = acc_q[0];
+      asm volatile("bar.sync 1, %0;" ::"n"(T3_EW * 32) : "memory");
+      if (it > 0 && e < C / 32) {
+        // channel c = 32 e' + lane is held by the warps with c0 == 32 e': C = 32 all eight, C = 64 the group g == e'
+        const int c = e * 32 + lane;
+        double s8 = 0.0, q8 = 0.0;
+#pragma unroll
+        for (int w = 0; w < T3_EW; ++w) {
+          if (C == 64 && (w >> 2) != e) continue;
+          s8 += (double)csum[w * 32 + lane];
+          q8 += (double)csq[w * 32 + lane];
+        }
+        atomicAdd(p.stats + c, s8);
+        atomicAdd(p.stats + C + c, q8);
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == PROD) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
-template <int C, int KT, int EW>
+template <int C, int KT>
 int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<C, KT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<C, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { rsa_set_error("conv_tc3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
   const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
-  cudaError_t le = launch_pdl(conv_tc3_kernel<C, KT, EW>, dim3(grid), dim3(T3Warps<KT, EW>::THREADS), (size_t)smem_bytes, st, maps, p);
+  cudaError_t le = launch_pdl(conv_tc3_kernel<C, KT>, dim3(grid), dim3(T3Warps<KT>::THREADS), (size_t)smem_bytes, st, maps, p);
   if (le != cudaSuccess) { rsa_set_error("conv_tc3: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
 
 }  // namespace
-
-static long long* g_t3_trace = nullptr;
-/* Diagnostic hook: when buf != NULL (device memory, 148*16 int64, zeroed by the caller) every following rsa_conv_tc3_fwd
- * launch adds, per CTA, the cycles its roles spent blocked: [0] producer on the A ring, [1] producer on the side ring,
- * [2] MMA on the accumulators (epilogue behind), [3] MMA on A tiles (TMA behind), [5] store warp on staged tiles,
- * [6] epilogue on accumulators (MMA behind), [7] epilogue on staging buffers, [8] epilogue on side tiles,
- * [9] epilogue total cycles, [10] sub-tiles.  scripts/trace_tc3.py prints the breakdown. */
-extern "C" int rsa_conv_tc3_set_trace(long long* buf) { g_t3_trace = buf; return RSA_OK; }
 
 /* Shapes the thin-layer kernels accept: 32 or 64 channels in and out, H a multiple of 16, W a multiple of 32. */
 extern "C" int rsa_conv_tc3_supported(int N, int H, int W, int C) {
@@ -577,9 +622,10 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
     } else { p.dil[b] = 1; p.halo[b] = 1; p.bias[b] = nullptr; }
   }
   // item = 16 x (8*KT) pixels; wide items amortise the halo, narrow ones keep the ring deep when shared memory is
-  // short (four resident branches, or 64 channels with a dilation-3 halo)
-  int KT = C == 32 ? (nbr > 1 ? 2 : 4) : (max_ad == 3 ? 1 : 2);
-  p.nsb = C == 32 ? 4 : 2;
+  // short (several resident branches, or 64 channels with a dilation-3 halo)
+  static const int kt_env = getenv("RSA_TC3_KT") ? atoi(getenv("RSA_TC3_KT")) : 0;
+  int KT = C == 32 ? (nbr > 2 ? 2 : 4) : (max_ad == 3 ? 1 : 2);
+  if (C == 32 && (kt_env == 2 || kt_env == 4)) KT = kt_env;
   // at most one addend: the identity input of the first branch (residual) or the running sum (accumulate)
   RSA_REQUIRE(!(residual && accumulate), RSA_ERR_SHAPE, "conv_tc3_fwd: residual and accumulate are exclusive");
   p.has_add = (residual || accumulate) ? 1 : 0;
@@ -590,25 +636,32 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   p.bnr_stats = bnr_stats; p.bnr_count = bnr_count; p.bnr_eps = bnr_eps; p.bnr_gamma = bnr_gamma; p.bnr_beta = bnr_beta;
   p.bnr_relu = bnr_relu;
   const int nside = p.has_add + p.has_mask + p.has_bnx;
-  p.nsb_log = p.nsb == 4 ? 2 : 1;
-  p.nsi = nside ? (C == 32 ? 4 : (nside == 2 ? 1 : 2)) : 0;     // 64 channels: shared memory is short, keep >= 2 A stages
-  p.nsi_log = p.nsi == 4 ? 2 : (p.nsi == 2 ? 1 : 0);
+  // side slices in flight per epilogue warp: HBM latency x the side stream's share of the bandwidth wants ~32 KB per SM
+  // (two slices ahead on eight warps); 64 channels carry 72 KB of weights and keep >= 2 operand stages instead
+  static const int sd_env = getenv("RSA_TC3_SDEPTH") ? atoi(getenv("RSA_TC3_SDEPTH")) : 0;
+  p.sdepth = C == 64 ? (nside == 2 ? 1 : 2) : (nside == 1 ? 3 : 2);
+  if (sd_env >= 1 && sd_env <= 4 && nside) p.sdepth = sd_env;
   auto plan = [&](int kt) {
     int slot = any_box ? kt * BOXB : 0;
     if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * kt + 2 * max_ad) * PITCH; slot = hb > slot ? hb : slot; }
     slot = (slot + 1023) & ~1023;
-    const Tc3Smem L0(C, nbr, p.nsb, nside, p.nsi, 0, slot);
+    const Tc3Smem L0(C, nbr, nside, p.sdepth, 0, slot);
     int ns = (227 * 1024 - L0.total - 256) / (slot + 16);
     p.slot_bytes = slot;
     p.nstages = ns > 8 ? 8 : ns;
   };
   plan(KT);
+  if (p.nstages < 2 && C == 32 && KT == 4) { KT = 2; plan(KT); }
   RSA_REQUIRE(p.nstages >= 2, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory budget allows only %d stage(s)", p.nstages);
+  static const int alt_env = getenv("RSA_TC3_ALT") ? atoi(getenv("RSA_TC3_ALT")) : 1;
+  p.alt = (!any_box && alt_env && nbr == 1 && C == 32) ? 1 : 0;   // measured: C = 64 (two chains per item) is faster with both warps on one item
+  if (p.alt) p.nstages &= ~1;                    // see conv_tc3_kernel: an even ring keeps every stage with one MMA warp
   p.tiles_w = W / (8 * KT); p.tiles_h = H / 16;
   p.items = p.tiles_w * p.tiles_h * N;
-  const Tc3Smem L(C, nbr, p.nsb, nside, p.nsi, p.nstages, p.slot_bytes);
+  const Tc3Smem L(C, nbr, nside, p.sdepth, p.nstages, p.slot_bytes);
   RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
-  p.stats = stats; p.relu = relu; p.trace = g_t3_trace;
+  p.stats = stats; p.relu = relu;
+  p.debug = getenv("RSA_TC3_DEBUG") ? atoi(getenv("RSA_TC3_DEBUG")) : 0;
   const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   Tc3Maps maps;
   for (int b = 0; b < nbr; ++b) {
@@ -630,36 +683,36 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   }
   for (int b = nbr; b < T3_MAXBR; ++b) { maps.a[b] = maps.a[0]; maps.w[b] = maps.w[0]; }
   {
-    // 16x8-pixel tiles: the TMA-stored output and the TMA-loaded epilogue side inputs share one box shape
-    auto enc_tile = [&](CUtensorMap* tm, const void* base) -> CUresult {
+    // epilogue slices: 8 x 4 pixels x 32 channels, SWIZZLE_64B for both channel counts (a 64-channel tensor is stored /
+    // loaded as two 32-channel halves by different warps); the TMA-stored output and the side inputs share the box shape
+    auto enc_slice = [&](CUtensorMap* tm, const void* base) -> CUresult {
       cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
       cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)C, 8, 16, 1};
+      cuuint32_t box[4] = {32, 8, 4, 1};
       cuuint32_t es[4] = {1, 1, 1, 1};
       return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
-    CUresult r = enc_tile(&maps.out, out);
+    CUresult r = enc_slice(&maps.out, out);
     RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
     maps.add = maps.out; maps.mask = maps.out; maps.bnx = maps.out;
     if (p.has_bnx) {
-      r = enc_tile(&maps.bnx, bnr_x);
+      r = enc_slice(&maps.bnx, bnr_x);
       RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(bnr_x) failed (%d)", (int)r);
     }
     if (p.has_add) {
-      r = enc_tile(&maps.add, residual ? residual : out);
+      r = enc_slice(&maps.add, residual ? residual : out);
       RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(addend) failed (%d)", (int)r);
     }
     if (p.has_mask) {
-      r = enc_tile(&maps.mask, mask);
+      r = enc_slice(&maps.mask, mask);
       RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_fwd: cuTensorMapEncodeTiled(mask) failed (%d)", (int)r);
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // eight epilogue warps: sixteen (EW = 16) measured 5-15 % slower on every shape - the epilogue's shared-memory accesses
-  // queue behind the tensor core's operand reads, so more warps only add contention
-  if (C == 32) return KT == 2 ? launch3<32, 2, 8>(maps, p, L.total, st) : launch3<32, 4, 8>(maps, p, L.total, st);
-  return KT == 1 ? launch3<64, 1, 8>(maps, p, L.total, st) : launch3<64, 2, 8>(maps, p, L.total, st);
+  if (C == 32) return KT == 2 ? launch3<32, 2>(maps, p, L.total, st) : launch3<32, 4>(maps, p, L.total, st);
+  return KT == 1 ? launch3<64, 1>(maps, p, L.total, st) : launch3<64, 2>(maps, p, L.total, st);
 }
 
 // =====================================================================================================

@@ -592,6 +592,26 @@ class Plan:
                 if b["fused"] else lib.conv_tc3_fwd([dy], [wt], None, [-dil], g, N, H, W, C))
         return lib.conv_tc3_fwd([dy], [wt], None, [-dil], g, N, H, W, C, mask=mask, accumulate=acc)
 
+    def _wide_dgrad(self, src, dy, wt, g, acc, mask, dil, N, H, W, C, Cdy):
+        """conv_tc2 data gradient (C >= 128 layers) into `src`, with the same fusion as _thin_dgrad: for
+        src = relu(BatchNorm(x)) written by this launch alone, the epilogue masks with the activated tensor (src > 0 is the
+        ReLU mask), stores g and accumulates FusedBatchNormGrad's {sum g, sum g * xhat} from the BatchNorm input tile and
+        the {mean, invstd} table of the forward statistics (written by the forward rsa_bn_apply launch).
+        Off unless RSA_BNR_WIDE=1: measured on the B200 (profiles/r2_wide_bnr.txt) the 22 saved reduction launches do not pay
+        for the longer register epilogue of conv_tc2 - the separate reductions overlap with convolutions on the other lane,
+        the fused ones sit on the critical path (13.88 -> 14.12 ms per step)."""
+        lib = self.lib
+        b = src.bn_src
+        plain = lambda: lib.conv_tc2_fwd(dy, None, wt, C, None, g, N, H, W, C, taps=9, dil=-dil, mask=mask, accumulate=acc)
+        if (b is not None and not acc and mask is None and b["relu"] and b.get("coef") is not None and C % 32 == 0
+                and b["x"].dtype == torch.bfloat16 and b["x"].shape == src.shape
+                and os.environ.get("RSA_BNR", "1") != "0" and os.environ.get("RSA_BNR_WIDE", "0") == "1"):
+            b["fused"] = True
+            return self._late(lambda: lib.conv_tc2_fwd(dy, None, wt, C, None, g, N, H, W, C, taps=9, dil=-dil, mask=src.data,
+                                                       stats=b["red"][0], bnr_x=b["x"].data, bnr_coef=b["coef"])
+                              if b["fused"] else plain())
+        return plain()
+
     def _late(self, make):
         """Bind a launch lazily: scratch views (statistics) only exist after _finalize_scratch()."""
         cell = []
@@ -708,8 +728,7 @@ class Plan:
                         self.bwd.append(self._tag(self._thin_dgrad(x, dy, tcw[1], g, acc, mask, dil, N, H, W, C),
                                                   "conv3x3_dgrad", flops, nb))
                     elif tcw is not None:
-                        self.bwd.append(self._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9,
-                                                                   dil=-dil, mask=mask, accumulate=acc),
+                        self.bwd.append(self._tag(self._wide_dgrad(x, dy, tcw[1], g, acc, mask, dil, N, H, W, C, cout),
                                                   "conv3x3_dgrad", flops, nb))
                     else:
                         self.bwd.append(self._tag(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask,
@@ -740,8 +759,13 @@ class Plan:
             for n in names:
                 self.bn_table.append((xs, C, n + "/moving_mean", n + "/moving_variance", cnt, cnt * full_mult))
             esz = x.data.element_size()
+            # C >= 128: the consumers' data gradients run on conv_tc2, whose fused BatchNorm-backward epilogue wants the
+            # {mean, invstd} table (see _wide_dgrad); the first block of this launch writes it
+            coef = None
+            if relu and C >= 128 and x.dtype == torch.bfloat16 and self.net.conv_engine != "igemm_simt":
+                coef = self.alloc((2 * C,), torch.float32)
             self.fwd.append(self._hb(self._late(lambda: lib.bn_apply(x.data, M, C, [o.data for o in outs], gam, bet, xs[0],
-                                                                      cnt, None, None, BN_EPS, relu)),
+                                                                      cnt, None, None, BN_EPS, relu, coef)),
                                      (1 + len(outs)) * M * C * esz))
             if derive:   # statistics of y = gamma*xhat+beta are known in closed form
                 o = outs[0]
@@ -751,7 +775,7 @@ class Plan:
                                                                         float(o.M), C)))
             reds = [self.zeroed(2 * C) for _ in names]
             for k, o in enumerate(outs):
-                o.bn_src = dict(x=x, xs=xs, cnt=cnt, gamma=gam[k], beta=bet[k], relu=relu, red=reds[k], fused=False)
+                o.bn_src = dict(x=x, xs=xs, cnt=cnt, gamma=gam[k], beta=bet[k], relu=relu, red=reds[k], fused=False, coef=coef)
 
             def bwd():
                 live = [k for k, o in enumerate(outs) if o.grad is not None]
@@ -1026,8 +1050,7 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
             if thin:
                 pl.bwd.append(pl._tag(pl._thin_dgrad(a, dy, tcw[1], g, acc, None, d, N, H, W, C), "conv3x3_dgrad", flops, nb))
             elif tcw is not None:
-                pl.bwd.append(pl._tag(lib.conv_tc2_fwd(dy, None, tcw[1], C, None, g, N, H, W, C, taps=9, dil=-d,
-                                                       accumulate=acc), "conv3x3_dgrad", flops, nb))
+                pl.bwd.append(pl._tag(pl._wide_dgrad(a, dy, tcw[1], g, acc, None, d, N, H, W, C, f), "conv3x3_dgrad", flops, nb))
             else:
                 pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
                                       "conv3x3_dgrad", flops, nb))
@@ -1161,7 +1184,7 @@ class Net:
         self.shadow_dirty = True
         engine = os.environ.get("RSA_CONV_ENGINE", "tc")
         emulated = getattr(self.lib, "is_emulation", False) and not getattr(self.lib, "emulates_tensor_core", False)
-        if self.act_dtype != torch.bfloat16 or emulated or engine != "tc" or not hasattr(self.lib, "conv_tc_fwd"):
+        if self.act_dtype != torch.bfloat16 or emulated or engine != "tc" or not hasattr(self.lib, "conv_tc2_fwd"):
             self.conv_engine = "igemm_simt"
             return
         okc = lambda c: c == 32 or (c >= 64 and c % 64 == 0)

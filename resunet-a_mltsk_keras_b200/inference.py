@@ -151,56 +151,93 @@ class SceneOnDevice:
         return self.labels, self.cm
 
 
+def _paste_rows(out, seg_pred, nw, patch_size, r0, r1):
+    """out[rows of tile-rows r0..r1) = tiles, converting to out's dtype on the way (one pass, no intermediate array)."""
+    ps = patch_size
+    for r in range(r0, r1):
+        t = seg_pred[r * nw:(r + 1) * nw]                               # [nw, ps, ps]
+        out[r * ps:(r + 1) * ps, :nw * ps].reshape(ps, nw, ps)[...] = np.swapaxes(t, 0, 1)
+
+
+def reconstruct_threaded(patch_size, seg_pred, shape):
+    """pred_recostruction for label tiles, tile-rows spread over the copy pool: a 6000 x 6000 float64 map is 288 MB of
+    freshly faulted pages, which one thread fills in ~150 ms."""
+    from . import keras_api as KA
+    h, w = shape
+    nh, nw = h // patch_size, w // patch_size
+    out = np.empty((h, w), dtype=np.float64)
+    out[nh * patch_size:, :] = 0
+    out[:nh * patch_size, nw * patch_size:] = 0
+    if nh * nw < 64:
+        _paste_rows(out, seg_pred, nw, patch_size, 0, nh)
+        return out
+    pool = KA._copy_pool()
+    step = max(1, -(-nh // 8))
+    futs = [pool.submit(_paste_rows, out, seg_pred, nw, patch_size, r, min(nh, r + step)) for r in range(0, nh, step)]
+    for f in futs:
+        f.result()
+    return out
+
+
 def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, num_classes=None):
     """Whole-scene inference (test_ISPRS.py:268-333): returns dict with
     ``seg_pred`` [P,ps,ps] int32, ``reconstructed`` (H,W) float64, and — when ``reference`` (H,W)
     integer labels is given — ``confusion`` (sklearn-shaped int64), ``labels`` and ``metrics``.
 
-    Host side: every batch is gathered from the scene straight into one of two pinned buffers (one multi-threaded copy, no
-    intermediate patch array) while the previous batch is still on the GPU; the reference labels go up once; the label
-    tiles come back in one copy at the end.  Under ``torch.distributed`` (one process per GPU) the patches are
-    independent: every rank predicts a contiguous share of them, the int64 confusion matrices are summed with one
-    all-reduce and the label tiles are all-gathered, so every rank returns the complete result (as
-    ``MirroredStrategy.predict`` does, test_ISPRS.py:276-277)."""
+    Host side: every batch (patches and, if given, their reference labels) is gathered from the scene straight into one
+    of two pinned buffers (one multi-threaded copy, no intermediate patch array) while the previous batch is still on the
+    GPU; the label tiles come back in one copy into pinned memory at the end and are pasted into the map by the same
+    thread pool.  Under ``torch.distributed`` (one process per GPU) the patches are independent: every rank
+    predicts a contiguous share of them, the int64 confusion matrices are summed with one all-reduce and the label tiles
+    are all-gathered, so every rank returns the complete result (as ``MirroredStrategy.predict`` does,
+    test_ISPRS.py:276-277)."""
     net = model.net
     lib = net.lib
     K = int(num_classes or net.num_classes)
     nh, nw, view = _patch_rows(image, patch_size)
+    rview = _patch_rows(reference, patch_size)[2] if reference is not None else None
     P = nh * nw
     dev = net.device
     on_gpu = dev.type == "cuda"
     dist, world, rank = _world()
     share = -(-P // world)                                   # patches per rank (the last ranks may get fewer / none)
     lo, hi = min(P, rank * share), min(P, (rank + 1) * share)
-    ref_dev = None
-    if reference is not None and hi > lo:
-        rp = extract_patches(np.asarray(reference), patch_size)[lo:hi]
-        ref_dev = torch.from_numpy(np.ascontiguousarray(rp, dtype=np.int32).reshape(hi - lo, -1)).to(dev)
-    local = torch.zeros((share, patch_size, patch_size), dtype=torch.int32, device=dev)
     cm = torch.zeros(K * K, dtype=torch.int64, device=dev)
     shape = (batch_size, patch_size, patch_size) + view.shape[4:]
-    key = ("scene", shape)
-    ring = getattr(model, "_scene_ring", {}).get(key)
-    if ring is None:
-        ring = [[torch.empty(shape, dtype=torch.float32, pin_memory=on_gpu), None] for _ in range(2)]
-        if not hasattr(model, "_scene_ring"):
-            model._scene_ring = {}
-        model._scene_ring[key] = ring
+    key = ("scene", shape, share)
+    cache = getattr(model, "_scene_ring", None)
+    if cache is None:
+        cache = model._scene_ring = {}
+    ent = cache.get(key)
+    if ent is None:
+        pin = dict(pin_memory=True) if on_gpu else {}
+        ent = cache[key] = dict(
+            x=[[torch.empty(shape, dtype=torch.float32, **pin), None] for _ in range(2)],
+            y=[torch.empty((batch_size, patch_size * patch_size), dtype=torch.int32, **pin) for _ in range(2)],
+            ydev=[torch.empty((batch_size, patch_size * patch_size), dtype=torch.int32, device=dev) for _ in range(2)],
+            local=torch.zeros((share, patch_size, patch_size), dtype=torch.int32, device=dev),
+            host=torch.empty((share, patch_size, patch_size), dtype=torch.int32, **pin))
+    local = ent["local"]
     for bi, i in enumerate(range(lo, hi, batch_size)):
         n = min(batch_size, hi - i)
-        buf = ring[bi & 1]
+        buf, ybuf, ydev = ent["x"][bi & 1], ent["y"][bi & 1], ent["ydev"][bi & 1]
         if buf[1] is not None:
-            buf[1].synchronize()                              # the H2D copy that last read this buffer has finished
+            buf[1].synchronize()                              # the H2D copies that last read these buffers have finished
         _gather_patches(view, nw, i, i + n, buf[0].numpy())     # np.copyto casts other dtypes to float32 on the way
+        if rview is not None:
+            _gather_patches(rview, nw, i, i + n, ybuf.numpy().reshape(batch_size, patch_size, patch_size))
         pl = net.plan(n, False, None)
         model._load_x(pl, buf[0][:n])                         # pinned tensor: asynchronous copy, no staging
+        tl = None
+        if rview is not None:
+            ydev[:n].copy_(ybuf[:n], non_blocking=True)
+            tl = ydev[:n].view(-1)
         if on_gpu:
             buf[1] = torch.cuda.Event()
             buf[1].record(torch.cuda.current_stream())
         model._execute(pl, False)
         prob = pl.outputs["seg"]
         lab = local[i - lo:i - lo + n].view(-1)
-        tl = ref_dev[i - lo:i - lo + n].reshape(-1) if ref_dev is not None else None
         lib.argmax_confusion(prob.data, prob.M, prob.C, lab, tl, K, cm if tl is not None else None)(model._stream())
     if world > 1:
         if on_gpu:
@@ -211,10 +248,13 @@ def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, n
         dist.all_gather(parts, local)
         seg_pred = torch.cat(parts)[:P].cpu().numpy()
     else:
-        seg_pred = local[:P].cpu().numpy()
+        ent["host"].copy_(local, non_blocking=True)
+        if on_gpu:
+            torch.cuda.current_stream().synchronize()
+        seg_pred = ent["host"][:P].numpy().copy()
     out = dict(seg_pred=seg_pred)
     h, w = np.asarray(image).shape[:2]
-    out["reconstructed"] = pred_recostruction(patch_size, seg_pred, np.zeros((h, w), dtype=np.uint8))
+    out["reconstructed"] = reconstruct_threaded(patch_size, seg_pred, (h, w))
     if reference is not None:
         full = cm.cpu().numpy().reshape(K, K)
         out["confusion_full"] = full

@@ -108,9 +108,14 @@ class EmulLib:
             stats[C:2 * C] += (v * v).sum(0)
         return self._wrap(run, "rsa_bn_stats")
 
-    def bn_apply(self, x, M, C, outs, gammas, betas, stats, count, mmeans, mvars, eps, relu):
+    def bn_apply(self, x, M, C, outs, gammas, betas, stats, count, mmeans, mvars, eps, relu, meaninv=None):
         def run():
             v = x.reshape(M, C).to(F64)
+            if meaninv is not None:
+                mu, inv = _mean_inv(stats, count, C, eps, None if mmeans is None else mmeans[0],
+                                    None if mvars is None else mvars[0])
+                meaninv[:C] = mu.to(meaninv.dtype)
+                meaninv[C:2 * C] = inv.to(meaninv.dtype)
             for k, o in enumerate(outs):
                 mu, inv = _mean_inv(stats, count, C, eps, None if mmeans is None else mmeans[k],
                                     None if mvars is None else mvars[k])
@@ -528,7 +533,6 @@ class EmulLibTC(EmulLib):
     def conv_tc2_fwd(self, x0, x1, wt, CoutP, bias, out, N, H, W, Cout, taps=1, dil=1, in_stride=1, ups=(),
                      residual=None, mask=None, stats=None, accumulate=False, relu=False, k_base=0, k_total=0,
                      out_stride=1, bnr_x=None, bnr_coef=None):
-        assert bnr_x is None, "the conv_tc2 fused-reduction epilogue is not emulated (unused by the graph)"
         C0 = x0.shape[-1]
         C1 = x1.shape[-1] if x1 is not None else 0
         K = C0 + C1
@@ -548,7 +552,18 @@ class EmulLibTC(EmulLib):
             for q, sh in ups:
                 qv = q.reshape(N, H >> sh, W >> sh, Cout).to(F64)
                 acc = acc + qv.repeat_interleave(1 << sh, 1).repeat_interleave(1 << sh, 2)
-            self._epilogue(acc, out, Cout, residual, mask, accumulate, relu, stats, out_stride)
+            if bnr_x is None:
+                self._epilogue(acc, out, Cout, residual, mask, accumulate, relu, stats, out_stride)
+                return
+            # fused BatchNorm-backward reductions: the stored value g is masked by the activated tensor `mask`; stats +=
+            # {sum g, sum g * xhat} with xhat from bnr_x and the {mean, invstd} table
+            assert stats is not None and mask is not None and out_stride == 1 and not accumulate and residual is None
+            g = acc * (mask.reshape(N, H, W, Cout).to(F64) > 0)
+            mean, inv = bnr_coef[:Cout].to(F64), bnr_coef[Cout:2 * Cout].to(F64)
+            xh = (bnr_x.reshape(N, H, W, Cout).to(F64) - mean) * inv
+            stats[:Cout] += g.reshape(-1, Cout).sum(0)
+            stats[Cout:2 * Cout] += (g * xh).reshape(-1, Cout).sum(0)
+            out.reshape(N, H, W, Cout).copy_(g.to(out.dtype))
         return self._wrap(run, "rsa_conv_tc2_fwd")
 
     def conv_tc3_fwd(self, xs, wts, biases, dils, out, N, H, W, C, residual=None, mask=None, stats=None,
@@ -615,7 +630,3 @@ class EmulLibTC(EmulLib):
             _store(z, v)
         return self._wrap(run, "rsa_head_fwd")
 
-    def conv_tc_fwd(self, x, wt, bias, out, N, H, W, Cin, Cout, taps, dil, residual=None, mask=None, stats=None,
-                    accumulate=False, relu=False):
-        return self.conv_tc2_fwd(x.reshape(N, H, W, Cin), None, wt, Cout, bias, out, N, H, W, Cout, taps=taps, dil=dil,
-                                 residual=residual, mask=mask, stats=stats, accumulate=accumulate, relu=relu)

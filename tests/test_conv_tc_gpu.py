@@ -1,4 +1,4 @@
-"""tcgen05/TMA convolution kernel (conv_tc.cu) through the C-ABI against the fp64 emulation of the same
+"""tcgen05/TMA convolution kernels (conv_tc.cu, conv_tc2.cu, conv_tc3.cu) through the C-ABI against the fp64 emulation of the same
 implicit GEMM on bf16-rounded operands.  Kept in its own file so that it runs in its own process on the
 GPU box.  Tolerance: 1e-2 of the output range (bf16 output rounding + fp32 accumulation order)."""
 import numpy as np
@@ -30,50 +30,6 @@ def rnd(shape, dtype, seed, scale=1.0):
 def _pack(w_hwio_flat, taps, cin, cout):
     w = w_hwio_flat.view(taps, cin, cout)
     return w.permute(0, 2, 1).contiguous().to(torch.bfloat16), w.contiguous().to(torch.bfloat16)
-
-
-@pytest.mark.parametrize("N,H,C,Co,d", [(2, 32, 32, 32, 1), (2, 32, 32, 32, 15), (2, 64, 32, 32, 31), (2, 32, 64, 64, 3),
-                                        (3, 16, 128, 128, 1), (2, 16, 256, 256, 15), (4, 8, 512, 512, 1),
-                                        (1, 8, 1024, 1024, 1), (16, 4, 1024, 1024, 1), (2, 16, 64, 128, 3)])
-def test_conv_tc_fwd_and_dgrad(lib, N, H, C, Co, d):
-    W = H
-    assert lib.conv_tc_supported(N, H, W, C, Co)
-    dt = torch.bfloat16
-    x = rnd((N, H, W, C), dt, 1)
-    w = rnd((9 * C * Co,), torch.float32, 2, 1.0 / (3 * C ** 0.5))
-    w = w.to(dt).float()                                    # the emulation sees the same bf16-rounded weights
-    b = rnd((Co,), torch.float32, 3)
-    wf, wb = _pack(w, 9, C, Co)
-    segs = [Seg(x, C, H, W, off_h=(ky - 1) * d, off_w=(kx - 1) * d, w_off=(ky * 3 + kx) * C * Co)
-            for ky in range(3) for kx in range(3)]
-    out = rnd((N, H, W, Co), dt, 4)
-    res = rnd((N, H, W, Co), dt, 5)
-    stats = torch.zeros(2 * Co, dtype=torch.float64)
-    EMU.igemm_fwd(segs, w, Co, False, b, out, N, H, W, Co, residual=res, stats=stats, accumulate=True)(0)
-    st = torch.cuda.current_stream().cuda_stream
-    d_out, d_stats = rnd((N, H, W, Co), dt, 4).cuda(), torch.zeros(2 * Co, dtype=torch.float64).cuda()
-    lib.conv_tc_fwd(x.cuda(), wf.cuda(), b.cuda(), d_out, N, H, W, C, Co, 9, d, residual=res.cuda(), stats=d_stats,
-                    accumulate=True)(st)
-    torch.cuda.synchronize()
-    scale = out.float().abs().max().item()
-    assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100, "forward"
-    np.testing.assert_allclose(d_stats.cpu().numpy(), stats.numpy(), rtol=2e-2, atol=2e-2 * N * H * W ** 0.5)
-    # relu + mask epilogue, no accumulate
-    mask = rnd((N, H, W, Co), dt, 6)
-    EMU.igemm_fwd(segs, w, Co, False, b, out, N, H, W, Co, relu=True, mask=mask)(0)
-    lib.conv_tc_fwd(x.cuda(), wf.cuda(), b.cuda(), d_out, N, H, W, C, Co, 9, d, relu=True, mask=mask.cuda())(st)
-    torch.cuda.synchronize()
-    assert (d_out.cpu().float() - out.float()).abs().max().item() <= scale / 100, "relu/mask"
-    # data gradient: negated dilation, [tap][Cin][Cout] copy
-    dy = rnd((N, H, W, Co), dt, 7)
-    sg = [Seg(dy, Co, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * Co)
-          for ky in range(3) for kx in range(3)]
-    dx = torch.zeros((N, H, W, C), dtype=dt)
-    EMU.igemm_fwd(sg, w, Co, True, None, dx, N, H, W, C)(0)
-    d_dx = torch.zeros((N, H, W, C), dtype=dt).cuda()
-    lib.conv_tc_fwd(dy.cuda(), wb.cuda(), None, d_dx, N, H, W, Co, C, 9, -d)(st)
-    torch.cuda.synchronize()
-    assert (d_dx.cpu().float() - dx.float()).abs().max().item() <= dx.float().abs().max().item() / 100, "dgrad"
 
 
 def test_pack_weights_tc(lib):
@@ -445,3 +401,48 @@ def test_conv_tc3_fused_bn_backward_reductions(lib, N, H, W, d, relu, C):
     tol = 2e-2 * (g.abs().sum(0).max().item() / 10 + 1)
     np.testing.assert_allclose(d_red[:C].cpu().numpy(), ref_s.numpy(), atol=tol)
     np.testing.assert_allclose(d_red[C:].cpu().numpy(), ref_q.numpy(), atol=tol)
+
+
+@pytest.mark.parametrize("N,H,C,d", [(2, 32, 128, 1), (2, 16, 256, 3), (4, 8, 512, 1), (16, 8, 1024, 1), (2, 64, 128, 15)])
+def test_conv_tc2_fused_bn_backward_reductions(lib, N, H, C, d):
+    """Data gradient of a C >= 128 layer into a = relu(BN(x)): the epilogue masks with the activated tensor, stores g and
+    accumulates FusedBatchNormGrad's {sum g, sum g*xhat} from x and the {mean, invstd} table (graph.Plan._wide_dgrad)."""
+    dt, eps, W = torch.bfloat16, 1e-3, H
+    dy = rnd((N, H, W, C), dt, 7)
+    w = rnd((9 * C * C,), torch.float32, 2, 1.0 / (3 * C ** 0.5)).to(dt).float()
+    _, wb = _pack(w, 9, C, C)
+    x = (rnd((N, H, W, C), torch.float32, 8) * 1.5 + 0.3).to(dt)
+    gamma, beta = rnd((C,), torch.float32, 9) * 0.5 + 1.0, rnd((C,), torch.float32, 10) * 0.3
+    xd = x.double().reshape(-1, C)
+    cnt = float(xd.shape[0])
+    fstats = torch.cat([xd.sum(0), (xd * xd).sum(0)])
+    mean = fstats[:C] / cnt
+    var = (fstats[C:] / cnt - mean * mean).clamp_min(0)
+    inv = 1.0 / torch.sqrt(var + eps)
+    xhat = (xd - mean) * inv
+    a = (gamma.double() * xhat + beta.double()).clamp_min(0).reshape(N, H, W, C).to(dt)       # the stored activation
+    # the {mean, invstd} table as the forward BatchNorm launch writes it
+    outs = [torch.zeros((N, H, W, C), dtype=dt).cuda()]
+    coef = torch.zeros(2 * C, dtype=torch.float32).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    lib.bn_apply(x.cuda(), N * H * W, C, outs, [gamma.cuda()], [beta.cuda()], fstats.cuda(), cnt, None, None, eps, True,
+                 coef)(st)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(coef[:C].cpu().numpy(), mean.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(coef[C:].cpu().numpy(), inv.numpy(), rtol=1e-5)
+    assert (outs[0].cpu().float() - a.float()).abs().max().item() <= 0.02 * a.float().abs().max().item()
+    sg = [Seg(dy, C, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * C)
+          for ky in range(3) for kx in range(3)]
+    da = torch.zeros((N, H, W, C), dtype=torch.float64)
+    EMU.igemm_fwd(sg, w, C, True, None, da, N, H, W, C)(0)
+    g = (da * (a.double() > 0)).reshape(-1, C)
+    d_out = torch.zeros((N, H, W, C), dtype=dt).cuda()
+    d_red = torch.zeros(2 * C, dtype=torch.float64).cuda()
+    lib.conv_tc2_fwd(dy.cuda(), None, wb.cuda(), C, None, d_out, N, H, W, C, taps=9, dil=-d, mask=a.cuda(), stats=d_red,
+                     bnr_x=x.cuda(), bnr_coef=coef)(st)
+    torch.cuda.synchronize()
+    scale = g.abs().max().item()
+    assert (d_out.cpu().double().reshape(-1, C) - g).abs().max().item() <= scale / 100
+    tol = 2e-2 * (g.abs().sum(0).max().item() / 10 + 1)
+    np.testing.assert_allclose(d_red[:C].cpu().numpy(), g.sum(0).numpy(), atol=tol)
+    np.testing.assert_allclose(d_red[C:].cpu().numpy(), (g * xhat).sum(0).numpy(), atol=tol)
