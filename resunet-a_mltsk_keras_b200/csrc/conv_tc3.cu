@@ -16,7 +16,10 @@
 // warps, the only hand-offs left are accumulator full / empty with the MMA warps.
 //
 //   * weights of all branches stay resident in shared memory for the life of the (persistent) CTA;
-//   * an item is 16 x (8*KT) pixels = KT accumulators; |d| <= 3: one halo box per item, larger dilations one box per tap;
+//   * an item is 16 x (8*KT) pixels = KT accumulators; |d| <= 3: one halo box per item, larger dilations one box per tap.
+//     Box mode is bound by L2 -> SM bandwidth (nine 32 KB boxes per 512-pixel item = 9.3 TB/s over 148 SMs at the measured
+//     64 us): releasing its stages in pairs (half the tcgen05.commit count) made it 15 % SLOWER because the producer then
+//     refills at twice the granularity - the ring depth, not the barrier traffic, is what it lives on;
 //   * up to four branches (ResBlock-a: dilations 1/3/15/31, model2.py:23-31) accumulate into the same TMEM tiles,
 //     so the branch sum and the identity add happen once, in the epilogue;
 //   * BatchNorm statistics of the stored values: per-thread partial sums over all the slices of a warp, one 32-wide shuffle

@@ -988,12 +988,35 @@ def _resblock(pl, x, f, dils, identity, relu_out=False):
     pl.block_bias_grad(out, [n[3] for n in names], f)
     if identity:
         pl.identity_add(x, out)
+    # C = 32 blocks on the tensor-core path: the second convolutions of the branches are issued as fused launches whose
+    # branches accumulate in the same TMEM tiles (north_star (1), model2.py:23-31) - the halo-mode dilations (1, 3) with the
+    # identity input in one launch, the box-mode ones (15, 31) in a second that adds onto it: `out` is written twice instead
+    # of four times and rounded to bf16 half as often.  (All four in one launch measured no faster than four single ones:
+    # 72 KB of resident weights leave too shallow an operand ring, profiles/r2_bench_conv.txt.)
+    fuse = (not pl.spec_only and len(dils) > 1 and f == x.C == 32 and os.environ.get("RSA_FUSE_BRANCHES", "1") != "0"
+            and pl.net.tc_weights(names[0][3], pl.N, x.H, x.W) is not None and pl.net.thin_ok(pl.N, x.H, x.W, x.C, f))
+    pending = []
     for i, d in enumerate(dils):
         with pl.lane(i if len(dils) > 1 else None):
             y1 = pl.conv3x3(a1[i], f, d, names[i][1], stats=True, bias_grad=False)   # bias before BN: zero gradient
             a2 = pl.bn(y1, [names[i][2]], relu=True)[0]
-            _conv_into(pl, a2, f, d, names[i][3], out, first=(i == 0), residual=x if identity else None,
-                       relu=relu_out and i == len(dils) - 1)
+            piece = _conv_into(pl, a2, f, d, names[i][3], out, first=(i == 0), residual=x if identity else None,
+                               relu=relu_out and i == len(dils) - 1, emit_fwd=not fuse)
+            pending.append((d, piece))
+    if fuse:
+        groups = [[p_ for p_ in pending if abs(p_[0]) <= 3], [p_ for p_ in pending if abs(p_[0]) > 3]]
+        groups = [g for g in groups if g]
+        lib, N, H, W, C = pl.lib, pl.N, x.H, x.W, x.C
+        for gi, grp in enumerate(groups):
+            xs, wts, bs, ds = [q[1][0] for q in grp], [q[1][1] for q in grp], [q[1][2] for q in grp], [q[0] for q in grp]
+            first, last = gi == 0, gi == len(groups) - 1
+            flops = 2.0 * N * H * W * 9 * C * f * len(grp)
+            nb = 2.0 * N * H * W * (C * len(grp) + f)
+            op = lib.conv_tc3_fwd(xs, wts, bs, ds, out.data, N, H, W, C, residual=x.data if (first and identity) else None,
+                                  accumulate=not first, relu=relu_out and last)
+            op.convs = len(grp)
+            pl.fwd.append(pl._tag(op, "conv3x3_fwd", flops, nb))
+            pl.fwd[-1].chain = out.data.data_ptr()
     if relu_out:
         # the block's only consumer applies Activation('relu') (combine, model2.py:82): fused into the last
         # branch's epilogue; the stored tensor is relu(out) and gradients written to it are masked with it
@@ -1001,12 +1024,14 @@ def _resblock(pl, x, f, dils, identity, relu_out=False):
     return out
 
 
-def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
+def _conv_into(pl, a, f, d, name, out, first, residual, relu=False, emit_fwd=True):
     """Second conv of a branch: writes (first) or accumulates into the block output; the first one
-    also adds the identity input so that the branch sum + identity never exist as separate tensors."""
+    also adds the identity input so that the branch sum + identity never exist as separate tensors.
+    emit_fwd=False: the caller issues the forward as part of a fused multi-branch launch and gets
+    (input, packed forward weights, bias) back; the backward launches are emitted here either way."""
     pl._reg_conv(name, 3, a.C, f)
     if pl.spec_only:
-        return
+        return None
     lib, N, H, W, C = pl.lib, pl.N, a.H, a.W, a.C
     W_ = pl.P(name + "/kernel")
     b_ = pl.P(name + "/bias")
@@ -1017,7 +1042,9 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
     nb = 2.0 * N * H * W * (C + f)
     tcw = pl.net.tc_weights(name, N, H, W)
     thin = tcw is not None and pl.net.thin_ok(N, H, W, C, f)
-    if thin:
+    if not emit_fwd:
+        assert thin
+    elif thin:
         pl.fwd.append(pl._tag(lib.conv_tc3_fwd([a.data], [tcw[0]], [b_], [d], out.data, N, H, W, C, residual=res,
                                                accumulate=not first, relu=relu), "conv3x3_fwd", flops, nb))
     elif tcw is not None:
@@ -1026,7 +1053,8 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
     else:
         pl.fwd.append(pl._tag(lib.igemm_fwd(segs, W_, f, False, b_, out.data, N, H, W, f, residual=res,
                                             accumulate=not first, relu=relu), "conv3x3_fwd", flops, nb))
-    pl.fwd[-1].chain = out.data.data_ptr()     # the branch sum is a read-modify-write sequence on `out`
+    if emit_fwd:
+        pl.fwd[-1].chain = out.data.data_ptr()     # the branch sum is a read-modify-write sequence on `out`
     if pl.training:
         def bwd():
             if out.grad is None:
@@ -1055,6 +1083,7 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False):
                 pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
                                       "conv3x3_dgrad", flops, nb))
         pl.tape.append(bwd)
+    return (a.data, tcw[0], b_) if thin else None
 
 
 def _psp(pl, x, f, v2):

@@ -689,13 +689,17 @@ class Model:
 
     def _dp_graph_backward(self, pl, fwd_from, head, tag):
         """Forward launches [fwd_from:], BN moving statistics, backward and the NCCL gradient sum of a data-parallel step,
-        graph-replayed.  The all-reduce is overlapped with backward: the parameter-heavy deep levels are final after
-        backward launch ks (distribute.two_phase_split) and travel over NVLink on NCCL's stream while the shallow levels'
-        backward (a second graph) still runs; the small remainder follows.  RSA_DP_GRAPH_OVERLAP=0: one all-reduce after
-        the whole backward."""
-        split = self.dp.two_phase_split(pl, self.net.params) if os.environ.get("RSA_DP_GRAPH_OVERLAP", "1") != "0" else None
+        graph-replayed.  The all-reduce is overlapped with backward: the flat gradient buffer becomes final from its END
+        (deep levels: backward reaches them first) towards its start, so after the launches distribute.phase_splits names a
+        suffix goes out on NCCL's stream while the next backward graph runs; only the last few per cent (shallow levels)
+        are reduced after the final launch.  RSA_DP_GRAPH_OVERLAP=0: one all-reduce after the whole backward;
+        RSA_DP_RANGES=1: the two-range schedule of round 1."""
+        splits = []
+        if os.environ.get("RSA_DP_GRAPH_OVERLAP", "1") != "0":
+            splits = self.dp.phase_splits(pl, self.net.params)
+            if os.environ.get("RSA_DP_RANGES", "2") == "1":
+                splits = splits[:1]
         grad = self.net.params.grad
-        ks = split[0] if split else len(pl.bwd) - 1
 
         def first(st):
             if head is not None:
@@ -703,17 +707,21 @@ class Model:
             self._run_ops(pl.fwd[fwd_from:], st)
             if pl.bn_update is not None:
                 pl.bn_update(st)
-            self._run_ops(pl.bwd[:ks + 1], st)
+            self._run_ops(pl.bwd[:(splits[0][0] + 1) if splits else len(pl.bwd)], st)
 
         self._graph((id(pl), tag + "1"), first)
-        if split is None:
+        if not splits:
             self.dp.all_reduce_sum_(grad)
             return
-        off = split[1]
-        h = self.dp.all_reduce_async(grad[off:])
-        self._graph((id(pl), tag + "2"), lambda st: self._run_ops(pl.bwd[ks + 1:], st))
-        self.dp.all_reduce_sum_(grad[:off])
-        h.wait()
+        handles, hi = [], grad.numel()
+        for i, (k, off) in enumerate(splits):
+            handles.append(self.dp.all_reduce_async(grad[off:hi]))
+            hi = off
+            k_next = splits[i + 1][0] if i + 1 < len(splits) else len(pl.bwd) - 1
+            self._graph((id(pl), tag + str(i + 2)), lambda st, a=k + 1, b=k_next + 1: self._run_ops(pl.bwd[a:b], st))
+        self.dp.all_reduce_sum_(grad[:hi])
+        for h in handles:
+            h.wait()
 
     def _collect(self, pl):
         """Device -> host read of the step results; returns the keras metrics list."""

@@ -27,7 +27,7 @@ for mode in ("1", "0", "0b", "0s"):   # "0b": the plain mode again = run-to-run 
         m = build_model((hw, hw, 3), n, True, "v2", dtype="bf16", seed=7)
         m.compile(optimizer=SGD(lr=1e-2, momentum=0.5), loss={h: Tanimoto_dual_loss() for h in heads})
     pl = m.net.plan(B, True, m.loss_spec)
-    split = m.dp.two_phase_split(pl, m.net.params) if mode == "1" else None
+    split = m.dp.phase_splits(pl, m.net.params) if mode == "1" else None
     out = [m.train_on_batch(x, y) for _ in range(4)]
     # the device-resident path of bench.py (_execute) as well
     m._push_lr(); m._execute(pl, True); torch.cuda.synchronize()
@@ -52,5 +52,5 @@ if rank == 0:
     print(f"multi-stream vs single-stream launches: max |loss diff| {ds_l:.3e}, checksum diff {ds_p:.3e}: {ser_ok}")
     print("ranks hold identical parameters:", same_ranks, "| losses overlap vs plain:", loss_ok, "| parameter checksums:", par_ok)
     print("losses (overlap):", a[0][:, 0], "(plain):", b[0][:, 0])
-    print("DP CHECK", "PASS" if (same_ranks and loss_ok and par_ok and ser_ok and a[3] is not None) else "FAIL")
+    print("DP CHECK", "PASS" if (same_ranks and loss_ok and par_ok and ser_ok and a[3]) else "FAIL")
 dist.barrier(); dist.destroy_process_group()

@@ -448,6 +448,9 @@ def test_gradient_readiness_bookkeeping_is_exact(dtype):
     buckets = dp._schedule(pl, ps)
     split = dp.two_phase_split(pl, ps, min_frac=0.3)
     assert split is not None and 0 < split[0] < len(pl.bwd) - 1 and 0 < split[1] < ps.n_train
+    ranges = dp.phase_splits(pl, ps, fracs=(0.3, 0.9))
+    assert len(ranges) == 2 and ranges[0] == split and ranges[1][0] > ranges[0][0] and ranges[1][1] < ranges[0][1]
+    assert ps.n_train - ranges[1][1] >= 0.9 * ps.n_train
     pl.scratch.zero_()
     ps.grad.zero_()
     if m.net.pack_launch is not None:
@@ -462,10 +465,12 @@ def test_gradient_readiness_bookkeeping_is_exact(dtype):
                 snaps[(lo, hi)] = ps.grad[lo:hi].clone()
         if i == split[0]:
             snaps["tail"] = ps.grad[split[1]:ps.n_train].clone()
-    assert len(snaps) == len(buckets) + 1
+        if i == ranges[1][0]:
+            snaps["tail2"] = ps.grad[ranges[1][1]:ranges[0][1]].clone()
+    assert len(snaps) == len(buckets) + 2
     assert float(ps.grad[:ps.n_train].abs().max()) > 0
     for key, snap in snaps.items():
-        lo, hi = (split[1], ps.n_train) if key == "tail" else key
+        lo, hi = (split[1], ps.n_train) if key == "tail" else ((ranges[1][1], ranges[0][1]) if key == "tail2" else key)
         assert torch.equal(snap, ps.grad[lo:hi]), key
 
 
