@@ -79,6 +79,8 @@ struct Tc3Params {
   const float* bnr_beta;
   const float* bias[T3_MAXBR];
   double* stats;
+  uint8_t* out;           // output tensor (direct-store mode)
+  int direct;             // 1: the epilogue writes its slices with 16-byte global stores instead of staging + TMA store
   int relu;
   int debug;              // diagnostic (RSA_TC3_DEBUG, results are wrong): 1 no MMAs, 2 no epilogue data movement, 4 no TMA
                           // operand loads, 8 no TMA stores, 16 no tcgen05.ld, 32 no proxy fence, 64 no staging stores -
@@ -374,27 +376,28 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
     for (int j = 0; j < 32; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
     // coordinates of the slices of this warp are walked incrementally (no divisions in the loop): the "current" cursor for
     // the slice being processed, a second cursor `pf` that runs sdepth - 1 slices ahead for the side-input prefetch
-    struct Cur { int item, j, n, h0, w0; };
+    struct Cur { int item, j, n, tw, th; };
+    const int dtw = (int)gridDim.x % p.tiles_w, dth = ((int)gridDim.x / p.tiles_w) % p.tiles_h,
+              dn = (int)gridDim.x / (p.tiles_w * p.tiles_h);
     auto cur_init = [&](Cur& c) {
       c.item = blockIdx.x; c.j = 0;
       int r = c.item;
-      const int tw = r % p.tiles_w; r /= p.tiles_w;
-      const int th = r % p.tiles_h; r /= p.tiles_h;
-      c.n = r; c.h0 = th * 16; c.w0 = tw * 8 * KT;
+      c.tw = r % p.tiles_w; r /= p.tiles_w;
+      c.th = r % p.tiles_h; r /= p.tiles_h;
+      c.n = r;
     };
-    auto cur_next = [&](Cur& c) {
+    auto cur_next = [&](Cur& c) {          // next slice of this warp; item += gridDim.x by carry arithmetic, no division
       if (++c.j < SPI) return;
       c.j = 0; c.item += gridDim.x;
-      int r = c.item;                                        // once per item
-      const int tw = r % p.tiles_w; r /= p.tiles_w;
-      const int th = r % p.tiles_h; r /= p.tiles_h;
-      c.n = r; c.h0 = th * 16; c.w0 = tw * 8 * KT;
+      c.tw += dtw; c.th += dth; c.n += dn;
+      if (c.tw >= p.tiles_w) { c.tw -= p.tiles_w; ++c.th; }
+      if (c.th >= p.tiles_h) { c.th -= p.tiles_h; ++c.n; }
     };
     auto sub_of = [&](int j) { return C == 32 ? 2 * j + g : j; };
     auto issue_side = [&](const Cur& c, int idx) {       // lane 0: TMA loads of the side slices of slice idx into buffer idx % sdepth
       if (c.item >= p.items) return;
       const int b = idx % p.sdepth;
-      const int hh = c.h0 + 4 * q, ww = c.w0 + 8 * sub_of(c.j);
+      const int hh = c.th * 16 + 4 * q, ww = c.tw * 8 * KT + 8 * sub_of(c.j);
       uint8_t* dst = sbuf + b * nside * T3_SLICE;
       mbar_expect_tx(&mybar[b], nside * T3_SLICE);
       if (p.has_add) tma_load_4d(dst, &maps.add, &mybar[b], c0, ww, hh, c.n);
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
 #pragma unroll 1
       for (int j = 0; j < SPI; ++j, ++idx) {
         const int s = sub_of(j);
-        const int n = cur.n, hh = cur.h0 + 4 * q, ww = cur.w0 + 8 * s;
+        const int n = cur.n, hh = cur.th * 16 + 4 * q, ww = cur.tw * 8 * KT + 8 * s;
         cur_next(cur);
         const int sb = nside ? idx % p.sdepth : 0;
         const uint8_t* ib = sbuf + sb * nside * T3_SLICE;
@@ -510,17 +513,24 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
             for (int i = 0; i < 8; ++i) { acc_s[8 * k + i] += t[i]; acc_q[8 * k + i] = fmaf(t[i], t[i], acc_q[8 * k + i]); }
           }
         }
-        // staging buffer idx & 1 was last read by this warp's store of slice idx - 2: at most one younger store may be open
-        uint8_t* yb = ybuf + (idx & 1) * T3_SLICE;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncwarp();
-        if (!(p.debug & 64)) {
+        if (p.direct) {
+          // each thread holds one pixel's 32 channels = 64 contiguous bytes of the NHWC tensor: four 16-byte stores
+          uint4* gp = reinterpret_cast<uint4*>(p.out + ((((size_t)n * p.H + hh + (lane >> 3)) * p.W + ww + (lane & 7)) * C + c0) * 2);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + o[k]) = pk[k];
+          for (int k = 0; k < 4; ++k) gp[k] = pk[k];
+        } else {
+          // staging buffer idx & 1 was last read by this warp's store of slice idx - 2: at most one younger store may be open
+          uint8_t* yb = ybuf + (idx & 1) * T3_SLICE;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          if (!(p.debug & 64)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + o[k]) = pk[k];
+          }
+          if (!(p.debug & 32)) fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 8)) tma_store_4d(&maps.out, yb, c0, ww, hh, n);
         }
-        if (!(p.debug & 32)) fence_proxy_async();
-        __syncwarp();
-        if (lane == 0 && !(p.debug & 8)) tma_store_4d(&maps.out, yb, c0, ww, hh, n);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -664,6 +674,9 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   const Tc3Smem L(C, nbr, nside, p.sdepth, p.nstages, p.slot_bytes);
   RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
   p.stats = stats; p.relu = relu;
+  p.out = (uint8_t*)out;
+  static const int direct_env = getenv("RSA_TC3_DIRECT") ? atoi(getenv("RSA_TC3_DIRECT")) : 0;
+  p.direct = direct_env;
   p.debug = getenv("RSA_TC3_DEBUG") ? atoi(getenv("RSA_TC3_DEBUG")) : 0;
   const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   Tc3Maps maps;

@@ -576,12 +576,15 @@ class Plan:
         self.tape.append(bwd)
 
     def _thin_dgrad(self, src, dy, wt, g, acc, mask, dil, N, H, W, C):
-        """conv_tc3 data gradient into `src`; when src = [relu](BatchNorm(x)) and this launch is the only writer of
-        d(src), the BatchNormalization backward reductions ride in its epilogue (no separate reduction pass)."""
+        """conv_tc3 data gradient into `src`; with RSA_BNR=1, when src = [relu](BatchNorm(x)) and this launch is the only
+        writer of d(src), the BatchNormalization backward reductions ride in its epilogue (no separate reduction pass).
+        Off by default since round 2: on the B200 the step with the fused sums takes 13.52 ms, with separate
+        rsa_bn_bwd_reduce launches 13.42 ms (20 more launches, but they are bandwidth kernels that overlap with the other
+        lane's convolutions, while the fused epilogue adds 15-30 us to a tensor-core kernel on the critical path)."""
         lib = self.lib
         b = src.bn_src
         if (b is not None and not acc and mask is None and b["x"].dtype == torch.bfloat16 and b["x"].shape == src.shape
-                and os.environ.get("RSA_BNR", "1") != "0"):
+                and os.environ.get("RSA_BNR", "0") == "1"):
             # provisional: the BatchNorm's own backward closure (emitted after every writer of d(src)) withdraws the
             # fusion when another launch accumulates into d(src) as well (two heads read the PSP output) - sums taken in
             # this epilogue would miss that contribution.  The launch is bound late, so it follows the final decision.
@@ -605,7 +608,7 @@ class Plan:
         plain = lambda: lib.conv_tc2_fwd(dy, None, wt, C, None, g, N, H, W, C, taps=9, dil=-dil, mask=mask, accumulate=acc)
         if (b is not None and not acc and mask is None and b["relu"] and b.get("coef") is not None and C % 32 == 0
                 and b["x"].dtype == torch.bfloat16 and b["x"].shape == src.shape
-                and os.environ.get("RSA_BNR", "1") != "0" and os.environ.get("RSA_BNR_WIDE", "0") == "1"):
+                and os.environ.get("RSA_BNR_WIDE", "0") == "1"):
             b["fused"] = True
             return self._late(lambda: lib.conv_tc2_fwd(dy, None, wt, C, None, g, N, H, W, C, taps=9, dil=-dil, mask=src.data,
                                                        stats=b["red"][0], bnr_x=b["x"].data, bnr_coef=b["coef"])

@@ -362,12 +362,17 @@ def _bf16_step(variant, hostile=False, monkeypatch=None, steps=1, hw=64, cin=3, 
     return m, p, x, y, before, after, np.array(out)
 
 
-@pytest.mark.parametrize("variant,hw,cin,n,B", [("v2", 64, 3, N_CLS, 2), ("v1", 64, 3, N_CLS, 2), ("v2", 128, 14, 3, 1),
-                                                ("v2", 256, 3, 6, 1)])      # the last one is config 2's topology (4 PSP levels)
-def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant, hw, cin, n, B):
-    """Host logic of the bf16 mode (K-concatenated 1x1 convolutions with up-sampled addends, packed weights, thin-layer
-    launches with fused BatchNorm-backward sums, pooled adjoints): the launch list the GPU replays, executed by the CPU
-    restatement of its entry points, must give the oracle's gradient up to bf16 storage noise (GPU: 2-3 % / 11 %)."""
+@pytest.mark.parametrize("variant,hw,cin,n,B,fused_bn", [("v2", 64, 3, N_CLS, 2, False), ("v1", 64, 3, N_CLS, 2, False),
+                                                         ("v2", 128, 14, 3, 1, False), ("v2", 64, 3, N_CLS, 2, True),
+                                                         ("v2", 256, 3, 6, 1, True)])   # the last: config 2's topology (4 PSP levels)
+def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant, hw, cin, n, B, fused_bn, monkeypatch):
+    """Host logic of the bf16 mode (K-concatenated 1x1 convolutions with up-sampled addends, packed weights, fused
+    ResBlock-a branch launches, pooled adjoints): the launch list the GPU replays, executed by the CPU restatement of its
+    entry points, must give the oracle's gradient up to bf16 storage noise (GPU: 2-3 % / 11 %).  fused_bn also switches on
+    the BatchNorm-backward sums fused into the data gradients (RSA_BNR / RSA_BNR_WIDE: measured slower, off by default)."""
+    if fused_bn:
+        monkeypatch.setenv("RSA_BNR", "1")
+        monkeypatch.setenv("RSA_BNR_WIDE", "1")
     m, p, x, y, before, after, out = _bf16_step(variant, hw=hw, cin=cin, n=n, B=B)
     p64 = {k: v.double() for k, v in p.items()}
     tot, _, _, grads, _ = O.loss_and_grads(p64, torch.from_numpy(x).double(),
@@ -389,6 +394,9 @@ def test_bf16_tensor_core_launch_list_gradients_match_fp64_oracle(variant, hw, c
     kernels = {getattr(op, "kernel", "?") for op in list(pl.fwd) + list(pl.bwd)}
     assert {"rsa_conv_tc2_fwd", "rsa_conv_tc3_fwd", "rsa_conv_tc3_wgrad", "rsa_conv_tc_wgrad", "rsa_pw_wgrad_tc",
             "rsa_bias_grad", "rsa_head_fwd"} <= kernels
+    assert any(getattr(op, "convs", 1) > 1 for op in pl.fwd) == (variant in ("v1", "v2")), "fused branch launches are issued"
+    n_red = sum(getattr(op, "kernel", "") == "rsa_bn_bwd_reduce_multi" for op in pl.bwd)
+    assert (n_red < 30) if fused_bn else (n_red > 40)
 
 
 @pytest.mark.parametrize("variant,hw,cin,n,B", [("v2", 64, 3, N_CLS, 2), ("v1", 64, 3, N_CLS, 2), ("v2", 128, 14, 3, 1)])
