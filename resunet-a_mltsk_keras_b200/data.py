@@ -218,10 +218,38 @@ def compute_mcc(tp, tn, fp, fn):
     return float((tp * tn - fp * fn) / den) if den > 0 else 0.0
 
 
+def _scalar_writers(log_dir, log):
+    """(train, val) TensorBoard writers like train_ISPRS.py:57-63 (`<log_dir>/train`, `<log_dir>/val`), or (None, None)."""
+    if not log_dir:
+        return None, None
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+    except Exception as e:          # tensorboard is an optional dependency
+        log(f"TensorBoard scalars disabled: {e}")
+        return None, None
+    return SummaryWriter(os.path.join(log_dir, "train")), SummaryWriter(os.path.join(log_dir, "val"))
+
+
+def add_tensorboard_scalars(train_writer, val_writer, epoch, metric_name, train_loss, val_loss, train_acc=None, val_acc=None,
+                            val_mcc=None):
+    """Same tags as the reference's add_tensorboard_scalars (train_ISPRS.py:35-53): <Task>/Loss, /Accuracy, /MCC."""
+    if train_writer is None:
+        return
+    train_writer.add_scalar(metric_name + "/Loss", train_loss, epoch)
+    if train_acc is not None:
+        train_writer.add_scalar(metric_name + "/Accuracy", train_acc, epoch)
+    val_writer.add_scalar(metric_name + "/Loss", val_loss, epoch)
+    if val_acc is not None:
+        val_writer.add_scalar(metric_name + "/Accuracy", val_acc, epoch)
+    if val_mcc is not None:
+        val_writer.add_scalar(metric_name + "/MCC", val_mcc, epoch)
+
+
 def train_model(net, train_loader, val_loader, epochs, results_path, patience=10, delta=0.001, metrics_names=None,
-                log=print, save_name="best_model.npz"):
+                log=print, save_name="best_model.npz", tensorboard_dir=None):
     """Epoch loop of the reference trainer: mean of the per-batch train_on_batch / test_on_batch vectors
-    (train_ISPRS.py:97-189), per-task table, MCC of the segmentation head, early stopping on the validation loss with
+    (train_ISPRS.py:97-189), per-task table, MCC of the segmentation head, TensorBoard scalars per task when
+    `tensorboard_dir` is given (train_ISPRS.py:35-63,226-268; rank 0 only), early stopping on the validation loss with
     `delta` / `patience` and a checkpoint of the best model (train_ISPRS.py:276-292).  Returns (net, history)."""
     names = list(metrics_names or net.metrics_names)
     dp = getattr(net, "dp", None)
@@ -229,6 +257,8 @@ def train_model(net, train_loader, val_loader, epochs, results_path, patience=10
     if not multi or dp.rank == 0:
         os.makedirs(results_path, exist_ok=True)
     min_loss, cont, history = float("inf"), 0, []
+    tw, vw = _scalar_writers(tensorboard_dir if (not multi or dp.rank == 0) else None, log)
+    tb_names = dict(Seg="Segmentation", Bound="Boundary", Dist="Distance", Color="Color", Total="Total")
     for epoch in range(epochs):
         tr = np.zeros(len(names))
         nb = 0
@@ -259,6 +289,7 @@ def train_model(net, train_loader, val_loader, epochs, results_path, patience=10
         log(f"{'Task':8s} {'Loss':>10s} {'Val Loss':>10s} {'Acc %':>9s} {'Val Acc %':>10s}")
         for t, l, vl, a, vacc in rows:
             log(f"{t:8s} {l:10.5f} {vl:10.5f} {100 * (a or 0):9.5f} {100 * (vacc or 0):10.5f}")
+            add_tensorboard_scalars(tw, vw, epoch, tb_names[t], l, vl, a, vacc, val_mcc=mcc if t == "Seg" else None)
         if mcc is not None:
             log(f"Validation MCC: {mcc:.5f}")
         val_loss = vam["loss"]
@@ -268,9 +299,12 @@ def train_model(net, train_loader, val_loader, epochs, results_path, patience=10
             log(f"EarlyStopping counter: {cont} out of {patience}")
             if cont >= patience:
                 log("Early Stopping! \t Training Stopped")
-                return net, history
+                break
         else:
             cont, min_loss = 0, val_loss
             log("Saving best model...")
             net.save(os.path.join(results_path, save_name))
+    for w_ in (tw, vw):
+        if w_ is not None:
+            w_.close()
     return net, history

@@ -125,8 +125,16 @@ def test_mcc_and_training_shell_early_stopping(tmp_path):
     net.e = -1
     lines = []
     _, hist = D.train_model(net, Train(), [(0, 0)] * 2, epochs=6, results_path=str(tmp_path / "res"), patience=3,
-                            delta=0.001, log=lines.append)
+                            delta=0.001, log=lines.append, tensorboard_dir=str(tmp_path / "tb"))
     # epochs 0,1 improve (saved); 2,3,4 are within/above min+delta -> counter 3 -> stop before epoch 5
     assert [e for e, _ in net.saved] == [0, 1]
     assert len(hist) == 5 and any("Early Stopping" in l for l in lines)
     assert hist[0]["mcc"] == pytest.approx(D.compute_mcc(8, 6, 1, 1))
+    # TensorBoard scalars with the reference's tags (train_ISPRS.py:35-53), one event file per writer
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    for split, want in (("train", {"Segmentation/Loss", "Segmentation/Accuracy", "Total/Loss"}),
+                        ("val", {"Segmentation/Loss", "Segmentation/Accuracy", "Segmentation/MCC", "Total/Loss"})):
+        acc = EventAccumulator(str(tmp_path / "tb" / split))
+        acc.Reload()
+        assert want <= set(acc.Tags()["scalars"]), (split, acc.Tags()["scalars"])
+        assert len(acc.Scalars("Total/Loss")) == 5
