@@ -227,7 +227,7 @@ class Dist:
         return t.item()
 
 
-def profile_single_stream(model, pl, pk):
+def profile_single_stream(model, pl, pk, cfg=2):
     """One single-stream pass of the step with CUDA events around EVERY launch.  The stream is first parked behind a
     ~25 ms spin kernel so that the host is hundreds of launches ahead: the events then time kernels that run back to
     back on the launching stream (no idle-start latency inside the intervals), like the launches of the replayed graph.
@@ -350,15 +350,15 @@ def profile_single_stream(model, pl, pk):
                     by_kernel={f"{tag} {kern}": dict(launches=n, ms=round(t, 4), tflops=round(f / (t * 1e-3) / 1e12, 1))
                                for (tag, kern), (n, t, f) in sorted(by_tag.items())},
                     by_kernel_note="per-launch event timing (upper bound of each kernel's time)")
-        tpath = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
-        if os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")      # ncu capture of config 2's launches
+        if cfg == 2 and os.path.exists(tpath):
             tj = json.load(open(tpath))
             roof.update(traffic=tj.get("mean_dram_bytes_per_launch"), traffic_source=tj.get("source"),
                         algorithmic_bytes_per_launch=tj.get("algorithmic_bytes_per_launch"),
                         l2_to_sm_bytes_per_launch=tj.get("mean_l2_to_sm_bytes_per_launch"),
                         tensor_pipe_active_pct=tj.get("mean_tensor_pipe_active_pct"))
         else:
-            roof.update(traffic=None, traffic_source="no ncu capture of this code under profiles/")
+            roof.update(traffic=None, traffic_source="no ncu capture of this configuration under profiles/")
     return roof, hbm_tab, sum(ms)
 
 
@@ -437,7 +437,7 @@ def run_train(args, D):
     roof = hbm_tab = None
     single_ms = None
     if D.rank == 0:
-        roof, hbm_tab, single_ms = profile_single_stream(model, pl, peaks())
+        roof, hbm_tab, single_ms = profile_single_stream(model, pl, peaks(), cfg)
         if roof is not None:
             roof["conv_share_of_single_stream_step"] = roof["conv_ms_per_step"] / single_ms
 

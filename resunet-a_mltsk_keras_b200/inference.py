@@ -179,6 +179,19 @@ def reconstruct_threaded(patch_size, seg_pred, shape):
     return out
 
 
+_FINISHER = None
+
+
+def _finisher():
+    """Two host threads that assemble finished batches (kept apart from the copy pool, whose workers the batch gather
+    saturates)."""
+    global _FINISHER
+    if _FINISHER is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _FINISHER = ThreadPoolExecutor(2)
+    return _FINISHER
+
+
 def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, num_classes=None):
     """Whole-scene inference (test_ISPRS.py:268-333): returns dict with
     ``seg_pred`` [P,ps,ps] int32, ``reconstructed`` (H,W) float64, and — when ``reference`` (H,W)
@@ -218,6 +231,26 @@ def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, n
             local=torch.zeros((share, patch_size, patch_size), dtype=torch.int32, device=dev),
             host=torch.empty((share, patch_size, patch_size), dtype=torch.int32, **pin))
     local = ent["local"]
+    h, w = np.asarray(image).shape[:2]
+    single = world == 1
+    if single:
+        # results are assembled on the host WHILE the GPU works: each batch's label tiles are copied to pinned memory
+        # behind its argmax launch and a worker thread moves them into the result arrays as soon as that copy has landed
+        seg_pred = np.empty((P, patch_size, patch_size), dtype=np.int32)
+        recon = np.empty((h, w), dtype=np.float64)
+        recon[nh * patch_size:, :] = 0
+        recon[:nh * patch_size, nw * patch_size:] = 0
+        finisher = _finisher()
+        pending = []
+
+        def finish(ev, i, n):
+            if ev is not None:
+                ev.synchronize()
+            tiles = ent["host"][i:i + n].numpy()
+            seg_pred[i:i + n] = tiles
+            for k in range(n):
+                r, c = divmod(i + k, nw)
+                recon[r * patch_size:(r + 1) * patch_size, c * patch_size:(c + 1) * patch_size] = tiles[k]
     for bi, i in enumerate(range(lo, hi, batch_size)):
         n = min(batch_size, hi - i)
         buf, ybuf, ydev = ent["x"][bi & 1], ent["y"][bi & 1], ent["ydev"][bi & 1]
@@ -239,7 +272,18 @@ def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, n
         prob = pl.outputs["seg"]
         lab = local[i - lo:i - lo + n].view(-1)
         lib.argmax_confusion(prob.data, prob.M, prob.C, lab, tl, K, cm if tl is not None else None)(model._stream())
-    if world > 1:
+        if single:
+            ent["host"][i:i + n].copy_(local[i:i + n], non_blocking=True)
+            ev = None
+            if on_gpu:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+            pending.append(finisher.submit(finish, ev, i, n))
+    if single:
+        for f in pending:
+            f.result()
+        out = dict(seg_pred=seg_pred, reconstructed=recon)
+    else:
         if on_gpu:
             torch.cuda.current_stream().synchronize()
         if reference is not None:
@@ -247,14 +291,7 @@ def predict_scene(model, image, reference=None, patch_size=256, batch_size=64, n
         parts = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(parts, local)
         seg_pred = torch.cat(parts)[:P].cpu().numpy()
-    else:
-        ent["host"].copy_(local, non_blocking=True)
-        if on_gpu:
-            torch.cuda.current_stream().synchronize()
-        seg_pred = ent["host"][:P].numpy().copy()
-    out = dict(seg_pred=seg_pred)
-    h, w = np.asarray(image).shape[:2]
-    out["reconstructed"] = reconstruct_threaded(patch_size, seg_pred, (h, w))
+        out = dict(seg_pred=seg_pred, reconstructed=reconstruct_threaded(patch_size, seg_pred, (h, w)))
     if reference is not None:
         full = cm.cpu().numpy().reshape(K, K)
         out["confusion_full"] = full
