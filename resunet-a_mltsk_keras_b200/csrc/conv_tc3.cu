@@ -128,8 +128,12 @@ struct Tc3Smem {
   }
 };
 
-template <int C, int KT>
-__global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
+// STATS = the launch accumulates BatchNorm statistics (64 partial sums per epilogue thread: 168 registers).  Launches without
+// them are compiled to 112 registers: 352 threads x 168 registers take 90 % of the register file and keep every other kernel
+// off the SM, 352 x 112 leave room for two CTAs of a bandwidth-bound kernel (BatchNorm apply / backward, 256 threads x 40-64
+// registers) to run BESIDE the persistent convolution CTA - the lanes of the step executor put them on concurrent streams.
+template <int C, int KT, bool STATS>
+__global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_constant__ Tc3Maps maps, const Tc3Params p) {
   constexpr int PITCH = T3<C>::PITCH, BOXB = T3<C>::BOXB, WBYTES = T3<C>::WBYTES;
   constexpr int EPI0 = T3Warps<KT>::EPI0, PROD = T3Warps<KT>::PROD, MMA0 = T3Warps<KT>::MMA0;
   constexpr int LPW = T3Warps<KT>::LPW;
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
   uint64_t* wbar = sbar + 4 * T3_EW;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool has_stats = p.stats != nullptr;
+  constexpr bool has_stats = STATS;
   // NACC accumulator stages of KT sub-tiles each.  The MMA warps may run NACC items ahead of the epilogue; with two stages
   // the loop MMA(it) -> commit -> epilogue sees it (~1.7k cycles later, scripts/iso_tc3.py) -> epilogue has read the item ->
   // MMA(it + 2) bounded an item at (commit latency + epilogue latency + MMA time) / 2 = ~4.5k cycles against 2.9k of MMAs.
@@ -371,9 +375,9 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) o[k] = srow + (((uint32_t)k ^ sw) << 4);
-    float acc_s[32], acc_q[32];                                 // BatchNorm statistics of this thread's pixels (all its slices)
+    float acc_s[STATS ? 32 : 1], acc_q[STATS ? 32 : 1];         // BatchNorm statistics of this thread's pixels (all its slices)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+    for (int j = 0; j < (STATS ? 32 : 1); ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
     // coordinates of the slices of this warp are walked incrementally (no divisions in the loop): the "current" cursor for
     // the slice being processed, a second cursor `pf` that runs sdepth - 1 slices ahead for the side-input prefetch
     struct Cur { int item, j, n, tw, th; };
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
             for (int i = 0; i < 8; ++i) f[8 * k + i] = t[i] > 0.f ? f[8 * k + i] : 0.f;
           }
         }
-        if (p.has_bnx) {
+        if constexpr (STATS) if (p.has_bnx) {
           // fused BatchNorm(+ReLU) backward reductions: f is d(relu(bn(x))); recompute the ReLU mask from x like the
           // forward did, keep g = f * mask as the stored value and accumulate {sum g, sum g * x}; the affine step from
           // sum g * x to sum g * xhat is applied once per channel at the end
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
           pk[k].x = pack_bf16x2(f[8 * k], f[8 * k + 1]); pk[k].y = pack_bf16x2(f[8 * k + 2], f[8 * k + 3]);
           pk[k].z = pack_bf16x2(f[8 * k + 4], f[8 * k + 5]); pk[k].w = pack_bf16x2(f[8 * k + 6], f[8 * k + 7]);
         }
-        if (has_stats && !p.has_bnx) {
+        if constexpr (STATS) if (!p.has_bnx) {
           // statistics of the stored (bf16-rounded) values
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (has_stats) {
+    if constexpr (STATS) {
       // 32-wide butterfly reduce-scatter over the warp's 32 pixel rows: lane l ends with channel c0 + l
 #pragma unroll
       for (int off = 16, nn = 16; nn >= 1; off >>= 1, nn >>= 1) {
@@ -578,19 +582,23 @@ __global__ void __launch_bounds__(T3Warps<KT>::THREADS, 1) conv_tc3_kernel(const
   }
 }
 
-template <int C, int KT>
-int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_t st) {
+template <int C, int KT, bool STATS>
+int launch3s(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<C, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<C, KT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { rsa_set_error("conv_tc3: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
   const int grid = p.items < rsa_num_sms() ? p.items : rsa_num_sms();
-  cudaError_t le = launch_pdl(conv_tc3_kernel<C, KT>, dim3(grid), dim3(T3Warps<KT>::THREADS), (size_t)smem_bytes, st, maps, p);
+  cudaError_t le = launch_pdl(conv_tc3_kernel<C, KT, STATS>, dim3(grid), dim3(T3Warps<KT>::THREADS), (size_t)smem_bytes, st, maps, p);
   if (le != cudaSuccess) { rsa_set_error("conv_tc3: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
+}
+template <int C, int KT>
+int launch3(const Tc3Maps& maps, const Tc3Params& p, int smem_bytes, cudaStream_t st) {
+  return p.stats ? launch3s<C, KT, true>(maps, p, smem_bytes, st) : launch3s<C, KT, false>(maps, p, smem_bytes, st);
 }
 
 }  // namespace
@@ -654,17 +662,20 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   static const int sd_env = getenv("RSA_TC3_SDEPTH") ? atoi(getenv("RSA_TC3_SDEPTH")) : 0;
   p.sdepth = C == 64 ? (nside == 2 ? 1 : 2) : (nside == 1 ? 3 : 2);
   if (sd_env >= 1 && sd_env <= 4 && nside) p.sdepth = sd_env;
-  auto plan = [&](int kt) {
+  // shared memory: leave ~8 KB of the SM to the bandwidth-bound kernels that run beside the persistent CTA (see
+  // conv_tc3_kernel) unless that costs an operand stage
+  auto plan = [&](int kt, int budget_kb) {
     int slot = any_box ? kt * BOXB : 0;
     if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * kt + 2 * max_ad) * PITCH; slot = hb > slot ? hb : slot; }
     slot = (slot + 1023) & ~1023;
     const Tc3Smem L0(C, nbr, nside, p.sdepth, 0, slot);
-    int ns = (227 * 1024 - L0.total - 256) / (slot + 16);
+    int ns = (budget_kb * 1024 - L0.total - 256) / (slot + 16);
     p.slot_bytes = slot;
     p.nstages = ns > 8 ? 8 : ns;
   };
-  plan(KT);
-  if (p.nstages < 2 && C == 32 && KT == 4) { KT = 2; plan(KT); }
+  plan(KT, 227);
+  if (p.nstages < 2 && C == 32 && KT == 4) { KT = 2; plan(KT, 227); }
+  { const int full = p.nstages; plan(KT, 219); if (p.nstages < full && p.nstages < 4) plan(KT, 227); }
   RSA_REQUIRE(p.nstages >= 2, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory budget allows only %d stage(s)", p.nstages);
   static const int alt_env = getenv("RSA_TC3_ALT") ? atoi(getenv("RSA_TC3_ALT")) : 1;
   p.alt = (!any_box && alt_env && nbr == 1 && C == 32) ? 1 : 0;   // measured: C = 64 (two chains per item) is faster with both warps on one item
