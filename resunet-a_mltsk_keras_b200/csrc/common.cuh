@@ -55,6 +55,11 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 #endif
+// streaming path of the thin 1x1 convolutions (pw_stream.cu); -100 = "not mine", otherwise the launch status
+int rsa_pw_stream_dispatch(const void* x0, int C0, const void* x1, int C1, const void* wt, const float* bias, void* out,
+                           const void* residual, const void* mask, double* stats, int N, int H, int W, int Cout,
+                           int in_stride, int nup, const void* const* up_ptrs, const int* up_shifts, int k_base, int k_total,
+                           int out_stride, int accumulate, int relu, cudaStream_t st);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- scalar / vector element access, always computing in fp32 ------------------------------

@@ -395,6 +395,16 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
               "conv_tc2_fwd: unsupported shape N=%d H=%d W=%d C0=%d C1=%d Cout=%d", N, H, W, C0, C1, Cout);
   RSA_REQUIRE(nup >= 0 && nup <= 4 && Cout <= 1024, RSA_ERR_SHAPE, "conv_tc2_fwd: nup/Cout out of range");
   RSA_REQUIRE(!(out_f32 && (accumulate || residual || mask)), RSA_ERR_SHAPE, "conv_tc2_fwd: fp32 output takes no bf16 side inputs");
+  for (int u = 0; u < nup; ++u)
+    RSA_REQUIRE(up_ptrs && up_shifts && up_ptrs[u] && up_shifts[u] >= 1 && up_shifts[u] <= 3, RSA_ERR_SHAPE, "conv_tc2_fwd: bad up-residual %d", u);
+  RSA_REQUIRE(!bnr_x || (stats && bnr_coef && Cout % 32 == 0 && !out_f32 && out_stride == 1), RSA_ERR_SHAPE,
+              "conv_tc2_fwd: BatchNorm-backward epilogue needs stats, coefficients and Cout %% 32 == 0");
+  // thin high-resolution 1x1 layers are HBM-bound: streaming kernel (pw_stream.cu), same contract
+  if (taps == 1 && !out_f32 && !bnr_x && (x1 ? C0 + C1 : C0) <= 64 && Cout <= 64) {
+    const int rc = rsa_pw_stream_dispatch(x0, C0, x1, C1, wt, bias, out, residual, mask, stats, N, H, W, Cout, in_stride, nup,
+                                          up_ptrs, up_shifts, k_base, k_total, out_stride, accumulate, relu, (cudaStream_t)stream);
+    if (rc != -100) return rc;
+  }
   EncodeTiledFn enc = get_encode();
   RSA_REQUIRE(enc, RSA_ERR_CUDA, "conv_tc2_fwd: cuTensorMapEncodeTiled not available from the driver");
   if (!x1) C1 = 0;
@@ -418,11 +428,8 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   p.bias = bias; p.out = out; p.out_f32 = out_f32; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.stats = stats; p.accumulate = accumulate; p.relu = relu; p.nup = nup;
   p.bnr_x = (const bf16*)bnr_x; p.bnr_coef = bnr_coef;
-  RSA_REQUIRE(!bnr_x || (stats && bnr_coef && Cout % 32 == 0 && !out_f32 && out_stride == 1), RSA_ERR_SHAPE,
-              "conv_tc2_fwd: BatchNorm-backward epilogue needs stats, coefficients and Cout %% 32 == 0");
   for (int u = 0; u < 4; ++u) {
     if (u < nup) {
-      RSA_REQUIRE(up_ptrs && up_shifts && up_ptrs[u] && up_shifts[u] >= 1 && up_shifts[u] <= 3, RSA_ERR_SHAPE, "conv_tc2_fwd: bad up-residual %d", u);
       p.up[u].q = (const bf16*)up_ptrs[u]; p.up[u].shift = up_shifts[u];
       p.up[u].Hq = H >> up_shifts[u]; p.up[u].Wq = W >> up_shifts[u];
     } else { p.up[u].q = nullptr; p.up[u].shift = 0; p.up[u].Hq = p.up[u].Wq = 1; }

@@ -162,6 +162,70 @@ def test_conv_tc2_pointwise_modes(lib, N, H, C0, C1, Co, stride, ups, f32):
     np.testing.assert_allclose(d_stats.cpu().numpy(), stats.numpy(), rtol=2e-2, atol=2e-2 * N * H * H ** 0.5)
 
 
+# every channel combination the streaming 1x1 kernel (pw_stream.cu, entered through rsa_conv_tc2_fwd) is compiled for, with the
+# epilogue options the plan uses on them: (C0, C1, Co, in_stride, out_stride, ups, residual, mask, accumulate, relu, stats, k_base, k_total)
+_PWS = [
+    (32, 0, 32, 1, 1, (), False, True, True, False, False, 0, 0),        # data gradient into a ReLU-masked, shared tensor
+    (32, 0, 32, 1, 1, (), False, False, False, False, True, 0, 0),       # plain + statistics
+    (32, 32, 32, 1, 1, (), False, False, False, True, True, 0, 0),       # combine: concat, ReLU, statistics
+    (32, 0, 32, 1, 1, (1, 2, 3), True, False, False, False, True, 32, 64),   # PSP output: three up-sampled addends + residual
+    (32, 0, 32, 1, 1, (1,), False, False, False, False, True, 16, 48),   # decoder combine: skip + up2(q)
+    (32, 0, 8, 1, 1, (), False, False, False, False, False, 0, 0),
+    (8, 0, 32, 1, 1, (), False, True, True, False, False, 0, 0),
+    (8, 0, 32, 1, 1, (), False, False, False, False, False, 8, 64),
+    (32, 0, 64, 2, 1, (), False, False, False, False, True, 0, 0),       # down convolution: stride 2
+    (64, 0, 32, 1, 2, (), False, True, True, False, False, 0, 0),        # its data gradient: strided accumulate
+    (64, 0, 16, 1, 1, (), False, False, False, True, False, 0, 0),
+    (16, 0, 64, 1, 1, (), False, True, False, False, False, 0, 0),
+    (16, 0, 32, 1, 1, (), False, False, False, False, True, 0, 48),
+    (16, 0, 16, 1, 1, (), True, False, False, False, False, 0, 0),
+    (8, 0, 8, 1, 1, (), False, False, True, False, True, 0, 0),
+    (8, 0, 16, 1, 1, (), False, False, False, False, False, 0, 0),
+    (8, 0, 64, 1, 1, (), False, False, False, False, True, 0, 0),
+    (16, 0, 8, 1, 1, (), False, False, False, False, False, 0, 0),
+    (32, 0, 16, 1, 1, (2,), False, False, False, False, False, 0, 0),
+    (64, 0, 8, 1, 1, (), False, False, False, False, True, 0, 0),
+    (64, 0, 32, 1, 1, (), False, False, False, False, True, 0, 0),
+    (32, 32, 16, 1, 1, (), False, False, False, False, False, 0, 0),
+    (32, 32, 8, 1, 1, (), False, True, False, False, False, 0, 0),
+]
+
+
+@pytest.mark.parametrize("C0,C1,Co,istr,ostr,ups,res,msk,acc,relu,stats,kb,kt", _PWS)
+@pytest.mark.parametrize("N,H", [(3, 32), (1, 4)])
+def test_pw_stream_modes(lib, N, H, C0, C1, Co, istr, ostr, ups, res, msk, acc, relu, stats, kb, kt):
+    from emul_lib import EmulLibTC
+    if ups and (H >> max(ups)) < 1:
+        pytest.skip("addend resolution below one pixel")
+    emu, dt = EmulLibTC(), torch.bfloat16
+    K, Hs, Ho = C0 + C1, H * istr, H * ostr
+    Kt = kt if kt else K
+    x0 = rnd((N, Hs, Hs, C0), dt, 1)
+    x1 = rnd((N, Hs, Hs, C1), dt, 2) if C1 else None
+    wt = rnd((1, Co, Kt), torch.float32, 3, 1.0 / K ** 0.5).to(dt)
+    b = rnd((Co,), torch.float32, 4)
+    qs = [(rnd((N, H >> s, H >> s, Co), dt, 10 + s), s) for s in ups]
+    r = rnd((N, Ho, Ho, Co), dt, 5) if res else None
+    m = rnd((N, Ho, Ho, Co), dt, 6) if msk else None
+    out0 = rnd((N, Ho, Ho, Co), dt, 7)
+    ref, st_ref = out0.clone(), torch.zeros(2 * Co, dtype=torch.float64)
+    kw = dict(taps=1, in_stride=istr, residual=r, mask=m, accumulate=acc, relu=relu, k_base=kb, k_total=kt, out_stride=ostr)
+    emu.conv_tc2_fwd(x0, x1, wt, Co, b, ref, N, H, H, Co, ups=qs, stats=st_ref if stats else None, **kw)(0)
+    d_out, d_st = out0.clone().cuda(), torch.zeros(2 * Co, dtype=torch.float64).cuda()
+    cu = lambda v: None if v is None else v.cuda()
+    kw.update(residual=cu(r), mask=cu(m))
+    lib.conv_tc2_fwd(x0.cuda(), cu(x1), wt.cuda(), Co, b.cuda(), d_out, N, H, H, Co, ups=[(q.cuda(), s) for q, s in qs],
+                     stats=d_st if stats else None, **kw)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    scale = ref.float().abs().max().item()
+    assert (d_out.cpu().float() - ref.float()).abs().max().item() <= scale / 100
+    if ostr == 2:      # pixels between the strided stores stay untouched
+        keep = torch.ones(Ho, Ho, dtype=torch.bool); keep[::2, ::2] = False
+        assert torch.equal(d_out.cpu()[:, keep], out0[:, keep])
+    if stats:
+        np.testing.assert_allclose(d_st.cpu().numpy(), st_ref.numpy(), rtol=2e-2, atol=2e-2 * N * H * H ** 0.5)
+
+
 @pytest.mark.parametrize("N,H,Cin,Cout,stride", [(2, 64, 32, 32, 1), (2, 32, 32, 64, 2), (2, 32, 16, 32, 1), (2, 32, 64, 16, 1),
                                                   (3, 16, 256, 512, 1), (2, 8, 1024, 256, 1), (16, 4, 512, 1024, 2),
                                                   (4, 64, 64, 128, 1), (2, 64, 128, 32, 1), (2, 64, 32, 8, 1), (2, 64, 8, 32, 1),
