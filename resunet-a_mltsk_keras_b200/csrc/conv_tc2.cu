@@ -43,26 +43,32 @@ struct ConvTc2Params {
   UpRes up[4];
 };
 
-template <int BN, int KC, int STAGES>
+// MT = 128-pixel sub-tiles per tile.  The 3x3 layers with C >= 128 are bound by L2 -> SM operand traffic (profiles/
+// r2_conv_traffic.txt: ~300 MB per launch, 32 B per clock and SM, tensor pipe 24-30 %): a 128 x 128 tile pulls as many weight
+// bytes as activation bytes per K chunk.  MT = 2 gives a CTA two accumulators that share every weight slice (a 256-pixel
+// TMA box, two MMAs per K step against the same B descriptor): 3/4 of the bytes per FLOP, one CTA per SM with eight
+// epilogue warps instead of two CTAs with four.
+template <int BN, int KC, int STAGES, int MT = 1>
 struct Smem2 {
-  static constexpr int A_BYTES = TILE_M * KC * 2;
+  static constexpr int A_BYTES = MT * TILE_M * KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING = STAGES * STAGE_BYTES;
   static constexpr int CS_BYTES = 2 * 512 * 8;            // per-CTA channel sums in double (Cout <= 512; wider layers flush per tile)
   static constexpr int BAR_OFF = RING + CS_BYTES;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
-  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+  static constexpr int ACC_COLS = MT * (BN < 32 ? 32 : BN);
   static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // power of two (BN in 16..256)
 };
 
-template <int BN, int KC, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
+template <int BN, int KC, int STAGES, int MT = 1>
+__global__ void __launch_bounds__(64 + 128 * MT, MT == 1 ? 2 : 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                const __grid_constant__ CUtensorMap tmA1,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const ConvTc2Params p) {
-  using L = Smem2<BN, KC, STAGES>;
+  using L = Smem2<BN, KC, STAGES, MT>;
   constexpr int SWZ = KC * 2;
+  constexpr int EPI_T = 128 * MT;               // epilogue threads: warps 2 .. 2 + 4 MT
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // double accumulators: the four epilogue warps add in whatever order they arrive, and double sums of fp32 partials
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
     if (p.nsrc > 1) prefetch_tmap(&tmA1);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * MT); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   if (p.stats && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < 1024; i += 128) csum[i] = 0.0;
+    for (int i = threadIdx.x - 64; i < 1024; i += EPI_T) csum[i] = 0.0;
   }
   pdl_wait();                        // everything above is private to the CTA; global memory is touched only below
   if (threadIdx.x == 0) pdl_launch_dependents();
@@ -157,7 +163,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
             const uint64_t bdesc = make_kmajor_desc_any(sa + L::A_BYTES, SWZ);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
-              umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)      // sub-tile m: rows 128 m .. of the box, its own accumulator, the same weights
+                umma_bf16(tacc + (uint32_t)(m * (L::ACC_COLS / MT)), adesc + (uint64_t)(m * ((TILE_M * KC * 2) >> 4) + 2 * k),
+                          bdesc + (uint64_t)(2 * k), idesc, accum);
               accum = 1;
             }
             umma_commit(&empty_bar[stage]);
@@ -168,8 +177,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
       }
     }
   } else {
-    // ===== epilogue warps 2..5 =====
-    const int q = warp & 3;
+    // ===== epilogue warps 2 .. 2 + 4 MT: TMEM lane quarter warp % 4 of sub-tile (warp - 2) / 4 =====
+    const int q = warp & 3, msub = (warp - 2) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
       const int nb = tile % p.ntn;
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
       const int acc = it & 1;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int r = q * 32 + lane;
+      const int r = msub * TILE_M + q * 32 + lane;
       const int pw = w0 + r % p.TW;
       const int ph = h0 + (r / p.TW) % p.TH;
       const int pn = n0 + r / (p.TW * p.TH);
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L::ACC_COLS + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L::ACC_COLS + msub * (L::ACC_COLS / MT) + c0), v);
         const int co = nb * BN + c0;
         const int nval = p.Cout - co < 32 ? p.Cout - co : 32;     // channels of this chunk that exist
         if (nval <= 0) continue;
@@ -318,8 +327,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
     if (p.stats && cs_smem) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < p.Cout; i += 128) {
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
+      for (int i = threadIdx.x - 64; i < p.Cout; i += EPI_T) {
         const double s = csum[i], sq = csq[i];
         if (s != 0.0 || sq != 0.0) {
           atomicAdd(p.stats + i, s);
@@ -336,19 +345,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc2_kernel(const __grid_cons
   }
 }
 
-template <int BN, int KC, int STAGES>
+template <int BN, int KC, int STAGES, int MT = 1>
 int launch2(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvTc2Params& p, cudaStream_t st) {
-  using L = Smem2<BN, KC, STAGES>;
+  using L = Smem2<BN, KC, STAGES, MT>;
   static_assert(L::TOTAL <= 227 * 1024, "smem budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, KC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, KC, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) { rsa_set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
     configured = true;
   }
   const int per_sm = (227 * 1024) / L::TOTAL >= 2 ? 2 : 1;       // co-resident persistent CTAs overlap their epilogues
   int grid = p.total < per_sm * rsa_num_sms() ? p.total : per_sm * rsa_num_sms();
-  cudaError_t le = launch_pdl(conv_tc2_kernel<BN, KC, STAGES>, dim3(grid), dim3(NTHREADS), (size_t)L::TOTAL, st, a0, a1, b, p);
+  cudaError_t le = launch_pdl(conv_tc2_kernel<BN, KC, STAGES, MT>, dim3(grid), dim3(64 + 128 * MT), (size_t)L::TOTAL, st, a0, a1, b, p);
   if (le != cudaSuccess) { rsa_set_error("conv_tc2: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
@@ -414,14 +423,25 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   p.nsrc = x1 ? 2 : 1; p.kch0 = (C0 + KC - 1) / KC; p.kch1 = C1 / KC;
   p.taps = taps; p.dil = dil; p.in_stride = in_stride;
   p.k_base = k_base; p.out_stride = out_stride;
-  p.TW = W < 16 ? W : 16;
-  p.TH = H < TILE_M / p.TW ? H : TILE_M / p.TW;
-  p.TN = TILE_M / (p.TW * p.TH);
-  p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
-  p.mtiles = p.tiles_w * p.tiles_h * ((N + p.TN - 1) / p.TN);
+  auto tile_geometry = [&](int pixels) {
+    p.TW = W < 16 ? W : 16;
+    p.TH = H < pixels / p.TW ? H : pixels / p.TW;
+    p.TN = pixels / (p.TW * p.TH);
+    p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
+    p.mtiles = p.tiles_w * p.tiles_h * ((N + p.TN - 1) / p.TN);
+  };
+  // two sub-tiles per CTA (see Smem2) where the layer is L2 -> SM bound and still fills the SMs: 3x3, 64-channel K chunks,
+  // Cout a multiple of 128, at least ~one 256-pixel tile per SM
+  static const int mt_env = getenv("RSA_TC2_MT") ? atoi(getenv("RSA_TC2_MT")) : 2;
+  int MT = 1;
+  if (mt_env == 2 && taps == 9 && KC == 64 && CoutP % 128 == 0 && !bnr_x) {
+    tile_geometry(2 * TILE_M);
+    if (p.TN <= 256 && p.mtiles * (CoutP / 128) >= 120) MT = 2;
+  }
+  if (MT == 1) tile_geometry(TILE_M);
   // N tile: as wide as the layer allows, but keep >= ~1 tile per SM on the deep (few-pixel) levels
   int BN = CoutP >= 128 ? 128 : (CoutP >= 64 ? 64 : (CoutP >= 32 ? 32 : 16));
-  if (BN == 128 && p.mtiles * (CoutP / 128) < 120) BN = 64;
+  if (MT == 1 && BN == 128 && p.mtiles * (CoutP / 128) < 120) BN = 64;
   RSA_REQUIRE(CoutP % BN == 0 && CoutP >= Cout, RSA_ERR_SHAPE, "conv_tc2_fwd: CoutP=%d must be a multiple of the N tile %d", CoutP, BN);
   p.ntn = CoutP / BN;
   p.total = p.mtiles * p.ntn;
@@ -466,6 +486,7 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (KC == 64) {
+    if (MT == 2) return launch2<128, 64, 4, 2>(tmA0, tmA1, tmB, p, st);
     if (BN == 128) return launch2<128, 64, 3>(tmA0, tmA1, tmB, p, st);
     if (BN == 64) return launch2<64, 64, 4>(tmA0, tmA1, tmB, p, st);
     if (BN == 32) return launch2<32, 64, 5>(tmA0, tmA1, tmB, p, st);

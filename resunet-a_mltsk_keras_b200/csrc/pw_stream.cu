@@ -6,15 +6,19 @@
 // persistent 128-pixel-tile kernel is not built for that (profiles/r2_step_launch_trace.txt: 88-136 us per launch at
 // 16 x 256 x 256 x 32 where the bytes take 21-42 us).  Its epilogue - one thread per pixel, side inputs (mask, running sum,
 // residual, up-sampled addends) fetched with dependent 16-byte loads after the accumulator arrives, two tiles in flight per
-// CTA - runs at the latency of those loads.  Here nothing is staged and nothing waits for anything else:
+// CTA - runs at the latency of those loads.  Here:
 //
-//   * a warp owns groups of 16 consecutive pixels; every thread issues ALL loads of its group (operand rows and side
-//     inputs) up front, so a resident warp keeps up to 6 KB in flight and 24 warps per SM cover the HBM latency;
-//   * the channel order inside a K step and inside the N dimension of a GEMM is free, so it is chosen such that the
-//     m16n8k16 fragment a thread owns is exactly a contiguous 16-byte piece of its pixel's NHWC row: the quad of a row
-//     reads / writes one contiguous 64-byte row, a warp instruction 512 contiguous bytes, no shared memory, no shuffles.
-//     K step s of a 32-channel block: thread t of the quad holds channels 8t+4s .. 8t+4s+3; output n-tile j: channels
-//     2 NT t + 2j, 2 NT t + 2j + 1 (NT = Cout / 8), so a thread stores 2 NT contiguous channels per row;
+//   * a warp owns groups of 16 consecutive pixels.  The channel order inside a K step and inside the N dimension of a GEMM
+//     is free, so it is chosen such that the m16n8k16 fragment a thread owns is exactly a contiguous 16-byte piece of its
+//     pixel's NHWC row: the quad of a row reads / writes one contiguous 64-byte row, a warp instruction 512 contiguous
+//     bytes, no shuffles.  K step s of a 32-channel block: thread t of the quad holds channels 8t+4s .. 8t+4s+3; output
+//     n-tile j: channels 2 NT t + 2j, 2 NT t + 2j + 1 (NT = Cout / 8), so a thread stores 2 NT contiguous channels per row;
+//   * HBM latency x bandwidth wants ~45 KB in flight per SM, more than registers can hold beside the fragments (the first
+//     version, every load of a group issued up front into registers, reached 0.3-0.65 of the copy peak,
+//     gpurun_out/r2s_bench_pw.txt).  So every lane copies ITS pieces of the next groups - operand rows, mask, running sum,
+//     residual, up-sampled addends - with cp.async into a private shared-memory FIFO (slot = lane, conflict-free, no
+//     barrier: a lane only ever reads what it copied itself), DEPTH groups ahead, and consumes the oldest group with
+//     ld.shared; the FIFO depth is sized per launch from the bytes a group moves;
 //   * the weights (at most 64 x 32) live in registers as B fragments for the whole kernel;
 //   * BatchNorm statistics of the stored values: per-thread partial sums over all its pixels, three shuffles over the rows
 //     of the fragment, per-warp slots summed in a fixed order, one double atomic per channel per CTA (reproducible).
@@ -28,24 +32,54 @@ namespace {
 
 constexpr int PWS_THREADS = 256;
 constexpr int PWS_WARPS = PWS_THREADS / 32;
-constexpr int PWS_OCC = 2;             // resident CTAs per SM the register budget is compiled for
+constexpr int PWS_OCC = 3;             // resident CTAs per SM the register budget is compiled for
+constexpr int PWS_MAXSIDE = 7;         // up-sampled addends (4), residual, running sum, mask
 
 struct PwsParams {
   const bf16* x0; const bf16* x1; const bf16* wt; const float* bias;
-  bf16* out; const bf16* residual; const bf16* mask; double* stats;
+  bf16* out; const bf16* mask; double* stats;
   int M, lw, lh;            // output pixels, log2 W, log2 H
   int in_stride, out_stride;
   int kt, k_base;           // weight row length (bf16 elements), first column used
-  int accumulate, relu, nup;
-  const bf16* upq[4]; int upshift[4];
+  int relu;
+  int nadd;                 // addends: side[0 .. nadd), shift > 0 = nearest up-sampling by 2^shift; the mask is side[nadd]
+  const bf16* side[PWS_MAXSIDE]; int shift[PWS_MAXSIDE];
+  int depth, stage_bytes;   // FIFO: groups in flight per warp, bytes of one group's pieces (all 32 lanes)
 };
 
-template <int C> struct PwsSrc { static constexpr int KS = C >= 32 ? C / 16 : (C > 0 ? 1 : 0); };
+template <int C> struct PwsSrc {
+  static constexpr int KS = C >= 32 ? C / 16 : (C > 0 ? 1 : 0);      // K steps
+  static constexpr int PC = C >= 32 ? C / 32 : (C > 0 ? 1 : 0);      // pieces per pixel row and thread
+  static constexpr int PB = C >= 32 ? 16 : C / 2;                    // bytes of a piece
+};
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// global -> shared copy of one piece (4 / 8 / 16 bytes); 16-byte pieces of the streamed tensors bypass L1
+template <int BYTES, bool STREAM> __device__ __forceinline__ void cp_piece(uint32_t dst, const void* src) {
+  if constexpr (BYTES == 16 && STREAM) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait(int pending) {       // all but the newest `pending` groups have landed
+  switch (pending) {
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    case 7: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ uint4 lds16(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
 }
 
 // first channel of the low half (logical columns 2t, 2t+1) of K step s; the high half (2t+8, 2t+9) follows 2 channels on
@@ -55,71 +89,46 @@ template <int C> __device__ __forceinline__ int pws_kch(int s, int t) {
   return 2 * t;
 }
 
-// A fragments of one source for rows r0 (fragment row g) and r1 (row g + 8); the pointers already include the quad offset
-template <int C, int BASE, int KTOT>
-__device__ __forceinline__ void pws_load_a(const bf16* r0, const bf16* r1, int t, uint32_t (&a)[KTOT][4]) {
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// copies of one source's pieces for this thread's two rows; slots advance by 512 bytes (32 lanes x 16)
+template <int C> __device__ __forceinline__ uint32_t pws_cp_src(uint32_t slot, const bf16* r0, const bf16* r1, int t) {
+  constexpr int PC = PwsSrc<C>::PC, PB = PwsSrc<C>::PB;
+#pragma unroll
+  for (int h = 0; h < PC; ++h) {
+    cp_piece<PB, true>(slot, r0 + 32 * h + (PB / 2) * t);
+    cp_piece<PB, true>(slot + 512, r1 + 32 * h + (PB / 2) * t);
+    slot += 1024;
+  }
+  return slot;
+}
+// A fragments of one source from the FIFO (piece order as pws_cp_src)
+template <int C, int BASE, int KTOT> __device__ __forceinline__ uint32_t pws_frag_a(uint32_t slot, uint32_t (&a)[KTOT][4]) {
   if constexpr (C >= 32) {
 #pragma unroll
     for (int h = 0; h < C / 32; ++h) {
-      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(r0 + 32 * h + 8 * t));
-      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(r1 + 32 * h + 8 * t));
+      const uint4 v0 = lds16(slot), v1 = lds16(slot + 512);
       a[BASE + 2 * h][0] = v0.x; a[BASE + 2 * h][1] = v1.x; a[BASE + 2 * h][2] = v0.y; a[BASE + 2 * h][3] = v1.y;
       a[BASE + 2 * h + 1][0] = v0.z; a[BASE + 2 * h + 1][1] = v1.z; a[BASE + 2 * h + 1][2] = v0.w; a[BASE + 2 * h + 1][3] = v1.w;
+      slot += 1024;
     }
-  } else if constexpr (C == 16) {
-    const uint2 v0 = __ldg(reinterpret_cast<const uint2*>(r0 + 4 * t));
-    const uint2 v1 = __ldg(reinterpret_cast<const uint2*>(r1 + 4 * t));
-    a[BASE][0] = v0.x; a[BASE][1] = v1.x; a[BASE][2] = v0.y; a[BASE][3] = v1.y;
-  } else if constexpr (C == 8) {
-    a[BASE][0] = __ldg(reinterpret_cast<const uint32_t*>(r0 + 2 * t));
-    a[BASE][1] = __ldg(reinterpret_cast<const uint32_t*>(r1 + 2 * t));
-    a[BASE][2] = 0u; a[BASE][3] = 0u;
+  } else if constexpr (C > 0) {
+    const uint4 v0 = lds16(slot), v1 = lds16(slot + 512);      // only the first PB bytes were copied
+    a[BASE][0] = v0.x; a[BASE][1] = v1.x;
+    a[BASE][2] = C == 16 ? v0.y : 0u; a[BASE][3] = C == 16 ? v1.y : 0u;
+    slot += 1024;
   }
-}
-
-// 2 NT contiguous channels of one pixel row (this thread's share), bf16 <-> fp32
-template <int NT, bool NC> __device__ __forceinline__ void pws_ld_raw(const bf16* p, uint32_t (&w)[NT]) {
-  if constexpr (NT >= 4) {
-#pragma unroll
-    for (int i = 0; i < NT / 4; ++i) {
-      const uint4 q = NC ? __ldg(reinterpret_cast<const uint4*>(p) + i) : *(reinterpret_cast<const uint4*>(p) + i);
-      w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
-    }
-  } else if constexpr (NT == 2) {
-    const uint2 q = NC ? __ldg(reinterpret_cast<const uint2*>(p)) : *reinterpret_cast<const uint2*>(p);
-    w[0] = q.x; w[1] = q.y;
-  } else {
-    w[0] = NC ? __ldg(reinterpret_cast<const uint32_t*>(p)) : *reinterpret_cast<const uint32_t*>(p);
-  }
-}
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-template <int NT, bool NC> __device__ __forceinline__ void pws_ld_row(const bf16* p, float (&v)[2 * NT]) {
-  uint32_t w[NT];
-  pws_ld_raw<NT, NC>(p, w);
-#pragma unroll
-  for (int i = 0; i < NT; ++i) { v[2 * i] = bf_lo(w[i]); v[2 * i + 1] = bf_hi(w[i]); }
-}
-template <int NT> __device__ __forceinline__ void pws_st_row(bf16* p, const float (&v)[2 * NT], uint32_t (&w)[NT]) {
-#pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  if constexpr (NT >= 4) {
-#pragma unroll
-    for (int i = 0; i < NT / 4; ++i) *(reinterpret_cast<uint4*>(p) + i) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-  } else if constexpr (NT == 2) {
-    *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
-  } else {
-    *reinterpret_cast<uint32_t*>(p) = w[0];
-  }
+  return slot;
 }
 
 template <int C0, int C1, int COUT, bool STATS>
 __global__ void __launch_bounds__(PWS_THREADS, PWS_OCC) pw_stream_kernel(const PwsParams p) {
   constexpr int KS0 = PwsSrc<C0>::KS, KS1 = PwsSrc<C1>::KS, NT = COUT / 8, NCH = 2 * NT;
+  constexpr int SP = NT >= 4 ? NT / 4 : 1;             // pieces per row of an output-shaped side tensor
+  constexpr int SB = NT >= 4 ? 16 : 4 * NT;            // their bytes
   static_assert((KS0 + KS1) * NT <= 16, "B fragments must fit in registers");
+  extern __shared__ uint4 pws_fifo[];
   __shared__ float wsum[STATS ? PWS_WARPS : 1][COUT], wsq[STATS ? PWS_WARPS : 1][COUT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   pdl_wait();
@@ -153,73 +162,128 @@ __global__ void __launch_bounds__(PWS_THREADS, PWS_OCC) pw_stream_kernel(const P
 
   const int wmask = (1 << p.lw) - 1, hmask = (1 << p.lh) - 1;
   const int ngroups = p.M >> 4;
-  for (int grp = blockIdx.x * PWS_WARPS + warp; grp < ngroups; grp += gridDim.x * PWS_WARPS) {
-    // the two rows of this thread: pixels m0 + g and m0 + g + 8
-    size_t src[2], dst[2];
-    int pn[2], ph[2], pw[2];
+  const int nside = p.nadd + (p.mask ? 1 : 0);
+  const int gstride = gridDim.x * PWS_WARPS;
+  const uint32_t fifo = (uint32_t)__cvta_generic_to_shared(pws_fifo) + (uint32_t)(warp * p.depth * p.stage_bytes) + (uint32_t)lane * 16u;
+  auto pix = [&](int m, size_t& src, size_t& dst, int& n, int& h, int& w) {
+    w = m & wmask; h = (m >> p.lw) & hmask; n = m >> (p.lw + p.lh);
+    const size_t strided = ((((size_t)n << (p.lh + 1)) + 2 * h) << (p.lw + 1)) + 2 * w;
+    src = p.in_stride == 1 ? (size_t)m : strided;
+    dst = p.out_stride == 1 ? (size_t)m : strided;
+  };
+  // every piece this thread will consume of group `grp`, into FIFO stage `stage`
+  auto issue = [&](int grp, int stage) {
+    if (grp < ngroups) {
+      size_t src[2], dst[2];
+      int pn[2], ph[2], pw[2];
+      pix((grp << 4) + g, src[0], dst[0], pn[0], ph[0], pw[0]);
+      pix((grp << 4) + g + 8, src[1], dst[1], pn[1], ph[1], pw[1]);
+      uint32_t slot = fifo + (uint32_t)(stage * p.stage_bytes);
+      slot = pws_cp_src<C0>(slot, p.x0 + src[0] * C0, p.x0 + src[1] * C0, t);
+      if constexpr (C1 > 0) slot = pws_cp_src<C1>(slot, p.x1 + src[0] * C1, p.x1 + src[1] * C1, t);
+      for (int k = 0; k < nside; ++k) {
+        const bf16* base = k < p.nadd ? p.side[k] : p.mask;
+        const int sh = k < p.nadd ? p.shift[k] : 0;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int m = (grp << 4) + g + 8 * r;
-      pw[r] = m & wmask; ph[r] = (m >> p.lw) & hmask; pn[r] = m >> (p.lw + p.lh);
-      src[r] = p.in_stride == 1 ? (size_t)m
-             : ((((size_t)pn[r] << (p.lh + 1)) + 2 * ph[r]) << (p.lw + 1)) + 2 * pw[r];
-      dst[r] = p.out_stride == 1 ? (size_t)m
-             : ((((size_t)pn[r] << (p.lh + 1)) + 2 * ph[r]) << (p.lw + 1)) + 2 * pw[r];
+        for (int r = 0; r < 2; ++r) {
+          const size_t q = sh ? ((((size_t)pn[r] << (p.lh - sh)) + (ph[r] >> sh)) << (p.lw - sh)) + (pw[r] >> sh) : dst[r];
+          const bf16* row = base + q * COUT + NCH * t;
+#pragma unroll
+          for (int i = 0; i < SP; ++i) {
+            if (sh) cp_piece<SB, false>(slot, row + 8 * i); else cp_piece<SB, true>(slot, row + 8 * i);
+            slot += 512;
+          }
+        }
+      }
     }
-    // ---- every load of the group is issued before anything is consumed
+    cp_commit();           // an empty group past the end keeps the wait count uniform
+  };
+
+  const int grp0 = blockIdx.x * PWS_WARPS + warp;
+  for (int s = 0; s < p.depth - 1; ++s) issue(grp0 + s * gstride, s);
+  int stage = 0;
+  for (int grp = grp0; grp < ngroups; grp += gstride) {
+    int nstage = stage + p.depth - 1;
+    if (nstage >= p.depth) nstage -= p.depth;
+    issue(grp + (p.depth - 1) * gstride, nstage);
+    cp_wait(p.depth - 1);
+    uint32_t slot = fifo + (uint32_t)(stage * p.stage_bytes);
+    if (++stage == p.depth) stage = 0;
     uint32_t a[KS0 + KS1][4];
-    pws_load_a<C0, 0>(p.x0 + src[0] * C0, p.x0 + src[1] * C0, t, a);
-    if constexpr (C1 > 0) pws_load_a<C1, KS0>(p.x1 + src[0] * C1, p.x1 + src[1] * C1, t, a);
-    float add[2][NCH];
-    uint32_t mk[2][NT];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) add[r][i] = bias_r[i];
-      float tv[NCH];
-      for (int u = 0; u < p.nup; ++u) {
-        const int sh = p.upshift[u];
-        const size_t qi = ((((size_t)pn[r] << (p.lh - sh)) + (ph[r] >> sh)) << (p.lw - sh)) + (pw[r] >> sh);
-        pws_ld_row<NT, true>(p.upq[u] + qi * COUT + NCH * t, tv);
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) add[r][i] += tv[i];
-      }
-      if (p.residual) {
-        pws_ld_row<NT, true>(p.residual + dst[r] * COUT + NCH * t, tv);
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) add[r][i] += tv[i];
-      }
-      if (p.accumulate) {
-        pws_ld_row<NT, false>(p.out + dst[r] * COUT + NCH * t, tv);
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) add[r][i] += tv[i];
-      }
-      if (p.mask) pws_ld_raw<NT, true>(p.mask + dst[r] * COUT + NCH * t, mk[r]);
-    }
+    slot = pws_frag_a<C0, 0>(slot, a);
+    slot = pws_frag_a<C1, KS0>(slot, a);
     // ---- K steps
     float acc[NT][4];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+    for (int j = 0; j < NT; ++j) {
+      acc[j][0] = bias_r[2 * j]; acc[j][1] = bias_r[2 * j + 1]; acc[j][2] = bias_r[2 * j]; acc[j][3] = bias_r[2 * j + 1];
+    }
 #pragma unroll
     for (int s = 0; s < KS0 + KS1; ++s)
 #pragma unroll
       for (int j = 0; j < NT; ++j) mma_bf16_16816(acc[j], a[s], b0[s][j], b1[s][j]);
-    // ---- epilogue: + bias + addends, ReLU, mask, store, statistics (order as conv_tc2's epilogue)
+    // ---- epilogue: + addends, ReLU, mask, store, statistics (order as conv_tc2's epilogue)
+    for (int k = 0; k < p.nadd; ++k) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < SP; ++i) {
+          const uint4 v = lds16(slot);
+          slot += 512;
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < (NT < 4 ? NT : 4); ++j) {
+            acc[4 * i + j][2 * r] += bf_lo(w[j]);
+            acc[4 * i + j][2 * r + 1] += bf_hi(w[j]);
+          }
+        }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = fmaxf(acc[j][i], 0.f);
+      }
+    }
+    if (p.mask) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < SP; ++i) {
+          const uint4 v = lds16(slot);
+          slot += 512;
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < (NT < 4 ? NT : 4); ++j) {
+            acc[4 * i + j][2 * r] = bf_lo(w[j]) > 0.f ? acc[4 * i + j][2 * r] : 0.f;
+            acc[4 * i + j][2 * r + 1] = bf_hi(w[j]) > 0.f ? acc[4 * i + j][2 * r + 1] : 0.f;
+          }
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      float f[NCH];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) { f[2 * j] = acc[j][2 * r] + add[r][2 * j]; f[2 * j + 1] = acc[j][2 * r + 1] + add[r][2 * j + 1]; }
-      if (p.relu) {
-#pragma unroll
-        for (int i = 0; i < NCH; ++i) f[i] = fmaxf(f[i], 0.f);
-      }
-      if (p.mask) {
-#pragma unroll
-        for (int j = 0; j < NT; ++j) { f[2 * j] = bf_lo(mk[r][j]) > 0.f ? f[2 * j] : 0.f; f[2 * j + 1] = bf_hi(mk[r][j]) > 0.f ? f[2 * j + 1] : 0.f; }
+      const int m = (grp << 4) + g + 8 * r;
+      size_t dst = (size_t)m;
+      if (p.out_stride != 1) {
+        const int w = m & wmask, h = (m >> p.lw) & hmask, n = m >> (p.lw + p.lh);
+        dst = ((((size_t)n << (p.lh + 1)) + 2 * h) << (p.lw + 1)) + 2 * w;
       }
       uint32_t pk[NT];
-      pws_st_row<NT>(p.out + dst[r] * COUT + NCH * t, f, pk);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        __nv_bfloat162 hh = __floats2bfloat162_rn(acc[j][2 * r], acc[j][2 * r + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      bf16* orow = p.out + dst * COUT + NCH * t;
+      if constexpr (NT >= 4) {
+#pragma unroll
+        for (int i = 0; i < NT / 4; ++i)
+          *(reinterpret_cast<uint4*>(orow) + i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      } else if constexpr (NT == 2) {
+        *reinterpret_cast<uint2*>(orow) = make_uint2(pk[0], pk[1]);
+      } else {
+        *reinterpret_cast<uint32_t*>(orow) = pk[0];
+      }
       if constexpr (STATS) {        // statistics of the stored (bf16-rounded) values
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
@@ -230,6 +294,7 @@ __global__ void __launch_bounds__(PWS_THREADS, PWS_OCC) pw_stream_kernel(const P
       }
     }
   }
+  cp_wait(0);
   if constexpr (STATS) {
     // rows of the fragment live in lanes that differ in bits 2..4
 #pragma unroll
@@ -255,21 +320,46 @@ __global__ void __launch_bounds__(PWS_THREADS, PWS_OCC) pw_stream_kernel(const P
   }
 }
 
-template <int C0, int C1, int COUT>
-int pws_launch(const PwsParams& p, cudaStream_t st) {
+template <int C0, int C1, int COUT, bool STATS>
+int pws_launch_k(PwsParams& p, cudaStream_t st) {
+  constexpr int NT = COUT / 8, SP = NT >= 4 ? NT / 4 : 1;
+  const int nside = p.nadd + (p.mask ? 1 : 0);
+  p.stage_bytes = (2 * (PwsSrc<C0>::PC + PwsSrc<C1>::PC) + 2 * SP * nside) * 512;
+  // FIFO depth: ~6 KB in flight per warp (24 warps per SM: ~140 KB, three times what latency x bandwidth asks for - the
+  // queueing under load is what the margin is for), at least 3 groups, bounded by shared memory for PWS_OCC CTAs per SM
+  int depth = 1 + (6144 + p.stage_bytes - 1) / p.stage_bytes;
+  if (depth < 3) depth = 3;
+  if (depth > 8) depth = 8;
+  const int budget = (227 * 1024 - PWS_OCC * 2048) / PWS_OCC;          // per CTA, static shared memory and reserve deducted
+  while (depth > 2 && PWS_WARPS * depth * p.stage_bytes > budget) --depth;
+  p.depth = depth;
+  const int smem = PWS_WARPS * depth * p.stage_bytes;
+  if (smem > 200 * 1024) return -100;                // more side tensors than the FIFO holds: the tcgen05 kernel takes it
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pw_stream_kernel<C0, C1, COUT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { rsa_set_error("pw_stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
+    configured = true;
+  }
   const int ngroups = p.M >> 4;
   int grid = (ngroups + PWS_WARPS - 1) / PWS_WARPS;
-  const int cap = PWS_OCC * rsa_num_sms();           // one resident wave, grid-stride inside
+  int per_sm = (227 * 1024) / (smem + 2048);
+  if (per_sm > PWS_OCC) per_sm = PWS_OCC;
+  if (per_sm < 1) per_sm = 1;
+  const int cap = per_sm * rsa_num_sms();            // one resident wave, grid-stride inside
   if (grid > cap) grid = cap;
-  cudaError_t le = p.stats ? launch_pdl(pw_stream_kernel<C0, C1, COUT, true>, dim3(grid), dim3(PWS_THREADS), (size_t)0, st, p)
-                           : launch_pdl(pw_stream_kernel<C0, C1, COUT, false>, dim3(grid), dim3(PWS_THREADS), (size_t)0, st, p);
+  cudaError_t le = launch_pdl(pw_stream_kernel<C0, C1, COUT, STATS>, dim3(grid), dim3(PWS_THREADS), (size_t)smem, st, p);
   if (le != cudaSuccess) { rsa_set_error("pw_stream: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
   RSA_CHECK_LAUNCH();
   return RSA_OK;
 }
+template <int C0, int C1, int COUT>
+int pws_launch(PwsParams& p, cudaStream_t st) {
+  return p.stats ? pws_launch_k<C0, C1, COUT, true>(p, st) : pws_launch_k<C0, C1, COUT, false>(p, st);
+}
 
 template <int C0, int C1>
-int pws_by_cout(int Cout, const PwsParams& p, cudaStream_t st) {
+int pws_by_cout(int Cout, PwsParams& p, cudaStream_t st) {
   constexpr int KS = PwsSrc<C0>::KS + PwsSrc<C1>::KS;
   switch (Cout) {
     case 8: return pws_launch<C0, C1, 8>(p, st);
@@ -304,15 +394,18 @@ int rsa_pw_stream_dispatch(const void* x0, int C0, const void* x1, int C1, const
   if ((uintptr_t)wt & 3) return -100;
   PwsParams p;
   p.x0 = (const bf16*)x0; p.x1 = (const bf16*)x1; p.wt = (const bf16*)wt; p.bias = bias;
-  p.out = (bf16*)out; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask; p.stats = stats;
+  p.out = (bf16*)out; p.mask = (const bf16*)mask; p.stats = stats;
   p.M = (int)M; p.lw = ilog2(W); p.lh = ilog2(H);
   p.in_stride = in_stride; p.out_stride = out_stride; p.kt = kt; p.k_base = k_base;
-  p.accumulate = accumulate; p.relu = relu; p.nup = nup;
-  for (int u = 0; u < 4; ++u) {
-    p.upq[u] = u < nup ? (const bf16*)up_ptrs[u] : nullptr;
-    p.upshift[u] = u < nup ? up_shifts[u] : 0;
-    if (u < nup && (((uintptr_t)up_ptrs[u] & 15) || up_shifts[u] > p.lw || up_shifts[u] > p.lh)) return -100;
+  p.relu = relu;
+  p.nadd = 0;
+  for (int u = 0; u < PWS_MAXSIDE; ++u) { p.side[u] = nullptr; p.shift[u] = 0; }
+  for (int u = 0; u < nup; ++u) {        // addend order of conv_tc2's epilogue: up-sampled, residual, running sum
+    if (((uintptr_t)up_ptrs[u] & 15) || up_shifts[u] > p.lw || up_shifts[u] > p.lh) return -100;
+    p.side[p.nadd] = (const bf16*)up_ptrs[u]; p.shift[p.nadd++] = up_shifts[u];
   }
+  if (residual) p.side[p.nadd++] = (const bf16*)residual;
+  if (accumulate) p.side[p.nadd++] = (const bf16*)out;
   if (C1 == 32) return pws_by_cout<32, 32>(Cout, p, st);
   switch (C0) {
     case 8: return pws_by_cout<8, 0>(Cout, p, st);

@@ -15,7 +15,7 @@ N, dt = a.N, torch.bfloat16
 st = torch.cuda.current_stream().cuda_stream
 try:
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    PEAK = float(PEAK.get("hbm_gbps_burst") or PEAK.get("hbm_gbps") or 0) or None
+    PEAK = float(PEAK.get("hbm_gbs") or 0) or None
 except Exception:
     PEAK = None
 NB = 4
