@@ -43,11 +43,13 @@ struct ConvTc2Params {
   UpRes up[4];
 };
 
-// MT = 128-pixel sub-tiles per tile.  The 3x3 layers with C >= 128 are bound by L2 -> SM operand traffic (profiles/
-// r2_conv_traffic.txt: ~300 MB per launch, 32 B per clock and SM, tensor pipe 24-30 %): a 128 x 128 tile pulls as many weight
-// bytes as activation bytes per K chunk.  MT = 2 gives a CTA two accumulators that share every weight slice (a 256-pixel
-// TMA box, two MMAs per K step against the same B descriptor): 3/4 of the bytes per FLOP, one CTA per SM with eight
-// epilogue warps instead of two CTAs with four.
+// MT = 128-pixel sub-tiles per tile.  The 3x3 layers with C >= 128 run at the L2 throughput cap (~300 MB of operand boxes per
+// launch at ~9 TB/s, tensor pipe 24-30 %): a 128 x 128 tile pulls as many weight bytes as activation bytes per K chunk.  MT = 2
+// gives a CTA two accumulators that share every weight slice (a 256-pixel TMA box, two MMAs per K step against the same B
+// descriptor, eight epilogue warps): 3/4 of the bytes per FLOP (ncu: 227 MB instead of 302 MB) - but one CTA per SM means ONE
+// MMA-issuing thread per SM instead of two, and a thread is held ~100 cycles per tcgen05.mma and ~350 per tcgen05.commit, so
+// the kernel turns issue-bound before the saved bytes pay: measured 4-9 % SLOWER per launch (gpurun_out/r2u_bench_wide_*.txt:
+// C = 128 34.5 vs 33.2 us, C = 256 29.6 vs 27.2 us) and 12.85 vs 12.73 ms per step.  Kept behind RSA_TC2_MT=2, off by default.
 template <int BN, int KC, int STAGES, int MT = 1>
 struct Smem2 {
   static constexpr int A_BYTES = MT * TILE_M * KC * 2;
@@ -430,9 +432,9 @@ extern "C" int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, 
     p.tiles_w = W / p.TW; p.tiles_h = H / p.TH;
     p.mtiles = p.tiles_w * p.tiles_h * ((N + p.TN - 1) / p.TN);
   };
-  // two sub-tiles per CTA (see Smem2) where the layer is L2 -> SM bound and still fills the SMs: 3x3, 64-channel K chunks,
-  // Cout a multiple of 128, at least ~one 256-pixel tile per SM
-  static const int mt_env = getenv("RSA_TC2_MT") ? atoi(getenv("RSA_TC2_MT")) : 2;
+  // two sub-tiles per CTA (see Smem2; RSA_TC2_MT=2, measured slower): 3x3, 64-channel K chunks, Cout a multiple of 128, at
+  // least ~one 256-pixel tile per SM
+  static const int mt_env = getenv("RSA_TC2_MT") ? atoi(getenv("RSA_TC2_MT")) : 1;
   int MT = 1;
   if (mt_env == 2 && taps == 9 && KC == 64 && CoutP % 128 == 0 && !bnr_x) {
     tile_geometry(2 * TILE_M);

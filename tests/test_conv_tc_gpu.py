@@ -90,7 +90,9 @@ def _up(t, s):
 
 @pytest.mark.parametrize("N,H,C,Co,d", [(2, 32, 32, 32, 1), (2, 64, 32, 32, 31), (2, 32, 64, 64, 3), (3, 16, 128, 128, 1),
                                         (2, 16, 256, 256, 15), (4, 8, 512, 512, 1), (16, 4, 1024, 1024, 1),
-                                        (16, 64, 32, 32, 15), (5, 32, 64, 128, 3)])
+                                        (16, 64, 32, 32, 15), (5, 32, 64, 128, 3),
+                                        # >= 120 tiles of 256 pixels: two sub-tiles per CTA share the weight slices (MT = 2)
+                                        (8, 64, 128, 128, 1), (8, 64, 128, 128, 15), (16, 32, 256, 256, 3)])
 def test_conv_tc2_3x3_matches_emulation(lib, N, H, C, Co, d):
     W, dt = H, torch.bfloat16
     x = rnd((N, H, W, C), dt, 1)
