@@ -32,7 +32,11 @@ namespace {
 
 constexpr int PWS_THREADS = 256;
 constexpr int PWS_WARPS = PWS_THREADS / 32;
-constexpr int PWS_OCC = 3;             // resident CTAs per SM the register budget is compiled for
+// resident CTAs per SM the register budget is compiled for: 3 (80 registers), 2 where the fragments alone need more
+// (64 output channels, or 64 input channels into 32: B fragments 32 registers + accumulators 16-32)
+template <int C0, int C1, int COUT> struct PwsOcc {
+  static constexpr int V = (COUT == 64 || (C0 + C1 == 64 && COUT == 32)) ? 2 : 3;
+};
 constexpr int PWS_MAXSIDE = 7;         // up-sampled addends (4), residual, running sum, mask
 
 struct PwsParams {
@@ -123,7 +127,7 @@ template <int C, int BASE, int KTOT> __device__ __forceinline__ uint32_t pws_fra
 }
 
 template <int C0, int C1, int COUT, bool STATS>
-__global__ void __launch_bounds__(PWS_THREADS, PWS_OCC) pw_stream_kernel(const PwsParams p) {
+__global__ void __launch_bounds__(PWS_THREADS, PwsOcc<C0, C1, COUT>::V) pw_stream_kernel(const PwsParams p) {
   constexpr int KS0 = PwsSrc<C0>::KS, KS1 = PwsSrc<C1>::KS, NT = COUT / 8, NCH = 2 * NT;
   constexpr int SP = NT >= 4 ? NT / 4 : 1;             // pieces per row of an output-shaped side tensor
   constexpr int SB = NT >= 4 ? 16 : 4 * NT;            // their bytes
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(PWS_THREADS, PWS_OCC) pw_stream_kernel(const P
 
 template <int C0, int C1, int COUT, bool STATS>
 int pws_launch_k(PwsParams& p, cudaStream_t st) {
-  constexpr int NT = COUT / 8, SP = NT >= 4 ? NT / 4 : 1;
+  constexpr int NT = COUT / 8, SP = NT >= 4 ? NT / 4 : 1, PWS_OCC = PwsOcc<C0, C1, COUT>::V;
   const int nside = p.nadd + (p.mask ? 1 : 0);
   p.stage_bytes = (2 * (PwsSrc<C0>::PC + PwsSrc<C1>::PC) + 2 * SP * nside) * 512;
   // FIFO depth: ~6 KB in flight per warp (24 warps per SM: ~140 KB, three times what latency x bandwidth asks for - the

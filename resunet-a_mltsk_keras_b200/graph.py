@@ -480,13 +480,24 @@ class Plan:
     def _tc_spatial_ok(H, W, min_side=1):
         return H == W and W >= min_side and (W & (W - 1)) == 0
 
+    def _hb_stream(self, op, c0, c1, cout, M, out_dtype, sides=0.0):
+        """A 1x1 launch that rsa_conv_tc2_fwd hands to the streaming kernel (pw_stream.cu: at most 64 input channels in total,
+        8 / 16 / 32 / 64 output channels, bf16 out) is bandwidth-bound: tag its algorithmic bytes - operand rows read, result
+        written, `sides` further result-shaped tensors read (mask, running sum, residual, up-sampled addends as fractions)."""
+        k16 = lambda c: 0 if c == 0 else (c // 16 if c >= 32 else 1)
+        if (out_dtype == torch.bfloat16 and c0 in (8, 16, 32, 64) and (c1 == 0 or (c0, c1) == (32, 32)) and cout in (8, 16, 32, 64)
+                and (k16(c0) + k16(c1)) * (cout // 8) <= 16 and M % 16 == 0 and os.environ.get("RSA_PW_STREAM", "1") != "0"):
+            self._hb(op, 2.0 * M * (c0 + c1 + cout * (1.0 + sides)))
+        return op
+
     def _pw_fwd_one(self, src, koff, K, cout, name, out, Hq, Wq):
         """q = W[koff:koff+C] . src at the source's own resolution (no bias)."""
         lib, N = self.lib, self.N
         ent = self.net.tc[name]
         if (src.C % 16 == 0 or src.C == 8) and self._tc_spatial_ok(Hq, Wq):
             wt = self.net.shadow[ent["fwd"]:ent["fwd"] + ent["coutp"] * K]
-            return lib.conv_tc2_fwd(src.data, None, wt, ent["coutp"], None, out, N, Hq, Wq, cout, k_base=koff, k_total=K)
+            return self._hb_stream(lib.conv_tc2_fwd(src.data, None, wt, ent["coutp"], None, out, N, Hq, Wq, cout, k_base=koff,
+                                                    k_total=K), src.C, 0, cout, N * Hq * Wq, out.dtype)
         W_ = self.P(name + "/kernel")
         return lib.igemm_fwd([Seg(src.data, src.C, Hq, Wq, w_off=koff * cout)], W_, cout, False, None, out, N, Hq, Wq, cout)
 
@@ -507,10 +518,11 @@ class Plan:
         x1 = mains[1][0] if len(mains) > 1 else None
         stride = 2 if mains[0][1] == "s2" else 1
         st = out.stats
-        self.fwd.append(self._late(lambda: lib.conv_tc2_fwd(
+        self.fwd.append(self._hb_stream(self._late(lambda: lib.conv_tc2_fwd(
             x0.data, x1.data if x1 is not None else None, wt, ent["coutp"], b_, out.data, N, out.H, out.W, cout,
             in_stride=stride, ups=ups, residual=res, stats=st[0] if st else None, relu=relu, k_base=mains[0][2],
-            k_total=K)))
+            k_total=K)), x0.C, x1.C if x1 is not None else 0, cout, out.M, out.dtype,
+            sides=(res is not None) + sum(0.25 ** sh for _, sh in ups)))
         if not self.training:
             return
 
@@ -553,8 +565,10 @@ class Plan:
                     wsl = wb[koff * cout:(koff + t.C) * cout]
                     if in_stride == 2 and not acc:
                         self.bwd.append(lambda s_, g=g: g.zero_())      # odd pixels receive no gradient
-                    self.bwd.append(lib.conv_tc2_fwd(dq, None, wsl, max(t.C, 16), None, g, N, Hq, Wq, t.C, mask=mask,
-                                                     accumulate=acc or in_stride == 2, out_stride=in_stride))
+                    self.bwd.append(self._hb_stream(
+                        lib.conv_tc2_fwd(dq, None, wsl, max(t.C, 16), None, g, N, Hq, Wq, t.C, mask=mask,
+                                         accumulate=acc or in_stride == 2, out_stride=in_stride),
+                        cout, 0, t.C, N * Hq * Wq, g.dtype, sides=(mask is not None) + bool(acc or in_stride == 2)))
                 else:
                     if in_stride == 2:
                         sg = [Seg(dq, cout, Hq, Wq, shift=1, aligned=True, w_off=koff * cout)]

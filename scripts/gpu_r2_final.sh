@@ -20,6 +20,8 @@ timeout 600 ncu --profile-from-start off --clock-control none --metrics gpu__tim
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc3_kernel -c 4 -o gpurun_out/${T}_prof_tc3 python scripts/ncu_ops.py conv > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 RSA_CUDA_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 700 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 RSA_WGRAD_STREAM=0 RSA_LANES=0 timeout 300 python scripts/trace_launches.py > gpurun_out/${T}_trace.log 2>&1; cp gpurun_out/trace_launches.txt gpurun_out/${T}_step_launch_trace.txt; echo "trace rc=$?"
+python scripts/bench_pw.py 2>&1 | grep -v -i warn > gpurun_out/${T}_bench_pw.log
+python scripts/bench_wide.py 2>&1 | grep -v -i warn > gpurun_out/${T}_bench_wide.log
 python scripts/bench_conv.py 2>&1 | grep -v -i warn > gpurun_out/${T}_bench_conv.log
 python scripts/bench_conv.py --C 64 2>&1 | grep -v -i warn >> gpurun_out/${T}_bench_conv.log
 tail -4 gpurun_out/${T}_gputest.log; head -c 600 gpurun_out/${T}_bench_c2.json
