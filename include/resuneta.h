@@ -182,7 +182,9 @@ int rsa_conv_tc_supported(int N, int H, int W, int Cin, int Cout);
  * [k_base, k_base+C0+C1) of wt's K dimension of length k_total (0 = C0+C1); out_stride 2 scatters the result to the even
  * pixels of a (2H,2W) tensor (data gradient of the stride-2 convolutions).  bnr_x / bnr_coef select the fused
  * BatchNormalization-backward reduction epilogue: `stats` += {sum g, sum g*xhat}, xhat = (bnr_x - mean)*invstd with
- * bnr_coef = rsa_bn_meaninv()'s [2][Cout] table (FusedBatchNormGrad's reductions, model2.py:17,21). */
+ * bnr_coef = rsa_bn_meaninv()'s [2][Cout] table (FusedBatchNormGrad's reductions, model2.py:17,21).
+ * taps = 1 launches with at most 64 input channels in total and 8 / 16 / 32 / 64 bf16 output channels (the thin 256x256 /
+ * 128x128 layers, HBM-bound) are executed by the streaming kernel of pw_stream.cu - same arguments, same epilogue order. */
 int rsa_conv_tc2_supported(int N, int H, int W, int C0, int C1, int Cout);
 int rsa_conv_tc2_fwd(const void* x0, int C0, const void* x1, int C1, const void* wt, int CoutP, const float* bias,
                      void* out, int out_f32, const void* residual, const void* mask, double* stats, int N, int H,

@@ -686,8 +686,11 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
   p.stats = stats; p.relu = relu;
   p.out = (uint8_t*)out;
-  static const int direct_env = getenv("RSA_TC3_DIRECT") ? atoi(getenv("RSA_TC3_DIRECT")) : 0;
-  p.direct = direct_env;
+  // result slices: staged in shared memory + TMA store, or four 16-byte global stores per thread.  The shared-memory port is
+  // the contended resource of the 32-channel halo launches (MMA operands, TMA fills, staging), where the direct stores
+  // measure 4-7 % faster; box mode and 64 channels are 5 % slower with them.  RSA_TC3_DIRECT=0 / 1 forces one way.
+  static const int direct_env = getenv("RSA_TC3_DIRECT") ? atoi(getenv("RSA_TC3_DIRECT")) : -1;
+  p.direct = direct_env >= 0 ? direct_env : (C == 32 && !any_box);
   p.debug = getenv("RSA_TC3_DEBUG") ? atoi(getenv("RSA_TC3_DEBUG")) : 0;
   const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   Tc3Maps maps;
