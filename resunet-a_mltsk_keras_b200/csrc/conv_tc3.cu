@@ -754,17 +754,22 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
 // further (LBO = d pixels).  C = 32: D_dy[128 x 32] = [tap(dy,-1) | tap(dy,0) | tap(dy,+1) | unused]; C = 64 (atoms of
 // 64 channels): D_dy,0 = [tap(dy,-1) | tap(dy,0)], D_dy,1 = [tap(dy,+1) | unused].  Three warps (one per tap row) issue
 // independent accumulation chains that run for the whole life of the persistent CTA; one red.global.add pass per CTA
-// at the end.  Large dilations (C = 32 only) use nine 16 x 8 boxes per item with LBO = one box.
+// at the end.  Large dilations (C = 32 only): the two-dimensional halo does not fit, so an item is a flat 2 x 128 pixel strip
+// and every tap row gets ONE band box 2 x (128 + 2d) pixels whose three column shifts are again the M atoms (LBO = d pixels):
+// 300-350 bytes of L2 traffic per pixel.  Images narrower than 128 pixels keep the first scheme, nine 16 x 8 boxes per item
+// with LBO = one box (640 bytes per pixel, 81-85 us per launch at 16 x 256 x 256 where the halo launches take 49-53).
 // =====================================================================================================
 namespace {
 
 constexpr int W3_THREADS = 256;   // warp 0 TMA, 1..3 MMA (tap row dy = warp - 1), 4..7 final reduction
 
 struct Wg3Params {
-  int N, H, W, dil, halo;
-  int IW;                 // item width in pixels: 16 (halo) or 8 (boxes); item height 16
+  int N, H, W, dil;
+  int halo;               // 1: one two-dimensional halo box per item, 2: one band box per tap row, 0: one box per tap
+  int IW, IH;             // item width / height in pixels: 16 x 16 (halo), 128 x 2 (bands), 8 x 16 (boxes)
   int items, tiles_w, tiles_h;
   int nstages, stage_bytes, a_bytes, a_tx;   // a_tx: bytes the halo box actually delivers
+  int band_bytes;         // bands: shared-memory pitch between the tap rows' boxes
   float* dw;
 };
 
@@ -823,12 +828,21 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
         int r = item;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h; r /= p.tiles_h;
-        const int n = r, h0 = th * 16, w0 = tw * p.IW;
+        const int n = r, h0 = th * p.IH, w0 = tw * p.IW;
         uint8_t* sa = smem + stage * p.stage_bytes;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (p.halo) {
+        if (p.halo == 1) {
           mbar_expect_tx(&full_bar[stage], p.a_tx + 16 * p.IW * PITCH);
           tma_load_4d(sa, &tmX, &full_bar[stage], 0, w0 - d, h0 - d, n);
+        } else if (p.halo == 2) {
+          int nrow = 0;
+          for (int dyi = 0; dyi < 3; ++dyi) { const int ch = h0 + (dyi - 1) * d; nrow += !(ch + p.IH <= 0 || ch >= p.H); }
+          mbar_expect_tx(&full_bar[stage], nrow * p.a_tx + p.IH * p.IW * PITCH);
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            const int ch = h0 + (dyi - 1) * d;
+            if (ch + p.IH <= 0 || ch >= p.H) continue;
+            tma_load_4d(sa + dyi * p.band_bytes, &tmX, &full_bar[stage], 0, w0 - d, ch, n);
+          }
         } else {
           int nrow = 0;
           for (int dyi = 0; dyi < 3; ++dyi) { const int ch = h0 + (dyi - 1) * d; nrow += !(ch + 16 <= 0 || ch >= p.H); }
@@ -858,20 +872,22 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
         int r = item;
         r /= p.tiles_w;
         const int th = r % p.tiles_h;
-        const int ch = th * 16 + (dyi - 1) * d;
+        const int ch = th * p.IH + (dyi - 1) * d;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
         const uint32_t sb = sa + p.a_bytes;
-        if (p.halo || !(ch + 16 <= 0 || ch >= p.H)) {
+        if (p.halo == 1 || !(ch + p.IH <= 0 || ch >= p.H)) {
           // A: atom i = tap (dy, dx = i - 1) (C = 32: four atoms, C = 64: two per chain); two 8-pixel K groups per MMA
           // = rows (2rp, 2rp+1), column block cb
-          const uint32_t a0 = p.halo ? sa + (uint32_t)((dyi * d * Wh) * PITCH) : sa + (uint32_t)(dyi * 3) * boxb;
+          const uint32_t a0 = p.halo == 1 ? sa + (uint32_t)((dyi * d * Wh) * PITCH)
+                            : (p.halo == 2 ? sa + (uint32_t)(dyi * p.band_bytes) : sa + (uint32_t)(dyi * 3) * boxb);
           const uint32_t arow = p.halo ? Wh * PITCH : p.IW * PITCH;
           const uint32_t lbo = p.halo ? d * PITCH : boxb;
           const uint32_t brow = p.IW * PITCH;
+          const int nrp = p.IH / 2;
 #pragma unroll 1
-          for (int rp = 0; rp < 8; ++rp) {
+          for (int rp = 0; rp < nrp; ++rp) {
             for (int cb = 0; cb < ncb; ++cb) {
               const uint64_t bdesc = w3_mndesc<C>(sb + 2 * rp * brow + cb * 8 * PITCH, 0, brow);
 #pragma unroll
@@ -896,11 +912,11 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
     if (nmine > 0) {
       for (int dyi = 0; dyi < 3; ++dyi) {
         // a tap row that was out of range for every item of this CTA never initialised its accumulator
-        bool any = p.halo;
+        bool any = p.halo == 1;
         if (!any) {
           for (int item = blockIdx.x; item < p.items && !any; item += gridDim.x) {
-            const int ch = ((item / p.tiles_w) % p.tiles_h) * 16 + (dyi - 1) * d;
-            any = !(ch + 16 <= 0 || ch >= p.H);
+            const int ch = ((item / p.tiles_w) % p.tiles_h) * p.IH + (dyi - 1) * d;
+            any = !(ch + p.IH <= 0 || ch >= p.H);
           }
         }
         if (!any) continue;
@@ -965,15 +981,25 @@ extern "C" int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int 
   const int PITCH = C * 2;
   Wg3Params p;
   p.N = N; p.H = H; p.W = W; p.dil = dil; p.dw = dw;
-  p.halo = dil <= 3;
-  p.IW = p.halo ? 16 : 8;
-  p.tiles_w = W / p.IW; p.tiles_h = H / 16;
+  static const int band_env = getenv("RSA_TC3_WG_BAND") ? atoi(getenv("RSA_TC3_WG_BAND")) : 1;
+  p.halo = dil <= 3 ? 1 : ((C == 32 && W % 128 == 0 && 128 + 2 * dil <= 256 && band_env) ? 2 : 0);
+  p.IW = p.halo == 1 ? 16 : (p.halo == 2 ? 128 : 8);
+  p.IH = p.halo == 2 ? 2 : 16;
+  p.tiles_w = W / p.IW; p.tiles_h = H / p.IH;
   p.items = p.tiles_w * p.tiles_h * N;
-  // the unused trailing M atom reads up to 2*dil pixels (halo) / one box past the A region: keep that inside the stage
-  const int a_raw = p.halo ? (16 + 2 * dil) * (p.IW + 2 * dil) * PITCH : 9 * 16 * p.IW * PITCH;
-  p.a_tx = a_raw;
+  // the unused trailing M atom reads up to 2*dil pixels (halo, bands) / one box past the A region: keep that inside the stage
+  p.band_bytes = 0;
+  int a_raw;
+  if (p.halo == 2) {
+    p.a_tx = p.IH * (p.IW + 2 * dil) * PITCH;                  // one band
+    p.band_bytes = (p.a_tx + 1023) & ~1023;
+    a_raw = 3 * p.band_bytes;
+  } else {
+    a_raw = p.halo ? (16 + 2 * dil) * (p.IW + 2 * dil) * PITCH : 9 * 16 * p.IW * PITCH;
+    p.a_tx = a_raw;
+  }
   p.a_bytes = (a_raw + 2 * dil * PITCH + 1023) & ~1023;
-  p.stage_bytes = p.a_bytes + 16 * p.IW * PITCH;
+  p.stage_bytes = p.a_bytes + p.IH * p.IW * PITCH;
   p.stage_bytes = (p.stage_bytes + 1023) & ~1023;
   int ns = (227 * 1024 - 2048) / p.stage_bytes;
   if (ns > 6) ns = 6;
@@ -990,9 +1016,10 @@ extern "C" int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int 
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  CUresult r = p.halo ? encode(&tmX, x, p.IW + 2 * dil, 16 + 2 * dil) : encode(&tmX, x, p.IW, 16);
+  CUresult r = p.halo == 1 ? encode(&tmX, x, p.IW + 2 * dil, 16 + 2 * dil)
+             : (p.halo == 2 ? encode(&tmX, x, p.IW + 2 * dil, p.IH) : encode(&tmX, x, p.IW, 16));
   RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
-  r = encode(&tmDY, dy, p.IW, 16);
+  r = encode(&tmDY, dy, p.IW, p.IH);
   RSA_REQUIRE(r == CUDA_SUCCESS, RSA_ERR_CUDA, "conv_tc3_wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
   if (C == 32) return launch_wg3<32>(tmX, tmDY, p, smem_bytes, (cudaStream_t)stream);
   return launch_wg3<64>(tmX, tmDY, p, smem_bytes, (cudaStream_t)stream);

@@ -409,7 +409,9 @@ def test_conv_tc3_fused_branches(lib, N, H, W, dils):
 
 
 @pytest.mark.parametrize("N,H,W,d", [(2, 32, 32, 1), (1, 16, 64, 3), (2, 32, 32, 15), (2, 64, 64, 31), (16, 64, 64, 1),
-                                     (1, 32, 32, 31), (3, 48, 96, 3)])
+                                     (1, 32, 32, 31), (3, 48, 96, 3),
+                                     # W a multiple of 128: one band box per tap row (incl. tap rows that never touch the image)
+                                     (1, 16, 128, 15), (2, 32, 256, 31), (3, 64, 128, 31), (1, 48, 128, 15)])
 @pytest.mark.parametrize("C", [32, 64])
 def test_conv_tc3_wgrad(lib, N, H, W, d, C):
     dt = torch.bfloat16
