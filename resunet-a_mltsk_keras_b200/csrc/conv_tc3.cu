@@ -66,6 +66,10 @@ struct Tc3Params {
   int nbr;
   int dil[T3_MAXBR];      // signed: negative = data gradient (taps mirrored)
   int halo[T3_MAXBR];     // 1: one halo box per item, 0: one box per tap
+  int band;               // 1: every branch has a large dilation and W is a multiple of 128: an item is KT image rows of 128
+                          // pixels (sub-tile = one row), each tap ROW is one band box KT x (128 + 2|d|) pixels and its three
+                          // column shifts are start addresses into it - 3 boxes of L2 traffic per item instead of 9
+  int IH, IWP;            // item height / width in pixels: 16 x 8 KT, or KT x 128 (band)
   int items, tiles_w, tiles_h;
   int nstages, slot_bytes;
   int alt;                      // 1: the two MMA warps take alternate items (every branch in halo mode, nstages even)
@@ -214,10 +218,22 @@ __global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_cons
         int r = item;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h; r /= p.tiles_h;
-        const int n = r, h0 = th * 16, w0 = tw * 8 * KT;
+        const int n = r, h0 = th * p.IH, w0 = tw * p.IWP;
         for (int b = 0; b < p.nbr; ++b) {
           const int d = p.dil[b], ad = d < 0 ? -d : d;
-          if (p.halo[b]) {
+          if (p.band) {
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const int ch = h0 + (dyi - 1) * d;
+              if (ch + KT <= 0 || ch >= p.H) continue;
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (p.debug & 4) mbar_expect_tx(&full_bar[stage], 0);
+              else {
+                mbar_expect_tx(&full_bar[stage], KT * (128 + 2 * ad) * PITCH);
+                tma_load_4d(ring + stage * p.slot_bytes, &maps.a[b], &full_bar[stage], 0, w0 - ad, ch, n);
+              }
+              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            }
+          } else if (p.halo[b]) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (p.debug & 4) mbar_expect_tx(&full_bar[stage], 0);
             else {
@@ -306,7 +322,7 @@ __global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_cons
       int tw = (int)blockIdx.x % p.tiles_w, th = ((int)blockIdx.x / p.tiles_w) % p.tiles_h;
       const int dtw = (int)gridDim.x % p.tiles_w, dth = ((int)gridDim.x / p.tiles_w) % p.tiles_h;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        const int h0 = th * 16, w0 = tw * 8 * KT;
+        const int h0 = th * p.IH, w0 = tw * p.IWP;
         tw += dtw; th += dth;                       // next item's tile coordinates without a division
         if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
         if (th >= p.tiles_h) th -= p.tiles_h;
@@ -318,7 +334,31 @@ __global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_cons
         for (int b = 0; b < p.nbr; ++b) {
           const int d = p.dil[b], ad = d < 0 ? -d : d;
           const uint32_t wb = wbase + b * WBYTES;
-          if (p.halo[b]) {
+          if (p.band) {
+            // sub-tile s = image row h0 + s: 16 groups of 8 consecutive pixels (SBO = 8 pixels); tap (dy, dx) = band dy, window
+            // shifted by dx * d pixels inside its row of 128 + 2|d|
+            const int Wb = 128 + 2 * ad;
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const int ch = h0 + (dyi - 1) * d;
+              if (ch + KT <= 0 || ch >= p.H) continue;
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(ring + stage * p.slot_bytes) + (uint32_t)((s * Wb + ad) * PITCH);
+              if (!(p.debug & 1)) {
+#pragma unroll
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                  const uint64_t adesc = t3_desc(bhi, sa + (dxi - 1) * d * PITCH);
+                  const uint64_t bdesc = t3_desc(bhi, wb + (dyi * 3 + dxi) * C * PITCH);
+#pragma unroll
+                  for (int k = 0; k < C / 16; ++k)
+                    umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, started | (dxi > 0) | (k > 0));
+                  }
+              }
+              started = 1;
+              umma_commit(&empty_bar[stage]);
+              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            }
+          } else if (p.halo[b]) {
             const int Wh = 8 * KT + 2 * ad;
             const uint32_t ahi = t3_desc_hi<C>(Wh * PITCH);
             mbar_wait(&full_bar[stage], phase);
@@ -401,7 +441,7 @@ __global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_cons
     auto issue_side = [&](const Cur& c, int idx) {       // lane 0: TMA loads of the side slices of slice idx into buffer idx % sdepth
       if (c.item >= p.items) return;
       const int b = idx % p.sdepth;
-      const int hh = c.th * 16 + 4 * q, ww = c.tw * 8 * KT + 8 * sub_of(c.j);
+      const int hh = c.th * p.IH + (p.band ? sub_of(c.j) : 4 * q), ww = c.tw * p.IWP + (p.band ? 32 * q : 8 * sub_of(c.j));
       uint8_t* dst = sbuf + b * nside * T3_SLICE;
       mbar_expect_tx(&mybar[b], nside * T3_SLICE);
       if (p.has_add) tma_load_4d(dst, &maps.add, &mybar[b], c0, ww, hh, c.n);
@@ -422,7 +462,7 @@ __global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_cons
 #pragma unroll 1
       for (int j = 0; j < SPI; ++j, ++idx) {
         const int s = sub_of(j);
-        const int n = cur.n, hh = cur.th * 16 + 4 * q, ww = cur.tw * 8 * KT + 8 * s;
+        const int n = cur.n, hh = cur.th * p.IH + (p.band ? s : 4 * q), ww = cur.tw * p.IWP + (p.band ? 32 * q : 8 * s);
         cur_next(cur);
         const int sb = nside ? idx % p.sdepth : 0;
         const uint8_t* ib = sbuf + sb * nside * T3_SLICE;
@@ -519,7 +559,8 @@ __global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_cons
         }
         if (p.direct) {
           // each thread holds one pixel's 32 channels = 64 contiguous bytes of the NHWC tensor: four 16-byte stores
-          uint4* gp = reinterpret_cast<uint4*>(p.out + ((((size_t)n * p.H + hh + (lane >> 3)) * p.W + ww + (lane & 7)) * C + c0) * 2);
+          const int lr = p.band ? 0 : lane >> 3, lc = p.band ? lane : lane & 7;      // this lane's pixel inside the slice
+          uint4* gp = reinterpret_cast<uint4*>(p.out + ((((size_t)n * p.H + hh + lr) * p.W + ww + lc) * C + c0) * 2);
 #pragma unroll
           for (int k = 0; k < 4; ++k) gp[k] = pk[k];
         } else {
@@ -647,6 +688,13 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   static const int kt_env = getenv("RSA_TC3_KT") ? atoi(getenv("RSA_TC3_KT")) : 0;
   int KT = C == 32 ? (nbr > 2 ? 2 : 4) : (max_ad == 3 ? 1 : 2);
   if (C == 32 && (kt_env == 2 || kt_env == 4)) KT = kt_env;
+  // band mode (Tc3Params::band): only large dilations in the launch, rows of 128 pixels, band boxes within TMA's 256 limit
+  static const int band_env = getenv("RSA_TC3_BAND") ? atoi(getenv("RSA_TC3_BAND")) : 1;
+  int big_ad = 0;
+  for (int b = 0; b < nbr; ++b) { const int ad = dils[b] < 0 ? -dils[b] : dils[b]; big_ad = ad > big_ad ? ad : big_ad; }
+  p.band = (band_env && any_box && !max_ad && W % 128 == 0 && 128 + 2 * big_ad <= 256 && H % KT == 0) ? 1 : 0;
+  p.IH = p.band ? KT : 16;
+  p.IWP = p.band ? 128 : 8 * KT;
   // at most one addend: the identity input of the first branch (residual) or the running sum (accumulate)
   RSA_REQUIRE(!(residual && accumulate), RSA_ERR_SHAPE, "conv_tc3_fwd: residual and accumulate are exclusive");
   p.has_add = (residual || accumulate) ? 1 : 0;
@@ -665,7 +713,7 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   // shared memory: leave ~8 KB of the SM to the bandwidth-bound kernels that run beside the persistent CTA (see
   // conv_tc3_kernel) unless that costs an operand stage
   auto plan = [&](int kt, int budget_kb) {
-    int slot = any_box ? kt * BOXB : 0;
+    int slot = any_box ? (p.band ? kt * (128 + 2 * big_ad) * PITCH : kt * BOXB) : 0;
     if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * kt + 2 * max_ad) * PITCH; slot = hb > slot ? hb : slot; }
     slot = (slot + 1023) & ~1023;
     const Tc3Smem L0(C, nbr, nside, p.sdepth, 0, slot);
@@ -674,13 +722,15 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
     p.nstages = ns > 8 ? 8 : ns;
   };
   plan(KT, 227);
-  if (p.nstages < 2 && C == 32 && KT == 4) { KT = 2; plan(KT, 227); }
+  if (p.nstages < 2 && C == 32 && KT == 4) { KT = 2; if (p.band) p.IH = KT; plan(KT, 227); }
+  if (p.nstages < 2 && p.band) { p.band = 0; p.IH = 16; plan(KT, 227); }      // bands too large beside the side slices: boxes
   { const int full = p.nstages; plan(KT, 219); if (p.nstages < full && p.nstages < 4) plan(KT, 227); }
   RSA_REQUIRE(p.nstages >= 2, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory budget allows only %d stage(s)", p.nstages);
   static const int alt_env = getenv("RSA_TC3_ALT") ? atoi(getenv("RSA_TC3_ALT")) : 1;
   p.alt = (!any_box && alt_env && nbr == 1 && C == 32) ? 1 : 0;   // measured: C = 64 (two chains per item) is faster with both warps on one item
   if (p.alt) p.nstages &= ~1;                    // see conv_tc3_kernel: an even ring keeps every stage with one MMA warp
-  p.tiles_w = W / (8 * KT); p.tiles_h = H / 16;
+  if (!p.band) p.IWP = 8 * KT;
+  p.tiles_w = W / p.IWP; p.tiles_h = H / p.IH;
   p.items = p.tiles_w * p.tiles_h * N;
   const Tc3Smem L(C, nbr, nside, p.sdepth, p.nstages, p.slot_bytes);
   RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
@@ -690,7 +740,7 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   // the contended resource of the 32-channel halo launches (MMA operands, TMA fills, staging), where the direct stores
   // measure 4-7 % faster; box mode and 64 channels are 5 % slower with them.  RSA_TC3_DIRECT=0 / 1 forces one way.
   static const int direct_env = getenv("RSA_TC3_DIRECT") ? atoi(getenv("RSA_TC3_DIRECT")) : -1;
-  p.direct = direct_env >= 0 ? direct_env : (C == 32 && !any_box);
+  p.direct = direct_env >= 0 ? direct_env : (C == 32 && (!any_box || p.band));
   p.debug = getenv("RSA_TC3_DEBUG") ? atoi(getenv("RSA_TC3_DEBUG")) : 0;
   const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   Tc3Maps maps;
@@ -699,6 +749,7 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)(p.halo[b] ? 8 * KT + 2 * ad : 8 * KT), (cuuint32_t)(p.halo[b] ? 16 + 2 * ad : 16), 1};
+    if (p.band) { box[1] = (cuuint32_t)(128 + 2 * ad); box[2] = (cuuint32_t)KT; }
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&maps.a[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xs[b]), gdim, gstr, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -719,6 +770,7 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
       cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
       cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
       cuuint32_t box[4] = {32, 8, 4, 1};
+      if (p.band) { box[1] = 32; box[2] = 1; }      // band items: a slice is 32 consecutive pixels of one image row
       cuuint32_t es[4] = {1, 1, 1, 1};
       return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -286,7 +286,9 @@ def _conv3_ref(x, w, C, d, N, H, W):
 
 @pytest.mark.parametrize("C", [32, 64])
 @pytest.mark.parametrize("N,H,W,d", [(2, 32, 32, 1), (1, 16, 64, 3), (2, 32, 32, 15), (2, 64, 64, 31), (3, 48, 96, 3),
-                                     (1, 32, 32, 31)])
+                                     (1, 32, 32, 31),
+                                     # W a multiple of 128 with a large dilation: band items (rows of 128 pixels, one box per tap row)
+                                     (1, 16, 128, 15), (2, 32, 256, 31), (3, 48, 128, 31), (1, 64, 128, 15)])
 def test_conv_tc3_single_branch(lib, N, H, W, d, C):
     dt = torch.bfloat16
     assert lib.conv_tc3_supported(N, H, W, C)
@@ -384,7 +386,8 @@ def test_conv_tc3_at_the_benchmarked_shapes(lib, N, H, W, C, d):
     assert float((d_dw.cpu().double() - dw.double()).norm() / dw.double().norm()) <= 1e-3, "wgrad"
 
 
-@pytest.mark.parametrize("N,H,W,dils", [(2, 64, 64, (1, 3, 15, 31)), (1, 32, 64, (1, 3, 15)), (2, 32, 32, (3, 31))])
+@pytest.mark.parametrize("N,H,W,dils", [(2, 64, 64, (1, 3, 15, 31)), (1, 32, 64, (1, 3, 15)), (2, 32, 32, (3, 31)),
+                                        (2, 32, 128, (15, 31)), (1, 64, 256, (15, 31)), (1, 32, 128, (1, 3, 15, 31))])
 def test_conv_tc3_fused_branches(lib, N, H, W, dils):
     """ResBlock-a branch sum + identity in one launch (model2.py:23-31)."""
     C, dt = 32, torch.bfloat16
