@@ -121,10 +121,10 @@ struct Tc3Maps { CUtensorMap a[T3_MAXBR]; CUtensorMap w[T3_MAXBR]; CUtensorMap o
 // shared-memory carve-up (offsets from the 1024-aligned base)
 struct Tc3Smem {
   int w_off, st_off, side_off, ring_off, misc_off, bar_off, total;
-  __host__ __device__ Tc3Smem(int C, int nbr, int nside, int sdepth, int nstages, int slot_bytes) {
+  __host__ __device__ Tc3Smem(int C, int nbr, int nside, int sdepth, int nstages, int slot_bytes, int direct) {
     w_off = 0;
     st_off = (nbr * 9 * C * C * 2 + 1023) & ~1023;
-    side_off = st_off + T3_EW * 2 * T3_SLICE;                 // [warp][2] staging slices
+    side_off = st_off + (direct ? 0 : T3_EW * 2 * T3_SLICE);  // [warp][2] staging slices (none with direct global stores)
     ring_off = side_off + T3_EW * sdepth * nside * T3_SLICE;  // [warp][sdepth][nside] side slices
     misc_off = ring_off + nstages * slot_bytes;               // bias[C], csum[8][32], csq[8][32], BN coefficients [4][C]
     bar_off = misc_off + (5 * C + 2 * T3_EW * 32) * 4;
@@ -148,7 +148,7 @@ __global__ void __maxnreg__(STATS ? 168 : 112) conv_tc3_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nside = p.has_add + p.has_mask + p.has_bnx;
-  const Tc3Smem L(C, p.nbr, nside, p.sdepth, p.nstages, p.slot_bytes);
+  const Tc3Smem L(C, p.nbr, nside, p.sdepth, p.nstages, p.slot_bytes, p.direct);
   uint8_t* wsm = smem + L.w_off;
   uint8_t* ring = smem + L.ring_off;
   float* bias_s = reinterpret_cast<float*>(smem + L.misc_off);
@@ -692,7 +692,12 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   static const int band_env = getenv("RSA_TC3_BAND") ? atoi(getenv("RSA_TC3_BAND")) : 1;
   int big_ad = 0;
   for (int b = 0; b < nbr; ++b) { const int ad = dils[b] < 0 ? -dils[b] : dils[b]; big_ad = ad > big_ad ? ad : big_ad; }
-  p.band = (band_env && any_box && !max_ad && W % 128 == 0 && 128 + 2 * big_ad <= 256 && H % KT == 0) ? 1 : 0;
+  // RSA_TC3_BAND: 0 off, 1 large dilations only, 2 every dilation >= RSA_TC3_BAND_MIN (experiment: bands against halo tiles)
+  static const int band_min = getenv("RSA_TC3_BAND_MIN") ? atoi(getenv("RSA_TC3_BAND_MIN")) : 1;
+  int small_ad = 1 << 30;
+  for (int b = 0; b < nbr; ++b) { const int ad = dils[b] < 0 ? -dils[b] : dils[b]; small_ad = ad < small_ad ? ad : small_ad; }
+  const bool band_ok = W % 128 == 0 && 128 + 2 * big_ad <= 256 && H % KT == 0;
+  p.band = (band_ok && ((band_env == 1 && any_box && !max_ad) || (band_env == 2 && small_ad >= band_min))) ? 1 : 0;
   p.IH = p.band ? KT : 16;
   p.IWP = p.band ? 128 : 8 * KT;
   // at most one addend: the identity input of the first branch (residual) or the running sum (accumulate)
@@ -712,35 +717,42 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   if (sd_env >= 1 && sd_env <= 4 && nside) p.sdepth = sd_env;
   // shared memory: leave ~8 KB of the SM to the bandwidth-bound kernels that run beside the persistent CTA (see
   // conv_tc3_kernel) unless that costs an operand stage
+  // result slices: staged in shared memory + TMA store, or four 16-byte global stores per thread.  The shared-memory port is
+  // the contended resource of the 32-channel halo and band launches (MMA operands, TMA fills, staging), where the direct
+  // stores measure 4-7 % faster; box mode and 64 channels are 5 % slower with them - unless the 32 KB of staging are what
+  // keeps a 64-channel launch with side inputs out of band mode (below).  RSA_TC3_DIRECT=0 / 1 forces one way.
+  static const int direct_env = getenv("RSA_TC3_DIRECT") ? atoi(getenv("RSA_TC3_DIRECT")) : -1;
+  p.direct = direct_env >= 0 ? direct_env : (C == 32 && (!any_box || p.band));
   auto plan = [&](int kt, int budget_kb) {
-    int slot = any_box ? (p.band ? kt * (128 + 2 * big_ad) * PITCH : kt * BOXB) : 0;
-    if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * kt + 2 * max_ad) * PITCH; slot = hb > slot ? hb : slot; }
+    int slot = any_box ? kt * BOXB : 0;
+    if (p.band) slot = kt * (128 + 2 * big_ad) * PITCH;
+    else if (max_ad) { const int hb = (16 + 2 * max_ad) * (8 * kt + 2 * max_ad) * PITCH; slot = hb > slot ? hb : slot; }
     slot = (slot + 1023) & ~1023;
-    const Tc3Smem L0(C, nbr, nside, p.sdepth, 0, slot);
+    const Tc3Smem L0(C, nbr, nside, p.sdepth, 0, slot, p.direct);
     int ns = (budget_kb * 1024 - L0.total - 256) / (slot + 16);
     p.slot_bytes = slot;
     p.nstages = ns > 8 ? 8 : ns;
   };
   plan(KT, 227);
   if (p.nstages < 2 && C == 32 && KT == 4) { KT = 2; if (p.band) p.IH = KT; plan(KT, 227); }
-  if (p.nstages < 2 && p.band) { p.band = 0; p.IH = 16; plan(KT, 227); }      // bands too large beside the side slices: boxes
+  if (p.nstages < 2 && p.band && !p.direct && direct_env < 0) { p.direct = 1; plan(KT, 227); }   // bands instead of staging
+  if (p.nstages < 2 && p.band) {                   // bands too large beside the side slices: boxes
+    p.band = 0; p.IH = 16;
+    if (direct_env < 0) p.direct = 0;
+    plan(KT, 227);
+  }
   { const int full = p.nstages; plan(KT, 219); if (p.nstages < full && p.nstages < 4) plan(KT, 227); }
   RSA_REQUIRE(p.nstages >= 2, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory budget allows only %d stage(s)", p.nstages);
   static const int alt_env = getenv("RSA_TC3_ALT") ? atoi(getenv("RSA_TC3_ALT")) : 1;
-  p.alt = (!any_box && alt_env && nbr == 1 && C == 32) ? 1 : 0;   // measured: C = 64 (two chains per item) is faster with both warps on one item
+  p.alt = (!any_box && !p.band && alt_env && nbr == 1 && C == 32) ? 1 : 0;   // measured: C = 64 (two chains per item) is faster with both warps on one item
   if (p.alt) p.nstages &= ~1;                    // see conv_tc3_kernel: an even ring keeps every stage with one MMA warp
   if (!p.band) p.IWP = 8 * KT;
   p.tiles_w = W / p.IWP; p.tiles_h = H / p.IH;
   p.items = p.tiles_w * p.tiles_h * N;
-  const Tc3Smem L(C, nbr, nside, p.sdepth, p.nstages, p.slot_bytes);
+  const Tc3Smem L(C, nbr, nside, p.sdepth, p.nstages, p.slot_bytes, p.direct);
   RSA_REQUIRE(L.total <= 227 * 1024, RSA_ERR_SHAPE, "conv_tc3_fwd: shared memory %d", L.total);
   p.stats = stats; p.relu = relu;
   p.out = (uint8_t*)out;
-  // result slices: staged in shared memory + TMA store, or four 16-byte global stores per thread.  The shared-memory port is
-  // the contended resource of the 32-channel halo launches (MMA operands, TMA fills, staging), where the direct stores
-  // measure 4-7 % faster; box mode and 64 channels are 5 % slower with them.  RSA_TC3_DIRECT=0 / 1 forces one way.
-  static const int direct_env = getenv("RSA_TC3_DIRECT") ? atoi(getenv("RSA_TC3_DIRECT")) : -1;
-  p.direct = direct_env >= 0 ? direct_env : (C == 32 && (!any_box || p.band));
   p.debug = getenv("RSA_TC3_DEBUG") ? atoi(getenv("RSA_TC3_DEBUG")) : 0;
   const CUtensorMapSwizzle swz = C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   Tc3Maps maps;
@@ -937,14 +949,19 @@ __global__ void __launch_bounds__(W3_THREADS, 1) conv_tc3_wgrad_kernel(const __g
           const uint32_t arow = p.halo ? Wh * PITCH : p.IW * PITCH;
           const uint32_t lbo = p.halo ? d * PITCH : boxb;
           const uint32_t brow = p.IW * PITCH;
-          const int nrp = p.IH / 2;
+          // the two 8-pixel K groups of an MMA: rows (2rp, 2rp+1) of one column block, or - items of a single row -
+          // two neighbouring column blocks
+          const int nrp = p.IH >= 2 ? p.IH / 2 : 1;
+          const uint32_t cstep = p.IH >= 2 ? 8 * PITCH : 16 * PITCH;
+          const uint32_t ksa = p.IH >= 2 ? arow : 8 * PITCH, ksb = p.IH >= 2 ? brow : 8 * PITCH;
+          const int ncbk = p.IH >= 2 ? ncb : ncb / 2;
 #pragma unroll 1
           for (int rp = 0; rp < nrp; ++rp) {
-            for (int cb = 0; cb < ncb; ++cb) {
-              const uint64_t bdesc = w3_mndesc<C>(sb + 2 * rp * brow + cb * 8 * PITCH, 0, brow);
+            for (int cb = 0; cb < ncbk; ++cb) {
+              const uint64_t bdesc = w3_mndesc<C>(sb + 2 * rp * brow + cb * cstep, 0, ksb);
 #pragma unroll
               for (int c = 0; c < NACC; ++c) {
-                const uint64_t adesc = w3_mndesc<C>(a0 + 2 * rp * arow + cb * 8 * PITCH + c * 2 * lbo, lbo, arow);
+                const uint64_t adesc = w3_mndesc<C>(a0 + 2 * rp * arow + cb * cstep + c * 2 * lbo, lbo, ksa);
                 umma_bf16(acc + c * C, adesc, bdesc, idesc, accum);
               }
               accum = 1;
@@ -1017,9 +1034,10 @@ int launch_wg3(const CUtensorMap& tmX, const CUtensorMap& tmDY, const Wg3Params&
 
 }  // namespace
 
-/* C = 32: any dilation; C = 64: dilations <= 3 (the nine boxes of a large dilation do not fit beside the dy tile). */
+/* C = 32: any dilation; C = 64: dilations <= 3, and larger ones where the band boxes apply (W a multiple of 128, band of
+ * 128 + 2 dil <= 256 pixels) - the nine boxes of a large dilation do not fit beside the dy tile. */
 extern "C" int rsa_conv_tc3_wgrad_supported(int N, int H, int W, int C, int dil) {
-  return rsa_conv_tc3_supported(N, H, W, C) && dil > 0 && (C == 32 || dil <= 3);
+  return rsa_conv_tc3_supported(N, H, W, C) && dil > 0 && (C == 32 || dil <= 3 || (W % 128 == 0 && 128 + 2 * dil <= 256));
 }
 
 /* dw[tap][ci][co] (fp32 HWIO, zeroed by the caller once per step) += sum_pix x[pix+off(tap), ci] * dy[pix, co] for the
@@ -1034,9 +1052,9 @@ extern "C" int rsa_conv_tc3_wgrad(const void* x, const void* dy, float* dw, int 
   Wg3Params p;
   p.N = N; p.H = H; p.W = W; p.dil = dil; p.dw = dw;
   static const int band_env = getenv("RSA_TC3_WG_BAND") ? atoi(getenv("RSA_TC3_WG_BAND")) : 1;
-  p.halo = dil <= 3 ? 1 : ((C == 32 && W % 128 == 0 && 128 + 2 * dil <= 256 && band_env) ? 2 : 0);
+  p.halo = dil <= 3 ? 1 : ((W % 128 == 0 && 128 + 2 * dil <= 256 && (band_env || C == 64)) ? 2 : 0);
   p.IW = p.halo == 1 ? 16 : (p.halo == 2 ? 128 : 8);
-  p.IH = p.halo == 2 ? 2 : 16;
+  p.IH = p.halo == 2 ? (C == 32 ? 2 : 1) : 16;         // 64 channels: single rows keep two stages in shared memory
   p.tiles_w = W / p.IW; p.tiles_h = H / p.IH;
   p.items = p.tiles_w * p.tiles_h * N;
   // the unused trailing M atom reads up to 2*dil pixels (halo, bands) / one box past the A region: keep that inside the stage

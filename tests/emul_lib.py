@@ -495,7 +495,7 @@ class EmulLibTC(EmulLib):
         return C in (32, 64) and N >= 1 and H >= 16 and H % 16 == 0 and W >= 32 and W % 32 == 0
 
     def conv_tc3_wgrad_supported(self, N, H, W, C, dil):
-        return self.conv_tc3_supported(N, H, W, C) and dil > 0 and (C == 32 or dil <= 3)
+        return self.conv_tc3_supported(N, H, W, C) and dil > 0 and (C == 32 or dil <= 3 or (W % 128 == 0 and 128 + 2 * dil <= 256))
 
     def pack_weights_tc(self, params, shadow, table, nlayers, max_elems):
         import struct
