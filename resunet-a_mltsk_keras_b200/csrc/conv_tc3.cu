@@ -688,6 +688,7 @@ extern "C" int rsa_conv_tc3_fwd(const void* const* xs, const void* const* wts, c
   static const int kt_env = getenv("RSA_TC3_KT") ? atoi(getenv("RSA_TC3_KT")) : 0;
   int KT = C == 32 ? (nbr > 2 ? 2 : 4) : (max_ad == 3 ? 1 : 2);
   if (C == 32 && (kt_env == 2 || kt_env == 4)) KT = kt_env;
+  if (C == 64 && (kt_env == 1 || kt_env == 2)) KT = kt_env;
   // band mode (Tc3Params::band): only large dilations in the launch, rows of 128 pixels, band boxes within TMA's 256 limit
   static const int band_env = getenv("RSA_TC3_BAND") ? atoi(getenv("RSA_TC3_BAND")) : 1;
   int big_ad = 0;
