@@ -60,6 +60,8 @@ int rsa_pw_stream_dispatch(const void* x0, int C0, const void* x1, int C1, const
                            const void* residual, const void* mask, double* stats, int N, int H, int W, int Cout,
                            int in_stride, int nup, const void* const* up_ptrs, const int* up_shifts, int k_base, int k_total,
                            int out_stride, int accumulate, int relu, cudaStream_t st);
+int rsa_pw_wgrad_stream_dispatch(const void* x, const void* dz, float* dw, int ldw, int N, int H, int W, int Cin, int Cout,
+                                 int in_stride, cudaStream_t st);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- scalar / vector element access, always computing in fp32 ------------------------------

@@ -508,6 +508,10 @@ extern "C" int rsa_pw_wgrad_tc(const void* x, const void* dz, float* dw, int ldw
   RSA_REQUIRE(p2(H) && p2(W) && W >= 4 && H >= 4 && p2(Cin) && Cin >= 8 && Cin <= 1024 && p2(Cout) && Cout >= 8 && Cout <= 1024 &&
                   (in_stride == 1 || in_stride == 2), RSA_ERR_SHAPE,
               "pw_wgrad_tc: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d stride=%d", N, H, W, Cin, Cout, in_stride);
+  if (Cin <= 64 && Cout <= 64) {      // thin layers are HBM-bound: streaming kernel (pw_stream.cu), same contract
+    const int rc = rsa_pw_wgrad_stream_dispatch(x, dz, dw, ldw, N, H, W, Cin, Cout, in_stride, (cudaStream_t)stream);
+    if (rc != -100) return rc;
+  }
   EncodeTiledFn enc = get_encode();
   RSA_REQUIRE(enc, RSA_ERR_CUDA, "pw_wgrad_tc: cuTensorMapEncodeTiled not available from the driver");
   PwWgradParams p;

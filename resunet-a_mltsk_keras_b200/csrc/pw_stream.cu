@@ -419,3 +419,186 @@ int rsa_pw_stream_dispatch(const void* x0, int C0, const void* x1, int C1, const
   }
   return -100;
 }
+
+// =====================================================================================================
+// Weight gradient of the same thin 1x1 convolutions:  dw[ci][co] += sum_pix x[pix, ci] * dz[pix, co]
+// (Conv2D 1x1 backward-filter, model2.py:37,84,92,103).  Two tensors are read once and 4-16 KB come out: HBM-bound.  The
+// tcgen05 kernel behind rsa_pw_wgrad_tc takes 36-74 us per launch at 16 x 256 x 256 (8-channel operands ride on half-empty
+// 16-channel TMA boxes) where the bytes take 13-21 us.  Same recipe as the forward kernel above: a warp owns groups of 16
+// pixels = one K step of mma.sync.m16n8k16 with M = ci, N = co; both operands are K-major in memory ([pixel][channel]), so
+// the fragments come out of a per-warp shared-memory FIFO through ldmatrix.trans (rows padded to an odd number of 16-byte
+// chunks: conflict-free), the FIFO is filled DEPTH groups ahead with cp.async, and the Cin x Cout accumulator lives in
+// registers for the whole kernel.  Warps are summed in a fixed order inside the CTA; CTAs add with fp32 atomics like every
+// other weight-gradient kernel here.
+// =====================================================================================================
+namespace {
+
+constexpr int PWG_THREADS = 256, PWG_WARPS = 8;
+// FIFO depth: four groups ahead, three where a group is large (64 channels on one side)
+__host__ __device__ constexpr int pwg_depth(int stage_bytes) { return stage_bytes > 3000 ? 3 : 4; }
+
+struct PwgParams {
+  const bf16* x; const bf16* dz; float* dw;
+  int ldw, M, lw, lh, in_stride;
+};
+
+// row pitch (bytes) of a [16 pixel][C channel] tile: an odd number of 16-byte chunks
+__host__ __device__ constexpr int pwg_pitch(int C) { return C == 8 ? 16 : C * 2 + 16; }
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(PWG_THREADS, 2) pw_wgrad_stream_kernel(const PwgParams p) {
+  constexpr int MT = CIN >= 16 ? CIN / 16 : 1, NT = COUT / 8;
+  constexpr int XP = pwg_pitch(CIN), ZP = pwg_pitch(COUT);
+  constexpr int XB = 16 * XP, STAGE = (16 * (XP + ZP) + 127) & ~127;
+  constexpr int XCH = CIN / 8, ZCH = COUT / 8;                 // 16-byte chunks per pixel row
+  constexpr int PWG_DEPTH = pwg_depth(STAGE);
+  static_assert(MT * NT <= 16, "accumulator must fit in registers");
+  extern __shared__ uint4 pwg_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const uint32_t fifo = (uint32_t)__cvta_generic_to_shared(pwg_smem) + (uint32_t)(warp * PWG_DEPTH * STAGE);
+  const int wmask = (1 << p.lw) - 1, hmask = (1 << p.lh) - 1;
+  const int ngroups = p.M >> 4, gstride = gridDim.x * PWG_WARPS;
+  auto issue = [&](int grp, int stage) {
+    if (grp < ngroups) {
+      const uint32_t base = fifo + (uint32_t)(stage * STAGE);
+      for (int c = lane; c < 16 * XCH; c += 32) {
+        const int row = c / XCH, ch = c % XCH, m = (grp << 4) + row;
+        size_t src = (size_t)m;
+        if (p.in_stride != 1) {
+          const int w = m & wmask, h = (m >> p.lw) & hmask, n = m >> (p.lw + p.lh);
+          src = ((((size_t)n << (p.lh + 1)) + 2 * h) << (p.lw + 1)) + 2 * w;
+        }
+        cp_piece<16, true>(base + (uint32_t)(row * XP + ch * 16), p.x + src * CIN + ch * 8);
+      }
+      for (int c = lane; c < 16 * ZCH; c += 32) {
+        const int row = c / ZCH, ch = c % ZCH;
+        cp_piece<16, true>(base + (uint32_t)(XB + row * ZP + ch * 16), p.dz + ((size_t)(grp << 4) + row) * COUT + ch * 8);
+      }
+    }
+    cp_commit();
+  };
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
+  // ldmatrix row addresses of this lane: matrices {pixels 0-7 | 8-15} x {channel block, next channel block}
+  const int lrow = (lane & 7) + ((lane >> 4) << 3), lblk = (lane >> 3) & 1;
+  const int grp0 = blockIdx.x * PWG_WARPS + warp;
+  for (int s = 0; s < PWG_DEPTH - 1; ++s) issue(grp0 + s * gstride, s);
+  int stage = 0;
+  for (int grp = grp0; grp < ngroups; grp += gstride) {
+    int nstage = stage + PWG_DEPTH - 1;
+    if (nstage >= PWG_DEPTH) nstage -= PWG_DEPTH;
+    __syncwarp();                    // every lane has finished reading the stage that is refilled now
+    issue(grp + (PWG_DEPTH - 1) * gstride, nstage);
+    cp_wait(PWG_DEPTH - 1);
+    __syncwarp();                    // the copies of all lanes are visible
+    const uint32_t base = fifo + (uint32_t)(stage * STAGE);
+    if (++stage == PWG_DEPTH) stage = 0;
+    uint32_t a[MT][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      // x4.trans: r0 = (px 0-7, ci 16i..+7), r1 = (px 0-7, ci 16i+8..), r2 = (px 8-15, ci 16i..), r3 = (px 8-15, ci 16i+8..)
+      // fragment order a0 a1 a2 a3 = (ci lo, px lo), (ci hi, px lo), (ci lo, px hi), (ci hi, px hi): the same
+      const int blk = CIN >= 16 ? 2 * i + lblk : 0;      // 8 channels: the upper rows of the m-tile repeat the lower ones
+      ldsm_x4_t(base + (uint32_t)(lrow * XP + blk * 16), a[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; j += 2) {
+      // r0 = (px 0-7, co 8j..), r1 = (px 0-7, co 8j+8..), r2 = (px 8-15, co 8j..), r3 = (px 8-15, co 8j+8..)
+      uint32_t b[4];
+      const int blk = NT >= 2 ? j + lblk : 0;
+      ldsm_x4_t(base + (uint32_t)(XB + lrow * ZP + blk * 16), b);
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        mma_bf16_16816(acc[i][j], a[i], b[0], b[2]);
+        if constexpr (NT >= 2) mma_bf16_16816(acc[i][j + 1], a[i], b[1], b[3]);
+      }
+    }
+  }
+  cp_wait(0);
+  __syncthreads();                   // the FIFO is dead: reuse it for the cross-warp sum
+  float* red = reinterpret_cast<float*>(pwg_smem);             // [warp][CIN][COUT]
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int ci = 16 * i + g + 8 * r, co = 8 * j + 2 * t;
+        if (ci < CIN) {
+          red[(warp * CIN + ci) * COUT + co] = acc[i][j][2 * r];
+          red[(warp * CIN + ci) * COUT + co + 1] = acc[i][j][2 * r + 1];
+        }
+      }
+  __syncthreads();
+  for (int e = threadIdx.x; e < CIN * COUT; e += PWG_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < PWG_WARPS; ++w) s += red[w * CIN * COUT + e];
+    atomicAdd(p.dw + (size_t)(e / COUT) * p.ldw + (e % COUT), s);
+  }
+}
+
+template <int CIN, int COUT>
+int pwg_launch(const PwgParams& p, cudaStream_t st) {
+  constexpr int STAGE = (16 * (pwg_pitch(CIN) + pwg_pitch(COUT)) + 127) & ~127;
+  constexpr int FIFO = PWG_WARPS * pwg_depth(STAGE) * STAGE, RED = PWG_WARPS * CIN * COUT * 4;
+  constexpr int SMEM = FIFO > RED ? FIFO : RED;
+  static_assert(SMEM <= 100 * 1024, "two CTAs per SM");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pw_wgrad_stream_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) { rsa_set_error("pw_wgrad_stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return RSA_ERR_CUDA; }
+    configured = true;
+  }
+  const int ngroups = p.M >> 4;
+  int grid = (ngroups + PWG_WARPS - 1) / PWG_WARPS;
+  if (grid > 2 * rsa_num_sms()) grid = 2 * rsa_num_sms();
+  cudaError_t le = launch_pdl(pw_wgrad_stream_kernel<CIN, COUT>, dim3(grid), dim3(PWG_THREADS), (size_t)SMEM, st, p);
+  if (le != cudaSuccess) { rsa_set_error("pw_wgrad_stream: launch: %s", cudaGetErrorString(le)); return RSA_ERR_CUDA; }
+  RSA_CHECK_LAUNCH();
+  return RSA_OK;
+}
+template <int CIN>
+int pwg_by_cout(int Cout, const PwgParams& p, cudaStream_t st) {
+  constexpr int MT = CIN >= 16 ? CIN / 16 : 1;
+  switch (Cout) {
+    case 8: return pwg_launch<CIN, 8>(p, st);
+    case 16: return pwg_launch<CIN, 16>(p, st);
+    case 32: return pwg_launch<CIN, 32>(p, st);
+    case 64: if constexpr (MT * 8 <= 16) return pwg_launch<CIN, 64>(p, st);
+  }
+  return -100;
+}
+
+}  // namespace
+
+/* Streaming path of rsa_pw_wgrad_tc (same contract): -100 = "not mine".  RSA_PW_STREAM=0 switches it off. */
+int rsa_pw_wgrad_stream_dispatch(const void* x, const void* dz, float* dw, int ldw, int N, int H, int W, int Cin, int Cout,
+                                 int in_stride, cudaStream_t st) {
+  static const int enabled = getenv("RSA_PW_STREAM") ? atoi(getenv("RSA_PW_STREAM")) : 1;
+  if (!enabled) return -100;
+  const long long M = (long long)N * H * W;
+  if (M % 16 || M > 0x7fffffffLL || (H & (H - 1)) || (W & (W - 1))) return -100;
+  if (((uintptr_t)x | (uintptr_t)dz) & 15) return -100;
+  PwgParams p;
+  p.x = (const bf16*)x; p.dz = (const bf16*)dz; p.dw = dw; p.ldw = ldw; p.M = (int)M; p.lw = ilog2(W); p.lh = ilog2(H);
+  p.in_stride = in_stride;
+  switch (Cin) {
+    case 8: return pwg_by_cout<8>(Cout, p, st);
+    case 16: return pwg_by_cout<16>(Cout, p, st);
+    case 32: return pwg_by_cout<32>(Cout, p, st);
+    case 64: return pwg_by_cout<64>(Cout, p, st);
+  }
+  return -100;
+}
