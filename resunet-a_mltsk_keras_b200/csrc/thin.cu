@@ -352,18 +352,35 @@ __global__ void __launch_bounds__(NT) head_fwd_bf16_kernel(const bf16* __restric
 // head backward, bf16 features: thread = (pixel, 8-channel group g)
 //   dh[p][8g+i] (=|+=) mask(h>0) * sum_j dz[p][j] w[(8g+i)*NO + j];  dw[c*NO+j] += sum_p h[p][c] dz[p][j];  db[j] += sum_p dz[p][j]
 // The weights are read from shared memory (the eight lanes that share g read the same words: broadcast), so that the
-// 8 x NO weight-gradient accumulators are the only per-thread state and two blocks fit an SM; two pixels per thread are
-// in flight.
+// 8 x NO weight-gradient accumulators are the only per-thread state and two blocks fit an SM.  Registers have no room for a
+// second pixel in flight (128 with the accumulators), and a warp that loads, waits and computes in turn ran this kernel at a
+// third of the HBM rate (74 us for 226 MB); so the operands arrive through a per-warp shared-memory FIFO filled HB_DEPTH
+// groups of eight pixels ahead with cp.async (pw_stream.cu's recipe: every lane copies the 16-byte pieces it consumes itself,
+// only the NO logit gradients of a pixel are shared by its quad).
+constexpr int HB_DEPTH = 4;                               // 40 KB of static shared memory with eight warps
+constexpr int HB_STAGE = 32 * 16 + 32 * 16 + 8 * 32;      // h pieces, previous dh pieces, dz rows (<= 8 floats) of 8 pixels
+
+__device__ __forceinline__ void hb_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void hb_cp4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <int NO>
 __global__ void __launch_bounds__(NT, 2) head_bwd_bf16_kernel(const bf16* __restrict__ h, const float* __restrict__ dz,
                                                               const float* __restrict__ w, int64_t M, bf16* __restrict__ dh,
                                                               int accumulate, int relu_mask, float* __restrict__ dw,
                                                               float* __restrict__ db) {
-  __shared__ float ws[32 * NO];
-  __shared__ float sh[NT / 32][33][NO];
+  static_assert(NO <= 8, "a pixel's logit gradients fill at most one 32-byte FIFO row");
+  __shared__ __align__(16) float ws[32 * NO];
+  __shared__ __align__(16) uint8_t fifo_s[(NT / 32) * HB_DEPTH * HB_STAGE];
+  float (*sh)[33][NO] = reinterpret_cast<float (*)[33][NO]>(fifo_s);      // block reduction, after the FIFO has drained
+  static_assert(sizeof(float) * (NT / 32) * 33 * NO <= sizeof(fifo_s), "reduction buffer aliases the FIFO");
   for (int i = threadIdx.x; i < 32 * NO; i += NT) ws[i] = w[i];
   __syncthreads();
-  const int g = threadIdx.x & 3;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int g = lane & 3, q = lane >> 2;                   // channel group, pixel of the group
   const float* wg = ws + g * 8 * NO;
   float acc[8][NO], accb[NO];
 #pragma unroll
@@ -372,54 +389,69 @@ __global__ void __launch_bounds__(NT, 2) head_bwd_bf16_kernel(const bf16* __rest
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i][j] = 0.f;
   }
-  constexpr int U = 2;
-  const int64_t stride = (int64_t)gridDim.x * (NT / 4);
-  for (int64_t p0 = (int64_t)blockIdx.x * (NT / 4) + (threadIdx.x >> 2); p0 < M; p0 += U * stride) {
-    uint4 hq[U], prev[U];
-    float zv[U][NO];
+  const uint32_t fifo = (uint32_t)__cvta_generic_to_shared(fifo_s) + (uint32_t)(wv * HB_DEPTH * HB_STAGE);
+  const int64_t ngroups = (M + 7) >> 3, gstride = (int64_t)gridDim.x * (NT / 32);
+  const bool with_prev = dh && accumulate;
+  auto issue = [&](int64_t grp, int stage) {
+    const int64_t p = grp * 8 + q;
+    if (grp < ngroups && p < M) {
+      const uint32_t base = fifo + (uint32_t)(stage * HB_STAGE);
+      hb_cp16(base + lane * 16, h + p * 32 + g * 8);
+      if (with_prev) hb_cp16(base + 512 + lane * 16, dh + p * 32 + g * 8);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + u * stride;
-      if (p < M) {
-        hq[u] = __ldg(reinterpret_cast<const uint4*>(h + p * 32 + g * 8));
+      for (int j = 0; j < NO; j += 4)
+        if (j + g < NO) hb_cp4(base + 1024 + q * 32 + (j + g) * 4, dz + p * NO + j + g);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t grp0 = (int64_t)blockIdx.x * (NT / 32) + wv;
+  for (int s = 0; s < HB_DEPTH - 1; ++s) issue(grp0 + s * gstride, s);
+  int stage = 0;
+  for (int64_t grp = grp0; grp < ngroups; grp += gstride) {
+    int nstage = stage + HB_DEPTH - 1;
+    if (nstage >= HB_DEPTH) nstage -= HB_DEPTH;
+    __syncwarp();                      // the quad has finished reading the dz row of the stage refilled now
+    issue(grp + (HB_DEPTH - 1) * gstride, nstage);
+    asm volatile("cp.async.wait_group %0;" ::"n"(HB_DEPTH - 1) : "memory");
+    __syncwarp();
+    const uint8_t* base = fifo_s + (wv * HB_DEPTH + stage) * HB_STAGE;
+    if (++stage == HB_DEPTH) stage = 0;
+    const int64_t p = grp * 8 + q;
+    if (p >= M) continue;
+    float hv[8], zv[8];
+    unpack_bf8(*reinterpret_cast<const uint4*>(base + lane * 16), hv);
+    {
+      const float4 z0 = *reinterpret_cast<const float4*>(base + 1024 + q * 32);
+      const float4 z1 = *reinterpret_cast<const float4*>(base + 1024 + q * 32 + 16);
+      zv[0] = z0.x; zv[1] = z0.y; zv[2] = z0.z; zv[3] = z0.w; zv[4] = z1.x; zv[5] = z1.y; zv[6] = z1.z; zv[7] = z1.w;
+    }
+    if (dh) {
+      float d[8];
 #pragma unroll
-        for (int j = 0; j < NO; ++j) zv[u][j] = __ldg(dz + p * NO + j);
-        if (dh && accumulate) prev[u] = *reinterpret_cast<const uint4*>(dh + p * 32 + g * 8);
+      for (int i = 0; i < 8; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < NO; ++j) a = fmaf(zv[j], wg[i * NO + j], a);
+        d[i] = (relu_mask && !(hv[i] > 0.f)) ? 0.f : a;
       }
+      if (accumulate) {
+        float pv[8];
+        unpack_bf8(*reinterpret_cast<const uint4*>(base + 512 + lane * 16), pv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += pv[i];
+      }
+      *reinterpret_cast<uint4*>(dh + p * 32 + g * 8) = pack_bf8(d);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + u * stride;
-      if (p < M) {
-        float hv[8];
-        unpack_bf8(hq[u], hv);
-        if (dh) {
-          float d[8];
+    for (int j = 0; j < NO; ++j) {
+      accb[j] += zv[j];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a = 0.f;
-#pragma unroll
-            for (int j = 0; j < NO; ++j) a = fmaf(zv[u][j], wg[i * NO + j], a);
-            d[i] = (relu_mask && !(hv[i] > 0.f)) ? 0.f : a;
-          }
-          if (accumulate) {
-            float pv[8];
-            unpack_bf8(prev[u], pv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d[i] += pv[i];
-          }
-          *reinterpret_cast<uint4*>(dh + p * 32 + g * 8) = pack_bf8(d);
-        }
-#pragma unroll
-        for (int j = 0; j < NO; ++j) {
-          accb[j] += zv[u][j];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(hv[i], zv[u][j], acc[i][j]);
-        }
-      }
+      for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(hv[i], zv[j], acc[i][j]);
     }
   }
-  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();                     // every warp is done with its FIFO: the buffer becomes the reduction scratch
+  // lanes that share a channel group differ in bits 2..4
 #pragma unroll
   for (int j = 0; j < NO; ++j) {
 #pragma unroll
