@@ -652,7 +652,6 @@ class Plan:
         dW = self.G(name + "/kernel")
         db = self.G(name + "/bias") if bias_grad else None
         self.bwd.append(lib.igemm_wgrad(segs, dy, dW, cout, db, N, out.H, out.W, cout))
-        self._ready(name + "/kernel", name + "/bias")
         pyr = {}
         koff = 0
         for t, mode, relu_in in inputs:
@@ -678,6 +677,7 @@ class Plan:
                 self.bwd.append(lib.igemm_fwd(sg, W_, cout, True, None, g, N, t.H, t.W, t.C, mask=mask,
                                               accumulate=acc))
             koff += t.C
+        self._ready(name + "/kernel", name + "/bias")         # after the data gradients, the last readers of the weights
 
     # ---------------------------------------------------------------------------------------------
     # 3x3 dilated 'same' convolution (ResBlock-a branches model2.py:19-24, heads :153-178)
@@ -735,7 +735,6 @@ class Plan:
                 else:
                     self.bwd.append(self._tag(lib.igemm_wgrad(segs, dy, dW, cout, db, N, H, W, cout),
                                               "conv3x3_wgrad", flops, nb))
-                self._ready(name + "/kernel", name + "/bias")
                 if x.needs_grad:
                     g, acc = self.gacc(x)
                     sg = [Seg(dy, cout, H, W, off_h=-(ky - 1) * dil, off_w=-(kx - 1) * dil,
@@ -750,6 +749,9 @@ class Plan:
                     else:
                         self.bwd.append(self._tag(lib.igemm_fwd(sg, W_, cout, True, None, g, N, H, W, C, mask=mask,
                                                                 accumulate=acc), "conv3x3_dgrad", flops, nb))
+                # after the data gradient: "ready" also means that no later launch READS this layer's weights (the step
+                # updates them and refreshes their bf16 copies while backward still runs, keras_api._early_opt_plan)
+                self._ready(name + "/kernel", name + "/bias")
             self.tape.append(bwd)
         return out
 
@@ -1088,7 +1090,6 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False, emit_fwd=Tru
             else:
                 pl.bwd.append(pl._tag(lib.igemm_wgrad(segs, dy, pl.G(name + "/kernel"), f, pl.G(name + "/bias"), N,
                                                       H, W, f), "conv3x3_wgrad", flops, nb))
-            pl._ready(name + "/kernel", name + "/bias")
             g, acc = pl.gacc(a)
             sg = [Seg(dy, f, H, W, off_h=-(ky - 1) * d, off_w=-(kx - 1) * d, w_off=(ky * 3 + kx) * C * f)
                   for ky in range(3) for kx in range(3)]
@@ -1099,6 +1100,7 @@ def _conv_into(pl, a, f, d, name, out, first, residual, relu=False, emit_fwd=Tru
             else:
                 pl.bwd.append(pl._tag(lib.igemm_fwd(sg, W_, f, True, None, g, N, H, W, C, accumulate=acc),
                                       "conv3x3_dgrad", flops, nb))
+            pl._ready(name + "/kernel", name + "/bias")      # after the data gradient, the last reader of the weights
         pl.tape.append(bwd)
     return (a.data, tcw[0], b_) if thin else None
 
@@ -1227,6 +1229,7 @@ class Net:
         self.tc = {}
         self.shadow = None
         self.pack_launch = None
+        self._pack_split = {}
         self.shadow_dirty = True
         engine = os.environ.get("RSA_CONV_ENGINE", "tc")
         emulated = getattr(self.lib, "is_emulation", False) and not getattr(self.lib, "emulates_tensor_core", False)
@@ -1265,6 +1268,27 @@ class Net:
                                                     max_elems)
         self.pack_launch.hbm_bytes = 8.0 * sum(e["taps"] * e["cin"] * e["cout"] for e in self.tc.values())
         self.conv_engine = "tcgen05 (3x3 fwd/dgrad/wgrad persistent TMA kernels; 1x1 on tensor cores where K,N % 16 == 0)"
+
+    def pack_launches_split(self, off):
+        """The bf16 weight refresh as two launches: the layers whose kernels start at a flat parameter offset >= off and
+        the rest - the step refreshes the first set as soon as the optimizer has updated those parameters, while the
+        backward of the shallow levels still runs (keras_api._train_step_overlapped).  (hi, lo); either may be None."""
+        key = ("split", int(off))
+        if key not in self._pack_split:
+            hi, lo = [], []
+            for name, e in self.tc.items():
+                ent = struct.pack("<qqqiiii", self.params.off[name + "/kernel"], e["fwd"], e["bwd"], e["taps"], e["cin"],
+                                  e["cout"], e["coutp"])
+                (hi if self.params.off[name + "/kernel"] >= off else lo).append((ent, e["taps"] * e["cin"] * e["cout"]))
+            launches = []
+            for part in (hi, lo):
+                if not part:
+                    launches.append(None)
+                    continue
+                tab = torch.frombuffer(bytearray(b"".join(t for t, _ in part)), dtype=torch.uint8).to(self.device)
+                launches.append(self.lib.pack_weights_tc(self.params.data, self.shadow, tab, len(part), max(n for _, n in part)))
+            self._pack_split[key] = tuple(launches)
+        return self._pack_split[key]
 
     def tc_weights(self, name, N, H, W):
         """(fwd copy, dgrad copy) bf16 views if the tensor-core kernel handles this layer at this size."""

@@ -495,16 +495,43 @@ class Model:
                         self._opt_state[k].copy_(torch.from_numpy(np.asarray(v)).to(dev))
             self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
             self._lr_host = torch.zeros(64, dtype=torch.float32, pin_memory=dev.type != "cpu")
-            lib, opt, n = self.net.lib, self.optimizer, ps.n_train
-            gs = 1.0 / (self.dp.world_size if self.dp else 1)
-            if isinstance(opt, Adam):
-                self._opt_launch = lib.adam_step(ps.data, ps.grad, self._opt_state["m"], self._opt_state["v"], n,
-                                                 self._lr_dev, opt.beta_1, opt.beta_2, opt.epsilon, gs)
-            else:
-                self._opt_launch = lib.sgd_step(ps.data, ps.grad, self._opt_state["vel"], n, self._lr_dev,
-                                                opt.momentum, gs)
+            opt, n = self.optimizer, ps.n_train
+            self._opt_launch = self._opt_range(0, n)
+            self._early_opt = {}
             # algorithmic HBM bytes per parameter: Adam reads p, g, m, v and writes p, m, v; SGD reads p, g, vel, writes p, vel
             self._opt_launch.hbm_bytes = float(n) * (28 if isinstance(opt, Adam) else 20)
+
+    def _opt_range(self, lo, hi):
+        """Optimizer launch over the flat parameter range [lo, hi) (the update is element-wise)."""
+        lib, opt, ps, st = self.net.lib, self.optimizer, self.net.params, self._opt_state
+        gs = 1.0 / (self.dp.world_size if self.dp else 1)
+        if isinstance(opt, Adam):
+            return lib.adam_step(ps.data[lo:hi], ps.grad[lo:hi], st["m"][lo:hi], st["v"][lo:hi], hi - lo, self._lr_dev,
+                                 opt.beta_1, opt.beta_2, opt.epsilon, gs)
+        return lib.sgd_step(ps.data[lo:hi], ps.grad[lo:hi], st["vel"][lo:hi], hi - lo, self._lr_dev, opt.momentum, gs)
+
+    def _early_opt_plan(self, pl):
+        """(k, [opt_hi, pack_hi], [opt_lo, pack_lo]) or None.  The flat gradient buffer becomes final from its END (the deep,
+        parameter-heavy levels: backward reaches them first), so after backward launch k the optimizer can already update
+        every parameter at offset >= o and the bf16 copies of those layers can be refreshed - ~98 % of the 1.5 GB the
+        optimizer and the refresh move - on a side stream while the shallow levels (a third of the backward time,
+        tensor-core bound) still run.  Same split as the data-parallel all-reduce ranges (distribute.phase_splits)."""
+        if os.environ.get("RSA_EARLY_OPT", "1") == "0" or self.net.pack_launch is None:
+            return None
+        if id(pl) not in self._early_opt:
+            from .distribute import DataParallel
+            helper = self.dp if self.dp is not None else DataParallel()
+            splits = helper.phase_splits(pl, self.net.params)
+            plan = None
+            if splits:
+                k, off = splits[-1]
+                n = self.net.params.n_train
+                pack_hi, pack_lo = self.net.pack_launches_split(off)
+                hi = [self._opt_range(off, n)] + ([pack_hi] if pack_hi is not None else [])
+                lo = [self._opt_range(0, off)] + ([pack_lo] if pack_lo is not None else [])
+                plan = (k, hi, lo)
+            self._early_opt[id(pl)] = plan
+        return self._early_opt[id(pl)]
 
     def _push_lr(self):
         opt = self.optimizer
@@ -654,10 +681,15 @@ class Model:
         """Graph-replayed training step whose label upload hides behind the forward pass: the network part of the
         forward only needs x, so the (much larger) one-hot label tensors are staged and copied on a second stream
         while the GPU already runs, and the loss/backward/optimizer graph waits for that copy's event."""
-        self.net.shadow_dirty = True
         main = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream()
+            self._opt_stream = torch.cuda.Stream()
+        dp = self.dp is not None and self.dp.world_size > 1
+        early = None if dp else self._early_opt_plan(pl)
+        if early is not None:
+            self.net.ensure_shadow(main.cuda_stream)      # first step / new weights; afterwards every step leaves them fresh
+        self.net.shadow_dirty = True
         nb = self._load_x(pl, x)
         self._push_lr()
         k = pl.n_fwd_net
@@ -665,7 +697,7 @@ class Model:
         def part_a(st):
             pl.scratch.zero_()
             self.net.params.grad.zero_()
-            if self.net.pack_launch is not None:
+            if self.net.pack_launch is not None and early is None:
                 self.net.pack_launch(st)
             self._run_ops(pl.fwd[:k], st)
 
@@ -680,11 +712,30 @@ class Model:
             nb += self._load_labels(pl, y)
             ev = self._copy_stream.record_event()
         main.wait_event(ev)
-        if self.dp is not None and self.dp.world_size > 1:
+        if dp:
             self._dp_graph_backward(pl, k, None, "B")
             self._graph((id(pl), "opt"), lambda st: self._opt_launch(st))
-        else:
+        elif early is None:
             self._graph((id(pl), "B+opt"), lambda st: (part_b(st), self._opt_launch(st)))
+        else:
+            ks, hi_ops, lo_ops = early
+
+            def part_b_early(st):
+                cur = torch.cuda.current_stream()
+                self._run_ops(pl.fwd[k:], st)
+                if pl.bn_update is not None:
+                    pl.bn_update(st)
+                self._run_ops(pl.bwd[:ks + 1], st)               # ends with every side launch joined: grad[off:] is final
+                self._opt_stream.wait_stream(cur)
+                for op in hi_ops:
+                    op(self._opt_stream.cuda_stream)
+                self._run_ops(pl.bwd[ks + 1:], st)
+                for op in lo_ops:
+                    op(st)
+                cur.wait_stream(self._opt_stream)
+
+            self._graph((id(pl), "B+early-opt"), part_b_early)
+            self.net.shadow_dirty = False                         # the step ended with the bf16 copies refreshed
         return nb
 
     def _dp_graph_backward(self, pl, fwd_from, head, tag):
