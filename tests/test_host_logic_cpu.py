@@ -482,6 +482,63 @@ def test_gradient_readiness_bookkeeping_is_exact(dtype):
         assert torch.equal(snap, ps.grad[lo:hi]), key
 
 
+def test_early_optimizer_and_weight_refresh_equal_the_serial_order(variant="v2"):
+    """keras_api._early_opt_plan: after backward launch k the step already updates the parameters at offsets >= o and refreshes
+    their bf16 copies while the remaining backward launches run.  That is only legal if none of those launches WRITES a
+    gradient or READS a weight (fp32 master or bf16 copy) of the early range - replay the launch list in both orders on the
+    deterministic emulation: parameters, optimizer slots and bf16 copies must agree bit for bit."""
+    from emul_lib import EmulLibTC
+    _capi.set_lib(EmulLibTC())
+    p = _rand_params(variant)
+    x, y = O.synth_batch(2, 64, 3, N_CLS, seed=11, block=16)
+
+    def run(early):
+        m = build_model((64, 64, 3), N_CLS, True, variant, dtype="bf16")
+        m.net.set_weights(p)
+        m.compile(optimizer=Adam(lr=1e-2), loss=_losses("tanimoto")[0], loss_weights=LW)
+        m._ensure_opt()
+        pl = m.net.plan(2, True, m.loss_spec)
+        plan = m._early_opt_plan(pl)
+        assert plan is not None and 0 < plan[0] < len(pl.bwd) - 1
+        k, hi_ops, lo_ops = plan
+        assert len(hi_ops) == 2 and len(lo_ops) >= 1, "optimizer + refresh of the early range, optimizer of the rest"
+        for _ in range(1):                  # equal parameters AND equal bf16 copies after one step: every later step is equal too
+            m._load_inputs(pl, x, y)
+            m._push_lr()
+            pl.scratch.zero_()
+            m.net.params.grad.zero_()
+            if not early:
+                m.net.pack_launch(0)
+            else:
+                m.net.ensure_shadow(0)
+            for op in pl.fwd:
+                op(0)
+            pl.bn_update(0)
+            if early:
+                for op in pl.bwd[:k + 1]:
+                    op(0)
+                for op in hi_ops:
+                    op(0)
+                for op in pl.bwd[k + 1:]:
+                    op(0)
+                for op in lo_ops:
+                    op(0)
+                m.net.shadow_dirty = False
+            else:
+                for op in pl.bwd:
+                    op(0)
+                m._opt_launch(0)
+        if not early:
+            m.net.pack_launch(0)
+        ps = m.net.params
+        return ps.data.clone(), m._opt_state["m"].clone(), m._opt_state["v"].clone(), m.net.shadow.clone(), plan
+
+    a, b = run(False), run(True)
+    assert torch.equal(a[0], b[0]), "parameters"
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), "optimizer slots"
+    assert torch.equal(a[3].view(torch.int16), b[3].view(torch.int16)), "bf16 weight copies"
+
+
 def test_bf16_weight_copies_follow_every_parameter_change():
     """The tensor-core path computes from packed bf16 copies of the fp32 master weights: they must be refreshed after
     set_weights, after a training step and after load_model before the next inference launch reads them."""
