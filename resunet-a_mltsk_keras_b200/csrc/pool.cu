@@ -8,6 +8,7 @@
 // Backward routes each pooled gradient to the first maximum of its window in row-major scan order
 // (the arg-max convention of the oracle) and the adjoint of nearest up-sampling is a window sum.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -269,6 +270,103 @@ __global__ void __launch_bounds__(NT) sumpool_pyr8_bf16x2_kernel(const bf16* __r
   }
 }
 
+// Backward of the 8-pixel pyramid with a WARP per (8 x 8 window, 32 channels), lane = channel: every pixel access of the warp
+// is one contiguous 64-byte row and all 64 loads of a lane are in flight at once.  Pass 1 reduces the 64 values of a lane to
+// three small words - for every 2x2 / 4x4 / 8x8 window the position of its FIRST maximum in row-major order (the first
+// maximum of a 4x4 window is the smallest row-major key among the first maxima of those of its 2x2 windows that attain the
+// 4x4 maximum, and likewise one level up) - after which x is no longer needed; pass 2 walks the window two rows at a time
+// and routes the pooled gradients by comparing positions.  The thread-per-(window, channel pair) kernel below needs 128
+// registers with spills for its two passes over x and ran at 0.23 of the HBM rate (122 us for 201 MB at 16 x 256 x 256 x 32).
+// CT = compile-time channel count (column offsets become immediates: 8 row pointers address all 64 loads), 0 = runtime C.
+template <int CT>
+__global__ void __launch_bounds__(NT, 2) maxpool_pyr8_bwd_warp_kernel(const bf16* __restrict__ x, int N, int H, int W, int Crt,
+                                                                      const bf16* __restrict__ dp2, const bf16* __restrict__ dp4,
+                                                                      const bf16* __restrict__ dp8, bf16* __restrict__ dx,
+                                                                      int accumulate) {
+  const int C = CT ? CT : Crt;
+  const int HB = H / 8, WB = W / 8, CB = C / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)N * HB * WB * CB;
+  const int64_t wstride = (int64_t)gridDim.x * (NT / 32);
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (int64_t wid = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5); wid < total; wid += wstride) {
+    const int c = (int)(wid % CB) * 32 + lane;
+    int64_t t = wid / CB;
+    const int wb = (int)(t % WB); t /= WB;
+    const int hb = (int)(t % HB);
+    const int n = (int)(t / HB);
+    const int64_t base = (((int64_t)n * H + hb * 8) * W + wb * 8) * C + c;
+    uint32_t xr[8][4];                 // two pixels per register: (i, 2k) in the low half, (i, 2k+1) in the high half
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = __ldg(xs + base + ((int64_t)i * W + 2 * k) * C), hi = __ldg(xs + base + ((int64_t)i * W + 2 * k + 1) * C);
+        xr[i][k] = lo | (hi << 16);
+      }
+    // ---- pass 1: first-maximum positions.  key of a pixel = 8 * row + column inside the 8 x 8 window; the 2 x 2 keys are kept
+    // as 2-bit local positions (one word), the 4 x 4 keys as four 6-bit fields
+    uint32_t f2 = 0, f4 = 0, k8 = 64;
+    float m8 = 0.f;
+#pragma unroll
+    for (int qi = 0; qi < 2; ++qi)
+#pragma unroll
+      for (int qj = 0; qj < 2; ++qj) {
+        float m4 = 0.f;
+        uint32_t k4 = 64;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int i = 2 * qi + u, j = 2 * qj + v;                  // 2 x 2 window (i, j): rows 2i, 2i+1, columns 2j, 2j+1
+            const float a = __uint_as_float(xr[2 * i][j] << 16), b = __uint_as_float(xr[2 * i][j] & 0xffff0000u);
+            const float cc = __uint_as_float(xr[2 * i + 1][j] << 16), d = __uint_as_float(xr[2 * i + 1][j] & 0xffff0000u);
+            const float m = fmaxf(fmaxf(a, b), fmaxf(cc, d));
+            const uint32_t loc = a == m ? 0u : (b == m ? 1u : (cc == m ? 2u : 3u));
+            f2 |= loc << (2 * (4 * i + j));
+            const uint32_t key = 16 * i + 2 * j + (loc & 1) + 8 * (loc >> 1);
+            // row-major order of the 4 x 4 window: a later 2 x 2 window wins only with a larger value or an earlier key
+            if ((u == 0 && v == 0) || m > m4 || (m == m4 && key < k4)) { m4 = m; k4 = key; }
+          }
+        f4 |= k4 << (6 * (2 * qi + qj));
+        if ((qi == 0 && qj == 0) || m4 > m8 || (m4 == m8 && k4 < k8)) { m8 = m4; k8 = k4; }
+      }
+    const float g8 = dp8 ? __bfloat162float(dp8[(((int64_t)n * (H / 8) + hb) * (W / 8) + wb) * C + c]) : 0.f;
+    // ---- pass 2: two image rows (four 2 x 2 windows) at a time
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      float prev[2][8], g2v[4];
+      if (accumulate) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) prev[i][j] = __bfloat162float(dx[base + ((int64_t)(2 * part + i) * W + j) * C]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        g2v[j] = dp2 ? __bfloat162float(dp2[(((int64_t)n * (H / 2) + hb * 4 + part) * (W / 2) + wb * 4 + j) * C + c]) : 0.f;
+      float g4v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        g4v[j] = dp4 ? __bfloat162float(dp4[(((int64_t)n * (H / 4) + hb * 2 + (part >> 1)) * (W / 4) + wb * 2 + j) * C + c]) : 0.f;
+#pragma unroll
+      for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = 2 * part + ii;
+          const uint32_t key = 8 * i + j;
+          float g = accumulate ? prev[ii][j] : 0.f;
+          const uint32_t loc = (f2 >> (2 * (4 * part + (j >> 1)))) & 3;       // first maximum of this pixel's 2 x 2 window
+          g += loc == (uint32_t)(2 * ii + (j & 1)) ? g2v[j >> 1] : 0.f;
+          const uint32_t key4 = (f4 >> (6 * (2 * (part >> 1) + (j >> 2)))) & 63;
+          g += key4 == key ? g4v[j >> 2] : 0.f;
+          g += k8 == key ? g8 : 0.f;
+          dx[base + ((int64_t)i * W + j) * C] = __float2bfloat16_rn(g);
+        }
+    }
+  }
+}
+
 // 2 x 2 window sums only (the adjoint of one nearest up-sampling by two: decoder combine, model2.py:84,91), bf16: a thread
 // owns a window and 8 channels - four 16-byte loads, one 16-byte store; the scalar generic kernel ran this at 0.2 of the
 // HBM rate (54 us for 84 MB at 16 x 256 x 256 x 32)
@@ -411,7 +509,12 @@ extern "C" int rsa_maxpool_pyr_bwd(const void* x, int dtype, int N, int H, int W
               "maxpool_pyr_bwd: H=%d W=%d must be multiples of %d", H, W, bs);
   cudaStream_t st = (cudaStream_t)stream;
   int grid = pyr_grid((int64_t)N * (H / bs) * (W / bs) * C);
-  if (dtype == RSA_BF16 && bs == 8 && C % 2 == 0) {
+  static const int warp_env = getenv("RSA_MAXPOOL_WARP") ? atoi(getenv("RSA_MAXPOOL_WARP")) : 1;
+  if (dtype == RSA_BF16 && bs == 8 && C == 32 && warp_env) {      // the full-resolution PSP of the last decoder level
+    const int gw = pyr_grid((int64_t)N * (H / 8) * (W / 8) * 32);
+    maxpool_pyr8_bwd_warp_kernel<32><<<gw, NT, 0, st>>>((const bf16*)x, N, H, W, C, (const bf16*)dp2, (const bf16*)dp4,
+                                                        (const bf16*)dp8, (bf16*)dx, accumulate);
+  } else if (dtype == RSA_BF16 && bs == 8 && C % 2 == 0) {
     const int g2 = pyr_grid((int64_t)N * (H / 8) * (W / 8) * (C / 2));
     maxpool_pyr8_bwd_bf16x2_kernel<<<g2, NT, 0, st>>>((const bf16*)x, N, H, W, C, (const bf16*)dp2, (const bf16*)dp4,
                                                       (const bf16*)dp8, (bf16*)dx, accumulate);

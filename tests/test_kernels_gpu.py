@@ -184,9 +184,11 @@ def test_bn_update_moving(lib):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("levels,H", [((2, 4, 8), 16), ((2, 4), 8), ((2,), 6)])
-def test_pool_pyramids(lib, dt, levels, H):
-    N, W, C = 2, H, 24
+@pytest.mark.parametrize("levels,H,C", [((2, 4, 8), 16, 24), ((2, 4), 8, 24), ((2,), 6, 24),
+                                        # 32 channels, 8-pixel windows: the warp-per-window backward kernel (bf16)
+                                        ((2, 4, 8), 16, 32), ((2, 4, 8), 40, 32), ((4, 8), 16, 32)])
+def test_pool_pyramids(lib, dt, levels, H, C):
+    N, W = 2, H
     x = rnd((N, H, W, C), dt, 1)
     p = {k: (torch.zeros((N, H // k, W // k, C), dtype=dt) if k in levels else None) for k in (2, 4, 8)}
     run_pair(lib, "maxpool_pyr_fwd", [x, N, H, W, C, p[2], p[4], p[8]], {}, [i for i, k in ((5, 2), (6, 4), (7, 8)) if k in levels], 0.0)
