@@ -19,7 +19,7 @@
 //     residual, up-sampled addends - with cp.async into a private shared-memory FIFO (slot = lane, conflict-free, no
 //     barrier: a lane only ever reads what it copied itself), DEPTH groups ahead, and consumes the oldest group with
 //     ld.shared; the FIFO depth is sized per launch from the bytes a group moves;
-//   * the weights (at most 64 x 32) live in registers as B fragments for the whole kernel;
+//   * the weights live in registers as B fragments for the whole kernel (64 x 64: in shared memory, one word per lane);
 //   * BatchNorm statistics of the stored values: per-thread partial sums over all its pixels, three shuffles over the rows
 //     of the fragment, per-warp slots summed in a fixed order, one double atomic per channel per CTA (reproducible).
 //
@@ -131,7 +131,11 @@ __global__ void __launch_bounds__(PWS_THREADS, PwsOcc<C0, C1, COUT>::V) pw_strea
   constexpr int KS0 = PwsSrc<C0>::KS, KS1 = PwsSrc<C1>::KS, NT = COUT / 8, NCH = 2 * NT;
   constexpr int SP = NT >= 4 ? NT / 4 : 1;             // pieces per row of an output-shaped side tensor
   constexpr int SB = NT >= 4 ? 16 : 4 * NT;            // their bytes
-  static_assert((KS0 + KS1) * NT <= 16, "B fragments must fit in registers");
+  // B fragments in registers while they fit (<= 32 words); 64 -> 64 channels keeps them in shared memory, one conflict-free
+  // word per lane and fragment (two ld.shared per MMA on a kernel that moves 4 KB per 32 MMAs)
+  constexpr bool BSM = (KS0 + KS1) * NT > 16;
+  constexpr int NBF = (KS0 + KS1) * NT;
+  __shared__ uint32_t wfr[BSM ? NBF : 1][2][32];
   extern __shared__ uint4 pws_fifo[];
   __shared__ float wsum[STATS ? PWS_WARPS : 1][COUT], wsq[STATS ? PWS_WARPS : 1][COUT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -139,23 +143,23 @@ __global__ void __launch_bounds__(PWS_THREADS, PwsOcc<C0, C1, COUT>::V) pw_strea
   if (threadIdx.x == 0) pdl_launch_dependents();
 
   // B fragments: n-tile j, fragment column g  <->  output channel 2 NT (g >> 1) + 2 j + (g & 1)
-  uint32_t b0[KS0 + KS1][NT], b1[KS0 + KS1][NT];
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
+  uint32_t b0[BSM ? 1 : KS0 + KS1][BSM ? 1 : NT], b1[BSM ? 1 : KS0 + KS1][BSM ? 1 : NT];
+  auto bfrag = [&](int s, int j, uint32_t& lo, uint32_t& hi) {          // K step s (both sources), n-tile j, this lane
     const int co = NCH * (g >> 1) + 2 * j + (g & 1);
     const bf16* wrow = p.wt + (size_t)co * p.kt + p.k_base;
+    const int ch = s < KS0 ? pws_kch<C0>(s, t) : C0 + pws_kch<C1 ? C1 : 8>(s - KS0, t);
+    const bool half = s < KS0 ? C0 == 8 : C1 == 8;                      // 8-channel source: the high half of the K step is empty
+    lo = __ldg(reinterpret_cast<const uint32_t*>(wrow + ch));
+    hi = half ? 0u : __ldg(reinterpret_cast<const uint32_t*>(wrow + ch + 2));
+  };
+  if constexpr (BSM) {
+    for (int e = warp; e < NBF; e += PWS_WARPS) bfrag(e / NT, e % NT, wfr[e][0][lane], wfr[e][1][lane]);
+    __syncthreads();
+  } else {
 #pragma unroll
-    for (int s = 0; s < KS0; ++s) {
-      const int ch = pws_kch<C0>(s, t);
-      b0[s][j] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ch));
-      b1[s][j] = C0 == 8 ? 0u : __ldg(reinterpret_cast<const uint32_t*>(wrow + ch + 2));
-    }
+    for (int j = 0; j < NT; ++j)
 #pragma unroll
-    for (int s = 0; s < KS1; ++s) {
-      const int ch = C0 + pws_kch<C1 ? C1 : 8>(s, t);
-      b0[KS0 + s][j] = __ldg(reinterpret_cast<const uint32_t*>(wrow + ch));
-      b1[KS0 + s][j] = C1 == 8 ? 0u : __ldg(reinterpret_cast<const uint32_t*>(wrow + ch + 2));
-    }
+      for (int s = 0; s < KS0 + KS1; ++s) bfrag(s, j, b0[s][j], b1[s][j]);
   }
   float bias_r[NCH];
 #pragma unroll
@@ -225,7 +229,10 @@ __global__ void __launch_bounds__(PWS_THREADS, PwsOcc<C0, C1, COUT>::V) pw_strea
 #pragma unroll
     for (int s = 0; s < KS0 + KS1; ++s)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) mma_bf16_16816(acc[j], a[s], b0[s][j], b1[s][j]);
+      for (int j = 0; j < NT; ++j) {
+        if constexpr (BSM) mma_bf16_16816(acc[j], a[s], wfr[s * NT + j][0][lane], wfr[s * NT + j][1][lane]);
+        else mma_bf16_16816(acc[j], a[s], b0[s][j], b1[s][j]);
+      }
     // ---- epilogue: + addends, ReLU, mask, store, statistics (order as conv_tc2's epilogue)
     for (int k = 0; k < p.nadd; ++k) {
 #pragma unroll
@@ -364,12 +371,11 @@ int pws_launch(PwsParams& p, cudaStream_t st) {
 
 template <int C0, int C1>
 int pws_by_cout(int Cout, PwsParams& p, cudaStream_t st) {
-  constexpr int KS = PwsSrc<C0>::KS + PwsSrc<C1>::KS;
   switch (Cout) {
     case 8: return pws_launch<C0, C1, 8>(p, st);
     case 16: return pws_launch<C0, C1, 16>(p, st);
     case 32: return pws_launch<C0, C1, 32>(p, st);
-    case 64: if constexpr (KS * 8 <= 16) return pws_launch<C0, C1, 64>(p, st);
+    case 64: return pws_launch<C0, C1, 64>(p, st);
   }
   return -100;
 }

@@ -484,9 +484,8 @@ class Plan:
         """A 1x1 launch that rsa_conv_tc2_fwd hands to the streaming kernel (pw_stream.cu: at most 64 input channels in total,
         8 / 16 / 32 / 64 output channels, bf16 out) is bandwidth-bound: tag its algorithmic bytes - operand rows read, result
         written, `sides` further result-shaped tensors read (mask, running sum, residual, up-sampled addends as fractions)."""
-        k16 = lambda c: 0 if c == 0 else (c // 16 if c >= 32 else 1)
         if (out_dtype == torch.bfloat16 and c0 in (8, 16, 32, 64) and (c1 == 0 or (c0, c1) == (32, 32)) and cout in (8, 16, 32, 64)
-                and (k16(c0) + k16(c1)) * (cout // 8) <= 16 and M % 16 == 0 and os.environ.get("RSA_PW_STREAM", "1") != "0"):
+                and M % 16 == 0 and os.environ.get("RSA_PW_STREAM", "1") != "0"):
             self._hb(op, 2.0 * M * (c0 + c1 + cout * (1.0 + sides)))
         return op
 

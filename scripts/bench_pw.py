@@ -53,7 +53,7 @@ CASES = [
     ("dgrad 64->32 out_stride 2 acc", 64, 0, 32, 128, 1, 2, (), 0, 0, 1, 0, 0, 0, 0),
     ("64->16", 64, 0, 16, 128, 1, 1, (), 0, 0, 0, 0, 1, 0, 0),
     ("16->64 dgrad", 16, 0, 64, 128, 1, 1, (), 0, 0, 0, 0, 0, 0, 0),
-    ("64->64 skip+up2 (tcgen05 path)", 64, 0, 64, 128, 1, 1, (1,), 0, 0, 0, 0, 1, 32, 96),
+    ("64->64 skip+up2", 64, 0, 64, 128, 1, 1, (1,), 0, 0, 0, 0, 1, 32, 96),
 ]
 for lab, C0, C1, Co, H, istr, ostr, ups, res, msk, acc, relu, stats, kb, kt in CASES:
     K = C0 + C1

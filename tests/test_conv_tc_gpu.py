@@ -190,6 +190,9 @@ _PWS = [
     (64, 0, 32, 1, 1, (), False, False, False, False, True, 0, 0),
     (32, 32, 16, 1, 1, (), False, False, False, False, False, 0, 0),
     (32, 32, 8, 1, 1, (), False, True, False, False, False, 0, 0),
+    (64, 0, 64, 1, 1, (1,), False, False, False, False, True, 32, 96),   # 64 -> 64 (B fragments in shared memory): skip + up2(q)
+    (64, 0, 64, 1, 1, (), False, True, True, False, False, 0, 0),
+    (32, 32, 64, 1, 1, (), True, False, False, True, True, 0, 0),
 ]
 
 
